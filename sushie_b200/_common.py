@@ -1,0 +1,261 @@
+"""Host-side pieces shared by ``infer_sushie`` and ``infer_sushie_ss``.
+
+Everything here mirrors behaviour of the reference that is part of the output contract
+(SURVEY.md appendix A): argument validation texts (``infer.py:241-401``,
+``infer_ss.py:111-259``), prior construction (``infer.py:367-445``), effect re-ordering
+(``infer.py:811-832``) and the result types (``infer.py:30-101``).  Arrays are numpy where
+the reference returns ``jax.Array``.
+"""
+from __future__ import annotations
+
+import math
+from typing import List, NamedTuple, Optional, Sequence, Tuple
+
+import numpy as np
+import pandas as pd
+
+from . import log
+
+__all__ = ["Prior", "Posterior", "SushieResult", "_PriorAdjustor"]
+
+
+class Prior(NamedTuple):
+    """Prior parameters: ``pi`` [p], ``resid_var`` [k,1], ``effect_covar`` [L,k,k]."""
+
+    pi: np.ndarray
+    resid_var: np.ndarray
+    effect_covar: np.ndarray
+
+
+class Posterior(NamedTuple):
+    """Posterior parameters: ``alpha`` [L,p], ``post_mean`` [L,p,k] (alpha-weighted),
+    ``post_mean_sq`` [L,p,k,k] (alpha-weighted), ``weighted_sum_covar`` [L,k,k],
+    ``kl`` [L], ``log_bf`` [L,p]."""
+
+    alpha: np.ndarray
+    post_mean: np.ndarray
+    post_mean_sq: np.ndarray
+    weighted_sum_covar: np.ndarray
+    kl: np.ndarray
+    log_bf: np.ndarray
+
+
+class SushieResult(NamedTuple):
+    """Inference result; field names, order and shapes follow the reference."""
+
+    priors: Prior
+    posteriors: Posterior
+    pip_all: np.ndarray
+    pip_cs: np.ndarray
+    cs: pd.DataFrame
+    alphas: pd.DataFrame
+    sample_size: np.ndarray
+    elbo: np.ndarray
+    elbo_increase: bool
+    l_order: np.ndarray
+
+
+class _PriorAdjustor(NamedTuple):
+    times: np.ndarray
+    plus: np.ndarray
+
+
+_CLI_HINT = " Specify a valid value using '--{flag}' for command-line usage or '{kw}=' for in-Python function calls."
+
+
+def check_scalar_options(L, min_tol, threshold, purity, max_select, min_snps, summary: bool) -> None:
+    """Scalar argument checks common to both entry points (same texts as the reference)."""
+    if L <= 0:
+        raise ValueError(f"Inferred L ({L}) is invalid, choose a positive L.")
+    if min_tol > 0.1:
+        log.logger.warning(f"Minimum intolerance ({min_tol}) is greater than 0.1. Inference may not be accurate.")
+    if not 0 < threshold < 1:
+        raise ValueError(
+            f"Credible set PIP threshold ({threshold}) must be greater than 0 and less than 1."
+            + _CLI_HINT.format(flag="threshold", kw="threshold")
+        )
+    if not 0 < purity < 1:
+        raise ValueError(
+            f"Purity threshold ({purity}) must be greater than or equal to 0 and less than 1. "
+            + _CLI_HINT.format(flag="purity", kw="purity")
+        )
+    if max_select <= 0:
+        raise ValueError(
+            "The maximum selected number of SNPs for purity must be greater than 0."
+            + _CLI_HINT.format(flag="max-select", kw="max_select")
+        )
+    if min_snps <= 0:
+        if summary:
+            raise ValueError("The minimum number of SNPs to fine-map is invalid. Choose a positive integer.")
+        raise ValueError(
+            "The minimum number of SNPs to fine-map must be greater than 0."
+            + _CLI_HINT.format(flag="min-snps", kw="min_snps")
+        )
+
+
+def check_snp_counts(n_snps: int, min_snps: int, L: int) -> None:
+    if min_snps < L:
+        raise ValueError(
+            f"The number of minimum common SNPs across ancestries ({min_snps}) is less than inferred L ({L})."
+            + " Specify a larger value using '--min-snps' for command-line usage"
+            + " or 'min_snps=' for in-Python function calls."
+        )
+    if n_snps < min_snps:
+        raise ValueError(
+            f"The number of common SNPs across ancestries ({n_snps}) is less than minimum common"
+            + " number of SNPs (100) specified."
+            + " Users can specify a smaller value using '--min-snps' for command-line usage"
+            + " or 'min_snps=' for in-Python function calls."
+        )
+
+
+def resolve_pi(pi, n_snps: int, summary: bool) -> Optional[np.ndarray]:
+    """``None`` keeps the uniform default (1/p); otherwise validate and normalise.
+
+    The two entry points normalise differently: individual level only when the sum exceeds
+    one (``infer.py:313``), summary level whenever it differs from one (``infer_ss.py:189``)."""
+    if pi is None:
+        return None
+    pi = np.asarray(pi)
+    if not (pi > 0).all():
+        raise ValueError("Prior probability/weights must be all positive values.")
+    if pi.shape[0] != n_snps:
+        raise ValueError(f"Prior probability/weights ({pi.shape[0]}) does not match the number of SNPs ({n_snps}).")
+    total = np.sum(pi)
+    if (total != 1) if summary else (total > 1):
+        log.logger.debug("Prior probability/weights sum is not equal to 1. Will normalize to sum to 1.")
+        pi = pi.astype(float) / total
+    return np.asarray(pi, dtype=float)
+
+
+def resolve_resid_var(resid_var, n_pop: int) -> Optional[List[float]]:
+    if resid_var is None:
+        return None
+    if len(resid_var) != n_pop:
+        raise ValueError(
+            f"Number of specified residual prior ({len(resid_var)}) does not match ancestry number ({n_pop})."
+        )
+    resid_var = [float(i) for i in resid_var]
+    if np.any(np.array(resid_var) <= 0):
+        raise ValueError(f"The input of residual prior ({resid_var}) is invalid (<0). Check your input.")
+    return resid_var
+
+
+def build_priors(n_pop: int, L: int, effect_var, rho, no_update: bool, summary: bool):
+    """Initial effect covariance [L,k,k] and the ``_PriorAdjustor`` (``infer.py:367-445``)."""
+    given_var, given_rho = effect_var, rho
+    if effect_var is None:
+        effect_var = [1e-3] * n_pop
+    else:
+        if len(effect_var) != n_pop:
+            raise ValueError(
+                f"Number of specified effect prior ({len(effect_var)}) does not match ancestry number ({n_pop})."
+            )
+        effect_var = [float(i) for i in effect_var]
+        if np.any(np.array(effect_var) <= 0):
+            raise ValueError(f"The effect size prior variance ({effect_var}) must be positive.")
+
+    n_rho = math.comb(n_pop, 2)
+    if rho is None:
+        rho = [0.1] * n_rho
+    else:
+        if n_pop == 1:
+            log.logger.debug("Running single-ancestry SuShiE. The '--rho' parameter is specified but will be ignored.")
+        if (len(rho) != n_rho) and n_pop != 1:
+            raise ValueError(f"Number of specified rho ({len(rho)}) does not match expected" + f" number {n_rho}.")
+        rho = [float(i) for i in rho]
+        # the individual-level entry point rejects |rho| == 1, the summary-level one accepts it
+        bad = (np.abs(np.array(rho)) > 1) if summary else (np.abs(np.array(rho)) >= 1)
+        if np.any(bad):
+            raise ValueError(f"Effect size prior correlation ({rho}) must be between -1 and 1 (inclusive).")
+
+    c0 = np.diag(np.asarray(effect_var, dtype=float))
+    ct = 0
+    for col in range(n_pop):
+        for row in range(1, n_pop):
+            if col < row:
+                cov = rho[ct] * np.sqrt(effect_var[row] * effect_var[col])
+                c0[row, col] = cov
+                c0[col, row] = cov
+                ct += 1
+
+    eye = np.eye(n_pop)
+    if no_update:
+        if given_var is None and given_rho is not None and n_pop != 1:
+            adj = _PriorAdjustor(times=eye, plus=c0 - np.diag(np.diag(c0)))
+            log.logger.info("No updates on the prior effect correlation rho while updating prior effect variance.")
+        elif given_var is not None and given_rho is None and n_pop != 1:
+            adj = _PriorAdjustor(times=np.ones((n_pop, n_pop)) - eye, plus=c0 * eye)
+            log.logger.info("No updates on the prior effect variance while updating prior effect correlation rho.")
+        else:
+            adj = _PriorAdjustor(times=np.zeros((n_pop, n_pop)), plus=c0.copy())
+            log.logger.info("No updates on the prior effect size variance/covariance matrix.")
+    else:
+        adj = _PriorAdjustor(times=np.ones((n_pop, n_pop)), plus=np.zeros((n_pop, n_pop)))
+    return np.stack([c0] * L), adj
+
+
+def _reorder_l(priors: Prior, posteriors: Posterior) -> Tuple[Prior, Posterior, np.ndarray]:
+    """Sort effects by descending nuclear norm of ``weighted_sum_covar`` (stable)."""
+    with np.errstate(all="ignore"):
+        try:
+            norm = np.linalg.svd(posteriors.weighted_sum_covar, compute_uv=False).sum(axis=1)
+        except np.linalg.LinAlgError:
+            norm = np.full(posteriors.weighted_sum_covar.shape[0], np.nan)
+    l_order = np.argsort(-norm, kind="stable")
+    priors = priors._replace(effect_covar=priors.effect_covar[l_order])
+    posteriors = Posterior(*[field[l_order] for field in posteriors])
+    return priors, posteriors, l_order
+
+
+def log_convergence(n_iter: int, max_iter: int, min_tol: float, elbo: np.ndarray, elbo_increase: bool) -> None:
+    """The reference's per-fit log lines (``infer.py:523-548``); users grep for them."""
+    cur = elbo[-1] if len(elbo) else float("nan")
+    if not elbo_increase:
+        log.logger.warning(
+            f"Optimization finished after {n_iter} iterations."
+            + f" ELBO decreased. Final ELBO score: {cur}. Return last iteration's results."
+            + " It can be precision issue,"
+            + " and adding 'import jax; jax.config.update('jax_enable_x64', True)' may fix it."
+            + " If this issue keeps rising for many genes, contact the developers."
+        )
+        return
+    digits = len(str(min_tol)) - str(min_tol).find(".") - 1
+    last = elbo[-2] if len(elbo) > 1 else -np.inf
+    if abs(cur - last) < min_tol:
+        log.logger.info(
+            f"Optimization concludes after {n_iter} iterations. Final ELBO score: {cur:.{digits}f}."
+            + f" Reach minimum tolerance threshold {min_tol}.",
+        )
+    elif n_iter == max_iter:
+        log.logger.info(
+            f"Optimization concludes after {n_iter} iterations. Final ELBO score: {cur:.{digits}f}."
+            + f" Reach maximum iteration threshold {max_iter}.",
+        )
+
+
+def assemble_result(fit, pi, sample_size, no_reorder, cs_builder) -> SushieResult:
+    """RawFit (engine output) -> SushieResult: re-order effects, then credible sets."""
+    k = fit.resid_var.shape[0]
+    L, p = fit.alpha.shape
+    if pi is None:
+        pi = np.ones(p) / float(p)
+    priors = Prior(pi=pi, resid_var=fit.resid_var.reshape(k, 1), effect_covar=fit.effect_covar)
+    posteriors = Posterior(
+        alpha=fit.alpha,
+        post_mean=fit.post_mean,
+        post_mean_sq=fit.post_mean_sq,
+        weighted_sum_covar=fit.weighted_sum_covar,
+        kl=fit.kl,
+        log_bf=fit.log_bf,
+    )
+    l_order = np.arange(L)
+    if not no_reorder:
+        log.logger.debug("Reordering effects based on Frobenius norm of effect size covariance prior.")
+        priors, posteriors, l_order = _reorder_l(priors, posteriors)
+    log.logger.debug("Computing credible sets.")
+    cs, full_alphas, pip_all, pip_cs = cs_builder(posteriors.alpha, posteriors.log_bf)
+    log.logger.debug("Inference and credible set computation complete. Beginning to write results.")
+    return SushieResult(
+        priors, posteriors, pip_all, pip_cs, cs, full_alphas, sample_size, fit.elbo, fit.elbo_increase, l_order
+    )

@@ -1,0 +1,137 @@
+"""Host work queue that shards independent fits over the GPUs of one box.
+
+Every locus (and every cross-validation fold / meta / mega fit of a locus) is an
+independent IBSS problem -- the reference parallelises only by running one process per gene
+(``misc/run_sushie.sh``) -- so there is no data-path collective: problems are cut into
+chunks (cost-sorted, longest first), one worker per GPU pulls chunks from a shared queue
+until it is empty, and results are put back in input order.  A locus is never split across
+GPUs.  The same planner is used by ``bench.py`` under ``torchrun`` (one process per GPU),
+where the queue head is a ``torch.distributed`` store counter instead of a thread lock.
+"""
+from __future__ import annotations
+
+import queue
+import threading
+from typing import Callable, Dict, List, Optional, Sequence, Tuple
+
+from . import _capi, config
+
+
+def estimate_bytes(prep) -> int:
+    """Device bytes one prepared problem needs (storage + state + double-buffered outputs)."""
+    pr = prep.problem
+    es = 8 if config.precision == 64 else 4
+    rows = int(sum(pr.n))
+    p_pad = (pr.p + 31) // 32 * 32
+    mats = rows * p_pad * es
+    state = 8 * (rows * (pr.L + 3) + pr.k * p_pad * 24)
+    out = 2 * 8 * pr.L * pr.p * (2 + pr.k + pr.k * pr.k)
+    staging = max(pr.n) * pr.p * 8
+    return mats + state + out + staging
+
+
+def plan_chunks(preps: Sequence, chunk_bytes: Optional[int] = None, chunk_loci: Optional[int] = None) -> List[List[int]]:
+    """Group problem indices into chunks.
+
+    Problems that cannot share a launch configuration (different ``max_iter`` /
+    ``min_tol``) never share a chunk.  Within a group, indices are sorted by descending
+    cost (longest-processing-time first) and cut where the memory budget or the locus
+    cap is reached."""
+    chunk_bytes = config.chunk_bytes if chunk_bytes is None else chunk_bytes
+    chunk_loci = config.chunk_loci if chunk_loci is None else chunk_loci
+    groups: Dict[Tuple, List[int]] = {}
+    for i, p in enumerate(preps):
+        groups.setdefault((p.max_iter, p.min_tol), []).append(i)
+    chunks: List[List[int]] = []
+    for ids in groups.values():
+        ids = sorted(ids, key=lambda i: (-preps[i].problem.cost, i))
+        cur: List[int] = []
+        cur_bytes = 0
+        for i in ids:
+            b = estimate_bytes(preps[i])
+            if cur and (cur_bytes + b > chunk_bytes or (chunk_loci and len(cur) >= chunk_loci)):
+                chunks.append(cur)
+                cur, cur_bytes = [], 0
+            cur.append(i)
+            cur_bytes += b
+        if cur:
+            chunks.append(cur)
+    # biggest chunks first so the tail of the queue is made of small work items
+    chunks.sort(key=lambda c: -sum(preps[i].problem.cost for i in c))
+    return chunks
+
+
+class ChunkQueue:
+    """Thread-safe queue head over a fixed chunk list (the in-process work queue)."""
+
+    def __init__(self, n_chunks: int):
+        self._q: "queue.SimpleQueue[int]" = queue.SimpleQueue()
+        for c in range(n_chunks):
+            self._q.put(c)
+
+    def next(self) -> Optional[int]:
+        try:
+            return self._q.get_nowait()
+        except queue.Empty:
+            return None
+
+
+class StoreQueue:
+    """Queue head shared by the ranks of a ``torch.distributed`` job: an atomic counter
+    in the rendezvous store (no tensors, no collective on the data path)."""
+
+    def __init__(self, store, n_chunks: int, key: str = "sushie_b200/chunk_head"):
+        self._store, self._n, self._key = store, n_chunks, key
+
+    def next(self) -> Optional[int]:
+        c = int(self._store.add(self._key, 1)) - 1
+        return c if c < self._n else None
+
+
+def drain(q, chunks: List[List[int]], preps: Sequence, runner: Callable, device: int, results: list, log: list) -> None:
+    """Worker loop: pull chunks until the queue is empty."""
+    while True:
+        c = q.next()
+        if c is None:
+            return
+        ids = chunks[c]
+        out = runner([preps[i] for i in ids], device)
+        for i, r in zip(ids, out):
+            results[i] = r
+        log.append((device, c, len(ids)))
+
+
+def run_sharded(preps: Sequence, runner: Callable, devices: Optional[Sequence[int]] = None) -> list:
+    """Run every prepared problem; one worker thread (one ``sb_ctx``) per device."""
+    if len(preps) == 0:
+        return []
+    if devices is None:
+        devices = config.devices or [0]
+    devices = list(devices)
+    chunks = plan_chunks(preps)
+    q = ChunkQueue(len(chunks))
+    results: list = [None] * len(preps)
+    trace: list = []
+    if len(devices) == 1:
+        drain(q, chunks, preps, runner, devices[0], results, trace)
+        return results
+    errors: list = []
+
+    def work(dev):
+        try:
+            drain(q, chunks, preps, runner, dev, results, trace)
+        except BaseException as exc:  # surfaced after join
+            errors.append(exc)
+
+    threads = [threading.Thread(target=work, args=(d,), daemon=True) for d in devices]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    if errors:
+        raise errors[0]
+    return results
+
+
+def device_count() -> int:
+    return _capi.device_count()

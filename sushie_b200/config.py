@@ -1,0 +1,28 @@
+"""Run-time selectors that replace the reference's ``--platform`` / ``--jax-precision``
+switches (``sushie/cli.py:2051-2055``): which GPU(s) to use and the device storage
+precision of genotypes / LD (arithmetic is always fp64)."""
+from __future__ import annotations
+
+import os
+from typing import List, Optional
+
+# 64 -> fp64 storage (parity mode, the reference CLI default); 32 -> fp32 storage.
+precision: int = int(os.environ.get("SUSHIE_B200_PRECISION", "64"))
+# GPU ordinals used by the batch entry points; None = device 0 only.
+devices: Optional[List[int]] = None
+# thread blocks cooperating on one locus; 0 lets the engine choose.
+team_size: int = int(os.environ.get("SUSHIE_B200_TEAM", "0"))
+# loci per device-resident chunk in the batch entry points (0 = size by memory budget).
+chunk_loci: int = int(os.environ.get("SUSHIE_B200_CHUNK", "0"))
+# device memory budget per chunk, bytes
+chunk_bytes: int = int(float(os.environ.get("SUSHIE_B200_CHUNK_GB", "24")) * (1 << 30))
+
+
+def storage_code() -> int:
+    from . import _capi
+
+    if precision == 64:
+        return _capi.SB_F64
+    if precision == 32:
+        return _capi.SB_F32
+    raise ValueError(f"sushie_b200.config.precision must be 32 or 64, got {precision}")

@@ -1,0 +1,186 @@
+"""Credible sets, purity and the output tables (reference ``make_cs``, ``infer.py:835-1008``).
+
+The selection logic (sort by alpha, cumulative cut at ``threshold``, optional
+``max_select`` sub-sample) runs on the host in numpy; the purity Gram matrices -- the only
+heavy part -- are computed on the GPU from the device-resident, standardised genotypes
+(or LD) through ``sb_batch_purity``.  The sub-sample reproduces
+``jax.random.choice(PRNGKey(seed), idx, (max_select,), replace=False)`` (threefry2x32,
+same un-split key for every effect, ``infer.py:894,940-943``).
+"""
+from __future__ import annotations
+
+from typing import Callable, List, Optional, Sequence, Tuple
+
+import numpy as np
+import pandas as pd
+
+from . import log
+from .utils import make_pip
+
+# ---- threefry2x32 counter PRNG (jax.random's default implementation) -------------------
+
+_U32 = np.uint32
+_ROTATIONS = ((13, 15, 26, 6), (17, 29, 16, 24))
+
+
+def _rol(v: np.ndarray, s: int) -> np.ndarray:
+    return (v << _U32(s)) | (v >> _U32(32 - s))
+
+
+def _threefry_pairs(k0: int, k1: int, c0: np.ndarray, c1: np.ndarray):
+    with np.errstate(over="ignore"):
+        ks = [_U32(k0), _U32(k1), _U32(k0) ^ _U32(k1) ^ _U32(0x1BD11BDA)]
+        x0 = c0.astype(_U32) + ks[0]
+        x1 = c1.astype(_U32) + ks[1]
+        for i in range(5):
+            for s in _ROTATIONS[i & 1]:
+                x0 = x0 + x1
+                x1 = _rol(x1, s) ^ x0
+            x0 = x0 + ks[(i + 1) % 3]
+            x1 = x1 + ks[(i + 2) % 3] + _U32(i + 1)
+    return x0, x1
+
+
+def _threefry_stream(key: Tuple[int, int], n: int) -> np.ndarray:
+    """``n`` 32-bit words for counters 0..n-1 in JAX's layout (first half / second half)."""
+    cnt = np.arange(n + (n & 1), dtype=_U32)
+    cnt[n:] = 0
+    h = cnt.size // 2
+    a, b = _threefry_pairs(key[0], key[1], cnt[:h], cnt[h:])
+    return np.concatenate([a, b])[:n]
+
+
+def _split2(key: Tuple[int, int]):
+    w = _threefry_stream(key, 4)
+    return (int(w[0]), int(w[1])), (int(w[2]), int(w[3]))
+
+
+def jax_choice_no_replace(seed: int, values: np.ndarray, n_draws: int) -> np.ndarray:
+    """First ``n_draws`` entries of JAX's sort-based shuffle of ``values``."""
+    key = ((int(seed) >> 32) & 0xFFFFFFFF, int(seed) & 0xFFFFFFFF)
+    out = np.array(values, copy=True)
+    rounds = int(np.ceil(3 * np.log(max(1, out.size)) / np.log(np.iinfo(np.uint32).max)))
+    for _ in range(rounds):
+        key, sub = _split2(key)
+        out = out[np.argsort(_threefry_stream(sub, out.size), kind="stable")]
+    return out[:n_draws]
+
+
+# ---- credible sets ----------------------------------------------------------------------
+
+
+def select_sets(alpha: np.ndarray, threshold: float, max_select: int, seed: int):
+    """Per effect: descending order, cumulative alpha, number of SNPs in the set and the
+    (possibly sub-sampled) SNP indices used for purity."""
+    n_l, p = alpha.shape
+    orders, csums, sizes, purity_idx = [], [], [], []
+    base = np.arange(p)
+    for ldx in range(n_l):
+        a = alpha[ldx]
+        # pandas ``sort_values(ascending=False)``: argsort of the reversed column, reversed
+        order = base[::-1][np.argsort(a[::-1], kind="quicksort")][::-1]
+        csum = np.cumsum(a[order])
+        n_row = int(np.count_nonzero(csum < threshold))
+        size = n_row if n_row == p else n_row + 1
+        idx = order[:size].astype(np.int64)
+        if idx.size > max_select:
+            idx = jax_choice_no_replace(seed, idx, max_select)
+        orders.append(order)
+        csums.append(csum)
+        sizes.append(size)
+        purity_idx.append(idx)
+    return orders, csums, sizes, purity_idx
+
+
+def combine_purity(min_abs: np.ndarray, ns: np.ndarray, purity_method: str) -> np.ndarray:
+    """min |corr| per (effect, ancestry) -> one purity per effect (``infer.py:952-965``)."""
+    ns = np.asarray(ns, dtype=float).reshape(-1)
+    if purity_method == "weighted":
+        return min_abs @ (ns / ns.sum())
+    if purity_method == "max":
+        return min_abs.max(axis=1)
+    if purity_method == "min":
+        return min_abs.min(axis=1)
+    raise ValueError(f"Invalid purity method {purity_method}. Choose from 'weighted', 'max', or 'min'.")
+
+
+def build_tables(
+    alpha: np.ndarray,
+    log_bf: np.ndarray,
+    ns: np.ndarray,
+    min_abs_corr: Callable[[List[np.ndarray]], np.ndarray],
+    threshold: float,
+    purity: float,
+    purity_method: str,
+    max_select: int,
+    seed: int,
+):
+    """Assemble ``cs``, ``alphas``, ``pip_all``, ``pip_cs`` exactly in the reference's schema.
+
+    ``min_abs_corr(list_of_index_arrays) -> [n_sets, k]`` supplies the purity raw material
+    (device kernel)."""
+    alpha = np.asarray(alpha, dtype=float)
+    log_bf = np.asarray(log_bf, dtype=float)
+    if purity_method not in ("weighted", "max", "min"):
+        raise ValueError(f"Invalid purity method {purity_method}. Choose from 'weighted', 'max', or 'min'.")
+    n_l, p = alpha.shape
+    orders, csums, sizes, purity_idx = select_sets(alpha, threshold, max_select, seed)
+    purities = combine_purity(np.asarray(min_abs_corr(purity_idx), dtype=float).reshape(n_l, -1), ns, purity_method)
+    kept = purities > purity
+
+    pip_all = make_pip(alpha)
+    pip_cs = make_pip(alpha[np.nonzero(kept)[0]])
+
+    columns = {"SNPIndex": np.arange(p)}
+    cs_parts = []
+    for ldx in range(n_l):
+        order, csum, size = orders[ldx], csums[ldx], sizes[ldx]
+        in_cs = np.zeros(p, dtype=np.int64)
+        in_cs[order[:size]] = 1
+        tag = f"l{ldx + 1}"
+        columns[f"alpha_{tag}"] = alpha[ldx]
+        columns[f"in_cs_{tag}"] = in_cs
+        columns[f"purity_{tag}"] = np.full(p, purities[ldx])
+        columns[f"kept_{tag}"] = np.full(p, int(kept[ldx]), dtype=np.int64)
+        columns[f"log_bf_{tag}"] = log_bf[ldx]
+        if kept[ldx]:
+            sel = order[:size]
+            cs_parts.append(
+                pd.DataFrame(
+                    {
+                        "CSIndex": np.full(size, ldx + 1, dtype=np.int64),
+                        "SNPIndex": sel.astype(np.int64),
+                        "alpha": alpha[ldx][sel],
+                        "c_alpha": csum[:size],
+                    }
+                )
+            )
+    columns["pip_all"] = pip_all
+    columns["pip_cs"] = pip_cs
+    full_alphas = pd.DataFrame(columns)
+
+    if cs_parts:
+        cs = pd.concat(cs_parts, ignore_index=True)
+    else:
+        cs = pd.DataFrame(
+            {
+                "CSIndex": np.zeros(0, dtype=np.int64),
+                "SNPIndex": np.zeros(0, dtype=np.int64),
+                "alpha": np.zeros(0),
+                "c_alpha": np.zeros(0),
+            }
+        )
+    snp_in_cs = cs.SNPIndex.values.astype(int)
+    if len(snp_in_cs) != len(np.unique(snp_in_cs)):
+        log.logger.warning(
+            "Same SNPs appear in different credible set, which is very unusual."
+            + " You may want to check this gene in details."
+        )
+    cs["pip_all"] = pip_all[snp_in_cs]
+    cs["pip_cs"] = pip_cs[snp_in_cs]
+
+    log.logger.info(
+        f"{len(cs.CSIndex.unique())} out of {n_l} credible sets remain after pruning based on purity ({purity})."
+        + " For detailed results, specify --alphas."
+    )
+    return cs, full_alphas, pip_all, pip_cs

@@ -1,0 +1,1036 @@
+// capi.cu -- host side of the C ABI declared in include/sushie_b200.h.
+//
+// Owns device memory (one arena per batch), uploads problems, runs the device-side
+// prologue (standardisation / XtX / Xty, reference infer.py:326-333,494 and
+// infer_ss.py:340-344), launches the persistent IBSS kernel (ibss_kernel.cuh) with a
+// thread-block-cluster or cooperative launch, and downloads results.  No CPU fallback.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/sushie_b200.h"
+#include "ibss_kernel.cuh"
+
+using sb::KMAX;
+using sb::LaunchParams;
+using sb::OutBuf;
+using sb::ProbDev;
+
+static thread_local std::string g_init_error;
+
+struct sb_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = true;
+  int num_sms = 0;
+  int smem_optin = 0;
+  int cluster_ok = 0;
+  int coop_ok = 0;
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  std::string err;
+};
+
+struct HostProb {
+  int K = 0, p = 0, L = 0, p_pad = 0, nrows = 0;
+  int n[KMAX] = {0, 0, 0, 0};
+  size_t out_off[2] = {0, 0};  // offsets of the two output blocks inside the arena
+  size_t elbo_off = 0, meta_off = 0;
+  double bytes_per_ser = 0.0;  // algorithmic: one traversal of X / LD at storage precision
+  std::vector<double> ecov0, rv0;
+  void* d_X[KMAX] = {nullptr, nullptr, nullptr, nullptr};
+};
+
+struct sb_batch {
+  bool ss = false;
+  int storage = SB_F64;
+  int n_probs = 0;
+  sb_opts opts{};
+  int team_size = 1;
+  int hw_cluster = 0;
+  int n_teams_cap = 0;
+  int smem_bytes = 0;
+  int G_max = 0, NS_max = 0;
+  unsigned char* arena = nullptr;
+  size_t arena_bytes = 0;
+  ProbDev* d_probs = nullptr;
+  int* d_ids = nullptr;     // problem ids grouped by K
+  int* d_queue = nullptr;   // [KMAX] one queue head per K group
+  int* d_slots = nullptr;
+  unsigned* d_bar = nullptr;
+  size_t metas_off = 0;
+  int group_start[KMAX + 2] = {0};
+  std::vector<HostProb> hp;
+  std::vector<ProbDev> pd;
+  double prologue_ms = 0.0;
+  int n_launches_create = 0;
+  bool ran = false;
+};
+
+#define SB_CUDA(call)                                                                       \
+  do {                                                                                      \
+    cudaError_t e_ = (call);                                                                \
+    if (e_ != cudaSuccess) {                                                                \
+      ctx->err = std::string(#call) + ": " + cudaGetErrorString(e_);                        \
+      return (e_ == cudaErrorMemoryAllocation) ? SB_ENOMEM : SB_ECUDA;                      \
+    }                                                                                       \
+  } while (0)
+
+static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// ------------------------------------------------------------------------------------------
+// kernel table
+
+template <int K, typename XT, bool SS>
+static const void* kfn() {
+  return reinterpret_cast<const void*>(&sb::ibss_kernel<K, XT, SS>);
+}
+static const void* pick_kernel(int K, int storage, bool ss) {
+  const bool f32 = storage == SB_F32;
+#define SB_PICK(KK)                                                                           \
+  case KK:                                                                                    \
+    return ss ? (f32 ? kfn<KK, float, true>() : kfn<KK, double, true>())                      \
+              : (f32 ? kfn<KK, float, false>() : kfn<KK, double, false>());
+  switch (K) {
+    SB_PICK(1)
+    SB_PICK(2)
+    SB_PICK(3)
+    SB_PICK(4)
+  }
+#undef SB_PICK
+  return nullptr;
+}
+
+// ------------------------------------------------------------------------------------------
+// context
+
+extern "C" int sb_version(void) { return SB_VERSION; }
+
+extern "C" int sb_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+  return n;
+}
+
+extern "C" const char* sb_last_error(const sb_ctx* ctx) { return ctx ? ctx->err.c_str() : g_init_error.c_str(); }
+
+extern "C" int sb_init(int device, sb_ctx** out) {
+  if (!out) return SB_EINVAL;
+  *out = nullptr;
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0) {
+    g_init_error = std::string("no usable CUDA device: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "count = 0");
+    return SB_ENODEV;
+  }
+  if (device < 0 || device >= n) {
+    g_init_error = "device index out of range";
+    return SB_EINVAL;
+  }
+  sb_ctx* ctx = new sb_ctx();
+  ctx->device = device;
+  cudaDeviceProp prop;
+  if ((e = cudaSetDevice(device)) != cudaSuccess || (e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) {
+    g_init_error = std::string("cudaSetDevice/GetDeviceProperties: ") + cudaGetErrorString(e);
+    delete ctx;
+    return SB_ECUDA;
+  }
+  if (prop.major < 9) {
+    g_init_error = "sushie_b200 needs bulk-async-copy hardware (built for sm_100a); found sm_" +
+                   std::to_string(prop.major) + std::to_string(prop.minor);
+    delete ctx;
+    return SB_ENODEV;
+  }
+  ctx->num_sms = prop.multiProcessorCount;
+  ctx->smem_optin = static_cast<int>(prop.sharedMemPerBlockOptin);
+  int v = 0;
+  cudaDeviceGetAttribute(&v, cudaDevAttrClusterLaunch, device);
+  ctx->cluster_ok = v;
+  cudaDeviceGetAttribute(&v, cudaDevAttrCooperativeLaunch, device);
+  ctx->coop_ok = v;
+  if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) {
+    g_init_error = std::string("cudaStreamCreate: ") + cudaGetErrorString(e);
+    delete ctx;
+    return SB_ECUDA;
+  }
+  for (auto& ev : ctx->ev) cudaEventCreate(&ev);
+  *out = ctx;
+  return SB_OK;
+}
+
+extern "C" int sb_destroy(sb_ctx* ctx) {
+  if (!ctx) return SB_OK;
+  cudaSetDevice(ctx->device);
+  for (auto& ev : ctx->ev)
+    if (ev) cudaEventDestroy(ev);
+  if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+  return SB_OK;
+}
+
+extern "C" int sb_set_stream(sb_ctx* ctx, void* cuda_stream) {
+  if (!ctx) return SB_EINVAL;
+  if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+  ctx->stream = static_cast<cudaStream_t>(cuda_stream);
+  ctx->own_stream = false;
+  return SB_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// geometry: rows per band / stages / sweep-1 segmentation for one problem
+
+struct Geometry {
+  int p_pad, G, NS, NSEG;
+  size_t smem;
+};
+
+static bool plan_geometry(int p, int n_max, int es, bool ss, int smem_budget, Geometry& g) {
+  g.p_pad = static_cast<int>(align_up(static_cast<size_t>(p), 32));
+  const size_t hdr = align_up(sizeof(sb::SmemHdr), 128);
+  const size_t fixed = hdr + static_cast<size_t>(g.p_pad) * sizeof(double) * (ss ? 1 : 2);
+  const size_t row_bytes = static_cast<size_t>(g.p_pad) * es;
+  if (fixed + 2 * row_bytes > static_cast<size_t>(smem_budget)) return false;
+  const int rows_fit = static_cast<int>((smem_budget - fixed) / row_bytes);
+  g.NS = rows_fit >= 3 ? 3 : 2;
+  g.G = std::max(1, std::min({sb::GMAX, rows_fit / g.NS, std::max(1, n_max)}));
+  // spend left-over shared memory on a 4th stage when bands are small
+  if (g.NS == 3 && rows_fit >= 4 * g.G && g.G * row_bytes < 48 * 1024) g.NS = 4;
+  int nseg = 1;
+  while (nseg * 2 <= sb::NW / g.G) nseg *= 2;
+  g.NSEG = nseg;
+  g.smem = fixed + static_cast<size_t>(g.NS) * g.G * row_bytes;
+  return true;
+}
+
+static int choose_team(const sb_ctx* ctx, int n_probs, double bytes_per_locus, int requested, int& hw_cluster) {
+  const int S = ctx->num_sms;
+  int c;
+  if (requested > 0) {
+    c = std::min(requested, S);
+  } else {
+    const int avail = std::max(1, S / std::max(1, n_probs));
+    const int want = std::max(1, static_cast<int>(bytes_per_locus / (256.0 * 1024.0)));
+    c = std::min(want, avail);
+    if (n_probs >= S) c = (want >= 8) ? 2 : 1;  // big batches: pairs halve the tail
+  }
+  if (c <= 16) {
+    int p2 = 1;
+    while (p2 * 2 <= c) p2 *= 2;
+    c = p2;
+    hw_cluster = (c > 1 && ctx->cluster_ok) ? 1 : 0;
+    if (c > 1 && !ctx->cluster_ok) hw_cluster = 0;
+  } else {
+    hw_cluster = 0;
+  }
+  if (c > 1 && !hw_cluster && !ctx->coop_ok) c = 1;
+  return c;
+}
+
+// ------------------------------------------------------------------------------------------
+// arena bookkeeping
+
+struct Bump {
+  size_t off = 0;
+  size_t take(size_t bytes, size_t align = 256) {
+    off = align_up(off, align);
+    const size_t o = off;
+    off += bytes;
+    return o;
+  }
+};
+
+struct ProbLayout {  // offsets inside the arena
+  size_t X[KMAX], y, logpi, pi_raw, xtx, ecov0, rv0, adjt, adjp, r, xb, bT, part, xty, rfull, statA, statB, statC,
+      trav, out[2], elbo, meta, z;
+  size_t out_fields[2][9];
+};
+
+static size_t out_block_bytes(int L, int p, int K) {
+  const size_t Lp = static_cast<size_t>(L) * p;
+  return sizeof(double) * (Lp + Lp * K + Lp * K * K + Lp + static_cast<size_t>(L) * K * K + L +
+                           static_cast<size_t>(L) * K * K + K + static_cast<size_t>(L) * K + 8);
+}
+
+static void out_block_fields(int L, int p, int K, size_t base, size_t (&f)[9]) {
+  const size_t Lp = static_cast<size_t>(L) * p;
+  size_t o = base;
+  f[0] = o; o += Lp * 8;                               // alpha
+  f[1] = o; o += Lp * K * 8;                           // pm
+  f[2] = o; o += Lp * K * K * 8;                       // pmsq
+  f[3] = o; o += Lp * 8;                               // lbf
+  f[4] = o; o += static_cast<size_t>(L) * K * K * 8;   // wsc
+  f[5] = o; o += static_cast<size_t>(L) * 8;           // kl
+  f[6] = o; o += static_cast<size_t>(L) * K * K * 8;   // ecov
+  f[7] = o; o += static_cast<size_t>(K) * 8;           // rv
+  f[8] = o;                                            // xtxb2
+}
+
+template <typename P>
+static int validate_common(sb_ctx* ctx, const P& pr, int i) {
+  if (pr.k < 1 || pr.k > KMAX) {
+    ctx->err = "problem " + std::to_string(i) + ": k=" + std::to_string(pr.k) + " unsupported (1.." +
+               std::to_string(KMAX) + ")";
+    return SB_EINVAL;
+  }
+  if (pr.p < 1 || pr.L < 1) {
+    ctx->err = "problem " + std::to_string(i) + ": p and L must be positive";
+    return SB_EINVAL;
+  }
+  if (!pr.resid_var || !pr.effect_covar) {
+    ctx->err = "problem " + std::to_string(i) + ": resid_var / effect_covar missing";
+    return SB_EINVAL;
+  }
+  if (!pr.em_update && (!pr.adj_times || !pr.adj_plus)) {
+    ctx->err = "problem " + std::to_string(i) + ": adj_times / adj_plus required when em_update == 0";
+    return SB_EINVAL;
+  }
+  return SB_OK;
+}
+
+static int elem_size(int dtype) { return dtype == SB_F64 ? 8 : (dtype == SB_F32 ? 4 : 1); }
+
+template <typename IT, typename XT>
+static void launch_prep_columns(const void* in, int in_ld, int n, int p, int p_pad, int flags, void* out,
+                                double* xtx, cudaStream_t st) {
+  const int T = 128;
+  sb::prep_columns_kernel<IT, XT><<<(p_pad + T - 1) / T, T, 0, st>>>(
+      static_cast<const IT*>(in), in_ld, n, p, p_pad, flags, static_cast<XT*>(out), xtx);
+}
+
+static void prep_columns_dispatch(int in_dtype, int storage, const void* in, int in_ld, int n, int p, int p_pad,
+                                  int flags, void* out, double* xtx, cudaStream_t st) {
+  if (storage == SB_F64) {
+    if (in_dtype == SB_F64) launch_prep_columns<double, double>(in, in_ld, n, p, p_pad, flags, out, xtx, st);
+    if (in_dtype == SB_F32) launch_prep_columns<float, double>(in, in_ld, n, p, p_pad, flags, out, xtx, st);
+    if (in_dtype == SB_I8) launch_prep_columns<int8_t, double>(in, in_ld, n, p, p_pad, flags, out, xtx, st);
+  } else {
+    if (in_dtype == SB_F64) launch_prep_columns<double, float>(in, in_ld, n, p, p_pad, flags, out, xtx, st);
+    if (in_dtype == SB_F32) launch_prep_columns<float, float>(in, in_ld, n, p, p_pad, flags, out, xtx, st);
+    if (in_dtype == SB_I8) launch_prep_columns<int8_t, float>(in, in_ld, n, p, p_pad, flags, out, xtx, st);
+  }
+}
+
+template <typename IT, typename XT>
+static void launch_pad_rows(const void* in, int n, int p, int p_pad, void* out, cudaStream_t st) {
+  const size_t total = static_cast<size_t>(n) * p_pad;
+  const int T = 256;
+  const int blocks = static_cast<int>(std::min<size_t>((total + T - 1) / T, 148 * 16));
+  sb::pad_rows_kernel<IT, XT><<<blocks, T, 0, st>>>(static_cast<const IT*>(in), n, p, p_pad, static_cast<XT*>(out));
+}
+
+// ------------------------------------------------------------------------------------------
+// batch creation (shared by individual / summary level)
+
+struct GenericProblem {
+  int K, p, L, em;
+  int n[KMAX];
+  const void* mat[KMAX];
+  int mat_dtype;
+  int standardize;
+  const double* vec[KMAX];  // y (individual) or z (summary)
+  double ns[KMAX];
+  const double *pi, *resid_var, *effect_covar, *adj_times, *adj_plus;
+};
+
+static int batch_create(sb_ctx* ctx, const std::vector<GenericProblem>& gp, bool ss, const sb_opts* opts_in,
+                        sb_batch** out) {
+  if (!ctx || !out) return SB_EINVAL;
+  *out = nullptr;
+  cudaSetDevice(ctx->device);
+  const int n_probs = static_cast<int>(gp.size());
+  if (n_probs < 1) {
+    ctx->err = "empty batch";
+    return SB_EINVAL;
+  }
+  sb_opts opts{};
+  opts.max_iter = 500;
+  opts.min_tol = 1e-4;
+  opts.storage = SB_F64;
+  if (opts_in) opts = *opts_in;
+  if (opts.max_iter < 1) {
+    ctx->err = "max_iter must be >= 1";
+    return SB_EINVAL;
+  }
+  if (opts.storage != SB_F64 && opts.storage != SB_F32) {
+    ctx->err = "storage must be SB_F64 or SB_F32";
+    return SB_EINVAL;
+  }
+  const int es = elem_size(opts.storage);
+  const int smem_budget = ctx->smem_optin - 1024;  // leave room for static shared memory
+
+  std::unique_ptr<sb_batch> b(new sb_batch());
+  b->ss = ss;
+  b->storage = opts.storage;
+  b->n_probs = n_probs;
+  b->opts = opts;
+  b->hp.resize(n_probs);
+  b->pd.resize(n_probs);
+
+  // geometry + team size
+  std::vector<Geometry> geo(n_probs);
+  double bytes_mean = 0.0;
+  size_t smem_max = 0;
+  for (int i = 0; i < n_probs; ++i) {
+    const GenericProblem& g = gp[i];
+    int n_max = 0;
+    double bytes = 0.0;
+    for (int k = 0; k < g.K; ++k) {
+      if (g.n[k] < 1) {
+        ctx->err = "problem " + std::to_string(i) + ": empty ancestry " + std::to_string(k);
+        return SB_EINVAL;
+      }
+      n_max = std::max(n_max, g.n[k]);
+      bytes += static_cast<double>(g.n[k]) * g.p * es;
+    }
+    if (!plan_geometry(g.p, n_max, es, ss, smem_budget, geo[i])) {
+      ctx->err = "problem " + std::to_string(i) + ": p=" + std::to_string(g.p) +
+                 " does not fit the shared-memory band pipeline at this storage precision";
+      return SB_EINVAL;
+    }
+    b->hp[i].bytes_per_ser = bytes;
+    bytes_mean += bytes / n_probs;
+    smem_max = std::max(smem_max, geo[i].smem);
+    b->G_max = std::max(b->G_max, geo[i].G);
+    b->NS_max = std::max(b->NS_max, geo[i].NS);
+  }
+  b->smem_bytes = static_cast<int>(smem_max);
+  b->team_size = choose_team(ctx, n_probs, bytes_mean, opts.team_size, b->hw_cluster);
+  const int C = b->team_size;
+
+  // arena layout
+  Bump bump;
+  std::vector<ProbLayout> lay(n_probs);
+  const size_t probs_off = bump.take(sizeof(ProbDev) * n_probs);
+  const size_t ids_off = bump.take(sizeof(int) * n_probs);
+  const size_t queue_off = bump.take(sizeof(int) * 64);
+  const size_t slots_off = bump.take(sizeof(int) * (ctx->num_sms + 8));
+  const size_t bar_off = bump.take(sizeof(unsigned) * 64 * (ctx->num_sms + 8));
+  const size_t metas_off = bump.take(sizeof(int) * 8 * n_probs);
+  const size_t elbos_off = bump.take(sizeof(double) * (opts.max_iter + 1) * static_cast<size_t>(n_probs));
+  size_t staging_bytes = 0;
+  for (int i = 0; i < n_probs; ++i) {
+    const GenericProblem& g = gp[i];
+    const Geometry& ge = geo[i];
+    ProbLayout& l = lay[i];
+    HostProb& h = b->hp[i];
+    h.K = g.K;
+    h.p = g.p;
+    h.L = g.L;
+    h.p_pad = ge.p_pad;
+    int nrows = 0;
+    for (int k = 0; k < g.K; ++k) {
+      h.n[k] = g.n[k];
+      nrows += g.n[k];
+      l.X[k] = bump.take(static_cast<size_t>(g.n[k]) * ge.p_pad * es);
+      const bool direct = (g.mat_dtype == opts.storage) && g.standardize == 0;
+      if (!direct) staging_bytes = std::max(staging_bytes, static_cast<size_t>(g.n[k]) * g.p * elem_size(g.mat_dtype));
+    }
+    h.nrows = nrows;
+    const size_t Kp = static_cast<size_t>(g.K) * ge.p_pad;
+    l.y = bump.take(sizeof(double) * nrows);
+    l.z = ss ? bump.take(sizeof(double) * nrows) : 0;
+    l.logpi = bump.take(sizeof(double) * g.p);
+    l.pi_raw = bump.take(sizeof(double) * g.p);
+    l.xtx = bump.take(sizeof(double) * Kp);
+    l.ecov0 = bump.take(sizeof(double) * g.L * g.K * g.K);
+    l.rv0 = bump.take(sizeof(double) * g.K);
+    l.adjt = bump.take(sizeof(double) * g.K * g.K);
+    l.adjp = bump.take(sizeof(double) * g.K * g.K);
+    l.r = bump.take(sizeof(double) * nrows);
+    l.xb = bump.take(sizeof(double) * nrows * g.L);
+    l.bT = bump.take(sizeof(double) * Kp);
+    l.part = ss ? 0 : bump.take(sizeof(double) * Kp * C);
+    l.xty = ss ? 0 : bump.take(sizeof(double) * Kp);
+    l.rfull = ss ? bump.take(sizeof(double) * nrows) : 0;
+    l.statA = bump.take(sizeof(double) * sb::STAT_STRIDE * C);
+    l.statB = bump.take(sizeof(double) * sb::STAT_STRIDE * C);
+    l.statC = bump.take(sizeof(double) * sb::STAT_STRIDE * C);
+    l.trav = bump.take(sizeof(double) * sb::TRAV_STRIDE * C * g.L);
+    for (int q = 0; q < 2; ++q) {
+      l.out[q] = bump.take(out_block_bytes(g.L, g.p, g.K));
+      out_block_fields(g.L, g.p, g.K, l.out[q], l.out_fields[q]);
+      h.out_off[q] = l.out[q];
+    }
+    l.elbo = elbos_off + sizeof(double) * (opts.max_iter + 1) * static_cast<size_t>(i);
+    l.meta = metas_off + sizeof(int) * 8 * static_cast<size_t>(i);
+    h.elbo_off = l.elbo;
+    h.meta_off = l.meta;
+  }
+  const size_t staging_off = bump.take(staging_bytes ? staging_bytes : 16);
+  b->arena_bytes = align_up(bump.off, 256);
+  {
+    cudaError_t e = cudaMalloc(&b->arena, b->arena_bytes);
+    if (e != cudaSuccess) {
+      ctx->err = "cudaMalloc(" + std::to_string(b->arena_bytes) + " bytes): " + cudaGetErrorString(e);
+      b->arena = nullptr;
+      return SB_ENOMEM;
+    }
+  }
+  unsigned char* A = b->arena;
+  b->d_probs = reinterpret_cast<ProbDev*>(A + probs_off);
+  b->d_ids = reinterpret_cast<int*>(A + ids_off);
+  b->d_queue = reinterpret_cast<int*>(A + queue_off);
+  b->d_slots = reinterpret_cast<int*>(A + slots_off);
+  b->d_bar = reinterpret_cast<unsigned*>(A + bar_off);
+  b->metas_off = metas_off;
+  cudaStream_t st = ctx->stream;
+  auto fail = [&](int code) {
+    cudaStreamSynchronize(st);
+    cudaFree(b->arena);
+    b->arena = nullptr;
+    return code;
+  };
+#define SB_CUDA_B(call)                                                          \
+  do {                                                                           \
+    cudaError_t e_ = (call);                                                     \
+    if (e_ != cudaSuccess) {                                                     \
+      ctx->err = std::string(#call) + ": " + cudaGetErrorString(e_);             \
+      return fail(SB_ECUDA);                                                     \
+    }                                                                            \
+  } while (0)
+
+  SB_CUDA_B(cudaEventRecord(ctx->ev[2], st));
+  int launches = 0;
+  std::vector<double> tmp;
+  for (int i = 0; i < n_probs; ++i) {
+    const GenericProblem& g = gp[i];
+    const Geometry& ge = geo[i];
+    const ProbLayout& l = lay[i];
+    HostProb& h = b->hp[i];
+    ProbDev& d = b->pd[i];
+    std::memset(&d, 0, sizeof(d));
+    d.K = g.K;
+    d.p = g.p;
+    d.L = g.L;
+    d.p_pad = ge.p_pad;
+    d.G = ge.G;
+    d.nstage = ge.NS;
+    d.nseg = ge.NSEG;
+    d.em = g.em;
+    int row = 0, band = 0;
+    for (int k = 0; k < g.K; ++k) {
+      d.n[k] = g.n[k];
+      d.row0[k] = row;
+      d.band0[k] = band;
+      row += g.n[k];
+      band += (g.n[k] + ge.G - 1) / ge.G;
+      d.X[k] = A + l.X[k];
+      h.d_X[k] = A + l.X[k];
+      d.nscale[k] = ss ? g.ns[k] : 1.0;
+      d.nsamp[k] = ss ? g.ns[k] : static_cast<double>(g.n[k]);
+    }
+    for (int k = g.K; k <= KMAX; ++k) {
+      d.row0[k] = row;
+      d.band0[k] = band;
+    }
+    d.y = reinterpret_cast<double*>(A + l.y);
+    d.logpi = reinterpret_cast<double*>(A + l.logpi);
+    d.xtx = reinterpret_cast<double*>(A + l.xtx);
+    d.ecov0 = reinterpret_cast<double*>(A + l.ecov0);
+    d.rv0 = reinterpret_cast<double*>(A + l.rv0);
+    d.adj_times = reinterpret_cast<double*>(A + l.adjt);
+    d.adj_plus = reinterpret_cast<double*>(A + l.adjp);
+    d.r = reinterpret_cast<double*>(A + l.r);
+    d.xb = reinterpret_cast<double*>(A + l.xb);
+    d.bT = reinterpret_cast<double*>(A + l.bT);
+    d.part = ss ? nullptr : reinterpret_cast<double*>(A + l.part);
+    d.xty = ss ? nullptr : reinterpret_cast<double*>(A + l.xty);
+    d.rfull = ss ? reinterpret_cast<double*>(A + l.rfull) : nullptr;
+    d.statA = reinterpret_cast<double*>(A + l.statA);
+    d.statB = reinterpret_cast<double*>(A + l.statB);
+    d.statC = reinterpret_cast<double*>(A + l.statC);
+    d.trav = reinterpret_cast<double*>(A + l.trav);
+    for (int q = 0; q < 2; ++q) {
+      OutBuf& o = d.out[q];
+      const size_t* f = l.out_fields[q];
+      o.alpha = reinterpret_cast<double*>(A + f[0]);
+      o.pm = reinterpret_cast<double*>(A + f[1]);
+      o.pmsq = reinterpret_cast<double*>(A + f[2]);
+      o.lbf = reinterpret_cast<double*>(A + f[3]);
+      o.wsc = reinterpret_cast<double*>(A + f[4]);
+      o.kl = reinterpret_cast<double*>(A + f[5]);
+      o.ecov = reinterpret_cast<double*>(A + f[6]);
+      o.rv = reinterpret_cast<double*>(A + f[7]);
+      o.xtxb2 = reinterpret_cast<double*>(A + f[8]);
+    }
+    d.elbo = reinterpret_cast<double*>(A + l.elbo);
+    d.meta = reinterpret_cast<int*>(A + l.meta);
+
+    // small vectors
+    const int KK = g.K * g.K;
+    h.ecov0.assign(g.effect_covar, g.effect_covar + static_cast<size_t>(g.L) * KK);
+    h.rv0.assign(g.resid_var, g.resid_var + g.K);
+    SB_CUDA_B(cudaMemcpyAsync(A + l.ecov0, g.effect_covar, sizeof(double) * g.L * KK, cudaMemcpyHostToDevice, st));
+    SB_CUDA_B(cudaMemcpyAsync(A + l.rv0, g.resid_var, sizeof(double) * g.K, cudaMemcpyHostToDevice, st));
+    tmp.assign(2 * KK, 0.0);
+    bool times_zero = true;
+    for (int t = 0; t < KK; ++t) {
+      tmp[t] = g.em ? 1.0 : g.adj_times[t];
+      tmp[KK + t] = g.em ? 0.0 : g.adj_plus[t];
+      if (tmp[t] != 0.0) times_zero = false;
+    }
+    d.skip_first_pass = (!g.em && times_zero) ? 1 : 0;
+    SB_CUDA_B(cudaMemcpyAsync(A + l.adjt, tmp.data(), sizeof(double) * KK, cudaMemcpyHostToDevice, st));
+    SB_CUDA_B(cudaMemcpyAsync(A + l.adjp, tmp.data() + KK, sizeof(double) * KK, cudaMemcpyHostToDevice, st));
+    // (pageable-source cudaMemcpyAsync returns once the source has been staged, so tmp may be reused)
+    if (g.pi) SB_CUDA_B(cudaMemcpyAsync(A + l.pi_raw, g.pi, sizeof(double) * g.p, cudaMemcpyHostToDevice, st));
+    sb::log_kernel<<<(g.p + 255) / 256, 256, 0, st>>>(
+        g.pi ? reinterpret_cast<const double*>(A + l.pi_raw) : nullptr, 1.0 / static_cast<double>(g.p),
+        reinterpret_cast<double*>(A + l.logpi), g.p);
+    ++launches;
+
+    // matrices and per-row vectors
+    for (int k = 0; k < g.K; ++k) {
+      const int n = g.n[k];
+      double* xtx_k = reinterpret_cast<double*>(A + l.xtx) + static_cast<size_t>(k) * ge.p_pad;
+      const bool direct = (g.mat_dtype == opts.storage) && g.standardize == 0;
+      if (direct) {
+        SB_CUDA_B(cudaMemcpy2DAsync(A + l.X[k], static_cast<size_t>(ge.p_pad) * es, g.mat[k],
+                                    static_cast<size_t>(g.p) * es, static_cast<size_t>(g.p) * es, n,
+                                    cudaMemcpyHostToDevice, st));
+        if (!ss) {
+          prep_columns_dispatch(opts.storage, opts.storage, A + l.X[k], ge.p_pad, n, g.p, ge.p_pad, 0, A + l.X[k],
+                                xtx_k, st);
+        } else if (ge.p_pad > g.p) {
+          SB_CUDA_B(cudaMemset2DAsync(A + l.X[k] + static_cast<size_t>(g.p) * es, static_cast<size_t>(ge.p_pad) * es,
+                                      0, static_cast<size_t>(ge.p_pad - g.p) * es, n, st));
+        }
+      } else {
+        SB_CUDA_B(cudaMemcpyAsync(A + staging_off, g.mat[k], static_cast<size_t>(n) * g.p * elem_size(g.mat_dtype),
+                                  cudaMemcpyHostToDevice, st));
+        if (!ss) {
+          prep_columns_dispatch(g.mat_dtype, opts.storage, A + staging_off, g.p, n, g.p, ge.p_pad, g.standardize,
+                                A + l.X[k], xtx_k, st);
+        } else {
+          if (g.mat_dtype == SB_F64 && opts.storage == SB_F32)
+            launch_pad_rows<double, float>(A + staging_off, n, g.p, ge.p_pad, A + l.X[k], st);
+          else if (g.mat_dtype == SB_F32 && opts.storage == SB_F64)
+            launch_pad_rows<float, double>(A + staging_off, n, g.p, ge.p_pad, A + l.X[k], st);
+          else {
+            ctx->err = "unsupported LD dtype / storage combination";
+            return fail(SB_EINVAL);
+          }
+        }
+      }
+      ++launches;
+      if (!ss) {
+        SB_CUDA_B(cudaMemcpyAsync(A + l.y + sizeof(double) * d.row0[k], g.vec[k], sizeof(double) * n,
+                                  cudaMemcpyHostToDevice, st));
+      } else {
+        SB_CUDA_B(cudaMemcpyAsync(A + l.z + sizeof(double) * d.row0[k], g.vec[k], sizeof(double) * n,
+                                  cudaMemcpyHostToDevice, st));
+        double* xty_k = reinterpret_cast<double*>(A + l.y) + d.row0[k];
+        const double* z_k = reinterpret_cast<const double*>(A + l.z) + d.row0[k];
+        if (opts.storage == SB_F64)
+          sb::prep_ss_kernel<double><<<(ge.p_pad + 127) / 128, 128, 0, st>>>(
+              reinterpret_cast<const double*>(A + l.X[k]), z_k, g.ns[k], g.p, ge.p_pad, xty_k, xtx_k);
+        else
+          sb::prep_ss_kernel<float><<<(ge.p_pad + 127) / 128, 128, 0, st>>>(
+              reinterpret_cast<const float*>(A + l.X[k]), z_k, g.ns[k], g.p, ge.p_pad, xty_k, xtx_k);
+        ++launches;
+      }
+    }
+  }
+  SB_CUDA_B(cudaGetLastError());
+  // problem table, ids grouped by K
+  {
+    std::vector<int> ids;
+    ids.reserve(n_probs);
+    for (int K = 1; K <= KMAX; ++K) {
+      b->group_start[K] = static_cast<int>(ids.size());
+      for (int i = 0; i < n_probs; ++i)
+        if (gp[i].K == K) ids.push_back(i);
+    }
+    b->group_start[KMAX + 1] = static_cast<int>(ids.size());
+    SB_CUDA_B(cudaMemcpyAsync(b->d_ids, ids.data(), sizeof(int) * n_probs, cudaMemcpyHostToDevice, st));
+    SB_CUDA_B(cudaMemcpyAsync(b->d_probs, b->pd.data(), sizeof(ProbDev) * n_probs, cudaMemcpyHostToDevice, st));
+    SB_CUDA_B(cudaEventRecord(ctx->ev[3], st));
+    SB_CUDA_B(cudaStreamSynchronize(st));
+  }
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[3]);
+  b->prologue_ms = ms;
+  b->n_launches_create = launches;
+  *out = b.release();
+  return SB_OK;
+#undef SB_CUDA_B
+}
+
+// ------------------------------------------------------------------------------------------
+// public batch API
+
+extern "C" int sb_batch_create_ind(sb_ctx* ctx, const sb_ind_problem* probs, int n_probs, const sb_opts* opts,
+                                   sb_batch** out) {
+  if (!ctx || !probs || !out) return SB_EINVAL;
+  std::vector<GenericProblem> gp(std::max(0, n_probs));
+  for (int i = 0; i < n_probs; ++i) {
+    const sb_ind_problem& pr = probs[i];
+    int rc = validate_common(ctx, pr, i);
+    if (rc != SB_OK) return rc;
+    if (!pr.n || !pr.X || !pr.y) {
+      ctx->err = "problem " + std::to_string(i) + ": n / X / y missing";
+      return SB_EINVAL;
+    }
+    if (pr.x_dtype != SB_F64 && pr.x_dtype != SB_F32 && pr.x_dtype != SB_I8) {
+      ctx->err = "problem " + std::to_string(i) + ": bad x_dtype";
+      return SB_EINVAL;
+    }
+    GenericProblem& g = gp[i];
+    g.K = pr.k;
+    g.p = pr.p;
+    g.L = pr.L;
+    g.em = pr.em_update ? 1 : 0;
+    g.mat_dtype = pr.x_dtype;
+    g.standardize = pr.standardize & 3;
+    for (int k = 0; k < pr.k; ++k) {
+      g.n[k] = pr.n[k];
+      g.mat[k] = pr.X[k];
+      g.vec[k] = pr.y[k];
+      g.ns[k] = pr.n[k];
+      if (!pr.X[k] || !pr.y[k]) {
+        ctx->err = "problem " + std::to_string(i) + ": null X / y pointer";
+        return SB_EINVAL;
+      }
+    }
+    g.pi = pr.pi;
+    g.resid_var = pr.resid_var;
+    g.effect_covar = pr.effect_covar;
+    g.adj_times = pr.adj_times;
+    g.adj_plus = pr.adj_plus;
+  }
+  return batch_create(ctx, gp, false, opts, out);
+}
+
+extern "C" int sb_batch_create_ss(sb_ctx* ctx, const sb_ss_problem* probs, int n_probs, const sb_opts* opts,
+                                  sb_batch** out) {
+  if (!ctx || !probs || !out) return SB_EINVAL;
+  std::vector<GenericProblem> gp(std::max(0, n_probs));
+  for (int i = 0; i < n_probs; ++i) {
+    const sb_ss_problem& pr = probs[i];
+    int rc = validate_common(ctx, pr, i);
+    if (rc != SB_OK) return rc;
+    if (!pr.ns || !pr.ld || !pr.z) {
+      ctx->err = "problem " + std::to_string(i) + ": ns / ld / z missing";
+      return SB_EINVAL;
+    }
+    if (pr.ld_dtype != SB_F64 && pr.ld_dtype != SB_F32) {
+      ctx->err = "problem " + std::to_string(i) + ": bad ld_dtype";
+      return SB_EINVAL;
+    }
+    GenericProblem& g = gp[i];
+    g.K = pr.k;
+    g.p = pr.p;
+    g.L = pr.L;
+    g.em = pr.em_update ? 1 : 0;
+    g.mat_dtype = pr.ld_dtype;
+    g.standardize = 0;
+    for (int k = 0; k < pr.k; ++k) {
+      g.n[k] = pr.p;  // rows of the LD matrix
+      g.mat[k] = pr.ld[k];
+      g.vec[k] = pr.z[k];
+      g.ns[k] = pr.ns[k];
+      if (!pr.ld[k] || !pr.z[k]) {
+        ctx->err = "problem " + std::to_string(i) + ": null ld / z pointer";
+        return SB_EINVAL;
+      }
+    }
+    g.pi = pr.pi;
+    g.resid_var = pr.resid_var;
+    g.effect_covar = pr.effect_covar;
+    g.adj_times = pr.adj_times;
+    g.adj_plus = pr.adj_plus;
+  }
+  return batch_create(ctx, gp, true, opts, out);
+}
+
+extern "C" int sb_batch_run(sb_ctx* ctx, sb_batch* b, sb_run_stats* stats) {
+  if (!ctx || !b || !b->arena) return SB_EINVAL;
+  cudaSetDevice(ctx->device);
+  cudaStream_t st = ctx->stream;
+  const int C = b->team_size;
+  SB_CUDA(cudaMemsetAsync(b->d_queue, 0, sizeof(int) * 64, st));
+  SB_CUDA(cudaMemsetAsync(b->d_bar, 0, sizeof(unsigned) * 64 * (ctx->num_sms + 8), st));
+  int launches = 0, teams_used = 0;
+  SB_CUDA(cudaEventRecord(ctx->ev[0], st));
+  for (int K = 1; K <= KMAX; ++K) {
+    const int g0 = b->group_start[K], g1 = b->group_start[K + 1];
+    if (g1 == g0) continue;
+    const void* fn = pick_kernel(K, b->storage, b->ss);
+    if (!fn) {
+      ctx->err = "no kernel for K=" + std::to_string(K);
+      return SB_EINVAL;
+    }
+    SB_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, b->smem_bytes));
+    if (b->hw_cluster && C > 8) SB_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+
+    cudaLaunchConfig_t cfg{};
+    cfg.blockDim = dim3(sb::NT);
+    cfg.dynamicSmemBytes = b->smem_bytes;
+    cfg.stream = st;
+    cudaLaunchAttribute attrs[2];
+    int na = 0;
+    int max_teams;
+    if (C == 1) {
+      int per_sm = 0;
+      SB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, sb::NT, b->smem_bytes));
+      max_teams = per_sm * ctx->num_sms;
+    } else if (b->hw_cluster) {
+      attrs[na].id = cudaLaunchAttributeClusterDimension;
+      attrs[na].val.clusterDim.x = C;
+      attrs[na].val.clusterDim.y = 1;
+      attrs[na].val.clusterDim.z = 1;
+      ++na;
+      cfg.attrs = attrs;
+      cfg.numAttrs = na;
+      cfg.gridDim = dim3(C);
+      int ncl = 0;
+      SB_CUDA(cudaOccupancyMaxActiveClusters(&ncl, fn, &cfg));
+      max_teams = ncl;
+    } else {
+      int per_sm = 0;
+      SB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, sb::NT, b->smem_bytes));
+      max_teams = (per_sm * ctx->num_sms) / C;
+      attrs[na].id = cudaLaunchAttributeCooperative;
+      attrs[na].val.cooperative = 1;
+      ++na;
+    }
+    if (max_teams < 1) {
+      ctx->err = "kernel does not fit on the device (team_size=" + std::to_string(C) + ", smem=" +
+                 std::to_string(b->smem_bytes) + ")";
+      return SB_EINVAL;
+    }
+    const int n_teams = std::min(max_teams, g1 - g0);
+    teams_used = std::max(teams_used, n_teams);
+    cfg.gridDim = dim3(n_teams * C);
+    cfg.attrs = attrs;
+    cfg.numAttrs = na;
+
+    LaunchParams lp{};
+    lp.probs = b->d_probs;
+    lp.prob_ids = b->d_ids + g0;
+    lp.n_ids = g1 - g0;
+    lp.queue = b->d_queue + (K - 1) * 8;
+    lp.team_slot = b->d_slots;
+    lp.team_bar = b->d_bar;
+    lp.team_size = C;
+    lp.hw_cluster = b->hw_cluster;
+    lp.max_iter = b->opts.max_iter;
+    lp.min_tol = b->opts.min_tol;
+    void* args[] = {&lp};
+    SB_CUDA(cudaLaunchKernelExC(&cfg, fn, args));
+    ++launches;
+  }
+  SB_CUDA(cudaEventRecord(ctx->ev[1], st));
+  SB_CUDA(cudaStreamSynchronize(st));
+  SB_CUDA(cudaGetLastError());
+  b->ran = true;
+  if (stats) {
+    std::memset(stats, 0, sizeof(*stats));
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]);
+    stats->device_ms = ms;
+    stats->prologue_ms = b->prologue_ms;
+    stats->n_launches = launches + b->n_launches_create;
+    stats->team_size = C;
+    stats->n_teams = teams_used;
+    stats->rows_per_band = b->G_max;
+    stats->n_stages = b->NS_max;
+    stats->smem_bytes = b->smem_bytes;
+    // iteration / SER counters from the per-problem meta words
+    std::vector<int> meta(static_cast<size_t>(b->n_probs) * 8);
+    SB_CUDA(cudaMemcpyAsync(meta.data(), b->arena + b->metas_off, sizeof(int) * 8 * b->n_probs,
+                            cudaMemcpyDeviceToHost, st));
+    SB_CUDA(cudaStreamSynchronize(st));
+    for (int i = 0; i < b->n_probs; ++i) {
+      stats->n_iter += meta[i * 8 + 0];
+      stats->n_ser += meta[i * 8 + 3];
+      stats->algorithmic_bytes += static_cast<double>(meta[i * 8 + 3]) * b->hp[i].bytes_per_ser;
+    }
+  }
+  return SB_OK;
+}
+
+extern "C" int sb_batch_fetch(sb_ctx* ctx, sb_batch* b, sb_result* results) {
+  if (!ctx || !b || !results || !b->arena) return SB_EINVAL;
+  if (!b->ran) {
+    ctx->err = "sb_batch_fetch before sb_batch_run";
+    return SB_EINVAL;
+  }
+  cudaSetDevice(ctx->device);
+  cudaStream_t st = ctx->stream;
+  std::vector<int> meta(static_cast<size_t>(b->n_probs) * 8);
+  SB_CUDA(cudaMemcpyAsync(meta.data(), b->arena + b->metas_off, sizeof(int) * 8 * b->n_probs, cudaMemcpyDeviceToHost,
+                          st));
+  SB_CUDA(cudaStreamSynchronize(st));
+  for (int i = 0; i < b->n_probs; ++i) {
+    const HostProb& h = b->hp[i];
+    sb_result& r = results[i];
+    const int n_iter = meta[i * 8 + 0], inc = meta[i * 8 + 1], fb = meta[i * 8 + 2];
+    r.n_iter = n_iter;
+    r.elbo_increase = inc;
+    r.status = 0;
+    const size_t Lp = static_cast<size_t>(h.L) * h.p;
+    const int K = h.K, KK = K * K;
+    if (r.elbo)
+      SB_CUDA(cudaMemcpyAsync(r.elbo, b->arena + h.elbo_off, sizeof(double) * (n_iter + 1), cudaMemcpyDeviceToHost, st));
+    if (fb < 0) {
+      // ELBO failed to improve in the very first iteration: the reference returns the
+      // initial state (zero posteriors, initial priors), infer.py:531-532.
+      if (r.alpha) std::memset(r.alpha, 0, sizeof(double) * Lp);
+      if (r.post_mean) std::memset(r.post_mean, 0, sizeof(double) * Lp * K);
+      if (r.post_mean_sq) std::memset(r.post_mean_sq, 0, sizeof(double) * Lp * KK);
+      if (r.log_bf) std::memset(r.log_bf, 0, sizeof(double) * Lp);
+      if (r.weighted_sum_covar) std::memset(r.weighted_sum_covar, 0, sizeof(double) * h.L * KK);
+      if (r.kl) std::memset(r.kl, 0, sizeof(double) * h.L);
+      if (r.effect_covar) std::memcpy(r.effect_covar, h.ecov0.data(), sizeof(double) * h.L * KK);
+      if (r.resid_var) std::memcpy(r.resid_var, h.rv0.data(), sizeof(double) * K);
+      continue;
+    }
+    size_t f[9];
+    out_block_fields(h.L, h.p, K, h.out_off[fb], f);
+    auto get = [&](double* dst, size_t off, size_t count) -> cudaError_t {
+      if (!dst) return cudaSuccess;
+      return cudaMemcpyAsync(dst, b->arena + off, sizeof(double) * count, cudaMemcpyDeviceToHost, st);
+    };
+    SB_CUDA(get(r.alpha, f[0], Lp));
+    SB_CUDA(get(r.post_mean, f[1], Lp * K));
+    SB_CUDA(get(r.post_mean_sq, f[2], Lp * KK));
+    SB_CUDA(get(r.log_bf, f[3], Lp));
+    SB_CUDA(get(r.weighted_sum_covar, f[4], static_cast<size_t>(h.L) * KK));
+    SB_CUDA(get(r.kl, f[5], h.L));
+    SB_CUDA(get(r.effect_covar, f[6], static_cast<size_t>(h.L) * KK));
+    SB_CUDA(get(r.resid_var, f[7], K));
+  }
+  SB_CUDA(cudaStreamSynchronize(st));
+  return SB_OK;
+}
+
+extern "C" int sb_batch_destroy(sb_ctx* ctx, sb_batch* b) {
+  if (!b) return SB_OK;
+  if (ctx) cudaSetDevice(ctx->device);
+  if (b->arena) cudaFree(b->arena);
+  delete b;
+  return SB_OK;
+}
+
+extern "C" int sb_batch_storage(sb_batch* b, int prob, int ancestry, void** d_ptr, int64_t* ld_elems) {
+  if (!b || prob < 0 || prob >= b->n_probs || ancestry < 0 || ancestry >= b->hp[prob].K) return SB_EINVAL;
+  if (d_ptr) *d_ptr = b->hp[prob].d_X[ancestry];
+  if (ld_elems) *ld_elems = b->hp[prob].p_pad;
+  return SB_OK;
+}
+
+extern "C" int sb_batch_purity(sb_ctx* ctx, sb_batch* b, int prob, const int32_t* idx, const int32_t* offsets,
+                               int n_sets, double* out_min_abs) {
+  if (!ctx || !b || !idx || !offsets || !out_min_abs || prob < 0 || prob >= b->n_probs || n_sets < 0)
+    return SB_EINVAL;
+  if (n_sets == 0) return SB_OK;
+  cudaSetDevice(ctx->device);
+  cudaStream_t st = ctx->stream;
+  const HostProb& h = b->hp[prob];
+  const int K = h.K;
+  const int total = offsets[n_sets];
+  int m_max = 0;
+  for (int s = 0; s < n_sets; ++s) {
+    const int m = offsets[s + 1] - offsets[s];
+    if (m < 1) {
+      ctx->err = "empty index set";
+      return SB_EINVAL;
+    }
+    m_max = std::max(m_max, m);
+  }
+  for (int t = 0; t < total; ++t)
+    if (idx[t] < 0 || idx[t] >= h.p) {
+      ctx->err = "SNP index out of range";
+      return SB_EINVAL;
+    }
+  const size_t smem = b->ss ? 0 : sizeof(double) * 32 * m_max;
+  if (smem > static_cast<size_t>(ctx->smem_optin) - 1024) {
+    ctx->err = "credible set too large for the purity kernel";
+    return SB_EINVAL;
+  }
+  unsigned char* d_buf = nullptr;
+  const size_t idx_b = align_up(sizeof(int) * total, 256), off_b = align_up(sizeof(int) * (n_sets + 1), 256);
+  const size_t ptr_b = 256, n_b = 256, out_b = align_up(sizeof(double) * n_sets * K, 256);
+  SB_CUDA(cudaMalloc(&d_buf, idx_b + off_b + ptr_b + n_b + out_b));
+  int* d_idx = reinterpret_cast<int*>(d_buf);
+  int* d_off = reinterpret_cast<int*>(d_buf + idx_b);
+  void** d_ptrs = reinterpret_cast<void**>(d_buf + idx_b + off_b);
+  int* d_n = reinterpret_cast<int*>(d_buf + idx_b + off_b + ptr_b);
+  double* d_out = reinterpret_cast<double*>(d_buf + idx_b + off_b + ptr_b + n_b);
+  auto bail = [&](cudaError_t e, const char* what) {
+    ctx->err = std::string(what) + ": " + cudaGetErrorString(e);
+    cudaStreamSynchronize(st);
+    cudaFree(d_buf);
+    return SB_ECUDA;
+  };
+  cudaError_t e;
+  if ((e = cudaMemcpyAsync(d_idx, idx, sizeof(int) * total, cudaMemcpyHostToDevice, st)) != cudaSuccess)
+    return bail(e, "purity H2D idx");
+  if ((e = cudaMemcpyAsync(d_off, offsets, sizeof(int) * (n_sets + 1), cudaMemcpyHostToDevice, st)) != cudaSuccess)
+    return bail(e, "purity H2D offsets");
+  if ((e = cudaMemcpyAsync(d_ptrs, h.d_X, sizeof(void*) * K, cudaMemcpyHostToDevice, st)) != cudaSuccess)
+    return bail(e, "purity H2D ptrs");
+  if ((e = cudaMemcpyAsync(d_n, h.n, sizeof(int) * K, cudaMemcpyHostToDevice, st)) != cudaSuccess)
+    return bail(e, "purity H2D n");
+  dim3 grid(n_sets, K);
+#define SB_PUR(XT, SSV)                                                                                        \
+  do {                                                                                                         \
+    auto kf = sb::purity_kernel<XT, SSV>;                                                                      \
+    if (smem > 48 * 1024) cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);    \
+    kf<<<grid, 256, smem, st>>>(reinterpret_cast<const XT* const*>(d_ptrs), d_n, h.p_pad, d_idx, d_off, K,     \
+                                d_out);                                                                        \
+  } while (0)
+  if (b->storage == SB_F64) {
+    if (b->ss)
+      SB_PUR(double, true);
+    else
+      SB_PUR(double, false);
+  } else {
+    if (b->ss)
+      SB_PUR(float, true);
+    else
+      SB_PUR(float, false);
+  }
+#undef SB_PUR
+  if ((e = cudaGetLastError()) != cudaSuccess) return bail(e, "purity launch");
+  if ((e = cudaMemcpyAsync(out_min_abs, d_out, sizeof(double) * n_sets * K, cudaMemcpyDeviceToHost, st)) !=
+      cudaSuccess)
+    return bail(e, "purity D2H");
+  if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return bail(e, "purity sync");
+  cudaFree(d_buf);
+  return SB_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// one-shot entry points
+
+template <typename P, typename CreateFn>
+static int one_shot(sb_ctx* ctx, const P* probs, int n, const sb_opts* opts, sb_result* results, sb_run_stats* stats,
+                    CreateFn create) {
+  sb_batch* b = nullptr;
+  int rc = create(ctx, probs, n, opts, &b);
+  if (rc != SB_OK) return rc;
+  rc = sb_batch_run(ctx, b, stats);
+  if (rc == SB_OK) rc = sb_batch_fetch(ctx, b, results);
+  sb_batch_destroy(ctx, b);
+  return rc;
+}
+
+extern "C" int sb_ibss_ind(sb_ctx* ctx, const sb_ind_problem* probs, int n_probs, const sb_opts* opts,
+                           sb_result* results, sb_run_stats* stats) {
+  if (!ctx || !probs || !results) return SB_EINVAL;
+  return one_shot(ctx, probs, n_probs, opts, results, stats, sb_batch_create_ind);
+}
+
+extern "C" int sb_ibss_ss(sb_ctx* ctx, const sb_ss_problem* probs, int n_probs, const sb_opts* opts,
+                          sb_result* results, sb_run_stats* stats) {
+  if (!ctx || !probs || !results) return SB_EINVAL;
+  return one_shot(ctx, probs, n_probs, opts, results, stats, sb_batch_create_ss);
+}

@@ -1,0 +1,1202 @@
+// ibss_kernel.cuh -- the persistent, device-resident IBSS loop for sm_100a.
+//
+// One *team* of thread blocks (a thread-block cluster with a hardware barrier, or a
+// co-resident group with a global-memory barrier) owns one locus from start to
+// convergence; teams pull loci from a device-side queue.  Inside a locus the whole
+// reference loop runs on device:
+//
+//   reference                                    here
+//   ------------------------------------------   -----------------------------------------
+//   infer.py:498-548 host loop + ELBO sync       iteration loop + on-device stop rule
+//   infer.py:618 lax.fori_loop over L            effect loop
+//   infer.py:640,653,676 three einsums over X    ONE streamed traversal of X per effect
+//                                                (traverse(): X b_new, residual update and
+//                                                 X^T r_next from the same shared-memory band)
+//   infer.py:692-745 _compute_posterior (x2)     posterior passes A / B1 / B2 (per-SNP k x k
+//                                                closed form, online log-sum-exp softmax)
+//   infer.py:128-159 _EMOptFunc/_NoopOptFunc     prior update between pass A and pass B
+//   infer.py:786-808 _eloglike/_erss             cached norms, no extra pass over X
+//   infer_ss.py:437-575                          same kernel, SS=true: rows are LD rows,
+//                                                no X^T r sweep, ERSS from cached vectors
+//
+// Genotype / LD bands are brought into shared memory with bulk asynchronous copies
+// (cp.async.bulk + mbarrier, i.e. the TMA engine, SASS UBLKCP) through a multi-stage ring
+// that keeps prefetching across the posterior phases, because the traversal order of X is
+// static.  All reductions are fixed-order (no floating-point atomics), so results are
+// bit-reproducible for a given team size.
+#pragma once
+#include <cuda_runtime.h>
+#include <math_constants.h>
+#include <stdint.h>
+
+namespace sb {
+
+constexpr int KMAX = 4;
+constexpr int NT = 256;  // threads per block
+constexpr int NW = NT / 32;
+constexpr int GMAX = 32;  // max rows per band
+constexpr int NSTAGE_MAX = 4;
+constexpr int NSYM_MAX = KMAX * (KMAX + 1) / 2;
+constexpr int STAT_STRIDE = 20;  // doubles per team-reduction record (>= 2 + NSYM_MAX + 2 + KMAX)
+constexpr int TRAV_STRIDE = 2 * KMAX;
+
+struct OutBuf {
+  double* alpha;  // [L][p]
+  double* pm;     // [L][p][K]
+  double* pmsq;   // [L][p][K][K]
+  double* lbf;    // [L][p]
+  double* wsc;    // [L][K][K]
+  double* kl;     // [L]
+  double* ecov;   // [L][K][K]
+  double* rv;     // [K]
+  double* xtxb2;  // [L][K]   sum_p XtX * E[b^2]  (ERSS term)
+};
+
+struct ProbDev {
+  int K, p, L, p_pad;
+  int n[KMAX];         // rows per ancestry (summary level: p)
+  int row0[KMAX + 1];  // offsets into the concatenated row space
+  int band0[KMAX + 1]; // band index offsets per ancestry
+  int G, nstage, nseg; // rows per band, ring stages, warps per row in sweep 1
+  int em;              // 1 = EM prior update, 0 = times/plus adjustor
+  int skip_first_pass; // adjustor.times == 0: the first posterior pass cannot matter
+  const void* X[KMAX]; // [n_k][p_pad] storage type
+  double nscale[KMAX]; // summary level: n_k (XtX = n LD); individual level: 1
+  double nsamp[KMAX];  // n_k as double for the ELBO
+  const double* y;     // [nrows]   (summary level: Xty [K][p] concatenated)
+  const double* logpi; // [p]
+  const double* xtx;   // [K][p_pad] diagonal of XtX
+  const double* ecov0; // [L][K][K]
+  const double* rv0;   // [K]
+  const double* adj_times;  // [K][K]
+  const double* adj_plus;   // [K][K]
+  double* r;      // [nrows] current residual (with the current effect added back)
+  double* xb;     // [L][nrows] cached X b_l  (summary level: XtX b_l)
+  double* bT;     // [K][p_pad] current effect, transposed
+  double* part;   // [team][K][p_pad] per-block partial X^T r   (individual level)
+  double* xty;    // [K][p_pad] reduced X^T r                    (individual level)
+  double* rfull;  // [nrows] full residual at iteration end      (summary level)
+  double* statA;  // [team][STAT_STRIDE]
+  double* statB;  // [team][STAT_STRIDE]
+  double* statC;  // [team][STAT_STRIDE]
+  double* trav;   // [L][team][TRAV_STRIDE]
+  OutBuf out[2];
+  double* elbo;   // [max_iter + 1]
+  int* meta;      // [0]=n_iter [1]=elbo_increase [2]=final buffer (-1: initial state) [3]=n_ser
+};
+
+struct LaunchParams {
+  const ProbDev* probs;
+  const int* prob_ids;  // problems of this launch (same K / mode / storage)
+  int n_ids;
+  int* queue;          // device work queue head
+  int* team_slot;      // [n_teams]
+  unsigned* team_bar;  // [n_teams][64] software barrier words
+  int team_size;
+  int hw_cluster;
+  int max_iter;
+  double min_tol;
+};
+
+// ---------------------------------------------------------------------------------------
+// PTX helpers
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t done;
+  const uint32_t addr = smem_u32(bar);
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+// Bulk asynchronous global->shared copy (TMA engine), completion counted on an mbarrier.
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_u32(unsigned* p, unsigned v) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+struct Team {
+  int size, rank, id;
+  int hw;
+  unsigned* bar;  // software barrier: bar[0] = arrivals, bar[32] = generation
+};
+
+__device__ __forceinline__ void team_sync(const Team& t) {
+  if (t.size == 1) {
+    __syncthreads();
+    return;
+  }
+  if (t.hw) {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+    return;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned gen = ld_acquire_u32(t.bar + 32);
+    __threadfence();
+    const unsigned prev = atomicAdd(t.bar, 1u);
+    if (prev == static_cast<unsigned>(t.size) - 1u) {
+      t.bar[0] = 0u;
+      __threadfence();
+      st_release_u32(t.bar + 32, gen + 1u);
+    } else {
+      while (ld_acquire_u32(t.bar + 32) == gen) {
+      }
+    }
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+// ---------------------------------------------------------------------------------------
+// storage-type helpers: one 16-byte shared-memory vector of genotypes -> doubles
+
+template <typename XT>
+struct Vec;
+template <>
+struct Vec<double> {
+  static constexpr int W = 2;
+  __device__ static __forceinline__ void load(const double* base, int v, double (&o)[2]) {
+    const double2 t = reinterpret_cast<const double2*>(base)[v];
+    o[0] = t.x;
+    o[1] = t.y;
+  }
+};
+template <>
+struct Vec<float> {
+  static constexpr int W = 4;
+  __device__ static __forceinline__ void load(const float* base, int v, double (&o)[4]) {
+    const float4 t = reinterpret_cast<const float4*>(base)[v];
+    o[0] = t.x;
+    o[1] = t.y;
+    o[2] = t.z;
+    o[3] = t.w;
+  }
+};
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// Shared-memory header (fixed part of the dynamic allocation).
+struct SmemHdr {
+  uint64_t mbar[NSTAGE_MAX];
+  ProbDev pb;                // the locus being processed
+  double partsum[2][GMAX];   // sweep-1 partial dot products [band parity][g * nseg + seg]
+  double rn[GMAX];           // next residual of the band's rows
+  double red[NW][STAT_STRIDE];
+  double tot[STAT_STRIDE];   // block / team totals
+  double cst[2 * KMAX * KMAX + 8];  // Cinv, misc per-pass constants
+  double trow[GMAX][2];      // per-row scalars of a traversal
+  int decision;
+  int pad_[3];
+};
+
+// Block-wide sum of NV values per thread; totals land in H->tot[0..NV) (valid for all
+// threads after return).  Fixed order => deterministic.
+template <int NV>
+__device__ __forceinline__ void block_sum(SmemHdr* H, double (&v)[NV]) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) v[i] = warp_sum(v[i]);
+  __syncthreads();  // protect red/tot from the previous use
+  if (lane == 0) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) H->red[w][i] = v[i];
+  }
+  __syncthreads();
+  if (threadIdx.x < NV) {
+    double s = 0.0;
+#pragma unroll
+    for (int ww = 0; ww < NW; ++ww) s += H->red[ww][threadIdx.x];
+    H->tot[threadIdx.x] = s;
+  }
+  __syncthreads();
+}
+
+__device__ __forceinline__ double block_max(SmemHdr* H, double v) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  v = warp_max(v);
+  __syncthreads();
+  if (lane == 0) H->red[w][0] = v;
+  __syncthreads();
+  double m = H->red[0][0];
+#pragma unroll
+  for (int ww = 1; ww < NW; ++ww) m = fmax(m, H->red[ww][0]);
+  return m;  // red is protected by the leading barrier of the next block_* call
+}
+
+// ---------------------------------------------------------------------------------------
+// k x k algebra (compile-time K, fully unrolled => registers)
+
+// General inverse + log|det| by Gauss-Jordan with partial pivoting (prior covariance; the
+// reference uses LU-based inv/slogdet, infer.py:704,764,778).  Run by one thread per pass.
+template <int K>
+__device__ void inv_logdet(const double* __restrict__ C, double* __restrict__ Cinv, double& logabsdet) {
+  double a[K][2 * K];
+  for (int i = 0; i < K; ++i)
+    for (int j = 0; j < K; ++j) {
+      a[i][j] = C[i * K + j];
+      a[i][K + j] = (i == j) ? 1.0 : 0.0;
+    }
+  double lad = 0.0;
+  for (int c = 0; c < K; ++c) {
+    int piv = c;
+    double best = fabs(a[c][c]);
+    for (int r = c + 1; r < K; ++r)
+      if (fabs(a[r][c]) > best) {
+        best = fabs(a[r][c]);
+        piv = r;
+      }
+    if (piv != c)
+      for (int j = 0; j < 2 * K; ++j) {
+        const double t = a[c][j];
+        a[c][j] = a[piv][j];
+        a[piv][j] = t;
+      }
+    const double d = a[c][c];
+    lad += log(fabs(d));
+    const double inv = 1.0 / d;
+    for (int j = 0; j < 2 * K; ++j) a[c][j] *= inv;
+    for (int r = 0; r < K; ++r)
+      if (r != c) {
+        const double f = a[r][c];
+        for (int j = 0; j < 2 * K; ++j) a[r][j] -= f * a[c][j];
+      }
+  }
+  for (int i = 0; i < K; ++i)
+    for (int j = 0; j < K; ++j) Cinv[i * K + j] = a[i][K + j];
+  logabsdet = lad;
+}
+
+// Per-SNP posterior (infer.py:704-719): S = (diag(d) + Cinv)^-1, mu = S r,
+// logdetA = log|diag(d) + Cinv| = -log|S|.  LDL^T without square roots; a non-positive
+// pivot (A not PD) yields NaN like the reference's Cholesky-based logpdf.
+template <int K>
+__device__ __forceinline__ void snp_posterior(const double (&Cinv)[K][K], const double (&d)[K],
+                                              const double (&r)[K], double (&S)[K][K], double (&mu)[K],
+                                              double& logdetA) {
+  double Lm[K][K];  // unit lower factor (strict lower part used)
+  double D[K], Dinv[K];
+  double det = 1.0;
+#pragma unroll
+  for (int j = 0; j < K; ++j) {
+    double dj = Cinv[j][j] + d[j];
+#pragma unroll
+    for (int t = 0; t < j; ++t) dj -= Lm[j][t] * Lm[j][t] * D[t];
+    if (!(dj > 0.0)) dj = CUDART_NAN;
+    D[j] = dj;
+    Dinv[j] = 1.0 / dj;
+    det *= dj;
+#pragma unroll
+    for (int i = j + 1; i < K; ++i) {
+      double s = Cinv[i][j];
+#pragma unroll
+      for (int t = 0; t < j; ++t) s -= Lm[i][t] * Lm[j][t] * D[t];
+      Lm[i][j] = s * Dinv[j];
+    }
+  }
+  logdetA = log(det);
+  // Li = Lm^-1 (unit lower)
+  double Li[K][K];
+#pragma unroll
+  for (int i = 0; i < K; ++i) {
+#pragma unroll
+    for (int j = 0; j < K; ++j) Li[i][j] = (i == j) ? 1.0 : 0.0;
+  }
+#pragma unroll
+  for (int j = 0; j < K; ++j) {
+#pragma unroll
+    for (int i = j + 1; i < K; ++i) {
+      double s = 0.0;
+#pragma unroll
+      for (int t = j; t < i; ++t) s -= Lm[i][t] * Li[t][j];
+      Li[i][j] = s;
+    }
+  }
+  // S = Li^T D^-1 Li
+#pragma unroll
+  for (int a = 0; a < K; ++a) {
+#pragma unroll
+    for (int b = a; b < K; ++b) {
+      double s = 0.0;
+#pragma unroll
+      for (int t = b; t < K; ++t) s += Li[t][a] * Dinv[t] * Li[t][b];
+      S[a][b] = s;
+      S[b][a] = s;
+    }
+  }
+#pragma unroll
+  for (int a = 0; a < K; ++a) {
+    double s = 0.0;
+#pragma unroll
+    for (int b = 0; b < K; ++b) s += S[a][b] * r[b];
+    mu[a] = s;
+  }
+}
+
+constexpr double LOG_2PI = 1.8378770664093454835606594728112;
+
+// ---------------------------------------------------------------------------------------
+// the kernel
+
+template <int K, typename XT, bool SS>
+__global__ void __launch_bounds__(NT, 1) ibss_kernel(const LaunchParams P) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  constexpr int NSYM = K * (K + 1) / 2;
+  constexpr int VW = Vec<XT>::W;
+  SmemHdr* H = reinterpret_cast<SmemHdr*>(smem_raw);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+  Team team;
+  team.size = P.team_size;
+  team.id = blockIdx.x / P.team_size;
+  team.rank = blockIdx.x % P.team_size;
+  team.hw = P.hw_cluster;
+  team.bar = P.team_bar + static_cast<size_t>(team.id) * 64;
+
+  if (tid == 0) {
+    for (int s = 0; s < NSTAGE_MAX; ++s) mbar_init(&H->mbar[s], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncthreads();
+
+  uint32_t phase_bits = 0;  // bit s = mbarrier parity of the next fill to consume in stage s
+
+  for (;;) {
+    // ---- pull the next locus from the device queue
+    if (team.rank == 0 && tid == 0) {
+      const int v = atomicAdd(P.queue, 1);
+      __stcg(&P.team_slot[team.id], v);
+    }
+    team_sync(team);
+    const int qi = __ldcg(&P.team_slot[team.id]);
+    if (qi >= P.n_ids) break;
+    {
+      const int* src = reinterpret_cast<const int*>(&P.probs[P.prob_ids[qi]]);
+      int* dst = reinterpret_cast<int*>(&H->pb);
+      for (int i = tid; i < static_cast<int>(sizeof(ProbDev) / sizeof(int)); i += NT) dst[i] = src[i];
+    }
+    __syncthreads();
+    const ProbDev& pb = H->pb;
+
+    const int p = pb.p, p_pad = pb.p_pad, L = pb.L;
+    const int G = pb.G, NS = pb.nstage, NSEG = pb.nseg;
+    const int NB = pb.band0[K];
+    const int nrows = pb.row0[K];
+    const int C = team.size, rank = team.rank;
+    const int nb_own = (NB > rank) ? (NB - rank + C - 1) / C : 0;  // bands owned by this block
+    const int pv = p_pad / VW;                                       // 16-byte vectors per row
+    const size_t row_bytes = static_cast<size_t>(p_pad) * sizeof(XT);
+    const size_t stage_bytes = row_bytes * G;
+
+    // dynamic shared-memory carve-up
+    double* bsm = reinterpret_cast<double*>(smem_raw + ((sizeof(SmemHdr) + 127) / 128) * 128);
+    double* acc = bsm + p_pad;  // individual level only
+    unsigned char* ring = reinterpret_cast<unsigned char*>(SS ? (bsm + p_pad) : (acc + p_pad));
+
+    // SNP slice of this block for the posterior phases
+    const int js = static_cast<int>((static_cast<long long>(p) * rank) / C);
+    const int je = static_cast<int>((static_cast<long long>(p) * (rank + 1)) / C);
+
+    // band decode: own position -> (ancestry, first row, rows)
+    auto band_of = [&](int pos, int& k, int& g0, int& rows) {
+      const int q = rank + pos * C;
+      k = 0;
+#pragma unroll
+      for (int kk = 1; kk < K; ++kk)
+        if (q >= pb.band0[kk]) k = kk;
+      g0 = (q - pb.band0[k]) * G;
+      rows = min(G, pb.n[k] - g0);
+    };
+    // producer (thread 0): start the bulk copies of own band `pos` into ring stage `st`
+    auto issue_fill = [&](int pos, int st) {
+      int k, g0, rows;
+      band_of(pos, k, g0, rows);
+      const unsigned char* src =
+          reinterpret_cast<const unsigned char*>(pb.X[k]) + static_cast<size_t>(g0) * row_bytes;
+      unsigned char* dst = ring + static_cast<size_t>(st) * stage_bytes;
+      mbar_expect_tx(&H->mbar[st], static_cast<uint32_t>(row_bytes * rows));
+      for (int g = 0; g < rows; ++g)
+        bulk_g2s(dst + g * row_bytes, src + g * row_bytes, static_cast<uint32_t>(row_bytes), &H->mbar[st]);
+    };
+
+    // ---- locus initialisation (state owned by this block: rows of its bands)
+    for (int pos = 0; pos < nb_own; ++pos) {
+      int k, g0, rows;
+      band_of(pos, k, g0, rows);
+      for (int t = tid; t < rows; t += NT) {
+        const int row = pb.row0[k] + g0 + t;
+        pb.r[row] = pb.y[row];
+        for (int l = 0; l < L; ++l) pb.xb[static_cast<size_t>(l) * nrows + row] = 0.0;
+      }
+    }
+    for (int idx = js + tid; idx < je; idx += NT)
+      for (int k = 0; k < K; ++k) pb.bT[k * p_pad + idx] = 0.0;
+    if (rank == C - 1)
+      for (int idx = p + tid; idx < p_pad; idx += NT)
+        for (int k = 0; k < K; ++k) pb.bT[k * p_pad + idx] = 0.0;
+
+    // ring prologue: keep NS fills in flight; positions wrap (the traversal order is static)
+    int prod_pos = 0;  // next own band position to issue (thread 0)
+    int cons_seq = 0;  // bands consumed so far in this locus (stage = cons_seq % NS)
+    __syncthreads();
+    if (tid == 0 && nb_own > 0) {
+      for (int s = 0; s < NS; ++s) {
+        issue_fill(prod_pos, s);
+        prod_pos = (prod_pos + 1 == nb_own) ? 0 : prod_pos + 1;
+      }
+    }
+
+    // ------------------------------------------------------------------------------
+    // one streamed traversal of X (individual) / LD (summary) for effect l:
+    //   v = X b_new ; xb[l] = v ; R = r - v ; r_next = R + xb[lnext] ; acc += X^T r_next
+    // first == true (individual level only): b = 0, produces X^T y.
+    auto traverse = [&](int l, bool first, bool last_effect) {
+      const int lnext = first ? 0 : ((l + 1 == L) ? 0 : l + 1);
+      double vsq[K], rsq[K];  // meaningful in threads < G only
+#pragma unroll
+      for (int k = 0; k < K; ++k) vsq[k] = rsq[k] = 0.0;
+      int cur_k = -1;
+      int pending_refill = -1;  // stage to refill once every thread has left its sweep 2
+
+      for (int pos = 0; pos < nb_own; ++pos) {
+        int k, g0, rows;
+        band_of(pos, k, g0, rows);
+        if (k != cur_k) {
+          // ancestry change: flush X^T r partial, load the new b, clear the accumulator
+          __syncthreads();
+          if (!SS && cur_k >= 0) {
+            double* dst = pb.part + (static_cast<size_t>(rank) * K + cur_k) * p_pad;
+            for (int j = tid; j < p_pad; j += NT) __stcg(&dst[j], acc[j]);
+          }
+          if (!first) {
+            const double* src = pb.bT + static_cast<size_t>(k) * p_pad;
+            for (int j = tid; j < p_pad; j += NT) bsm[j] = __ldcg(&src[j]);
+          }
+          if (!SS) {
+            __syncthreads();
+            for (int j = tid; j < p_pad; j += NT) acc[j] = 0.0;
+          }
+          cur_k = k;
+          __syncthreads();
+        }
+        const int st = cons_seq % NS;
+        const XT* tile = reinterpret_cast<const XT*>(ring + static_cast<size_t>(st) * stage_bytes);
+
+        // designated threads prefetch the per-row state while the band lands
+        double r_old = 0.0, xb_next = 0.0;
+        const int row = pb.row0[k] + g0 + tid;
+        if (tid < rows) {
+          r_old = pb.r[row];
+          xb_next = pb.xb[static_cast<size_t>(lnext) * nrows + row];
+        }
+        mbar_wait(&H->mbar[st], (phase_bits >> st) & 1u);
+
+        // sweep 1: v[g] = <X[g,:], b>
+        if (!first) {
+          const int nworkers = NW / NSEG;  // row workers of NSEG warps each
+          const int wk = warp / NSEG, seg = warp % NSEG;
+          if (wk < nworkers) {
+            for (int g = wk; g < rows; g += nworkers) {
+              const XT* xr = tile + static_cast<size_t>(g) * p_pad;
+              double a0 = 0.0, a1 = 0.0;
+              for (int v = seg * 32 + lane; v < pv; v += NSEG * 32) {
+                double x[VW];
+                Vec<XT>::load(xr, v, x);
+                const double* bb = bsm + v * VW;
+#pragma unroll
+                for (int u = 0; u < VW; u += 2) {
+                  const double2 b2 = *reinterpret_cast<const double2*>(bb + u);
+                  a0 = fma(x[u], b2.x, a0);
+                  a1 = fma(x[u + 1], b2.y, a1);
+                }
+              }
+              const double s = warp_sum(a0 + a1);
+              if (lane == 0) H->partsum[cons_seq & 1][g * NSEG + seg] = s;
+            }
+          }
+        }
+        __syncthreads();  // (A) partial sums visible; every thread has left the previous sweep 2
+        if (tid == 0 && pending_refill >= 0) {
+          issue_fill(prod_pos, pending_refill);
+          prod_pos = (prod_pos + 1 == nb_own) ? 0 : prod_pos + 1;
+        }
+        if (tid < rows) {
+          double v = 0.0;
+          if (!first) {
+            for (int s = 0; s < NSEG; ++s) v += H->partsum[cons_seq & 1][tid * NSEG + s];
+            v *= pb.nscale[k];
+            pb.xb[static_cast<size_t>(l) * nrows + row] = v;
+          }
+          const double Rfull = r_old - v;
+          const double rnext = Rfull + xb_next;
+          pb.r[row] = rnext;
+          H->rn[tid] = rnext;
+          // b_l^T XtX b_l (infer_ss.py:572)  |  |X b_l|^2 (infer.py:806)
+          const double vterm = SS ? bsm[g0 + tid] * v : v * v;
+          if (SS && last_effect) pb.rfull[row] = Rfull;
+#pragma unroll
+          for (int kk = 0; kk < K; ++kk)
+            if (kk == k) {
+              vsq[kk] += vterm;
+              rsq[kk] += Rfull * Rfull;  // |y - X sum_l b_l|^2 at the last effect (infer.py:804)
+            }
+        }
+        if (!SS) {
+          __syncthreads();  // (B) r_next visible
+          // sweep 2: acc[j] += sum_g X[g, j] * r_next[g]
+          for (int gc = 0; gc < rows; gc += 8) {
+            double rr[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) rr[u] = (gc + u < rows) ? H->rn[gc + u] : 0.0;
+            for (int v = tid; v < pv; v += NT) {
+              double a[VW];
+#pragma unroll
+              for (int u = 0; u < VW; u += 2) {
+                const double2 t = *reinterpret_cast<const double2*>(acc + v * VW + u);
+                a[u] = t.x;
+                a[u + 1] = t.y;
+              }
+#pragma unroll
+              for (int u = 0; u < 8; ++u) {
+                if (gc + u < rows) {
+                  double x[VW];
+                  Vec<XT>::load(tile + static_cast<size_t>(gc + u) * p_pad, v, x);
+#pragma unroll
+                  for (int e = 0; e < VW; ++e) a[e] = fma(x[e], rr[u], a[e]);
+                }
+              }
+#pragma unroll
+              for (int u = 0; u < VW; u += 2)
+                *reinterpret_cast<double2*>(acc + v * VW + u) = make_double2(a[u], a[u + 1]);
+            }
+          }
+        }
+        phase_bits ^= (1u << st);
+        pending_refill = st;
+        cons_seq += 1;
+      }
+      // tail: flush the last ancestry, refill the last consumed stage
+      __syncthreads();
+      if (tid == 0 && pending_refill >= 0) {
+        issue_fill(prod_pos, pending_refill);
+        prod_pos = (prod_pos + 1 == nb_own) ? 0 : prod_pos + 1;
+      }
+      if (!SS) {
+        if (cur_k >= 0) {
+          double* dst = pb.part + (static_cast<size_t>(rank) * K + cur_k) * p_pad;
+          for (int j = tid; j < p_pad; j += NT) __stcg(&dst[j], acc[j]);
+        }
+        // ancestries in which this block owns no band contribute zeros
+        for (int k = 0; k < K; ++k) {
+          const int b0 = pb.band0[k], b1 = pb.band0[k + 1];
+          const int first_q = b0 + (((rank - b0) % C) + C) % C;  // first band index == rank (mod C)
+          const bool owns = first_q < b1;
+          if (!owns) {
+            double* dst = pb.part + (static_cast<size_t>(rank) * K + k) * p_pad;
+            for (int j = tid; j < p_pad; j += NT) __stcg(&dst[j], 0.0);
+          }
+        }
+      }
+      // per-traversal scalars: fixed-order serial sum over the designated threads
+      __syncthreads();
+#pragma unroll
+      for (int k = 0; k < K; ++k) {
+        if (tid < GMAX) {
+          H->trow[tid][0] = vsq[k];
+          H->trow[tid][1] = rsq[k];
+        }
+        __syncthreads();
+        if (tid == 0 && !first) {
+          double a = 0.0, b = 0.0;
+          for (int g = 0; g < GMAX; ++g) {
+            a += H->trow[g][0];
+            b += H->trow[g][1];
+          }
+          double* dst = pb.trav + (static_cast<size_t>(l) * C + rank) * TRAV_STRIDE;
+          __stcg(&dst[k], a);
+          __stcg(&dst[KMAX + k], b);
+        }
+        __syncthreads();
+      }
+    };
+
+    // ------------------------------------------------------------------------------
+    // team combine of per-block (max, scaled sums) records written to `stat`:
+    // rec[0] = m, rec[1..nv] = sums scaled by exp(-m).  Result in H->tot[0..nv] (tot[0] = m).
+    auto team_combine = [&](double* stat, int nv) {
+      // every block holds its own record in H->tot already (tot[0]=m, tot[1..nv])
+      if (C == 1) return;
+      if (tid <= nv) __stcg(&stat[static_cast<size_t>(rank) * STAT_STRIDE + tid], H->tot[tid]);
+      team_sync(team);
+      if (warp == 0) {
+        double m = -CUDART_INF;
+        for (int c = lane; c < C; c += 32) m = fmax(m, __ldcg(&stat[static_cast<size_t>(c) * STAT_STRIDE]));
+        m = warp_max(m);
+        // NaN anywhere must poison the result like the reference's softmax would
+        for (int i = 1; i <= nv; ++i) {
+          double s = 0.0;
+          for (int c = lane; c < C; c += 32) {
+            const double mc = __ldcg(&stat[static_cast<size_t>(c) * STAT_STRIDE]);
+            const double vc = __ldcg(&stat[static_cast<size_t>(c) * STAT_STRIDE + i]);
+            const double sc = (mc == -CUDART_INF) ? 0.0 : exp(mc - m);
+            s += (mc != mc) ? mc : vc * sc;
+          }
+          s = warp_sum(s);
+          if (lane == 0) H->tot[i] = s;
+        }
+        if (lane == 0) H->tot[0] = m;
+      }
+      __syncthreads();
+    };
+
+    // ------------------------------------------------------------------------------
+    // posterior phases of effect l in iteration `it` (writes out[buf], bT)
+    auto posterior = [&](int l, int it) {
+      const int buf = it & 1;
+      const OutBuf& ob = pb.out[buf];
+      const double* ecov_prev = (it == 0) ? pb.ecov0 : pb.out[buf ^ 1].ecov;
+      const double* rv_prev = (it == 0) ? pb.rv0 : pb.out[buf ^ 1].rv;
+      double rv[K];
+#pragma unroll
+      for (int k = 0; k < K; ++k) rv[k] = __ldcg(&rv_prev[k]);
+
+      // P1 (individual level): reduce the per-block partial X^T r over the team, own slice
+      if (!SS) {
+        for (int j = js + tid; j < je; j += NT) {
+#pragma unroll
+          for (int k = 0; k < K; ++k) {
+            double s = 0.0;
+            for (int c = 0; c < C; ++c) s += __ldcg(&pb.part[(static_cast<size_t>(c) * K + k) * p_pad + j]);
+            pb.xty[k * p_pad + j] = s;
+          }
+        }
+      }
+      auto load_snp = [&](int j, double (&d)[K], double (&r)[K]) {
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+          const double xty = SS ? __ldcg(&pb.r[pb.row0[k] + j]) : pb.xty[k * p_pad + j];
+          r[k] = xty / rv[k];                        // rTZDinv   (infer.py:677)
+          d[k] = pb.xtx[k * p_pad + j] / rv[k];      // inv_shat2 (infer.py:680)
+        }
+      };
+      auto load_cinv = [&](const double* Cmat, double (&Cinv)[K][K], double& logdetC) {
+        __syncthreads();
+        if (tid == 0) {
+          double ci[K * K], lad;
+          inv_logdet<K>(Cmat, ci, lad);
+          for (int i = 0; i < K * K; ++i) H->cst[i] = ci[i];
+          H->cst[K * K] = lad;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int a = 0; a < K; ++a)
+#pragma unroll
+          for (int b = 0; b < K; ++b) Cinv[a][b] = H->cst[a * K + b];
+        logdetC = H->cst[K * K];
+      };
+
+      double Cnew[K * K];
+      // ---- pass A: posterior under the old prior, only to update the prior (infer.py:138,153)
+      if (!pb.skip_first_pass) {
+        double Cold[K * K];
+#pragma unroll
+        for (int i = 0; i < K * K; ++i) Cold[i] = __ldcg(&ecov_prev[l * K * K + i]);
+        double Cinv[K][K], logdetC;
+        load_cinv(Cold, Cinv, logdetC);
+        double m = -CUDART_INF;
+        double sv[1 + NSYM];
+#pragma unroll
+        for (int i = 0; i < 1 + NSYM; ++i) sv[i] = 0.0;
+        for (int j = js + tid; j < je; j += NT) {
+          double d[K], r[K], S[K][K], mu[K], lda;
+          load_snp(j, d, r);
+          snp_posterior<K>(Cinv, d, r, S, mu, lda);
+          double q = 0.0;
+#pragma unroll
+          for (int k = 0; k < K; ++k) q += r[k] * mu[k];
+          const double lbf = 0.5 * (K * LOG_2PI - lda + q);  // infer.py:712-719
+          const double w = pb.logpi[j] + lbf;
+          double e;
+          if (w > m) {  // online softmax: rescale the running sums
+            const double sc = exp(m - w);
+#pragma unroll
+            for (int i = 0; i < 1 + NSYM; ++i) sv[i] *= sc;
+            m = w;
+            e = 1.0;
+          } else {
+            e = (w == -CUDART_INF) ? 0.0 : exp(w - m);  // NaN w propagates
+          }
+          sv[0] += e;
+          int t = 1;
+#pragma unroll
+          for (int a = 0; a < K; ++a)
+#pragma unroll
+            for (int b = a; b < K; ++b) sv[t++] += e * (S[a][b] + mu[a] * mu[b]);
+        }
+        const double mb = block_max(H, m);
+        const double sc = (m == -CUDART_INF) ? 0.0 : exp(m - mb);
+#pragma unroll
+        for (int i = 0; i < 1 + NSYM; ++i) sv[i] *= sc;
+        block_sum<1 + NSYM>(H, sv);
+        if (tid == 0) {
+          for (int i = NSYM; i >= 0; --i) H->tot[i + 1] = H->tot[i];
+          H->tot[0] = mb;
+        }
+        __syncthreads();
+        team_combine(pb.statA, 1 + NSYM);
+        const double ssum = H->tot[1];
+        int t = 2;
+#pragma unroll
+        for (int a = 0; a < K; ++a)
+#pragma unroll
+          for (int b = a; b < K; ++b) {
+            const double wv = H->tot[t++] / ssum;  // weighted_sum_covar (infer.py:726)
+            Cnew[a * K + b] = wv;
+            Cnew[b * K + a] = wv;
+          }
+        if (!pb.em) {
+#pragma unroll
+          for (int i = 0; i < K * K; ++i) Cnew[i] = Cnew[i] * pb.adj_times[i] + pb.adj_plus[i];  // infer.py:155-157
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < K * K; ++i) Cnew[i] = pb.adj_plus[i];
+      }
+
+      // ---- pass B1: posterior under the new prior; unnormalised rows + online statistics
+      constexpr int NVB = 1 + NSYM + 2 + K;  // s, W, sum e*kl_beta, sum e*lbf, sum e*xtx*Mkk
+      {
+        double Cinv[K][K], logdetC;
+        load_cinv(Cnew, Cinv, logdetC);
+        double m = -CUDART_INF;
+        double sv[NVB];
+#pragma unroll
+        for (int i = 0; i < NVB; ++i) sv[i] = 0.0;
+        for (int j = js + tid; j < je; j += NT) {
+          double d[K], r[K], S[K][K], mu[K], lda;
+          load_snp(j, d, r);
+          snp_posterior<K>(Cinv, d, r, S, mu, lda);
+          double q = 0.0;
+#pragma unroll
+          for (int k = 0; k < K; ++k) q += r[k] * mu[k];
+          const double lbf = 0.5 * (K * LOG_2PI - lda + q);
+          const double w = pb.logpi[j] + lbf;
+          // KL(N(mu,S) || N(0,C))  (infer.py:755-783)
+          double tr = 0.0, quad = 0.0;
+#pragma unroll
+          for (int a = 0; a < K; ++a)
+#pragma unroll
+            for (int b = 0; b < K; ++b) {
+              tr += Cinv[a][b] * S[b][a];
+              quad += mu[a] * Cinv[a][b] * mu[b];
+            }
+          const double klb = 0.5 * (tr - K + quad + logdetC + lda);
+          // unnormalised rows (scaled by alpha in pass B2)
+          const size_t lj = static_cast<size_t>(l) * p + j;
+          ob.lbf[lj] = lbf;
+          ob.alpha[lj] = w;
+#pragma unroll
+          for (int a = 0; a < K; ++a) {
+            ob.pm[lj * K + a] = mu[a];
+#pragma unroll
+            for (int b = 0; b < K; ++b) ob.pmsq[(lj * K + a) * K + b] = S[a][b] + mu[a] * mu[b];
+          }
+          double e;
+          if (w > m) {
+            const double sc = exp(m - w);
+#pragma unroll
+            for (int i = 0; i < NVB; ++i) sv[i] *= sc;
+            m = w;
+            e = 1.0;
+          } else {
+            e = (w == -CUDART_INF) ? 0.0 : exp(w - m);
+          }
+          sv[0] += e;
+          int t = 1;
+#pragma unroll
+          for (int a = 0; a < K; ++a)
+#pragma unroll
+            for (int b = a; b < K; ++b) sv[t++] += e * (S[a][b] + mu[a] * mu[b]);
+          sv[t++] += e * klb;
+          sv[t++] += e * lbf;
+#pragma unroll
+          for (int k = 0; k < K; ++k) sv[t++] += e * pb.xtx[k * p_pad + j] * (S[k][k] + mu[k] * mu[k]);
+        }
+        const double mb = block_max(H, m);
+        const double sc = (m == -CUDART_INF) ? 0.0 : exp(m - mb);
+#pragma unroll
+        for (int i = 0; i < NVB; ++i) sv[i] *= sc;
+        block_sum<NVB>(H, sv);
+        if (tid == 0) {
+          for (int i = NVB - 1; i >= 0; --i) H->tot[i + 1] = H->tot[i];
+          H->tot[0] = mb;
+        }
+        __syncthreads();
+        team_combine(pb.statB, NVB);
+      }
+      // ---- pass B2: normalise, publish b_l (transposed) for the traversal
+      {
+        const double mt = H->tot[0], ssum = H->tot[1];
+        for (int j = js + tid; j < je; j += NT) {
+          const size_t lj = static_cast<size_t>(l) * p + j;
+          const double w = ob.alpha[lj];
+          const double al = exp(w - mt) / ssum;  // softmax (infer.py:721)
+          ob.alpha[lj] = al;
+#pragma unroll
+          for (int a = 0; a < K; ++a) {
+            const double bm = ob.pm[lj * K + a] * al;
+            ob.pm[lj * K + a] = bm;
+            __stcg(&pb.bT[a * p_pad + j], bm);
+#pragma unroll
+            for (int b = 0; b < K; ++b) ob.pmsq[(lj * K + a) * K + b] *= al;
+          }
+        }
+        if (rank == 0 && tid == 0) {
+          int t = 2;
+          for (int a = 0; a < K; ++a)
+            for (int b = a; b < K; ++b) {
+              const double wv = H->tot[t++] / ssum;
+              ob.wsc[(l * K + a) * K + b] = wv;
+              ob.wsc[(l * K + b) * K + a] = wv;
+            }
+          const double klb = H->tot[t++] / ssum;
+          const double elbf = H->tot[t++] / ssum;
+          // KL(alpha || pi) = sum alpha (log alpha - log pi) = E[lbf] - logsumexp  (infer.py:748-752)
+          __stcg(&ob.kl[l], (elbf - (mt + log(ssum))) + klb);
+          for (int k = 0; k < K; ++k) __stcg(&ob.xtxb2[l * K + k], H->tot[t++] / ssum);
+          for (int i = 0; i < K * K; ++i) __stcg(&ob.ecov[l * K * K + i], Cnew[i]);
+        }
+      }
+    };
+
+    // ------------------------------------------------------------------------------
+    // the IBSS loop
+    if (!SS) {
+      traverse(0, true, false);  // X^T y for the first effect
+    }
+    team_sync(team);
+
+    int n_iter = 0, inc_flag = 1, final_buf = -1, n_ser = 0;
+    double elbo_last = -CUDART_INF;
+    if (rank == 0 && tid == 0) pb.elbo[0] = -CUDART_INF;
+
+    for (int it = 0; it < P.max_iter; ++it) {
+      const int buf = it & 1;
+      for (int l = 0; l < L; ++l) {
+        posterior(l, it);
+        team_sync(team);
+        traverse(l, false, l + 1 == L);
+        team_sync(team);
+        n_ser += 1;
+      }
+      // ---- ELBO, residual variance, stop rule (infer.py:622-633, 517-548)
+      const OutBuf& ob = pb.out[buf];
+      const double* rv_prev = (it == 0) ? pb.rv0 : pb.out[buf ^ 1].rv;
+      double* erss_sm = H->cst;  // [K]
+      if (SS) {
+        // terms 2 and 3 of infer_ss.py:555-575 from E[beta], Xty and the full residual
+        double tv[2 * K];
+#pragma unroll
+        for (int i = 0; i < 2 * K; ++i) tv[i] = 0.0;
+        for (int j = js + tid; j < je; j += NT) {
+#pragma unroll
+          for (int k = 0; k < K; ++k) {
+            double eb = 0.0;
+            for (int l = 0; l < L; ++l) eb += ob.pm[(static_cast<size_t>(l) * p + j) * K + k];
+            const double xty = pb.y[pb.row0[k] + j];
+            tv[k] += eb * xty;                                         // E[b]^T Xty
+            tv[K + k] += eb * (xty - __ldcg(&pb.rfull[pb.row0[k] + j]));  // E[b]^T XtX E[b]
+          }
+        }
+        block_sum<2 * K>(H, tv);
+        if (C > 1) {
+          if (tid < 2 * K) __stcg(&pb.statC[static_cast<size_t>(rank) * STAT_STRIDE + tid], H->tot[tid]);
+          team_sync(team);
+          if (tid < 2 * K) {
+            double s = 0.0;
+            for (int c = 0; c < C; ++c) s += __ldcg(&pb.statC[static_cast<size_t>(c) * STAT_STRIDE + tid]);
+            H->tot[tid] = s;
+          }
+          __syncthreads();
+        }
+      }
+      // per (l, k) traversal scalars summed over the team in fixed order
+      __syncthreads();
+      if (tid < K) {
+        const int k = tid;
+        double e;
+        if (SS) {
+          double t4 = 0.0, t5 = 0.0;
+          for (int l = 0; l < L; ++l) {
+            for (int c = 0; c < C; ++c) t4 += __ldcg(&pb.trav[(static_cast<size_t>(l) * C + c) * TRAV_STRIDE + k]);
+            t5 += __ldcg(&ob.xtxb2[l * K + k]);
+          }
+          e = pb.nsamp[k] - 2.0 * H->tot[k] + H->tot[K + k] - t4 + t5;
+        } else {
+          double rs = 0.0;
+          for (int c = 0; c < C; ++c)
+            rs += __ldcg(&pb.trav[(static_cast<size_t>(L - 1) * C + c) * TRAV_STRIDE + KMAX + k]);
+          double t2 = 0.0;
+          for (int l = 0; l < L; ++l) {
+            double vs = 0.0;
+            for (int c = 0; c < C; ++c) vs += __ldcg(&pb.trav[(static_cast<size_t>(l) * C + c) * TRAV_STRIDE + k]);
+            t2 += __ldcg(&ob.xtxb2[l * K + k]) - vs;
+          }
+          e = rs + t2;
+        }
+        erss_sm[k] = e;
+      }
+      __syncthreads();
+      if (tid == 0) {
+        double exp_ll = 0.0;
+        for (int k = 0; k < K; ++k) {
+          const double s2 = __ldcg(&rv_prev[k]);
+          exp_ll += -(0.5 * pb.nsamp[k]) * log(2.0 * CUDART_PI * s2) - (0.5 / s2) * erss_sm[k];
+        }
+        double kls = 0.0;
+        for (int l = 0; l < L; ++l) kls += __ldcg(&ob.kl[l]);
+        const double cur = exp_ll - kls;
+        // elbo_increase = cur >= last or isclose(cur, last, rtol=1e-5, atol=1e-8)
+        const bool inc = (cur >= elbo_last) || (fabs(cur - elbo_last) <= (1e-8 + 1e-5 * fabs(elbo_last)));
+        int dec = 0;  // 0 continue, 1 converged, 2 ELBO decreased -> revert
+        if (!inc)
+          dec = 2;
+        else if (fabs(cur - elbo_last) < P.min_tol)
+          dec = 1;
+        H->decision = dec;
+        H->cst[KMAX] = cur;
+        if (rank == 0) {
+          pb.elbo[it + 1] = cur;
+          for (int k = 0; k < K; ++k) __stcg(&ob.rv[k], erss_sm[k] / pb.nsamp[k]);
+        }
+      }
+      __syncthreads();
+      const int dec = H->decision;
+      elbo_last = H->cst[KMAX];
+      n_iter = it + 1;
+      if (dec == 2) {
+        inc_flag = 0;
+        final_buf = (it == 0) ? -1 : (buf ^ 1);
+        break;
+      }
+      final_buf = buf;
+      if (dec == 1) break;
+      team_sync(team);  // new residual variances visible to every block
+    }
+    if (rank == 0 && tid == 0) {
+      pb.meta[0] = n_iter;
+      pb.meta[1] = inc_flag;
+      pb.meta[2] = final_buf;
+      pb.meta[3] = n_ser;
+    }
+    // drain the speculative prefetches so the ring can be re-pointed at the next locus
+    if (nb_own > 0) {
+      for (int s = 0; s < NS; ++s) {
+        const int st = (cons_seq + s) % NS;
+        mbar_wait(&H->mbar[st], (phase_bits >> st) & 1u);
+        phase_bits ^= (1u << st);
+      }
+    }
+    team_sync(team);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// prologue kernels
+
+// Column statistics + standardisation: in [n][p] (any input type) -> out [n][p_pad] storage,
+// xtx[j] = sum_n out^2.  One thread per column (coalesced across the warp).
+// Restates infer.py:326-333 (centre, scale by the population std) and infer.py:494.
+template <typename IT, typename XT>
+__global__ void prep_columns_kernel(const IT* in, int in_ld, int n, int p, int p_pad, int flags, XT* out,
+                                    double* __restrict__ xtx) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= p_pad) return;
+  if (j >= p) {
+    for (int i = 0; i < n; ++i) out[static_cast<size_t>(i) * p_pad + j] = XT(0);
+    xtx[j] = 0.0;
+    return;
+  }
+  double mean = 0.0, sd = 1.0;
+  if (flags & 1) {
+    double s = 0.0;
+    for (int i = 0; i < n; ++i) s += static_cast<double>(in[static_cast<size_t>(i) * in_ld + j]);
+    mean = s / n;
+  }
+  if (flags & 2) {
+    // numpy.std of the centred column: sqrt(mean(|x - mean(x)|^2))
+    double s1 = 0.0;
+    for (int i = 0; i < n; ++i) s1 += static_cast<double>(in[static_cast<size_t>(i) * in_ld + j]) - mean;
+    const double m2 = s1 / n;
+    double s2 = 0.0;
+    for (int i = 0; i < n; ++i) {
+      const double c = (static_cast<double>(in[static_cast<size_t>(i) * in_ld + j]) - mean) - m2;
+      s2 += c * c;
+    }
+    sd = sqrt(s2 / n);
+  }
+  double ss = 0.0;
+  for (int i = 0; i < n; ++i) {
+    double v = static_cast<double>(in[static_cast<size_t>(i) * in_ld + j]) - mean;
+    if (flags & 2) v /= sd;
+    const XT sv = static_cast<XT>(v);
+    out[static_cast<size_t>(i) * p_pad + j] = sv;
+    const double back = static_cast<double>(sv);
+    ss += back * back;
+  }
+  xtx[j] = ss;
+}
+
+// Summary-level prologue (infer_ss.py:340-344): Xty = sqrt(n) sqrt(n/(n+z^2)) z,
+// diag(XtX) = n * LD_jj, log pi.
+template <typename XT>
+__global__ void prep_ss_kernel(const XT* __restrict__ ld, const double* __restrict__ z, double ns, int p,
+                               int p_pad, double* __restrict__ xty, double* __restrict__ xtx) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= p_pad) return;
+  if (j >= p) {
+    xtx[j] = 0.0;
+    return;
+  }
+  const double zz = z[j];
+  const double s2 = ns / (ns + zz * zz);
+  xty[j] = sqrt(ns) * sqrt(s2) * zz;
+  xtx[j] = ns * static_cast<double>(ld[static_cast<size_t>(j) * p_pad + j]);
+}
+
+// log pi (infer.py:721); in == nullptr means the uniform default 1/p (infer.py:302-303)
+__global__ void log_kernel(const double* __restrict__ in, double uniform, double* __restrict__ out, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = log(in ? in[i] : uniform);
+}
+
+// Pad-copy rows: in [n][p] -> out [n][p_pad] with zero tail, optional type conversion.
+template <typename IT, typename XT>
+__global__ void pad_rows_kernel(const IT* __restrict__ in, int n, int p, int p_pad, XT* __restrict__ out) {
+  const size_t total = static_cast<size_t>(n) * p_pad;
+  for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const size_t i = idx / p_pad;
+    const int j = static_cast<int>(idx - i * p_pad);
+    out[idx] = (j < p) ? static_cast<XT>(in[i * p + j]) : XT(0);
+  }
+}
+
+// Purity (infer.py:946-956): min |X_sel^T X_sel| / n over all pairs of a credible set.
+// One block per (set, ancestry); the selected columns are gathered into shared memory in
+// row chunks and the m x m Gram entries are accumulated by the threads that own them.
+template <typename XT, bool SS>
+__global__ void purity_kernel(const XT* const* __restrict__ Xk, const int* __restrict__ nk, int p_pad,
+                              const int* __restrict__ idx, const int* __restrict__ offsets, int K,
+                              double* __restrict__ out) {
+  extern __shared__ __align__(16) unsigned char pur_smem[];
+  const int set = blockIdx.x, k = blockIdx.y;
+  const int o0 = offsets[set], m = offsets[set + 1] - o0;
+  const int* sel = idx + o0;
+  const XT* X = Xk[k];
+  const int n = nk[k];
+  double best = CUDART_INF;
+  if (SS) {
+    for (int e = threadIdx.x; e < m * m; e += blockDim.x) {
+      const int a = e / m, b = e % m;
+      best = fmin(best, fabs(static_cast<double>(X[static_cast<size_t>(sel[a]) * p_pad + sel[b]])));
+    }
+  } else {
+    constexpr int RC = 32;  // rows per chunk
+    double* tile = reinterpret_cast<double*>(pur_smem);  // [RC][m]
+    // each thread owns pairs e = tid, tid + T, ... of the upper triangle (incl. diagonal);
+    // to keep registers bounded we process pairs in rounds of PR per thread.
+    constexpr int PR = 8;
+    const int npairs = m * (m + 1) / 2;
+    for (int base = 0; base < npairs; base += PR * blockDim.x) {
+      double accv[PR];
+      int pa[PR], pb2[PR];
+#pragma unroll
+      for (int u = 0; u < PR; ++u) {
+        accv[u] = 0.0;
+        const int e = base + u * blockDim.x + threadIdx.x;
+        int a = 0, b = 0;
+        if (e < npairs) {
+          // row a of the upper triangle: first index with a*(2m-a+1)/2 <= e
+          a = static_cast<int>((2.0 * m + 1.0 - sqrt((2.0 * m + 1.0) * (2.0 * m + 1.0) - 8.0 * e)) * 0.5);
+          while (a * (2 * m - a + 1) / 2 > e) --a;
+          while ((a + 1) * (2 * m - a) / 2 <= e) ++a;
+          b = a + (e - a * (2 * m - a + 1) / 2);
+        }
+        pa[u] = a;
+        pb2[u] = b;
+      }
+      for (int r0 = 0; r0 < n; r0 += RC) {
+        const int rc = min(RC, n - r0);
+        __syncthreads();
+        for (int t = threadIdx.x; t < rc * m; t += blockDim.x) {
+          const int rr = t / m, c = t % m;
+          tile[rr * m + c] = static_cast<double>(X[static_cast<size_t>(r0 + rr) * p_pad + sel[c]]);
+        }
+        __syncthreads();
+#pragma unroll
+        for (int u = 0; u < PR; ++u) {
+          const int e = base + u * blockDim.x + threadIdx.x;
+          if (e < npairs) {
+            double s = accv[u];
+            for (int rr = 0; rr < rc; ++rr) s = fma(tile[rr * m + pa[u]], tile[rr * m + pb2[u]], s);
+            accv[u] = s;
+          }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < PR; ++u) {
+        const int e = base + u * blockDim.x + threadIdx.x;
+        if (e < npairs) best = fmin(best, fabs(accv[u] / n));
+      }
+    }
+  }
+  // block min
+  __shared__ double red[32];
+  for (int o = 16; o > 0; o >>= 1) best = fmin(best, __shfl_xor_sync(0xffffffffu, best, o));
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = best;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double b = red[0];
+    for (int w = 1; w < static_cast<int>(blockDim.x >> 5); ++w) b = fmin(b, red[w]);
+    out[set * K + k] = b;
+  }
+}
+
+}  // namespace sb

@@ -1,0 +1,238 @@
+"""Individual-level SuShiE on the GPU: drop-in for ``sushie.infer`` of the reference.
+
+``infer_sushie`` keeps the reference signature, validation, defaults and result layout
+(``/root/reference/sushie/infer.py:162-587``).  The host does only what the reference
+does outside its jitted function (validation, covariate residualisation, phenotype
+centring/scaling, prior set-up); genotype standardisation, the whole IBSS loop with its
+stopping rule, and the purity Gram matrices run in the CUDA engine behind the C ABI
+(``include/sushie_b200.h``).  There is no CPU fallback.
+
+Deliberate differences from the reference:
+  * the caller's ``Xs`` / ``ys`` lists are not mutated;
+  * arrays in the result are numpy, not ``jax.Array``;
+  * at most ``SB_MAX_ANCESTRIES`` (4) ancestries.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+from . import _capi, config, cs as _cs, log, utils
+from ._common import (
+    Posterior,
+    Prior,
+    SushieResult,
+    _PriorAdjustor,
+    _reorder_l,
+    assemble_result,
+    build_priors,
+    check_scalar_options,
+    check_snp_counts,
+    log_convergence,
+    resolve_pi,
+    resolve_resid_var,
+)
+
+__all__ = [
+    "Prior",
+    "Posterior",
+    "SushieResult",
+    "infer_sushie",
+    "infer_sushie_batch",
+    "make_cs",
+    "_PriorAdjustor",
+    "_reorder_l",
+]
+
+
+class _Prepared:
+    """One validated problem: engine arguments + what the epilogue needs."""
+
+    def __init__(self, problem, pi, sample_size, max_iter, min_tol, cs_args, no_reorder):
+        self.problem = problem
+        self.pi = pi
+        self.sample_size = sample_size
+        self.max_iter = max_iter
+        self.min_tol = min_tol
+        self.cs_args = cs_args
+        self.no_reorder = no_reorder
+
+
+def _prepare(
+    Xs, ys, covar, L, no_scale, no_regress, no_update, pi, resid_var, effect_var, rho,
+    max_iter, min_tol, threshold, purity, purity_method, max_select, min_snps, no_reorder, seed,
+) -> _Prepared:
+    if len(Xs) == len(ys):
+        n_pop = len(Xs)
+    else:
+        raise ValueError(
+            f"The number of geno ({len(Xs)}) and pheno ({len(ys)}) data does not match. Check your input."
+        )
+    for idx in range(n_pop):
+        if Xs[idx].shape[0] != ys[idx].shape[0]:
+            raise ValueError(
+                f"Ancestry {idx + 1}: The sample size of geno ({Xs[idx].shape[0]}) "
+                + f"and pheno ({ys[idx].shape[0]}) data does not match. Check your input."
+            )
+    for idx in range(1, n_pop):
+        if Xs[idx - 1].shape[1] != Xs[idx].shape[1]:
+            raise ValueError(
+                f"Ancestry {idx} and ancestry {idx} do not have "
+                + f"the same number of SNPs ({Xs[idx - 1].shape[1]} vs {Xs[idx].shape[1]})."
+            )
+    check_scalar_options(L, min_tol, threshold, purity, max_select, min_snps, summary=False)
+    if n_pop > _capi.SB_MAX_ANCESTRIES:
+        raise ValueError(
+            f"sushie_b200 supports at most {_capi.SB_MAX_ANCESTRIES} ancestries per fit ({n_pop} given)."
+        )
+    n_snps = Xs[0].shape[1]
+    pi = resolve_pi(pi, n_snps, summary=False)
+
+    # covariates: QR residualisation on the host, as the reference does before its jitted loop
+    mats: List[np.ndarray] = list(Xs)
+    phen: List[np.ndarray] = [np.asarray(y, dtype=float) for y in ys]
+    if covar is not None:
+        for idx in range(n_pop):
+            mats[idx], phen[idx] = utils.regress_covar(
+                np.asarray(mats[idx], dtype=float), phen[idx], np.asarray(covar[idx], dtype=float), no_regress
+            )
+    for idx in range(n_pop):
+        y = phen[idx] - np.mean(phen[idx])
+        if not no_scale:
+            y = y / np.std(y)
+        phen[idx] = np.squeeze(y)
+
+    given_resid = resolve_resid_var(resid_var, n_pop)
+    if given_resid is None:
+        given_resid = [np.var(y, ddof=1) for y in phen]
+    check_snp_counts(n_snps, min_snps, L)
+    effect_covar, adj = build_priors(n_pop, L, effect_var, rho, no_update, summary=False)
+
+    standardize = _capi.SB_CENTER | (0 if no_scale else _capi.SB_SCALE)
+    problem = _capi.IndProblem(
+        mats, phen, L, pi, given_resid, effect_covar, adj.times, adj.plus, em_update=not no_update,
+        standardize=standardize,
+    )
+    sample_size = np.asarray([m.shape[0] for m in mats])[:, np.newaxis]
+    cs_args = dict(threshold=threshold, purity=purity, purity_method=purity_method, max_select=max_select, seed=seed)
+    return _Prepared(problem, pi, sample_size, max_iter, min_tol, cs_args, no_reorder)
+
+
+def _finish(batch: "_capi.Batch", index: int, prep: _Prepared, fit) -> SushieResult:
+    log_convergence(fit.n_iter, prep.max_iter, prep.min_tol, fit.elbo, fit.elbo_increase)
+
+    def builder(alpha, log_bf):
+        return _cs.build_tables(
+            alpha, log_bf, prep.sample_size, lambda sets: batch.purity(index, sets), **prep.cs_args
+        )
+
+    return assemble_result(fit, prep.pi, prep.sample_size, prep.no_reorder, builder)
+
+
+def _run_prepared(preps: Sequence[_Prepared], device: int = 0) -> List[SushieResult]:
+    """Fit a list of prepared problems that share max_iter / min_tol on one GPU."""
+    eng = _capi.get_engine(device)
+    opts = eng.make_opts(preps[0].max_iter, preps[0].min_tol, config.storage_code(), config.team_size)
+    with eng.create_batch([p.problem for p in preps], opts) as batch:
+        batch.run()
+        fits = batch.fetch()
+        return [_finish(batch, i, p, f) for i, (p, f) in enumerate(zip(preps, fits))]
+
+
+def infer_sushie(
+    Xs: List[np.ndarray],
+    ys: List[np.ndarray],
+    covar: utils.ListArrayOrNone = None,
+    L: int = 10,
+    no_scale: bool = False,
+    no_regress: bool = False,
+    no_update: bool = False,
+    pi: np.ndarray = None,
+    resid_var: utils.ListFloatOrNone = None,
+    effect_var: utils.ListFloatOrNone = None,
+    rho: utils.ListFloatOrNone = None,
+    max_iter: int = 500,
+    min_tol: float = 1e-4,
+    threshold: float = 0.95,
+    purity: float = 0.5,
+    purity_method: str = "weighted",
+    max_select: int = 250,
+    min_snps: int = 100,
+    no_reorder: bool = False,
+    seed: int = 12345,
+) -> SushieResult:
+    """Fine-map one locus from individual-level data (same arguments as the reference)."""
+    prep = _prepare(
+        Xs, ys, covar, L, no_scale, no_regress, no_update, pi, resid_var, effect_var, rho,
+        max_iter, min_tol, threshold, purity, purity_method, max_select, min_snps, no_reorder, seed,
+    )
+    device = (config.devices or [0])[0]
+    return _run_prepared([prep], device)[0]
+
+
+def infer_sushie_batch(problems: Sequence[dict], devices: Optional[Sequence[int]] = None, **common) -> List[SushieResult]:
+    """Throughput entry point: many loci in one call.
+
+    ``problems`` is a sequence of dicts with at least ``Xs`` and ``ys`` (plus any
+    per-locus ``infer_sushie`` keyword); ``common`` holds keywords shared by all loci.
+    Loci are sharded over ``devices`` by a host work queue (``sushie_b200.batch``);
+    results come back in input order."""
+    from . import batch as _batch
+
+    preps = []
+    for pr in problems:
+        kw = dict(common)
+        kw.update(pr)
+        preps.append(_prepare_kw(**kw))
+    return _batch.run_sharded(preps, _run_prepared, devices)
+
+
+def _prepare_kw(
+    Xs, ys, covar=None, L=10, no_scale=False, no_regress=False, no_update=False, pi=None, resid_var=None,
+    effect_var=None, rho=None, max_iter=500, min_tol=1e-4, threshold=0.95, purity=0.5, purity_method="weighted",
+    max_select=250, min_snps=100, no_reorder=False, seed=12345,
+) -> _Prepared:
+    return _prepare(
+        Xs, ys, covar, L, no_scale, no_regress, no_update, pi, resid_var, effect_var, rho,
+        max_iter, min_tol, threshold, purity, purity_method, max_select, min_snps, no_reorder, seed,
+    )
+
+
+def make_cs(
+    alpha: np.ndarray,
+    log_bf: np.ndarray,
+    ns: np.ndarray,
+    Xs: np.ndarray = None,
+    lds: np.ndarray = None,
+    threshold: float = 0.9,
+    purity: float = 0.5,
+    purity_method: str = "weighted",
+    max_select: int = 500,
+    seed: int = 12345,
+):
+    """Credible sets from a posterior (reference ``make_cs``, ``infer.py:835-1008``).
+
+    ``Xs`` ([k][n_i, p], centred/scaled) or ``lds`` ([k, p, p]) is uploaded once and the
+    purity Gram matrices are computed on the GPU."""
+    if Xs is None and lds is None:
+        raise ValueError("Both Xs and lds are None. Please specify at least one of them.")
+    alpha = np.asarray(alpha, dtype=float)
+    n_l, p = alpha.shape
+    ns_arr = np.asarray(ns, dtype=float).reshape(-1)
+    k = len(Xs) if Xs is not None else len(lds)
+    eye = np.stack([np.eye(k) * 1e-3])
+    eng = _capi.get_engine((config.devices or [0])[0])
+    opts = eng.make_opts(1, 1e-4, _capi.SB_F64, 1)
+    if Xs is not None:
+        mats = [np.asarray(x, dtype=float)[: int(n)] for x, n in zip(Xs, ns_arr)]  # drop zero padding rows
+        holder = _capi.IndProblem(mats, [np.zeros(m.shape[0]) for m in mats], 1, None, np.ones(k), eye,
+                                  np.ones((k, k)), np.zeros((k, k)), True, standardize=0)
+    else:
+        holder = _capi.SsProblem([np.asarray(m, dtype=float) for m in lds], ns_arr, [np.zeros(p)] * k, 1, None,
+                                 np.ones(k), eye, np.ones((k, k)), np.zeros((k, k)), True)
+    with eng.create_batch([holder], opts) as batch:
+        return _cs.build_tables(
+            alpha, log_bf, ns_arr, lambda sets: batch.purity(0, sets), threshold, purity, purity_method,
+            max_select, seed,
+        )

@@ -1,0 +1,187 @@
+"""GPU parity tests: the CUDA path through the Python API / C ABI vs the committed oracle
+goldens (tests/golden/*.npz, produced by tests/golden/make_golden.py)."""
+import numpy as np
+import pytest
+
+from parity import assert_fit_matches
+
+pytestmark = pytest.mark.gpu
+
+SYN_CASES = {
+    "k1": dict(k=1, kw=dict(L=5)),
+    "k2": dict(k=2, kw=dict(L=5)),
+    "k3": dict(k=3, kw=dict(L=6)),
+    "k3null": dict(k=3, kw=dict(L=4)),
+    "k2noupd": dict(k=2, kw=dict(L=4, no_update=True)),
+    "k2rho": dict(k=2, kw=dict(L=4, no_update=True, rho=[0.5])),
+    "k2var": dict(k=2, kw=dict(L=4, no_update=True, effect_var=[0.01, 0.02])),
+    "k2noscale": dict(k=2, kw=dict(L=4, no_scale=True)),
+    "k4": dict(k=4, kw=dict(L=4)),
+}
+
+
+def _syn_inputs(g, tag, k, as_float=True):
+    Xs = [g[f"{tag}_X{i}"] for i in range(k)]
+    if as_float:
+        Xs = [x.astype(np.float64) for x in Xs]
+    ys = [g[f"{tag}_y{i}"].copy() for i in range(k)]
+    return Xs, ys
+
+
+@pytest.mark.parametrize("tol_tag,tol", [("tol3", 1e-3), ("tol4", 1e-4)])
+def test_bundled_individual_example(engine_lib, golden_ind, tol_tag, tol):
+    """Config 1: bundled EUR+AFR genotypes + covariates, L=10."""
+    import sushie_b200
+
+    g = golden_ind
+    Xs = [g["X0"].astype(np.float64), g["X1"].astype(np.float64)]
+    ys = [g["y0"].copy(), g["y1"].copy()]
+    covar = [g["covar0"], g["covar1"]]
+    res = sushie_b200.infer_sushie(Xs, ys, covar, L=10, min_tol=tol)
+    assert_fit_matches(res, g, tol_tag)
+    snp = g["snp"]
+    top = set(snp[np.argsort(-res.pip_all)[:2]])
+    assert top == {"rs1886340", "rs10914958"}  # documented causal SNPs, docs/manual.rst:88
+
+
+@pytest.mark.parametrize("tag", ["k2", "k3"])
+@pytest.mark.parametrize("tol_tag,tol", [("tol3", 1e-3), ("tol4", 1e-4)])
+def test_bundled_summary_example(engine_lib, golden_ss, tag, tol_tag, tol):
+    """Config 2: bundled LD + GWAS z-scores."""
+    import sushie_b200
+
+    g = golden_ss
+    res = sushie_b200.infer_sushie_ss(g[f"{tag}_lds"], g[f"{tag}_ns"], g[f"{tag}_zs"], L=10, min_tol=tol)
+    assert_fit_matches(res, g, f"{tag}_{tol_tag}")
+    top = set(g[f"{tag}_snp"][np.argsort(-res.pip_all)[:2]])
+    assert top == {"rs1886340", "rs10914958"}
+
+
+@pytest.mark.parametrize("tag", sorted(SYN_CASES))
+def test_synthetic_small(engine_lib, golden_syn, tag):
+    import sushie_b200
+
+    case = SYN_CASES[tag]
+    Xs, ys = _syn_inputs(golden_syn, tag, case["k"])
+    res = sushie_b200.infer_sushie(Xs, ys, min_tol=1e-4, **case["kw"])
+    assert_fit_matches(res, golden_syn, tag)
+
+
+def test_int8_genotypes_match_float(engine_lib, golden_syn):
+    """Hard-call int8 input is standardised on device exactly like float input."""
+    import sushie_b200
+
+    Xi, ys = _syn_inputs(golden_syn, "k3", 3, as_float=False)
+    assert Xi[0].dtype == np.int8
+    res = sushie_b200.infer_sushie(Xi, ys, min_tol=1e-4, L=6)
+    assert_fit_matches(res, golden_syn, "k3")
+
+
+@pytest.mark.parametrize("team", [1, 2, 4, 8, 16, 24])
+def test_team_sizes_agree_with_oracle(engine_lib, golden_syn, team):
+    """Cluster teams (hardware barrier, 2..16 blocks) and co-operative teams (24 blocks,
+    global-memory barrier) all reproduce the oracle."""
+    import sushie_b200
+    from sushie_b200 import config
+
+    old = config.team_size
+    config.team_size = team
+    try:
+        Xs, ys = _syn_inputs(golden_syn, "k3", 3)
+        res = sushie_b200.infer_sushie(Xs, ys, min_tol=1e-4, L=6)
+        assert_fit_matches(res, golden_syn, "k3")
+        res = sushie_b200.infer_sushie_ss(golden_ss_inputs()[0], golden_ss_inputs()[1], golden_ss_inputs()[2], L=10, min_tol=1e-3)
+        assert_fit_matches(res, golden_ss_inputs()[3], "k2_tol3")
+    finally:
+        config.team_size = old
+
+
+def golden_ss_inputs():
+    import os
+
+    from conftest import GOLDEN
+
+    g = np.load(os.path.join(GOLDEN, "example_ss.npz"))
+    return g["k2_lds"], g["k2_ns"], g["k2_zs"], g
+
+
+def test_batch_mixed_shapes_matches_single(engine_lib, golden_syn):
+    """Ragged p / n and mixed k in one device-resident batch == the same loci one by one."""
+    import sushie_b200
+
+    problems = []
+    for tag in ("k1", "k2", "k3", "k3null", "k4"):
+        case = SYN_CASES[tag]
+        Xs, ys = _syn_inputs(golden_syn, tag, case["k"])
+        problems.append(dict(Xs=Xs, ys=ys, **case["kw"]))
+    out = sushie_b200.infer_sushie_batch(problems, min_tol=1e-4)
+    for tag, res in zip(("k1", "k2", "k3", "k3null", "k4"), out):
+        assert_fit_matches(res, golden_syn, tag)
+
+
+def test_fp32_storage_is_close(engine_lib, golden_syn):
+    """fp32 device storage (fp64 arithmetic) is reported, not gated at 1e-4: it must find
+    the same credible sets and PIPs within 1e-2 on a well-powered locus."""
+    import sushie_b200
+    from sushie_b200 import config
+
+    old = config.precision
+    config.precision = 32
+    try:
+        Xs, ys = _syn_inputs(golden_syn, "k2", 2)
+        res = sushie_b200.infer_sushie(Xs, ys, min_tol=1e-4, L=5)
+    finally:
+        config.precision = old
+    assert np.max(np.abs(res.pip_all - golden_syn["k2_pip_all"])) < 1e-2
+    assert set(res.cs.SNPIndex.values.tolist()) == set(golden_syn["k2_cs_snp"].tolist())
+
+
+def test_make_cs_standalone_matches_oracle(engine_lib, golden_syn):
+    """Public make_cs (device purity) vs the pandas oracle on the same posterior."""
+    import sushie_b200
+    from oracle import credible_sets, ibss
+
+    Xs, ys = _syn_inputs(golden_syn, "k3", 3)
+    Xstd, _ = ibss.prepare_individual(Xs, ys)
+    alpha, log_bf = golden_syn["k3_alpha"], golden_syn["k3_log_bf"]
+    ns = np.array([[x.shape[0]] for x in Xs])
+    for method in ("weighted", "max", "min"):
+        for max_select in (500, 40):
+            cs_o, al_o, pa_o, pc_o = credible_sets.make_cs(alpha, log_bf, ns, Xs=Xstd, threshold=0.9, purity=0.5,
+                                                          purity_method=method, max_select=max_select, seed=12345)
+            cs_g, al_g, pa_g, pc_g = sushie_b200.make_cs(alpha, log_bf, ns, Xs=Xstd, threshold=0.9, purity=0.5,
+                                                        purity_method=method, max_select=max_select, seed=12345)
+            assert list(al_o.columns) == list(al_g.columns)
+            np.testing.assert_allclose(al_g.values.astype(float), al_o.values.astype(float), atol=1e-9)
+            assert np.array_equal(cs_g.SNPIndex.values, cs_o.SNPIndex.values.astype(int))
+            assert np.array_equal(cs_g.CSIndex.values, cs_o.CSIndex.values.astype(int))
+            np.testing.assert_allclose(pc_g, pc_o, atol=1e-12)
+
+
+def test_headline_shape_fixed_iterations(engine_lib):
+    """Full headline shape (k=3, n=500, p=2000, L=10): a fixed 12 outer iterations must
+    match the oracle's ELBO trace and PIPs, plus size-independent invariants."""
+    import sushie_b200
+    from oracle import ibss
+
+    rng = np.random.default_rng(20260001)
+    k, n, p, L = 3, 500, 2000, 10
+    Xs = [rng.binomial(2, rng.uniform(0.05, 0.5, size=p), size=(n, p)).astype(np.float64) for _ in range(k)]
+    for X in Xs:
+        X[0, X.std(axis=0) == 0] = 1.0
+    causal = [150, 1200]
+    ys = []
+    for X in Xs:
+        Xs_std = (X - X.mean(0)) / X.std(0)
+        ys.append(Xs_std[:, causal] @ np.array([0.35, -0.3]) + rng.standard_normal(n))
+    res = sushie_b200.infer_sushie(Xs, ys, L=L, max_iter=12, min_tol=0.0)
+    ref = ibss.fit_individual(Xs, ys, L=L, max_iter=12, min_tol=0.0)
+    assert len(res.elbo) == len(ref.elbo) == 13
+    np.testing.assert_allclose(res.elbo[1:], ref.elbo[1:], rtol=1e-6)
+    assert np.max(np.abs(res.pip_all - ibss.make_pip(ref.posteriors.alpha))) <= 1e-4
+    # invariants
+    assert np.all(np.diff(res.elbo[1:]) >= -1e-5 * np.abs(res.elbo[1:-1]) - 1e-8)
+    np.testing.assert_allclose(res.posteriors.alpha.sum(axis=1), 1.0, atol=1e-10)
+    assert np.all((res.pip_all >= 0) & (res.pip_all <= 1))
+    ev = np.linalg.eigvalsh(res.posteriors.weighted_sum_covar)
+    assert np.all(ev >= -1e-12)
