@@ -1,0 +1,487 @@
+#!/usr/bin/env python
+"""Benchmark of the IBSS hot path on BASELINE.json's headline workload.
+
+Workload (config 3): a batch of synthetic 3-ancestry individual-level loci,
+n = 500 per ancestry, p = 2000 SNPs, L = 10, fitted to convergence with the Python-API
+defaults (max_iter = 500, min_tol = 1e-4).  One "step" = one pass of the whole batch
+through the IBSS engine.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--genes B]
+  python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+  python bench.py --impl reference        # the numpy restatement of the reference on host cores
+
+Prints ONE JSON line (rank 0).  `value` = loci/s with standardised fp64 genotypes already
+resident in HBM (device time by CUDA events on the engine's stream, max over ranks);
+`e2e` = loci/s through the C ABI with host buffers (int8 genotypes in pinned memory in,
+full posterior tables out), copies inside the timed region.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+K_ANC, N_IND, P_SNP, L_EFF = 3, 500, 2000, 10
+RHO_ANC = (0.90, 0.80, 0.85)
+SEED0 = 20260000
+HBM_FALLBACK_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md fallback
+
+
+# ----------------------------------------------------------------------------------------
+# synthetic loci
+
+
+def make_gene(g: int, n: int = N_IND, p: int = P_SNP):
+    """Gene g: AR(1)-latent haplotypes -> 0/1/2 genotypes (int8), y = X_std b + e at h2 = 0.2."""
+    from scipy.signal import lfilter
+    from scipy.stats import norm
+
+    rng = np.random.default_rng(SEED0 + g)
+    Xs, ys = [], []
+    maf = rng.uniform(0.05, 0.5, size=p)
+    thr = norm.ppf(1.0 - maf)
+    n_causal = g % 4
+    causal = rng.choice(p, size=n_causal, replace=False) if n_causal else np.zeros(0, dtype=int)
+    cov = 0.8 * np.ones((K_ANC, K_ANC)) + 0.2 * np.eye(K_ANC)
+    b = rng.multivariate_normal(np.zeros(K_ANC), cov, size=n_causal) if n_causal else np.zeros((0, K_ANC))
+    for a in range(K_ANC):
+        rho = RHO_ANC[a]
+        c = math.sqrt(1.0 - rho * rho)
+        geno = np.zeros((n, p), dtype=np.int8)
+        for _ in range(2):
+            e = rng.standard_normal((n, p))
+            e[:, 0] /= c
+            z = lfilter([c], [1.0, -rho], e, axis=1)
+            geno += (z > thr).astype(np.int8)
+        sd = geno.std(axis=0)
+        for j in np.nonzero(sd == 0)[0]:
+            geno[0, j] = 1 if geno[0, j] == 0 else geno[0, j] - 1
+        Xs.append(geno)
+        if n_causal:
+            gf = geno[:, causal].astype(np.float64)
+            gstd = (gf - gf.mean(0)) / gf.std(0)
+            gv = gstd @ b[:, a]
+            s2e = np.var(gv) * (1.0 / 0.2 - 1.0)
+            ys.append(gv + rng.standard_normal(n) * math.sqrt(s2e))
+        else:
+            ys.append(rng.standard_normal(n))
+    return Xs, ys
+
+
+def _gen_into(args):
+    g, n, p = args
+    return make_gene(g, n, p)
+
+
+def generate_genes(first: int, count: int, workers: int, n=N_IND, p=P_SNP):
+    import multiprocessing as mp
+
+    jobs = [(first + i, n, p) for i in range(count)]
+    if workers <= 1 or count < 4:
+        return [make_gene(*j) for j in jobs]
+    with mp.get_context("fork").Pool(workers) as pool:
+        return pool.map(_gen_into, jobs, chunksize=max(1, count // (workers * 4)))
+
+
+# ----------------------------------------------------------------------------------------
+# CPU legs (the only places allowed to execute oracle/)
+
+
+def _oracle_fit(args):
+    os.environ["OMP_NUM_THREADS"] = "1"
+    os.environ["OPENBLAS_NUM_THREADS"] = "1"
+    os.environ["MKL_NUM_THREADS"] = "1"
+    try:
+        from threadpoolctl import threadpool_limits
+
+        threadpool_limits(1)
+    except Exception:
+        pass
+    from oracle import ibss
+
+    g, max_iter, min_tol, n, p = args
+    Xs, ys = make_gene(g, n, p)
+    t0 = time.perf_counter()
+    fit = ibss.fit_individual([x.astype(np.float64) for x in Xs], ys, L=L_EFF, max_iter=max_iter, min_tol=min_tol)
+    return time.perf_counter() - t0, fit.n_iter
+
+
+def cpu_pass(first_gene: int, n_loci: int, cores: int, max_iter: int, min_tol: float, n=N_IND, p=P_SNP):
+    """Fit n_loci genes with the numpy oracle, one process per core.  Returns (seconds, iters)."""
+    import multiprocessing as mp
+
+    jobs = [(first_gene + i, max_iter, min_tol, n, p) for i in range(n_loci)]
+    t0 = time.perf_counter()
+    with mp.get_context("fork").Pool(min(cores, n_loci)) as pool:
+        out = pool.map(_oracle_fit, jobs, chunksize=1)
+    wall = time.perf_counter() - t0
+    return wall, int(sum(o[1] for o in out))
+
+
+# ----------------------------------------------------------------------------------------
+# helpers
+
+
+class ClockSampler:
+    """nvidia-smi clock / throttle-reason sampler running during the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.path = tempfile.mktemp(prefix="sb_clocks_", suffix=".csv")
+        self.proc = None
+        self.gpu = gpu_index
+
+    def start(self):
+        try:
+            self.fh = open(self.path, "w")
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200"],
+                stdout=self.fh, stderr=subprocess.DEVNULL,
+            )
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.fh.close()
+        sm, mx, reasons = [], [], set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        try:
+            for line in open(self.path):
+                f = [x.strip() for x in line.split(",")]
+                if len(f) < 7:
+                    continue
+                try:
+                    sm.append(float(f[0]))
+                    mx.append(float(f[1]))
+                except ValueError:
+                    continue
+                for nm, v in zip(names, f[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+def hbm_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return HBM_FALLBACK_GBS, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic_per_launch():
+    """dram read+write bytes per launch of the IBSS kernel from the committed ncu summary."""
+    path = os.path.join(ROOT, "profiles", "ncu_summary.json")
+    try:
+        with open(path) as fh:
+            return json.load(fh).get("dram_bytes_per_launch")
+    except Exception:
+        return None
+
+
+def prep_y(ys):
+    out, rv = [], []
+    for y in ys:
+        y = y - y.mean()
+        y = y / y.std()
+        out.append(y)
+        rv.append(np.var(y, ddof=1))
+    return out, rv
+
+
+# ----------------------------------------------------------------------------------------
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    sample = max(1, min(cores, args.ref_loci or cores))
+    times, iters = [], 0
+    for _ in range(args.warmup):  # warm-up passes are bounded: 2 loci x 10 iterations (imports, page-in)
+        cpu_pass(0, min(2, sample), cores, 10, 0.0)
+    for _ in range(args.steps):
+        wall, it = cpu_pass(0, sample, cores, args.max_iter, args.min_tol)
+        times.append(wall)
+        iters += it
+    ms = 1e3 * float(np.mean(times))
+    value = sample / (ms / 1e3)
+    line = {
+        "impl": "reference",
+        "metric": "loci_per_sec",
+        "value": value,
+        "unit": "loci/s",
+        "n_gpus": args.gpus,
+        "steps": args.steps,
+        "warmup": args.warmup,
+        "ms_per_step": ms,
+        "higher_is_better": True,
+        "scaling": "weak",
+        "vs_baseline": None,
+        "dtype": "f64",
+        "data": "synthetic",
+        "config": workload_config(args, sample),
+        "cpu_baseline": {
+            "value": value, "unit": "loci/s", "cores": min(cores, sample), "kind": "port",
+            "sample": f"first {sample} loci of the workload per step, one numpy-oracle process per core "
+                      f"(reference JAX path not installable: no jax/equinox wheels)",
+        },
+        "e2e": {"value": value, "unit": "loci/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "iters_per_sec": iters / (sum(times)),
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, genes_per_gpu):
+    return {
+        "workload": "config 3: synthetic 3-ancestry individual-level loci (AR(1) haplotypes, h2=0.2, 0-3 causal)",
+        "k": K_ANC, "n_per_ancestry": N_IND, "p": P_SNP, "L": L_EFF,
+        "genes_per_gpu": genes_per_gpu, "max_iter": args.max_iter, "min_tol": args.min_tol,
+        "stop_rule": "to convergence (Python API defaults)",
+        "l2": "inputs_larger_than_L2 (24 MB fp64 per locus, batch >> 126 MB)",
+        "parallelism": f"loci sharded over {args.gpus} GPU(s), no data-path collective",
+    }
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--genes", type=int, default=1000, help="loci per GPU per step")
+    ap.add_argument("--max-iter", type=int, default=500)
+    ap.add_argument("--min-tol", type=float, default=1e-4)
+    ap.add_argument("--team", type=int, default=0)
+    ap.add_argument("--ref-loci", type=int, default=0)
+    ap.add_argument("--cpu-loci", type=int, default=0, help="loci in the cpu_baseline sample (0 = one per core)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-steps", type=int, default=1)
+    args = ap.parse_args()
+
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    cores = os.cpu_count() or 1
+    B = args.genes
+
+    # ---- host work before CUDA exists in this process: data generation, CPU baseline
+    gen_workers = max(1, cores // max(1, world))
+    t0 = time.time()
+    genes = generate_genes(rank * B, B, gen_workers)
+    t_gen = time.time() - t0
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        sample = args.cpu_loci or min(cores, B)
+        wall, it = cpu_pass(0, sample, cores, args.max_iter, args.min_tol)
+        cpu_baseline = {
+            "value": sample / wall, "unit": "loci/s", "cores": min(cores, sample), "kind": "port",
+            "sample": f"first {sample} loci of the workload, numpy oracle, one process per core, {wall:.1f} s wall",
+            "iters_per_sec": it / wall,
+        }
+
+    import torch
+    import torch.distributed as dist
+
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    from sushie_b200 import _capi
+    from sushie_b200._common import build_priors
+
+    eng = _capi.Engine(local_rank)
+    effect_covar, adj = build_priors(K_ANC, L_EFF, None, None, False, summary=False)
+
+    # pinned host buffers: int8 genotypes in, posterior tables out
+    x_pin = torch.empty((B, K_ANC, N_IND, P_SNP), dtype=torch.int8).pin_memory()
+    x_np = x_pin.numpy()
+    for i, (Xs, _) in enumerate(genes):
+        for a in range(K_ANC):
+            x_np[i, a] = Xs[a]
+    ys_all = [g[1] for g in genes]
+    del genes
+
+    def build_problems():
+        probs = []
+        for i in range(B):
+            ys, rv = prep_y(ys_all[i])
+            probs.append(_capi.IndProblem(
+                [x_np[i, a] for a in range(K_ANC)], ys, L_EFF, None, rv, effect_covar, adj.times, adj.plus,
+                em_update=True, standardize=_capi.SB_CENTER | _capi.SB_SCALE))
+        return probs
+
+    opts = eng.make_opts(args.max_iter, args.min_tol, _capi.SB_F64, args.team)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- resident arm: upload + standardise once, then W warm-up and K timed passes
+    probs = build_problems()
+    batch = eng.create_batch(probs, opts)
+    for _ in range(args.warmup):
+        st = batch.run()
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    t_wall0 = time.perf_counter()
+    dev_ms, n_ser, n_iter, alg_bytes, launches = 0.0, 0, 0, 0.0, 0
+    for _ in range(args.steps):
+        st = batch.run()
+        dev_ms += st["device_ms"]
+        n_ser += st["n_ser"]
+        n_iter += st["n_iter"]
+        alg_bytes += st["algorithmic_bytes"]
+        launches += 1
+    barrier()
+    wall_ms = 1e3 * (time.perf_counter() - t_wall0)
+    clocks = sampler.stop()
+    fits = batch.fetch()
+    pip_sum = float(sum(np.sum(-np.expm1(np.log1p(-f.alpha).sum(axis=0))) for f in fits[:8]))
+    geom = {k: st[k] for k in ("team_size", "n_teams", "rows_per_band", "n_stages", "smem_bytes")}
+    batch.close()
+    del fits
+
+    # ---- end-to-end arm: host buffers through the C ABI, copies in the timed region
+    e2e = None
+    if not args.no_e2e:
+        import ctypes as C
+
+        sizes = [L_EFF * P_SNP, L_EFF * P_SNP * K_ANC, L_EFF * P_SNP * K_ANC * K_ANC, L_EFF * K_ANC * K_ANC,
+                 L_EFF, L_EFF * P_SNP, L_EFF * K_ANC * K_ANC, K_ANC, args.max_iter + 1]
+        names = ["alpha", "post_mean", "post_mean_sq", "weighted_sum_covar", "kl", "log_bf", "effect_covar",
+                 "resid_var", "elbo"]
+        per = sum(sizes)
+        out_pin = torch.empty((B, per), dtype=torch.float64).pin_memory()
+        out_np = out_pin.numpy()
+        res = (_capi.SbResult * B)()
+        pd_t = C.POINTER(C.c_double)
+        for i in range(B):
+            off = 0
+            for nm, sz in zip(names, sizes):
+                setattr(res[i], nm, out_np[i, off:off + sz].ctypes.data_as(pd_t))
+                off += sz
+        e2e_ms = []
+        for s in range(1 + args.e2e_steps):
+            barrier()
+            t0 = time.perf_counter()
+            probs = build_problems()  # host prologue (phenotype centring/scaling, priors)
+            arr = (_capi.SbIndProblem * B)()
+            for i, pr in enumerate(probs):
+                pr.fill(arr[i])
+            stats = _capi.SbRunStats()
+            eng._check(eng.lib.sb_ibss_ind(eng._ctx, arr, B, C.byref(opts), res, C.byref(stats)), "sb_ibss_ind")
+            barrier()
+            if s >= 1:
+                e2e_ms.append(1e3 * (time.perf_counter() - t0))
+        e2e_step = float(np.mean(e2e_ms))
+        h2d = B * (K_ANC * N_IND * P_SNP + 8 * (K_ANC * N_IND + 2 * K_ANC + L_EFF * K_ANC * K_ANC + 2 * K_ANC * K_ANC))
+        d2h = B * 8 * (per - (args.max_iter + 1)) + 8 * int(stats.n_iter) + 8 * B
+        e2e = {"ms": e2e_step, "h2d": h2d, "d2h": d2h, "launches": int(stats.n_launches)}
+
+    # ---- reduce over ranks (max time), gather a small result record with NCCL
+    if world > 1:
+        t = torch.tensor([dev_ms, wall_ms, e2e["ms"] if e2e else 0.0], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dev_ms, wall_ms = float(t[0]), float(t[1])
+        if e2e:
+            e2e["ms"] = float(t[2])
+        cnt = torch.tensor([n_ser, n_iter, alg_bytes, pip_sum], device="cuda", dtype=torch.float64)
+        gathered = [torch.zeros_like(cnt) for _ in range(world)]
+        dist.all_gather(gathered, cnt)
+        n_ser = int(sum(float(g[0]) for g in gathered))
+        n_iter = int(sum(float(g[1]) for g in gathered))
+        alg_bytes = float(sum(float(g[2]) for g in gathered))
+
+    if rank == 0:
+        ms_per_step = dev_ms / args.steps
+        total_loci = B * world
+        value = total_loci / (ms_per_step / 1e3)
+        peak, peak_src = hbm_peak()
+        # per-GPU achieved bandwidth of the single persistent launch
+        achieved = (alg_bytes / world) / (dev_ms / 1e3) / 1e9
+        line = {
+            "metric": "loci_per_sec",
+            "value": value,
+            "unit": "loci/s",
+            "n_gpus": world,
+            "steps": args.steps,
+            "warmup": args.warmup,
+            "ms_per_step": ms_per_step,
+            "higher_is_better": True,
+            "scaling": "weak",
+            "vs_baseline": None,
+            "dtype": "f64",
+            "data": "synthetic",
+            "config": workload_config(args, B),
+            "iters_per_sec": n_iter / (dev_ms / 1e3),
+            "ser_per_sec": n_ser / (dev_ms / 1e3),
+            "mean_iters_per_locus": n_iter / (total_loci * args.steps),
+            "wall_ms_per_step": wall_ms / args.steps,
+            "gpu_launches": launches,
+            "kernel": dict(geom, name="sb::ibss_kernel<3,double,false>", launches_per_step=1),
+            "roofline": {
+                "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": ncu_traffic_per_launch(), "peak_source": peak_src,
+                "algorithmic_bytes_per_ser": K_ANC * N_IND * P_SNP * 8,
+                "note": "achieved = (#single-effect updates x k*n*p*8 B) / CUDA-event time of the launch, per GPU",
+            },
+            "clocks": {"sm_mhz": clocks["sm_mhz"], "sm_max_mhz": clocks["sm_max_mhz"], "reasons": clocks["reasons"],
+                       "samples": clocks["samples"]},
+            "datagen_s": t_gen,
+            "check_pip_sum_first8": pip_sum,
+        }
+        if e2e:
+            line["e2e"] = {
+                "value": total_loci / (e2e["ms"] / 1e3), "unit": "loci/s",
+                "h2d_bytes_per_step": e2e["h2d"] * world, "d2h_bytes_per_step": e2e["d2h"] * world,
+                "ms_per_step": e2e["ms"], "gpu_launches_per_step": e2e["launches"],
+                "path": "sb_ibss_ind (C ABI): pinned int8 genotypes -> device standardise -> IBSS -> posterior tables to pinned host",
+            }
+        if cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -186,15 +186,40 @@ extern "C" int sb_set_stream(sb_ctx* ctx, void* cuda_stream) {
 // geometry: rows per band / stages / sweep-1 segmentation for one problem
 
 struct Geometry {
-  int p_pad, G, NS, NSEG;
+  int p_pad, G, NS, NSEG, fast;
   size_t smem;
 };
 
 static bool plan_geometry(int p, int n_max, int es, bool ss, int smem_budget, Geometry& g) {
   g.p_pad = static_cast<int>(align_up(static_cast<size_t>(p), 32));
   const size_t hdr = align_up(sizeof(sb::SmemHdr), 128);
-  const size_t fixed = hdr + static_cast<size_t>(g.p_pad) * sizeof(double) * (ss ? 1 : 2);
   const size_t row_bytes = static_cast<size_t>(g.p_pad) * es;
+  const int pv = static_cast<int>(row_bytes / 16);  // 16-byte vectors per row
+  // register-tile traversal (individual level): every thread owns CPT vectors of GR rows
+  g.fast = 0;
+  if (!ss) {
+    int gr = 0;
+    if (pv > sb::NT && pv <= 4 * sb::NT) {
+      g.fast = 1;
+      gr = 4;
+    } else if (pv > 4 * sb::NT && pv <= 8 * sb::NT) {
+      g.fast = 2;
+      gr = 2;
+    }
+    if (g.fast) {
+      const int rows_fit = static_cast<int>((smem_budget - hdr) / row_bytes);
+      if (rows_fit >= 2 * gr) {
+        g.G = gr;
+        g.NS = std::min(sb::NSTAGE_MAX, rows_fit / gr);
+        if (g.NS > 3) g.NS = 3;
+        g.NSEG = 1;
+        g.smem = hdr + static_cast<size_t>(g.NS) * g.G * row_bytes;
+        return true;
+      }
+      g.fast = 0;
+    }
+  }
+  const size_t fixed = hdr + static_cast<size_t>(g.p_pad) * sizeof(double) * (ss ? 1 : 2);
   if (fixed + 2 * row_bytes > static_cast<size_t>(smem_budget)) return false;
   const int rows_fit = static_cast<int>((smem_budget - fixed) / row_bytes);
   g.NS = rows_fit >= 3 ? 3 : 2;
@@ -246,18 +271,18 @@ struct Bump {
 };
 
 struct ProbLayout {  // offsets inside the arena
-  size_t X[KMAX], y, logpi, pi_raw, xtx, ecov0, rv0, adjt, adjp, r, xb, bT, part, xty, rfull, statA, statB, statC,
+  size_t X[KMAX], y, logpi, pi_raw, xtx, ecov0, rv0, adjt, adjp, r, xb, part, xty, rfull, statA, statB, statC,
       trav, out[2], elbo, meta, z;
-  size_t out_fields[2][9];
+  size_t out_fields[2][10];
 };
 
 static size_t out_block_bytes(int L, int p, int K) {
   const size_t Lp = static_cast<size_t>(L) * p;
   return sizeof(double) * (Lp + Lp * K + Lp * K * K + Lp + static_cast<size_t>(L) * K * K + L +
-                           static_cast<size_t>(L) * K * K + K + static_cast<size_t>(L) * K + 8);
+                           static_cast<size_t>(L) * K * K + K + static_cast<size_t>(L) * K + 2 * static_cast<size_t>(L) + 8);
 }
 
-static void out_block_fields(int L, int p, int K, size_t base, size_t (&f)[9]) {
+static void out_block_fields(int L, int p, int K, size_t base, size_t (&f)[10]) {
   const size_t Lp = static_cast<size_t>(L) * p;
   size_t o = base;
   f[0] = o; o += Lp * 8;                               // alpha
@@ -268,7 +293,8 @@ static void out_block_fields(int L, int p, int K, size_t base, size_t (&f)[9]) {
   f[5] = o; o += static_cast<size_t>(L) * 8;           // kl
   f[6] = o; o += static_cast<size_t>(L) * K * K * 8;   // ecov
   f[7] = o; o += static_cast<size_t>(K) * 8;           // rv
-  f[8] = o;                                            // xtxb2
+  f[8] = o; o += static_cast<size_t>(L) * K * 8;       // xtxb2
+  f[9] = o;                                            // lse
 }
 
 template <typename P>
@@ -444,7 +470,6 @@ static int batch_create(sb_ctx* ctx, const std::vector<GenericProblem>& gp, bool
     l.adjp = bump.take(sizeof(double) * g.K * g.K);
     l.r = bump.take(sizeof(double) * nrows);
     l.xb = bump.take(sizeof(double) * nrows * g.L);
-    l.bT = bump.take(sizeof(double) * Kp);
     l.part = ss ? 0 : bump.take(sizeof(double) * Kp * C);
     l.xty = ss ? 0 : bump.take(sizeof(double) * Kp);
     l.rfull = ss ? bump.take(sizeof(double) * nrows) : 0;
@@ -512,6 +537,7 @@ static int batch_create(sb_ctx* ctx, const std::vector<GenericProblem>& gp, bool
     d.G = ge.G;
     d.nstage = ge.NS;
     d.nseg = ge.NSEG;
+    d.fast = ge.fast;
     d.em = g.em;
     int row = 0, band = 0;
     for (int k = 0; k < g.K; ++k) {
@@ -538,7 +564,6 @@ static int batch_create(sb_ctx* ctx, const std::vector<GenericProblem>& gp, bool
     d.adj_plus = reinterpret_cast<double*>(A + l.adjp);
     d.r = reinterpret_cast<double*>(A + l.r);
     d.xb = reinterpret_cast<double*>(A + l.xb);
-    d.bT = reinterpret_cast<double*>(A + l.bT);
     d.part = ss ? nullptr : reinterpret_cast<double*>(A + l.part);
     d.xty = ss ? nullptr : reinterpret_cast<double*>(A + l.xty);
     d.rfull = ss ? reinterpret_cast<double*>(A + l.rfull) : nullptr;
@@ -558,6 +583,7 @@ static int batch_create(sb_ctx* ctx, const std::vector<GenericProblem>& gp, bool
       o.ecov = reinterpret_cast<double*>(A + f[6]);
       o.rv = reinterpret_cast<double*>(A + f[7]);
       o.xtxb2 = reinterpret_cast<double*>(A + f[8]);
+      o.lse = reinterpret_cast<double*>(A + f[9]);
     }
     d.elbo = reinterpret_cast<double*>(A + l.elbo);
     d.meta = reinterpret_cast<int*>(A + l.meta);
@@ -892,7 +918,7 @@ extern "C" int sb_batch_fetch(sb_ctx* ctx, sb_batch* b, sb_result* results) {
       if (r.resid_var) std::memcpy(r.resid_var, h.rv0.data(), sizeof(double) * K);
       continue;
     }
-    size_t f[9];
+    size_t f[10];
     out_block_fields(h.L, h.p, K, h.out_off[fb], f);
     auto get = [&](double* dst, size_t off, size_t count) -> cudaError_t {
       if (!dst) return cudaSuccess;

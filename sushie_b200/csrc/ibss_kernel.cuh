@@ -29,6 +29,8 @@
 #include <math_constants.h>
 #include <stdint.h>
 
+#include <type_traits>
+
 namespace sb {
 
 constexpr int KMAX = 4;
@@ -50,6 +52,7 @@ struct OutBuf {
   double* ecov;   // [L][K][K]
   double* rv;     // [K]
   double* xtxb2;  // [L][K]   sum_p XtX * E[b^2]  (ERSS term)
+  double* lse;    // [L][2]   softmax normaliser of each effect: (max, sum exp(w - max))
 };
 
 struct ProbDev {
@@ -60,6 +63,7 @@ struct ProbDev {
   int G, nstage, nseg; // rows per band, ring stages, warps per row in sweep 1
   int em;              // 1 = EM prior update, 0 = times/plus adjustor
   int skip_first_pass; // adjustor.times == 0: the first posterior pass cannot matter
+  int fast;            // traversal variant: 0 generic, 1 register tile 4x4, 2 register tile 8x2
   const void* X[KMAX]; // [n_k][p_pad] storage type
   double nscale[KMAX]; // summary level: n_k (XtX = n LD); individual level: 1
   double nsamp[KMAX];  // n_k as double for the ELBO
@@ -72,7 +76,6 @@ struct ProbDev {
   const double* adj_plus;   // [K][K]
   double* r;      // [nrows] current residual (with the current effect added back)
   double* xb;     // [L][nrows] cached X b_l  (summary level: XtX b_l)
-  double* bT;     // [K][p_pad] current effect, transposed
   double* part;   // [team][K][p_pad] per-block partial X^T r   (individual level)
   double* xty;    // [K][p_pad] reduced X^T r                    (individual level)
   double* rfull;  // [nrows] full residual at iteration end      (summary level)
@@ -373,6 +376,9 @@ constexpr double LOG_2PI = 1.8378770664093454835606594728112;
 // ---------------------------------------------------------------------------------------
 // the kernel
 
+template <int N>
+using IntC = std::integral_constant<int, N>;
+
 template <int K, typename XT, bool SS>
 __global__ void __launch_bounds__(NT, 1) ibss_kernel(const LaunchParams P) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -423,11 +429,14 @@ __global__ void __launch_bounds__(NT, 1) ibss_kernel(const LaunchParams P) {
     const int pv = p_pad / VW;                                       // 16-byte vectors per row
     const size_t row_bytes = static_cast<size_t>(p_pad) * sizeof(XT);
     const size_t stage_bytes = row_bytes * G;
+    const int fast = pb.fast;  // register-tile traversal variant (0 = generic shared-memory path)
 
-    // dynamic shared-memory carve-up
+    // dynamic shared-memory carve-up: [header][b (generic path)][acc (generic, individual)][ring]
     double* bsm = reinterpret_cast<double*>(smem_raw + ((sizeof(SmemHdr) + 127) / 128) * 128);
-    double* acc = bsm + p_pad;  // individual level only
-    unsigned char* ring = reinterpret_cast<unsigned char*>(SS ? (bsm + p_pad) : (acc + p_pad));
+    double* acc = bsm + p_pad;
+    unsigned char* ring =
+        fast ? reinterpret_cast<unsigned char*>(bsm)
+             : reinterpret_cast<unsigned char*>(SS ? (bsm + p_pad) : (acc + p_pad));
 
     // SNP slice of this block for the posterior phases
     const int js = static_cast<int>((static_cast<long long>(p) * rank) / C);
@@ -437,22 +446,27 @@ __global__ void __launch_bounds__(NT, 1) ibss_kernel(const LaunchParams P) {
     auto band_of = [&](int pos, int& k, int& g0, int& rows) {
       const int q = rank + pos * C;
       k = 0;
+      int b0 = 0, nk = pb.n[0];
 #pragma unroll
       for (int kk = 1; kk < K; ++kk)
-        if (q >= pb.band0[kk]) k = kk;
-      g0 = (q - pb.band0[k]) * G;
-      rows = min(G, pb.n[k] - g0);
+        if (q >= pb.band0[kk]) {
+          k = kk;
+          b0 = pb.band0[kk];
+          nk = pb.n[kk];
+        }
+      g0 = (q - b0) * G;
+      rows = min(G, nk - g0);
     };
-    // producer (thread 0): start the bulk copies of own band `pos` into ring stage `st`
+    // producer: one bulk copy of own band `pos` (rows are contiguous) into ring stage `st`
     auto issue_fill = [&](int pos, int st) {
       int k, g0, rows;
       band_of(pos, k, g0, rows);
       const unsigned char* src =
           reinterpret_cast<const unsigned char*>(pb.X[k]) + static_cast<size_t>(g0) * row_bytes;
       unsigned char* dst = ring + static_cast<size_t>(st) * stage_bytes;
-      mbar_expect_tx(&H->mbar[st], static_cast<uint32_t>(row_bytes * rows));
-      for (int g = 0; g < rows; ++g)
-        bulk_g2s(dst + g * row_bytes, src + g * row_bytes, static_cast<uint32_t>(row_bytes), &H->mbar[st]);
+      const uint32_t bytes = static_cast<uint32_t>(row_bytes * rows);
+      mbar_expect_tx(&H->mbar[st], bytes);
+      bulk_g2s(dst, src, bytes, &H->mbar[st]);
     };
 
     // ---- locus initialisation (state owned by this block: rows of its bands)
@@ -465,11 +479,6 @@ __global__ void __launch_bounds__(NT, 1) ibss_kernel(const LaunchParams P) {
         for (int l = 0; l < L; ++l) pb.xb[static_cast<size_t>(l) * nrows + row] = 0.0;
       }
     }
-    for (int idx = js + tid; idx < je; idx += NT)
-      for (int k = 0; k < K; ++k) pb.bT[k * p_pad + idx] = 0.0;
-    if (rank == C - 1)
-      for (int idx = p + tid; idx < p_pad; idx += NT)
-        for (int k = 0; k < K; ++k) pb.bT[k * p_pad + idx] = 0.0;
 
     // ring prologue: keep NS fills in flight; positions wrap (the traversal order is static)
     int prod_pos = 0;  // next own band position to issue (thread 0)
@@ -482,11 +491,242 @@ __global__ void __launch_bounds__(NT, 1) ibss_kernel(const LaunchParams P) {
       }
     }
 
+    // b_l[j] for ancestry k from the un-normalised rows of pass B (alpha slot holds the log
+    // weights, pm the per-SNP posterior means): b = softmax(w)_j * mu_jk  (infer.py:721-723)
+    auto effect_b = [&](const OutBuf& ob, int l, int k, int j, double mt, double inv_s) -> double {
+      if (j >= p) return 0.0;
+      const size_t lj = static_cast<size_t>(l) * p + j;
+      const double w = __ldcg(&ob.alpha[lj]);
+      return exp(w - mt) * inv_s * __ldcg(&ob.pm[lj * K + k]);
+    };
+
+    // per-traversal scalars: fixed-order serial sum over the designated threads
+    auto store_trav = [&](int l, bool first, const double (&vsq)[K], const double (&rsq)[K]) {
+      __syncthreads();
+#pragma unroll
+      for (int k = 0; k < K; ++k) {
+        if (tid < GMAX) {
+          H->trow[tid][0] = vsq[k];
+          H->trow[tid][1] = rsq[k];
+        }
+        __syncthreads();
+        if (tid == 0 && !first) {
+          double a = 0.0, b = 0.0;
+          for (int g = 0; g < GMAX; ++g) {
+            a += H->trow[g][0];
+            b += H->trow[g][1];
+          }
+          double* dst = pb.trav + (static_cast<size_t>(l) * C + rank) * TRAV_STRIDE;
+          __stcg(&dst[k], a);
+          __stcg(&dst[KMAX + k], b);
+        }
+        __syncthreads();
+      }
+    };
+    auto zero_unowned_partials = [&]() {
+      for (int k = 0; k < K; ++k) {
+        const int b0 = pb.band0[k], b1 = pb.band0[k + 1];
+        const int first_q = b0 + (((rank - b0) % C) + C) % C;  // first band index == rank (mod C)
+        if (!(first_q < b1)) {
+          double* dst = pb.part + (static_cast<size_t>(rank) * K + k) * p_pad;
+          for (int j = tid; j < p_pad; j += NT) __stcg(&dst[j], 0.0);
+        }
+      }
+    };
+
     // ------------------------------------------------------------------------------
     // one streamed traversal of X (individual) / LD (summary) for effect l:
-    //   v = X b_new ; xb[l] = v ; R = r - v ; r_next = R + xb[lnext] ; acc += X^T r_next
+    //   v = X b_l ; xb[l] = v ; R = r - v ; r_next = R + xb[lnext] ; acc += X^T r_next
     // first == true (individual level only): b = 0, produces X^T y.
-    auto traverse = [&](int l, bool first, bool last_effect) {
+    //
+    // Register-tile variant: every thread owns CPT 16-byte column vectors and keeps them for
+    // all GR rows of the band in registers, so the band is read from shared memory once and
+    // both sweeps run from registers; b and the X^T r accumulators live in registers too.
+    auto traverse_fast = [&](auto cpt_c, auto gr_c, int l, bool first, bool last_effect, int buf, double mt,
+                             double inv_s) {
+      constexpr int CPT = decltype(cpt_c)::value;
+      constexpr int GR = decltype(gr_c)::value;
+      const OutBuf& ob = pb.out[buf];
+      const int lnext = first ? 0 : ((l + 1 == L) ? 0 : l + 1);
+      double vsq[K], rsq[K];  // meaningful in threads < GR only
+#pragma unroll
+      for (int k = 0; k < K; ++k) vsq[k] = rsq[k] = 0.0;
+      double bq[CPT][VW], aq[CPT][VW];
+#pragma unroll
+      for (int c = 0; c < CPT; ++c)
+#pragma unroll
+        for (int u = 0; u < VW; ++u) bq[c][u] = aq[c][u] = 0.0;
+      int cur_k = -1;
+
+      auto flush_acc = [&](int k) {
+        double* dst = pb.part + (static_cast<size_t>(rank) * K + k) * p_pad;
+#pragma unroll
+        for (int c = 0; c < CPT; ++c) {
+          const int v = tid + c * NT;
+          if (v < pv) {
+#pragma unroll
+            for (int u = 0; u < VW; u += 2)
+              __stcg(reinterpret_cast<double2*>(dst + v * VW + u), make_double2(aq[c][u], aq[c][u + 1]));
+          }
+        }
+      };
+
+      for (int pos = 0; pos < nb_own; ++pos) {
+        int k, g0, rows;
+        band_of(pos, k, g0, rows);
+        if (k != cur_k) {
+          if (!SS && cur_k >= 0) flush_acc(cur_k);
+#pragma unroll
+          for (int c = 0; c < CPT; ++c) {
+            const int v = tid + c * NT;
+#pragma unroll
+            for (int u = 0; u < VW; ++u) {
+              aq[c][u] = 0.0;
+              bq[c][u] = (first || v >= pv) ? 0.0 : effect_b(ob, l, k, v * VW + u, mt, inv_s);
+            }
+          }
+          cur_k = k;
+        }
+        const int st = cons_seq % NS;
+        const XT* tile = reinterpret_cast<const XT*>(ring + static_cast<size_t>(st) * stage_bytes);
+        const int row_base = pb.row0[k] + g0;
+        const double nsc = pb.nscale[k];
+
+        // per-row state (same addresses for every thread: broadcast loads), in flight while the band lands
+        double r_old[GR], xb_next[GR];
+#pragma unroll
+        for (int g = 0; g < GR; ++g) {
+          r_old[g] = 0.0;
+          xb_next[g] = 0.0;
+          if (g < rows) {
+            r_old[g] = pb.r[row_base + g];
+            xb_next[g] = pb.xb[static_cast<size_t>(lnext) * nrows + row_base + g];
+          }
+        }
+        mbar_wait(&H->mbar[st], (phase_bits >> st) & 1u);
+
+        // the band -> registers (the only shared-memory read of the genotypes)
+        double x[GR][CPT][VW];
+#pragma unroll
+        for (int g = 0; g < GR; ++g)
+#pragma unroll
+          for (int c = 0; c < CPT; ++c) {
+            const int v = tid + c * NT;
+            if (g < rows && v < pv) {
+              Vec<XT>::load(tile + static_cast<size_t>(g) * p_pad, v, x[g][c]);
+            } else {
+#pragma unroll
+              for (int u = 0; u < VW; ++u) x[g][c][u] = 0.0;
+            }
+          }
+
+        // sweep 1: per-thread partial dot products, transposed butterfly reduction over the warp
+        const int pbuf = cons_seq & 1;
+        if (!first) {
+          double ps[GR];
+#pragma unroll
+          for (int g = 0; g < GR; ++g) {
+            double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+            for (int c = 0; c < CPT; ++c)
+#pragma unroll
+              for (int u = 0; u < VW; u += 2) {
+                s0 = fma(x[g][c][u], bq[c][u], s0);
+                s1 = fma(x[g][c][u + 1], bq[c][u + 1], s1);
+              }
+            ps[g] = s0 + s1;
+          }
+          // after the butterfly, lanes with (lane / (32 / GR)) == g hold the warp total of row g
+          double t;
+          if constexpr (GR == 4) {
+            const bool hi = lane & 16;
+            double k0 = hi ? ps[2] : ps[0], k1 = hi ? ps[3] : ps[1];
+            const double s0 = hi ? ps[0] : ps[2], s1 = hi ? ps[1] : ps[3];
+            k0 += __shfl_xor_sync(0xffffffffu, s0, 16);
+            k1 += __shfl_xor_sync(0xffffffffu, s1, 16);
+            const bool hi2 = lane & 8;
+            t = hi2 ? k1 : k0;
+            const double s = hi2 ? k0 : k1;
+            t += __shfl_xor_sync(0xffffffffu, s, 8);
+            t += __shfl_xor_sync(0xffffffffu, t, 4);
+            t += __shfl_xor_sync(0xffffffffu, t, 2);
+            t += __shfl_xor_sync(0xffffffffu, t, 1);
+          } else if constexpr (GR == 2) {
+            const bool hi = lane & 16;
+            t = hi ? ps[1] : ps[0];
+            const double s = hi ? ps[0] : ps[1];
+            t += __shfl_xor_sync(0xffffffffu, s, 16);
+            t += __shfl_xor_sync(0xffffffffu, t, 8);
+            t += __shfl_xor_sync(0xffffffffu, t, 4);
+            t += __shfl_xor_sync(0xffffffffu, t, 2);
+            t += __shfl_xor_sync(0xffffffffu, t, 1);
+          } else {
+            t = warp_sum(ps[0]);
+          }
+          if ((lane & (32 / GR - 1)) == 0) H->partsum[pbuf][(lane / (32 / GR)) * NW + warp] = t;
+        }
+        __syncthreads();  // (A) partial sums visible; every thread holds its tile in registers
+        if (tid == 0) {   // the stage is free again: refill it with the band NS positions ahead
+          issue_fill(prod_pos, st);
+          prod_pos = (prod_pos + 1 == nb_own) ? 0 : prod_pos + 1;
+        }
+        // every thread finishes the row sums itself (no second barrier)
+        double rn[GR];
+#pragma unroll
+        for (int g = 0; g < GR; ++g) {
+          double v = 0.0;
+          if (!first) {
+            const double2* ps2 = reinterpret_cast<const double2*>(&H->partsum[pbuf][g * NW]);
+#pragma unroll
+            for (int w = 0; w < NW / 2; ++w) {
+              const double2 q = ps2[w];
+              v += q.x;
+              v += q.y;
+            }
+            v *= nsc;
+          }
+          const double Rfull = r_old[g] - v;
+          rn[g] = Rfull + xb_next[g];
+          if (tid == g && g < rows) {  // designated thread of row g: publish the row state
+            const int row = row_base + g;
+            if (!first) pb.xb[static_cast<size_t>(l) * nrows + row] = v;
+            pb.r[row] = rn[g];
+            double vterm = v * v;  // |X b_l|^2 (infer.py:806)
+            if (SS) {
+              vterm = effect_b(ob, l, k, g0 + g, mt, inv_s) * v;  // b_l^T XtX b_l (infer_ss.py:572)
+              if (last_effect) pb.rfull[row] = Rfull;
+            }
+#pragma unroll
+            for (int kk = 0; kk < K; ++kk)
+              if (kk == k) {
+                vsq[kk] += vterm;
+                rsq[kk] += Rfull * Rfull;  // |y - X sum_l b_l|^2 at the last effect (infer.py:804)
+              }
+          }
+        }
+        // sweep 2: X^T r_next accumulated in registers
+        if (!SS) {
+#pragma unroll
+          for (int g = 0; g < GR; ++g)
+#pragma unroll
+            for (int c = 0; c < CPT; ++c)
+#pragma unroll
+              for (int u = 0; u < VW; ++u) aq[c][u] = fma(x[g][c][u], rn[g], aq[c][u]);
+        }
+        phase_bits ^= (1u << st);
+        cons_seq += 1;
+      }
+      if (!SS) {
+        if (cur_k >= 0) flush_acc(cur_k);
+        zero_unowned_partials();
+      }
+      store_trav(l, first, vsq, rsq);
+    };
+
+    // Generic variant (any p that fits, any G <= GMAX): b and the accumulators in shared memory,
+    // two sweeps over the shared-memory band separated by a barrier.
+    auto traverse_generic = [&](int l, bool first, bool last_effect, int buf, double mt, double inv_s) {
+      const OutBuf& ob = pb.out[buf];
       const int lnext = first ? 0 : ((l + 1 == L) ? 0 : l + 1);
       double vsq[K], rsq[K];  // meaningful in threads < G only
 #pragma unroll
@@ -504,14 +744,10 @@ __global__ void __launch_bounds__(NT, 1) ibss_kernel(const LaunchParams P) {
             double* dst = pb.part + (static_cast<size_t>(rank) * K + cur_k) * p_pad;
             for (int j = tid; j < p_pad; j += NT) __stcg(&dst[j], acc[j]);
           }
-          if (!first) {
-            const double* src = pb.bT + static_cast<size_t>(k) * p_pad;
-            for (int j = tid; j < p_pad; j += NT) bsm[j] = __ldcg(&src[j]);
-          }
-          if (!SS) {
-            __syncthreads();
+          if (!first)
+            for (int j = tid; j < p_pad; j += NT) bsm[j] = effect_b(ob, l, k, j, mt, inv_s);
+          if (!SS)
             for (int j = tid; j < p_pad; j += NT) acc[j] = 0.0;
-          }
           cur_k = k;
           __syncthreads();
         }
@@ -622,38 +858,18 @@ __global__ void __launch_bounds__(NT, 1) ibss_kernel(const LaunchParams P) {
           double* dst = pb.part + (static_cast<size_t>(rank) * K + cur_k) * p_pad;
           for (int j = tid; j < p_pad; j += NT) __stcg(&dst[j], acc[j]);
         }
-        // ancestries in which this block owns no band contribute zeros
-        for (int k = 0; k < K; ++k) {
-          const int b0 = pb.band0[k], b1 = pb.band0[k + 1];
-          const int first_q = b0 + (((rank - b0) % C) + C) % C;  // first band index == rank (mod C)
-          const bool owns = first_q < b1;
-          if (!owns) {
-            double* dst = pb.part + (static_cast<size_t>(rank) * K + k) * p_pad;
-            for (int j = tid; j < p_pad; j += NT) __stcg(&dst[j], 0.0);
-          }
-        }
+        zero_unowned_partials();
       }
-      // per-traversal scalars: fixed-order serial sum over the designated threads
-      __syncthreads();
-#pragma unroll
-      for (int k = 0; k < K; ++k) {
-        if (tid < GMAX) {
-          H->trow[tid][0] = vsq[k];
-          H->trow[tid][1] = rsq[k];
-        }
-        __syncthreads();
-        if (tid == 0 && !first) {
-          double a = 0.0, b = 0.0;
-          for (int g = 0; g < GMAX; ++g) {
-            a += H->trow[g][0];
-            b += H->trow[g][1];
-          }
-          double* dst = pb.trav + (static_cast<size_t>(l) * C + rank) * TRAV_STRIDE;
-          __stcg(&dst[k], a);
-          __stcg(&dst[KMAX + k], b);
-        }
-        __syncthreads();
-      }
+      store_trav(l, first, vsq, rsq);
+    };
+
+    auto traverse = [&](int l, bool first, bool last_effect, int buf, double mt, double inv_s) {
+      if (fast == 1)
+        traverse_fast(IntC<4>{}, IntC<4>{}, l, first, last_effect, buf, mt, inv_s);
+      else if (fast == 2)
+        traverse_fast(IntC<8>{}, IntC<2>{}, l, first, last_effect, buf, mt, inv_s);
+      else
+        traverse_generic(l, first, last_effect, buf, mt, inv_s);
     };
 
     // ------------------------------------------------------------------------------
@@ -686,7 +902,9 @@ __global__ void __launch_bounds__(NT, 1) ibss_kernel(const LaunchParams P) {
     };
 
     // ------------------------------------------------------------------------------
-    // posterior phases of effect l in iteration `it` (writes out[buf], bT)
+    // posterior phases of effect l in iteration `it`: writes the un-normalised rows of out[buf]
+    // (alpha slot = log weights, pm = mu_j, pmsq = S_j + mu_j mu_j^T, lbf) and the per-effect
+    // scalars; the softmax normaliser (m, sum) is returned through H->tot[0], H->tot[1].
     auto posterior = [&](int l, int it) {
       const int buf = it & 1;
       const OutBuf& ob = pb.out[buf];
@@ -799,7 +1017,7 @@ __global__ void __launch_bounds__(NT, 1) ibss_kernel(const LaunchParams P) {
         for (int i = 0; i < K * K; ++i) Cnew[i] = pb.adj_plus[i];
       }
 
-      // ---- pass B1: posterior under the new prior; unnormalised rows + online statistics
+      // ---- pass B: posterior under the new prior; un-normalised rows + online statistics
       constexpr int NVB = 1 + NSYM + 2 + K;  // s, W, sum e*kl_beta, sum e*lbf, sum e*xtx*Mkk
       {
         double Cinv[K][K], logdetC;
@@ -827,15 +1045,15 @@ __global__ void __launch_bounds__(NT, 1) ibss_kernel(const LaunchParams P) {
               quad += mu[a] * Cinv[a][b] * mu[b];
             }
           const double klb = 0.5 * (tr - K + quad + logdetC + lda);
-          // unnormalised rows (scaled by alpha in pass B2)
+          // un-normalised rows (scaled by alpha once, when the locus is finished)
           const size_t lj = static_cast<size_t>(l) * p + j;
-          ob.lbf[lj] = lbf;
-          ob.alpha[lj] = w;
+          __stcg(&ob.lbf[lj], lbf);
+          __stcg(&ob.alpha[lj], w);
 #pragma unroll
           for (int a = 0; a < K; ++a) {
-            ob.pm[lj * K + a] = mu[a];
+            __stcg(&ob.pm[lj * K + a], mu[a]);
 #pragma unroll
-            for (int b = 0; b < K; ++b) ob.pmsq[(lj * K + a) * K + b] = S[a][b] + mu[a] * mu[b];
+            for (int b = 0; b < K; ++b) __stcg(&ob.pmsq[(lj * K + a) * K + b], S[a][b] + mu[a] * mu[b]);
           }
           double e;
           if (w > m) {
@@ -870,23 +1088,9 @@ __global__ void __launch_bounds__(NT, 1) ibss_kernel(const LaunchParams P) {
         __syncthreads();
         team_combine(pb.statB, NVB);
       }
-      // ---- pass B2: normalise, publish b_l (transposed) for the traversal
+      // per-effect scalars (one writer)
       {
         const double mt = H->tot[0], ssum = H->tot[1];
-        for (int j = js + tid; j < je; j += NT) {
-          const size_t lj = static_cast<size_t>(l) * p + j;
-          const double w = ob.alpha[lj];
-          const double al = exp(w - mt) / ssum;  // softmax (infer.py:721)
-          ob.alpha[lj] = al;
-#pragma unroll
-          for (int a = 0; a < K; ++a) {
-            const double bm = ob.pm[lj * K + a] * al;
-            ob.pm[lj * K + a] = bm;
-            __stcg(&pb.bT[a * p_pad + j], bm);
-#pragma unroll
-            for (int b = 0; b < K; ++b) ob.pmsq[(lj * K + a) * K + b] *= al;
-          }
-        }
         if (rank == 0 && tid == 0) {
           int t = 2;
           for (int a = 0; a < K; ++a)
@@ -901,6 +1105,8 @@ __global__ void __launch_bounds__(NT, 1) ibss_kernel(const LaunchParams P) {
           __stcg(&ob.kl[l], (elbf - (mt + log(ssum))) + klb);
           for (int k = 0; k < K; ++k) __stcg(&ob.xtxb2[l * K + k], H->tot[t++] / ssum);
           for (int i = 0; i < K * K; ++i) __stcg(&ob.ecov[l * K * K + i], Cnew[i]);
+          __stcg(&ob.lse[2 * l], mt);
+          __stcg(&ob.lse[2 * l + 1], ssum);
         }
       }
     };
@@ -908,7 +1114,7 @@ __global__ void __launch_bounds__(NT, 1) ibss_kernel(const LaunchParams P) {
     // ------------------------------------------------------------------------------
     // the IBSS loop
     if (!SS) {
-      traverse(0, true, false);  // X^T y for the first effect
+      traverse(0, true, false, 0, 0.0, 0.0);  // X^T y for the first effect
     }
     team_sync(team);
 
@@ -920,8 +1126,8 @@ __global__ void __launch_bounds__(NT, 1) ibss_kernel(const LaunchParams P) {
       const int buf = it & 1;
       for (int l = 0; l < L; ++l) {
         posterior(l, it);
-        team_sync(team);
-        traverse(l, false, l + 1 == L);
+        const double mt = H->tot[0], inv_s = 1.0 / H->tot[1];
+        traverse(l, false, l + 1 == L, buf, mt, inv_s);
         team_sync(team);
         n_ser += 1;
       }
@@ -938,7 +1144,8 @@ __global__ void __launch_bounds__(NT, 1) ibss_kernel(const LaunchParams P) {
 #pragma unroll
           for (int k = 0; k < K; ++k) {
             double eb = 0.0;
-            for (int l = 0; l < L; ++l) eb += ob.pm[(static_cast<size_t>(l) * p + j) * K + k];
+            for (int l = 0; l < L; ++l)
+              eb += effect_b(ob, l, k, j, __ldcg(&ob.lse[2 * l]), 1.0 / __ldcg(&ob.lse[2 * l + 1]));
             const double xty = pb.y[pb.row0[k] + j];
             tv[k] += eb * xty;                                         // E[b]^T Xty
             tv[K + k] += eb * (xty - __ldcg(&pb.rfull[pb.row0[k] + j]));  // E[b]^T XtX E[b]
@@ -1024,6 +1231,25 @@ __global__ void __launch_bounds__(NT, 1) ibss_kernel(const LaunchParams P) {
       pb.meta[1] = inc_flag;
       pb.meta[2] = final_buf;
       pb.meta[3] = n_ser;
+    }
+    // ---- normalise the returned buffer once: alpha = softmax(w), alpha-weighted mean / second moment
+    if (final_buf >= 0) {
+      const OutBuf& ob = pb.out[final_buf];
+      for (int l = 0; l < L; ++l) {
+        const double mt = __ldcg(&ob.lse[2 * l]), ssum = __ldcg(&ob.lse[2 * l + 1]);
+        for (int j = js + tid; j < je; j += NT) {
+          const size_t lj = static_cast<size_t>(l) * p + j;
+          const double al = exp(__ldcg(&ob.alpha[lj]) - mt) / ssum;  // softmax (infer.py:721)
+          ob.alpha[lj] = al;
+#pragma unroll
+          for (int a = 0; a < K; ++a) {
+            ob.pm[lj * K + a] = __ldcg(&ob.pm[lj * K + a]) * al;
+#pragma unroll
+            for (int b = 0; b < K; ++b)
+              ob.pmsq[(lj * K + a) * K + b] = __ldcg(&ob.pmsq[(lj * K + a) * K + b]) * al;
+          }
+        }
+      }
     }
     // drain the speculative prefetches so the ring can be re-pointed at the next locus
     if (nb_own > 0) {
