@@ -85,6 +85,9 @@ def make_cs(
 
         full_alphas[f"purity_l{ldx + 1}"] = avg_corr
         if avg_corr > purity:
+            # the reference concatenates onto an empty frame whose column order
+            # (CSIndex, SNPIndex, alpha, c_alpha) wins (infer.py:898,970)
+            tmp_cs = tmp_cs[["CSIndex", "SNPIndex", "alpha", "c_alpha"]]
             cs = pd.concat([cs, tmp_cs], ignore_index=True) if len(cs) else tmp_cs.reset_index(drop=True)
             full_alphas[f"kept_l{ldx + 1}"] = 1
         else:

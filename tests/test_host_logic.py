@@ -1,0 +1,217 @@
+"""Host-side logic that needs no GPU: validation texts, prior construction, credible-set
+selection and table assembly (with a numpy purity callback), chunk planning, C-ABI export."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+import sushie_b200
+from sushie_b200 import _capi, _common, batch, cs as cs_mod, utils
+from oracle import credible_sets, ibss, threefry
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _xy(n=60, p=120, k=2, seed=0):
+    rng = np.random.default_rng(seed)
+    return [rng.standard_normal((n, p)) for _ in range(k)], [rng.standard_normal(n) for _ in range(k)]
+
+
+def test_validation_messages_individual():
+    Xs, ys = _xy()
+    with pytest.raises(ValueError, match=r"The number of geno \(2\) and pheno \(1\) data does not match"):
+        sushie_b200.infer_sushie(Xs, ys[:1])
+    with pytest.raises(ValueError, match=r"Ancestry 1: The sample size of geno \(60\) and pheno \(59\)"):
+        sushie_b200.infer_sushie(Xs, [ys[0][:59], ys[1]])
+    with pytest.raises(ValueError, match=r"Inferred L \(0\) is invalid, choose a positive L\."):
+        sushie_b200.infer_sushie(Xs, ys, L=0)
+    with pytest.raises(ValueError, match=r"Credible set PIP threshold \(1\.5\) must be greater than 0 and less than 1\."):
+        sushie_b200.infer_sushie(Xs, ys, threshold=1.5)
+    with pytest.raises(ValueError, match=r"Purity threshold \(0\) must be greater than or equal to 0 and less than 1\."):
+        sushie_b200.infer_sushie(Xs, ys, purity=0)
+    with pytest.raises(ValueError, match=r"maximum selected number of SNPs for purity must be greater than 0"):
+        sushie_b200.infer_sushie(Xs, ys, max_select=0)
+    with pytest.raises(ValueError, match=r"minimum number of SNPs to fine-map must be greater than 0"):
+        sushie_b200.infer_sushie(Xs, ys, min_snps=0)
+    with pytest.raises(ValueError, match=r"minimum common SNPs across ancestries \(5\) is less than inferred L \(10\)"):
+        sushie_b200.infer_sushie(Xs, ys, min_snps=5)
+    with pytest.raises(ValueError, match=r"common SNPs across ancestries \(120\) is less than minimum common number of SNPs \(100\)"):
+        sushie_b200.infer_sushie(Xs, ys, min_snps=200)
+    with pytest.raises(ValueError, match=r"Prior probability/weights must be all positive values\."):
+        sushie_b200.infer_sushie(Xs, ys, pi=np.zeros(120))
+    with pytest.raises(ValueError, match=r"Prior probability/weights \(3\) does not match the number of SNPs \(120\)"):
+        sushie_b200.infer_sushie(Xs, ys, pi=np.ones(3))
+    with pytest.raises(ValueError, match=r"Number of specified residual prior \(1\) does not match ancestry number \(2\)"):
+        sushie_b200.infer_sushie(Xs, ys, resid_var=[1.0])
+    with pytest.raises(ValueError, match=r"The input of residual prior \(\[1\.0, -1\.0\]\) is invalid"):
+        sushie_b200.infer_sushie(Xs, ys, resid_var=[1.0, -1.0])
+    with pytest.raises(ValueError, match=r"Number of specified effect prior \(3\) does not match ancestry number \(2\)"):
+        sushie_b200.infer_sushie(Xs, ys, effect_var=[1, 2, 3])
+    with pytest.raises(ValueError, match=r"The effect size prior variance \(\[1\.0, 0\.0\]\) must be positive"):
+        sushie_b200.infer_sushie(Xs, ys, effect_var=[1, 0])
+    with pytest.raises(ValueError, match=r"Number of specified rho \(2\) does not match expected number 1\."):
+        sushie_b200.infer_sushie(Xs, ys, rho=[0.1, 0.2])
+    with pytest.raises(ValueError, match=r"Effect size prior correlation \(\[1\.0\]\) must be between -1 and 1"):
+        sushie_b200.infer_sushie(Xs, ys, rho=[1.0])  # |rho| == 1 rejected at individual level (infer.py:398)
+
+
+def test_validation_messages_summary():
+    p = 120
+    lds = [np.eye(p), np.eye(p)]
+    zs = [np.zeros(p), np.zeros(p)]
+    ns = np.array([[100], [120]])
+    with pytest.raises(ValueError, match=r"number of LD matrices \(1\) does not match the number of ancestries \(2\)"):
+        sushie_b200.infer_sushie_ss(lds[:1], ns, zs)
+    with pytest.raises(ValueError, match="LD matrices do not have the same shape"):
+        sushie_b200.infer_sushie_ss([np.eye(p), np.eye(p + 1)], ns, zs)
+    with pytest.raises(ValueError, match="LD matrices are not square matrices"):
+        sushie_b200.infer_sushie_ss([np.ones((p, p + 1))] * 2, ns, zs)
+    with pytest.raises(ValueError, match="Z scores are not provided"):
+        sushie_b200.infer_sushie_ss(lds, ns, None)
+    with pytest.raises(ValueError, match=r"number of Z scores \(1\) does not match"):
+        sushie_b200.infer_sushie_ss(lds, ns, zs[:1])
+    with pytest.raises(ValueError, match="Z scores do not have the same number of SNPs as the LD matrices"):
+        sushie_b200.infer_sushie_ss(lds, ns, [np.zeros(p - 1)] * 2)
+    with pytest.raises(ValueError, match="minimum number of SNPs to fine-map is invalid. Choose a positive integer"):
+        sushie_b200.infer_sushie_ss(lds, ns, zs, min_snps=0)
+    # |rho| == 1 is accepted at summary level (infer_ss.py:256) and then needs a GPU: EngineError, not ValueError
+    with pytest.raises(_capi.EngineError):
+        if _capi.device_count() > 0:
+            raise _capi.EngineError("GPU present: covered by the gpu suite")
+        sushie_b200.infer_sushie_ss(lds, ns, zs, rho=[1.0])
+
+
+def test_no_cpu_fallback_without_gpu():
+    """The product path must fail loudly when no CUDA device is usable."""
+    if _capi.device_count() > 0:
+        pytest.skip("a GPU is present")
+    Xs, ys = _xy()
+    with pytest.raises(_capi.EngineError, match="sb_init"):
+        sushie_b200.infer_sushie(Xs, ys, L=2)
+
+
+def test_prior_construction_matches_oracle():
+    for k, ev, rho, no_update in [(1, None, None, False), (2, None, [0.5], True), (3, [0.1, 0.2, 0.3], None, True),
+                                  (3, [0.1, 0.2, 0.3], [0.1, 0.2, 0.3], True), (4, None, None, False)]:
+        ec, adj = _common.build_priors(k, 3, ev, rho, no_update, summary=False)
+        ev_o = [1e-3] * k if ev is None else ev
+        rho_o = [0.1] * (k * (k - 1) // 2) if rho is None else rho
+        c0 = ibss.build_effect_covar(k, [float(v) for v in ev_o], [float(v) for v in rho_o])
+        t, pl = ibss.build_adjustor(k, c0, no_update, ev, rho)
+        np.testing.assert_array_equal(ec, np.stack([c0] * 3))
+        np.testing.assert_array_equal(adj.times, t)
+        np.testing.assert_array_equal(adj.plus, pl)
+
+
+def test_pi_normalisation_rules():
+    pi = np.full(10, 0.05)  # sums to 0.5
+    np.testing.assert_array_equal(_common.resolve_pi(pi, 10, summary=False), pi)       # infer.py:313 only if > 1
+    np.testing.assert_allclose(_common.resolve_pi(pi, 10, summary=True), pi / 0.5)     # infer_ss.py:189 if != 1
+    np.testing.assert_allclose(_common.resolve_pi(pi * 4, 10, summary=False).sum(), 1.0)
+
+
+def test_threefry_product_matches_oracle():
+    for seed in (0, 12345, 2**40 + 7):
+        for n, m in ((10, 3), (251, 250), (1900, 250)):
+            vals = np.random.default_rng(n).permutation(5000)[:n]
+            a = cs_mod.jax_choice_no_replace(seed, vals, m)
+            b = threefry.choice_without_replacement(threefry.prng_key(seed), vals, m)
+            assert np.array_equal(a, b)
+
+
+def _numpy_purity(Xstd):
+    def f(sets):
+        out = np.empty((len(sets), len(Xstd)))
+        for s, idx in enumerate(sets):
+            for k, X in enumerate(Xstd):
+                out[s, k] = np.min(np.abs(X[:, idx].T @ X[:, idx] / X.shape[0]))
+        return out
+    return f
+
+
+@pytest.mark.parametrize("method", ["weighted", "max", "min"])
+@pytest.mark.parametrize("max_select", [500, 30])
+def test_build_tables_matches_oracle_make_cs(golden_syn, method, max_select):
+    """Credible-set selection / table assembly vs the pandas oracle (purity supplied by numpy
+    here; on the GPU box the same function is fed by the purity kernel)."""
+    g = golden_syn
+    Xs = [g[f"k3_X{i}"].astype(float) for i in range(3)]
+    ys = [g[f"k3_y{i}"] for i in range(3)]
+    Xstd, _ = ibss.prepare_individual(Xs, ys)
+    ns = np.array([[x.shape[0]] for x in Xs])
+    alpha, log_bf = g["k3_alpha"], g["k3_log_bf"]
+    cs_o, al_o, pa_o, pc_o = credible_sets.make_cs(alpha, log_bf, ns, Xs=Xstd, threshold=0.9, purity=0.4,
+                                                  purity_method=method, max_select=max_select, seed=7)
+    cs_g, al_g, pa_g, pc_g = cs_mod.build_tables(alpha, log_bf, ns, _numpy_purity(Xstd), 0.9, 0.4, method,
+                                                max_select, 7)
+    assert list(al_g.columns) == list(al_o.columns)
+    np.testing.assert_allclose(al_g.values.astype(float), al_o.values.astype(float), atol=1e-12)
+    assert list(cs_g.columns) == list(cs_o.columns)
+    np.testing.assert_allclose(cs_g.values.astype(float), cs_o.values.astype(float), atol=1e-12)
+    np.testing.assert_allclose(pa_g, pa_o, atol=1e-15)
+    np.testing.assert_allclose(pc_g, pc_o, atol=1e-15)
+
+
+def test_build_tables_invalid_method():
+    with pytest.raises(ValueError, match="Invalid purity method"):
+        cs_mod.build_tables(np.ones((1, 3)) / 3, np.zeros((1, 3)), np.array([10]), lambda s: np.ones((1, 1)), 0.9,
+                            0.5, "median", 10, 1)
+
+
+def test_utils_ols_and_rint():
+    rng = np.random.default_rng(1)
+    X = rng.standard_normal((80, 3))
+    y = X @ [1.0, -2.0, 0.5] + 0.1 * rng.standard_normal(80)
+    resid, adj_r, pval = utils.ols(X, y)
+    design = np.column_stack([np.ones(80), X])
+    beta = np.linalg.lstsq(design, y, rcond=None)[0]
+    np.testing.assert_allclose(resid[:, 0], y - design @ beta, atol=1e-10)
+    assert adj_r[0] > 0.99 and pval.shape == (4, 1)
+    np.testing.assert_allclose(ibss.ols_residual(X, y), resid, atol=1e-10)
+    r = utils.rint(np.array([3.0, 1.0, 2.0]))
+    assert r[1] < r[2] < r[0] and abs(r[2]) < 1e-12
+
+
+def test_plan_chunks_covers_everything_once():
+    class P:  # minimal stand-in for a prepared problem
+        def __init__(self, p, tol):
+            self.problem = type("X", (), dict(n=[100, 100], p=p, L=10, k=2, cost=200.0 * p * 10))()
+            self.max_iter, self.min_tol = 500, tol
+    preps = [P(100 + 7 * i, 1e-4 if i % 3 else 1e-3) for i in range(40)]
+    chunks = batch.plan_chunks(preps, chunk_bytes=3_000_000, chunk_loci=0)
+    flat = sorted(i for c in chunks for i in c)
+    assert flat == list(range(40))
+    for c in chunks:  # launch-compatible problems only
+        assert len({(preps[i].max_iter, preps[i].min_tol) for i in c}) == 1
+    q = batch.ChunkQueue(len(chunks))
+    got = []
+    while (c := q.next()) is not None:
+        got.append(c)
+    assert sorted(got) == list(range(len(chunks)))
+
+
+def test_c_abi_exports_every_declared_symbol(engine_lib):
+    header = open(os.path.join(ROOT, "include", "sushie_b200.h")).read()
+    declared = set(re.findall(r"\b(sb_[a-z_0-9]+)\s*\(", header))
+    assert declared == set(_capi.EXPORTED_SYMBOLS)
+    for name in declared:
+        assert hasattr(engine_lib, name), name
+    assert engine_lib.sb_version() == 100
+    # struct layouts on the Python side must match the C side (sizes are a cheap proxy)
+    assert ctypes.sizeof(_capi.SbOpts) == 40
+    assert ctypes.sizeof(_capi.SbResult) == 9 * 8 + 16
+    assert ctypes.sizeof(_capi.SbRunStats) == 64
+    assert ctypes.sizeof(_capi.SbIndProblem) == 96
+    assert ctypes.sizeof(_capi.SbSsProblem) == 96
+
+
+def test_product_never_imports_the_oracle():
+    """The oracle is test infrastructure: nothing under sushie_b200/ may reference it."""
+    pkg = os.path.join(ROOT, "sushie_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for fn in files:
+            if fn.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, fn)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", text, re.M), fn
