@@ -481,10 +481,11 @@ __global__ void __launch_bounds__(NT, 1) ibss_kernel(const LaunchParams P) {
     }
 
     // ring prologue: keep NS fills in flight; positions wrap (the traversal order is static)
-    int prod_pos = 0;  // next own band position to issue (thread 0)
+    const int producer_tid = fast ? NT - 32 : 0;  // the thread that issues bulk copies (owns prod_pos)
+    int prod_pos = 0;  // next own band position to issue (producer thread only)
     int cons_seq = 0;  // bands consumed so far in this locus (stage = cons_seq % NS)
     __syncthreads();
-    if (tid == 0 && nb_own > 0) {
+    if (tid == producer_tid && nb_own > 0) {
       for (int s = 0; s < NS; ++s) {
         issue_fill(prod_pos, s);
         prod_pos = (prod_pos + 1 == nb_own) ? 0 : prod_pos + 1;
@@ -546,24 +547,34 @@ __global__ void __launch_bounds__(NT, 1) ibss_kernel(const LaunchParams P) {
                              double inv_s) {
       constexpr int CPT = decltype(cpt_c)::value;
       constexpr int GR = decltype(gr_c)::value;
+      constexpr int PRODUCER_TID = NT - 32;  // lane 0 of the last warp issues the bulk copies
       const OutBuf& ob = pb.out[buf];
       const int lnext = first ? 0 : ((l + 1 == L) ? 0 : l + 1);
       double vsq[K], rsq[K];  // meaningful in threads < GR only
 #pragma unroll
       for (int k = 0; k < K; ++k) vsq[k] = rsq[k] = 0.0;
       double bq[CPT][VW], aq[CPT][VW];
+      double x[GR][CPT][VW];  // the band slice of this thread; columns past the row end stay 0
+      uint32_t vmask = 0;     // bit c: this thread owns a c-th column vector
 #pragma unroll
-      for (int c = 0; c < CPT; ++c)
+      for (int c = 0; c < CPT; ++c) {
+        if (tid + c * NT < pv) vmask |= (1u << c);
 #pragma unroll
-        for (int u = 0; u < VW; ++u) bq[c][u] = aq[c][u] = 0.0;
+        for (int u = 0; u < VW; ++u) {
+          bq[c][u] = aq[c][u] = 0.0;
+#pragma unroll
+          for (int g = 0; g < GR; ++g) x[g][c][u] = 0.0;
+        }
+      }
       int cur_k = -1;
+      int st = cons_seq % NS;
 
       auto flush_acc = [&](int k) {
         double* dst = pb.part + (static_cast<size_t>(rank) * K + k) * p_pad;
 #pragma unroll
         for (int c = 0; c < CPT; ++c) {
-          const int v = tid + c * NT;
-          if (v < pv) {
+          if (vmask & (1u << c)) {
+            const int v = tid + c * NT;
 #pragma unroll
             for (int u = 0; u < VW; u += 2)
               __stcg(reinterpret_cast<double2*>(dst + v * VW + u), make_double2(aq[c][u], aq[c][u + 1]));
@@ -582,43 +593,48 @@ __global__ void __launch_bounds__(NT, 1) ibss_kernel(const LaunchParams P) {
 #pragma unroll
             for (int u = 0; u < VW; ++u) {
               aq[c][u] = 0.0;
-              bq[c][u] = (first || v >= pv) ? 0.0 : effect_b(ob, l, k, v * VW + u, mt, inv_s);
+              bq[c][u] = (first || !(vmask & (1u << c))) ? 0.0 : effect_b(ob, l, k, v * VW + u, mt, inv_s);
             }
           }
           cur_k = k;
         }
-        const int st = cons_seq % NS;
         const XT* tile = reinterpret_cast<const XT*>(ring + static_cast<size_t>(st) * stage_bytes);
         const int row_base = pb.row0[k] + g0;
         const double nsc = pb.nscale[k];
+        const bool full_rows = (rows == GR);
 
         // per-row state (same addresses for every thread: broadcast loads), in flight while the band lands
         double r_old[GR], xb_next[GR];
+        const double* rp = pb.r + row_base;
+        const double* xp = pb.xb + static_cast<size_t>(lnext) * nrows + row_base;
 #pragma unroll
         for (int g = 0; g < GR; ++g) {
-          r_old[g] = 0.0;
-          xb_next[g] = 0.0;
-          if (g < rows) {
-            r_old[g] = pb.r[row_base + g];
-            xb_next[g] = pb.xb[static_cast<size_t>(lnext) * nrows + row_base + g];
-          }
+          const bool ok = full_rows || g < rows;
+          r_old[g] = ok ? rp[g] : 0.0;
+          xb_next[g] = ok ? xp[g] : 0.0;
         }
         mbar_wait(&H->mbar[st], (phase_bits >> st) & 1u);
 
         // the band -> registers (the only shared-memory read of the genotypes)
-        double x[GR][CPT][VW];
+        if (full_rows) {
 #pragma unroll
-        for (int g = 0; g < GR; ++g)
+          for (int g = 0; g < GR; ++g)
 #pragma unroll
-          for (int c = 0; c < CPT; ++c) {
-            const int v = tid + c * NT;
-            if (g < rows && v < pv) {
-              Vec<XT>::load(tile + static_cast<size_t>(g) * p_pad, v, x[g][c]);
-            } else {
+            for (int c = 0; c < CPT; ++c)
+              if (vmask & (1u << c)) Vec<XT>::load(tile + static_cast<size_t>(g) * p_pad, tid + c * NT, x[g][c]);
+        } else {
 #pragma unroll
-              for (int u = 0; u < VW; ++u) x[g][c][u] = 0.0;
+          for (int g = 0; g < GR; ++g)
+#pragma unroll
+            for (int c = 0; c < CPT; ++c) {
+              if (g < rows) {
+                if (vmask & (1u << c)) Vec<XT>::load(tile + static_cast<size_t>(g) * p_pad, tid + c * NT, x[g][c]);
+              } else {
+#pragma unroll
+                for (int u = 0; u < VW; ++u) x[g][c][u] = 0.0;
+              }
             }
-          }
+        }
 
         // sweep 1: per-thread partial dot products, transposed butterfly reduction over the warp
         const int pbuf = cons_seq & 1;
@@ -666,24 +682,20 @@ __global__ void __launch_bounds__(NT, 1) ibss_kernel(const LaunchParams P) {
           if ((lane & (32 / GR - 1)) == 0) H->partsum[pbuf][(lane / (32 / GR)) * NW + warp] = t;
         }
         __syncthreads();  // (A) partial sums visible; every thread holds its tile in registers
-        if (tid == 0) {   // the stage is free again: refill it with the band NS positions ahead
+        if (tid == PRODUCER_TID) {  // the stage is free again: refill it with the band NS positions ahead
           issue_fill(prod_pos, st);
           prod_pos = (prod_pos + 1 == nb_own) ? 0 : prod_pos + 1;
         }
-        // every thread finishes the row sums itself (no second barrier)
+        // every thread finishes the row sums itself (no second barrier); fixed pairwise order
         double rn[GR];
 #pragma unroll
         for (int g = 0; g < GR; ++g) {
           double v = 0.0;
           if (!first) {
             const double2* ps2 = reinterpret_cast<const double2*>(&H->partsum[pbuf][g * NW]);
-#pragma unroll
-            for (int w = 0; w < NW / 2; ++w) {
-              const double2 q = ps2[w];
-              v += q.x;
-              v += q.y;
-            }
-            v *= nsc;
+            static_assert(NW == 8, "pairwise tree below assumes 8 warps");
+            const double2 q0 = ps2[0], q1 = ps2[1], q2 = ps2[2], q3 = ps2[3];
+            v = (((q0.x + q0.y) + (q1.x + q1.y)) + ((q2.x + q2.y) + (q3.x + q3.y))) * nsc;
           }
           const double Rfull = r_old[g] - v;
           rn[g] = Rfull + xb_next[g];
@@ -715,6 +727,7 @@ __global__ void __launch_bounds__(NT, 1) ibss_kernel(const LaunchParams P) {
         }
         phase_bits ^= (1u << st);
         cons_seq += 1;
+        st = (st + 1 == NS) ? 0 : st + 1;
       }
       if (!SS) {
         if (cur_k >= 0) flush_acc(cur_k);
@@ -916,21 +929,38 @@ __global__ void __launch_bounds__(NT, 1) ibss_kernel(const LaunchParams P) {
 
       // P1 (individual level): reduce the per-block partial X^T r over the team, own slice
       if (!SS) {
+        const double* __restrict__ part = pb.part;
+        double* __restrict__ xty_w = pb.xty;
         for (int j = js + tid; j < je; j += NT) {
+          double s[K];
 #pragma unroll
-          for (int k = 0; k < K; ++k) {
-            double s = 0.0;
-            for (int c = 0; c < C; ++c) s += __ldcg(&pb.part[(static_cast<size_t>(c) * K + k) * p_pad + j]);
-            pb.xty[k * p_pad + j] = s;
+          for (int k = 0; k < K; ++k) s[k] = 0.0;
+          for (int c = 0; c < C; ++c) {
+#pragma unroll
+            for (int k = 0; k < K; ++k) s[k] += __ldcg(&part[(static_cast<size_t>(c) * K + k) * p_pad + j]);
           }
+#pragma unroll
+          for (int k = 0; k < K; ++k) xty_w[k * p_pad + j] = s[k];
         }
       }
-      auto load_snp = [&](int j, double (&d)[K], double (&r)[K]) {
+      // raw per-SNP inputs (X^T r, XtX, log pi); fetched one SNP ahead of the arithmetic
+      constexpr int NRAW = 2 * K + 1;
+      const double* __restrict__ xty_r = pb.xty;
+      const double* __restrict__ xtx_r = pb.xtx;
+      const double* __restrict__ lpi_r = pb.logpi;
+      auto fetch = [&](int j, double (&raw)[NRAW]) {
 #pragma unroll
         for (int k = 0; k < K; ++k) {
-          const double xty = SS ? __ldcg(&pb.r[pb.row0[k] + j]) : pb.xty[k * p_pad + j];
-          r[k] = xty / rv[k];                        // rTZDinv   (infer.py:677)
-          d[k] = pb.xtx[k * p_pad + j] / rv[k];      // inv_shat2 (infer.py:680)
+          raw[k] = SS ? __ldcg(&pb.r[pb.row0[k] + j]) : xty_r[k * p_pad + j];
+          raw[K + k] = xtx_r[k * p_pad + j];
+        }
+        raw[2 * K] = lpi_r[j];
+      };
+      auto unpack = [&](const double (&raw)[NRAW], double (&d)[K], double (&r)[K]) {
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+          r[k] = raw[k] / rv[k];      // rTZDinv   (infer.py:677)
+          d[k] = raw[K + k] / rv[k];  // inv_shat2 (infer.py:680)
         }
       };
       auto load_cinv = [&](const double* Cmat, double (&Cinv)[K][K], double& logdetC) {
@@ -961,15 +991,21 @@ __global__ void __launch_bounds__(NT, 1) ibss_kernel(const LaunchParams P) {
         double sv[1 + NSYM];
 #pragma unroll
         for (int i = 0; i < 1 + NSYM; ++i) sv[i] = 0.0;
+        double nxt[NRAW];
+        if (js + tid < je) fetch(js + tid, nxt);
         for (int j = js + tid; j < je; j += NT) {
+          double raw[NRAW];
+#pragma unroll
+          for (int i = 0; i < NRAW; ++i) raw[i] = nxt[i];
+          if (j + NT < je) fetch(j + NT, nxt);
           double d[K], r[K], S[K][K], mu[K], lda;
-          load_snp(j, d, r);
+          unpack(raw, d, r);
           snp_posterior<K>(Cinv, d, r, S, mu, lda);
           double q = 0.0;
 #pragma unroll
           for (int k = 0; k < K; ++k) q += r[k] * mu[k];
           const double lbf = 0.5 * (K * LOG_2PI - lda + q);  // infer.py:712-719
-          const double w = pb.logpi[j] + lbf;
+          const double w = raw[2 * K] + lbf;
           double e;
           if (w > m) {  // online softmax: rescale the running sums
             const double sc = exp(m - w);
@@ -1026,15 +1062,21 @@ __global__ void __launch_bounds__(NT, 1) ibss_kernel(const LaunchParams P) {
         double sv[NVB];
 #pragma unroll
         for (int i = 0; i < NVB; ++i) sv[i] = 0.0;
+        double nxt[NRAW];
+        if (js + tid < je) fetch(js + tid, nxt);
         for (int j = js + tid; j < je; j += NT) {
+          double raw[NRAW];
+#pragma unroll
+          for (int i = 0; i < NRAW; ++i) raw[i] = nxt[i];
+          if (j + NT < je) fetch(j + NT, nxt);
           double d[K], r[K], S[K][K], mu[K], lda;
-          load_snp(j, d, r);
+          unpack(raw, d, r);
           snp_posterior<K>(Cinv, d, r, S, mu, lda);
           double q = 0.0;
 #pragma unroll
           for (int k = 0; k < K; ++k) q += r[k] * mu[k];
           const double lbf = 0.5 * (K * LOG_2PI - lda + q);
-          const double w = pb.logpi[j] + lbf;
+          const double w = raw[2 * K] + lbf;
           // KL(N(mu,S) || N(0,C))  (infer.py:755-783)
           double tr = 0.0, quad = 0.0;
 #pragma unroll
@@ -1074,7 +1116,7 @@ __global__ void __launch_bounds__(NT, 1) ibss_kernel(const LaunchParams P) {
           sv[t++] += e * klb;
           sv[t++] += e * lbf;
 #pragma unroll
-          for (int k = 0; k < K; ++k) sv[t++] += e * pb.xtx[k * p_pad + j] * (S[k][k] + mu[k] * mu[k]);
+          for (int k = 0; k < K; ++k) sv[t++] += e * raw[K + k] * (S[k][k] + mu[k] * mu[k]);
         }
         const double mb = block_max(H, m);
         const double sc = (m == -CUDART_INF) ? 0.0 : exp(m - mb);
