@@ -282,6 +282,7 @@ def main():
     ap.add_argument("--max-iter", type=int, default=500)
     ap.add_argument("--min-tol", type=float, default=1e-4)
     ap.add_argument("--team", type=int, default=0)
+    ap.add_argument("--single-phase", action="store_true")
     ap.add_argument("--ref-loci", type=int, default=0)
     ap.add_argument("--cpu-loci", type=int, default=0, help="loci in the cpu_baseline sample (0 = one per core)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -346,7 +347,7 @@ def main():
                 em_update=True, standardize=_capi.SB_CENTER | _capi.SB_SCALE))
         return probs
 
-    opts = eng.make_opts(args.max_iter, args.min_tol, _capi.SB_F64, args.team)
+    opts = eng.make_opts(args.max_iter, args.min_tol, _capi.SB_F64, args.team, args.single_phase)
 
     def barrier():
         if world > 1:

@@ -52,6 +52,9 @@ extern "C" {
 #define SB_F32 1
 #define SB_I8 2 /* input only: hard-call genotypes 0/1/2 */
 
+/* sb_opts.flags */
+#define SB_FLAG_SINGLE_PHASE 1 /* keep one team size for the whole batch (no suspend / regroup phases) */
+
 /* sb_ind_problem.standardize bits (device-side restatement of infer.py:326-333) */
 #define SB_CENTER 1
 #define SB_SCALE 2
@@ -99,8 +102,9 @@ typedef struct {
   int32_t max_iter;          /* reference default 500 */
   double min_tol;            /* reference default 1e-4 (CLI 1e-3) */
   int32_t storage;           /* device storage of X / LD: SB_F64 (parity mode) or SB_F32 */
-  int32_t team_size;         /* thread blocks cooperating on one locus; 0 = choose */
-  int32_t reserved[4];
+  int32_t team_size;         /* thread blocks cooperating on one locus in the first phase; 0 = choose */
+  int32_t flags;             /* SB_FLAG_* */
+  int32_t reserved[3];
 } sb_opts;
 
 /* Caller-allocated result of one problem.  Any pointer may be NULL to skip that field. */

@@ -16,6 +16,7 @@ import numpy as np
 SB_MAX_ANCESTRIES = 4
 SB_F64, SB_F32, SB_I8 = 0, 1, 2
 SB_CENTER, SB_SCALE = 1, 2
+SB_FLAG_SINGLE_PHASE = 1
 
 _LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_lib", "libsushie_b200.so")
 
@@ -83,7 +84,8 @@ class SbOpts(C.Structure):
         ("min_tol", C.c_double),
         ("storage", C.c_int32),
         ("team_size", C.c_int32),
-        ("reserved", C.c_int32 * 4),
+        ("flags", C.c_int32),
+        ("reserved", C.c_int32 * 3),
     ]
 
 
@@ -340,9 +342,10 @@ class Engine:
         self._check(self.lib.sb_set_stream(self._ctx, C.c_void_p(cuda_stream_handle)), "sb_set_stream")
 
     @staticmethod
-    def make_opts(max_iter=500, min_tol=1e-4, storage=SB_F64, team_size=0) -> SbOpts:
+    def make_opts(max_iter=500, min_tol=1e-4, storage=SB_F64, team_size=0, single_phase=False) -> SbOpts:
         o = SbOpts()
         o.max_iter, o.min_tol, o.storage, o.team_size = int(max_iter), float(min_tol), int(storage), int(team_size)
+        o.flags = SB_FLAG_SINGLE_PHASE if single_phase else 0
         return o
 
     # ---- resident batches -------------------------------------------------------------

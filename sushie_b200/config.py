@@ -12,6 +12,8 @@ precision: int = int(os.environ.get("SUSHIE_B200_PRECISION", "64"))
 devices: Optional[List[int]] = None
 # thread blocks cooperating on one locus; 0 lets the engine choose.
 team_size: int = int(os.environ.get("SUSHIE_B200_TEAM", "0"))
+# keep one team size for a whole batch (disables the suspend / regroup phases)
+single_phase: bool = bool(int(os.environ.get("SUSHIE_B200_SINGLE_PHASE", "0")))
 # loci per device-resident chunk in the batch entry points (0 = size by memory budget).
 chunk_loci: int = int(os.environ.get("SUSHIE_B200_CHUNK", "0"))
 # device memory budget per chunk, bytes

@@ -65,6 +65,12 @@ struct sb_batch {
   int* d_slots = nullptr;
   unsigned* d_bar = nullptr;
   size_t metas_off = 0;
+  int* d_ctl = nullptr;
+  double* d_scratch = nullptr;
+  long long scratch_stride = 0;
+  int off_stat = 0, off_trav = 0;
+  int phases = 0;
+  std::vector<int> ids_host;
   int group_start[KMAX + 2] = {0};
   std::vector<HostProb> hp;
   std::vector<ProbDev> pd;
@@ -242,7 +248,7 @@ static int choose_team(const sb_ctx* ctx, int n_probs, double bytes_per_locus, i
     const int avail = std::max(1, S / std::max(1, n_probs));
     const int want = std::max(1, static_cast<int>(bytes_per_locus / (256.0 * 1024.0)));
     c = std::min(want, avail);
-    if (n_probs >= S) c = (want >= 8) ? 2 : 1;  // big batches: pairs halve the tail
+    if (n_probs >= S) c = 1;  // big batches: one block per locus, the phased schedule handles the tail
   }
   if (c <= 16) {
     int p2 = 1;
@@ -271,8 +277,7 @@ struct Bump {
 };
 
 struct ProbLayout {  // offsets inside the arena
-  size_t X[KMAX], y, logpi, pi_raw, xtx, ecov0, rv0, adjt, adjp, r, xb, part, xty, rfull, statA, statB, statC,
-      trav, out[2], elbo, meta, z;
+  size_t X[KMAX], y, logpi, pi_raw, xtx, ecov0, rv0, adjt, adjp, r, xb, xty, rfull, out[2], elbo, meta, z;
   size_t out_fields[2][10];
 };
 
@@ -435,11 +440,14 @@ static int batch_create(sb_ctx* ctx, const std::vector<GenericProblem>& gp, bool
   const size_t probs_off = bump.take(sizeof(ProbDev) * n_probs);
   const size_t ids_off = bump.take(sizeof(int) * n_probs);
   const size_t queue_off = bump.take(sizeof(int) * 64);
-  const size_t slots_off = bump.take(sizeof(int) * (ctx->num_sms + 8));
+  const size_t slots_off = bump.take(sizeof(int) * 2 * (ctx->num_sms + 8));
+  const size_t ctl_off = bump.take(sizeof(int) * 64);
   const size_t bar_off = bump.take(sizeof(unsigned) * 64 * (ctx->num_sms + 8));
   const size_t metas_off = bump.take(sizeof(int) * 8 * n_probs);
   const size_t elbos_off = bump.take(sizeof(double) * (opts.max_iter + 1) * static_cast<size_t>(n_probs));
   size_t staging_bytes = 0;
+  size_t Kp_max = 0;
+  int L_max = 1;
   for (int i = 0; i < n_probs; ++i) {
     const GenericProblem& g = gp[i];
     const Geometry& ge = geo[i];
@@ -470,13 +478,10 @@ static int batch_create(sb_ctx* ctx, const std::vector<GenericProblem>& gp, bool
     l.adjp = bump.take(sizeof(double) * g.K * g.K);
     l.r = bump.take(sizeof(double) * nrows);
     l.xb = bump.take(sizeof(double) * nrows * g.L);
-    l.part = ss ? 0 : bump.take(sizeof(double) * Kp * C);
     l.xty = ss ? 0 : bump.take(sizeof(double) * Kp);
     l.rfull = ss ? bump.take(sizeof(double) * nrows) : 0;
-    l.statA = bump.take(sizeof(double) * sb::STAT_STRIDE * C);
-    l.statB = bump.take(sizeof(double) * sb::STAT_STRIDE * C);
-    l.statC = bump.take(sizeof(double) * sb::STAT_STRIDE * C);
-    l.trav = bump.take(sizeof(double) * sb::TRAV_STRIDE * C * g.L);
+    Kp_max = std::max(Kp_max, Kp);
+    L_max = std::max(L_max, g.L);
     for (int q = 0; q < 2; ++q) {
       l.out[q] = bump.take(out_block_bytes(g.L, g.p, g.K));
       out_block_fields(g.L, g.p, g.K, l.out[q], l.out_fields[q]);
@@ -488,6 +493,11 @@ static int batch_create(sb_ctx* ctx, const std::vector<GenericProblem>& gp, bool
     h.meta_off = l.meta;
   }
   const size_t staging_off = bump.take(staging_bytes ? staging_bytes : 16);
+  // per-block scratch: partial X^T r, three reduction records, per-traversal scalars
+  const int off_stat = static_cast<int>(align_up(Kp_max, 16));
+  const int off_trav = off_stat + 3 * sb::STAT_STRIDE + 4;
+  const size_t scratch_stride = align_up(static_cast<size_t>(off_trav) + static_cast<size_t>(L_max) * sb::TRAV_STRIDE, 32);
+  const size_t scratch_off = bump.take(sizeof(double) * scratch_stride * (ctx->num_sms + 8));
   b->arena_bytes = align_up(bump.off, 256);
   {
     cudaError_t e = cudaMalloc(&b->arena, b->arena_bytes);
@@ -504,6 +514,11 @@ static int batch_create(sb_ctx* ctx, const std::vector<GenericProblem>& gp, bool
   b->d_slots = reinterpret_cast<int*>(A + slots_off);
   b->d_bar = reinterpret_cast<unsigned*>(A + bar_off);
   b->metas_off = metas_off;
+  b->d_ctl = reinterpret_cast<int*>(A + ctl_off);
+  b->d_scratch = reinterpret_cast<double*>(A + scratch_off);
+  b->scratch_stride = static_cast<long long>(scratch_stride);
+  b->off_stat = off_stat;
+  b->off_trav = off_trav;
   cudaStream_t st = ctx->stream;
   auto fail = [&](int code) {
     cudaStreamSynchronize(st);
@@ -564,13 +579,8 @@ static int batch_create(sb_ctx* ctx, const std::vector<GenericProblem>& gp, bool
     d.adj_plus = reinterpret_cast<double*>(A + l.adjp);
     d.r = reinterpret_cast<double*>(A + l.r);
     d.xb = reinterpret_cast<double*>(A + l.xb);
-    d.part = ss ? nullptr : reinterpret_cast<double*>(A + l.part);
     d.xty = ss ? nullptr : reinterpret_cast<double*>(A + l.xty);
     d.rfull = ss ? reinterpret_cast<double*>(A + l.rfull) : nullptr;
-    d.statA = reinterpret_cast<double*>(A + l.statA);
-    d.statB = reinterpret_cast<double*>(A + l.statB);
-    d.statC = reinterpret_cast<double*>(A + l.statC);
-    d.trav = reinterpret_cast<double*>(A + l.trav);
     for (int q = 0; q < 2; ++q) {
       OutBuf& o = d.out[q];
       const size_t* f = l.out_fields[q];
@@ -674,6 +684,7 @@ static int batch_create(sb_ctx* ctx, const std::vector<GenericProblem>& gp, bool
         if (gp[i].K == K) ids.push_back(i);
     }
     b->group_start[KMAX + 1] = static_cast<int>(ids.size());
+    b->ids_host = ids;
     SB_CUDA_B(cudaMemcpyAsync(b->d_ids, ids.data(), sizeof(int) * n_probs, cudaMemcpyHostToDevice, st));
     SB_CUDA_B(cudaMemcpyAsync(b->d_probs, b->pd.data(), sizeof(ProbDev) * n_probs, cudaMemcpyHostToDevice, st));
     SB_CUDA_B(cudaEventRecord(ctx->ev[3], st));
@@ -775,14 +786,28 @@ extern "C" int sb_batch_create_ss(sb_ctx* ctx, const sb_ss_problem* probs, int n
   return batch_create(ctx, gp, true, opts, out);
 }
 
+// Team-size ladder for the phased schedule: hardware clusters up to 16 blocks, then
+// co-operative (global-barrier) teams up to the whole device.
+static int next_team_size(const sb_ctx* ctx, int remaining, int current) {
+  const int S = ctx->num_sms;
+  const int ladder[] = {1, 2, 4, 8, 16, 32, 64, S};
+  int best = current;
+  for (int c : ladder) {
+    if (c <= current) continue;
+    if (c > 16 && !ctx->coop_ok) break;
+    if (c > 1 && c <= 16 && !ctx->cluster_ok) continue;
+    if (S / c >= remaining) best = c;
+  }
+  return best;
+}
+
 extern "C" int sb_batch_run(sb_ctx* ctx, sb_batch* b, sb_run_stats* stats) {
   if (!ctx || !b || !b->arena) return SB_EINVAL;
   cudaSetDevice(ctx->device);
   cudaStream_t st = ctx->stream;
-  const int C = b->team_size;
-  SB_CUDA(cudaMemsetAsync(b->d_queue, 0, sizeof(int) * 64, st));
-  SB_CUDA(cudaMemsetAsync(b->d_bar, 0, sizeof(unsigned) * 64 * (ctx->num_sms + 8), st));
-  int launches = 0, teams_used = 0;
+  SB_CUDA(cudaMemsetAsync(b->arena + b->metas_off, 0, sizeof(int) * 8 * b->n_probs, st));
+  int launches = 0, teams_used = 0, phases = 0;
+  std::vector<int> meta(static_cast<size_t>(b->n_probs) * 8);
   SB_CUDA(cudaEventRecord(ctx->ev[0], st));
   for (int K = 1; K <= KMAX; ++K) {
     const int g0 = b->group_start[K], g1 = b->group_start[K + 1];
@@ -793,69 +818,112 @@ extern "C" int sb_batch_run(sb_ctx* ctx, sb_batch* b, sb_run_stats* stats) {
       return SB_EINVAL;
     }
     SB_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, b->smem_bytes));
-    if (b->hw_cluster && C > 8) SB_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    SB_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
 
-    cudaLaunchConfig_t cfg{};
-    cfg.blockDim = dim3(sb::NT);
-    cfg.dynamicSmemBytes = b->smem_bytes;
-    cfg.stream = st;
-    cudaLaunchAttribute attrs[2];
-    int na = 0;
-    int max_teams;
-    if (C == 1) {
-      int per_sm = 0;
-      SB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, sb::NT, b->smem_bytes));
-      max_teams = per_sm * ctx->num_sms;
-    } else if (b->hw_cluster) {
-      attrs[na].id = cudaLaunchAttributeClusterDimension;
-      attrs[na].val.clusterDim.x = C;
-      attrs[na].val.clusterDim.y = 1;
-      attrs[na].val.clusterDim.z = 1;
-      ++na;
+    // Phased schedule: run with the current team size until half of the teams have run out of
+    // work, suspend the loci still in flight at their next iteration boundary, and continue
+    // them with larger teams, so the tail of the batch keeps every SM busy.
+    std::vector<int> ids(b->ids_host.begin() + g0, b->ids_host.begin() + g1);
+    int C = b->team_size;
+    int hw = b->hw_cluster;
+    bool first_phase = true;
+    while (!ids.empty()) {
+      // (re)upload the id list of this phase: a previous run leaves the last phase's list behind
+      SB_CUDA(cudaMemcpyAsync(b->d_ids + g0, ids.data(), sizeof(int) * ids.size(), cudaMemcpyHostToDevice, st));
+      cudaLaunchConfig_t cfg{};
+      cfg.blockDim = dim3(sb::NT);
+      cfg.dynamicSmemBytes = b->smem_bytes;
+      cfg.stream = st;
+      cudaLaunchAttribute attrs[2];
+      int na = 0;
+      int max_teams;
+      if (C == 1) {
+        int per_sm = 0;
+        SB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, sb::NT, b->smem_bytes));
+        max_teams = per_sm * ctx->num_sms;
+      } else if (hw) {
+        attrs[na].id = cudaLaunchAttributeClusterDimension;
+        attrs[na].val.clusterDim.x = C;
+        attrs[na].val.clusterDim.y = 1;
+        attrs[na].val.clusterDim.z = 1;
+        ++na;
+        cfg.attrs = attrs;
+        cfg.numAttrs = na;
+        cfg.gridDim = dim3(C);
+        int ncl = 0;
+        SB_CUDA(cudaOccupancyMaxActiveClusters(&ncl, fn, &cfg));
+        max_teams = ncl;
+      } else {
+        int per_sm = 0;
+        SB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, sb::NT, b->smem_bytes));
+        max_teams = (per_sm * ctx->num_sms) / C;
+        attrs[na].id = cudaLaunchAttributeCooperative;
+        attrs[na].val.cooperative = 1;
+        ++na;
+      }
+      max_teams = std::min(max_teams, ctx->num_sms / C);
+      if (max_teams < 1) {
+        ctx->err = "kernel does not fit on the device (team_size=" + std::to_string(C) + ", smem=" +
+                   std::to_string(b->smem_bytes) + ")";
+        return SB_EINVAL;
+      }
+      const int n_ids = static_cast<int>(ids.size());
+      const int n_teams = std::min(max_teams, n_ids);
+      teams_used = std::max(teams_used, n_teams);
+      cfg.gridDim = dim3(n_teams * C);
       cfg.attrs = attrs;
       cfg.numAttrs = na;
-      cfg.gridDim = dim3(C);
-      int ncl = 0;
-      SB_CUDA(cudaOccupancyMaxActiveClusters(&ncl, fn, &cfg));
-      max_teams = ncl;
-    } else {
-      int per_sm = 0;
-      SB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, sb::NT, b->smem_bytes));
-      max_teams = (per_sm * ctx->num_sms) / C;
-      attrs[na].id = cudaLaunchAttributeCooperative;
-      attrs[na].val.cooperative = 1;
-      ++na;
-    }
-    if (max_teams < 1) {
-      ctx->err = "kernel does not fit on the device (team_size=" + std::to_string(C) + ", smem=" +
-                 std::to_string(b->smem_bytes) + ")";
-      return SB_EINVAL;
-    }
-    const int n_teams = std::min(max_teams, g1 - g0);
-    teams_used = std::max(teams_used, n_teams);
-    cfg.gridDim = dim3(n_teams * C);
-    cfg.attrs = attrs;
-    cfg.numAttrs = na;
 
-    LaunchParams lp{};
-    lp.probs = b->d_probs;
-    lp.prob_ids = b->d_ids + g0;
-    lp.n_ids = g1 - g0;
-    lp.queue = b->d_queue + (K - 1) * 8;
-    lp.team_slot = b->d_slots;
-    lp.team_bar = b->d_bar;
-    lp.team_size = C;
-    lp.hw_cluster = b->hw_cluster;
-    lp.max_iter = b->opts.max_iter;
-    lp.min_tol = b->opts.min_tol;
-    void* args[] = {&lp};
-    SB_CUDA(cudaLaunchKernelExC(&cfg, fn, args));
-    ++launches;
+      const int bigger = (b->opts.flags & SB_FLAG_SINGLE_PHASE) ? C : next_team_size(ctx, 1, C);
+      SB_CUDA(cudaMemsetAsync(b->d_queue, 0, sizeof(int) * 64, st));
+      SB_CUDA(cudaMemsetAsync(b->d_ctl, 0, sizeof(int) * 64, st));
+      SB_CUDA(cudaMemsetAsync(b->d_bar, 0, sizeof(unsigned) * 64 * (ctx->num_sms + 8), st));
+
+      LaunchParams lp{};
+      lp.probs = b->d_probs;
+      lp.prob_ids = b->d_ids + g0;
+      lp.n_ids = n_ids;
+      lp.queue = b->d_queue + (K - 1) * 8;
+      lp.team_slot = b->d_slots;
+      lp.team_bar = b->d_bar;
+      lp.team_size = C;
+      lp.hw_cluster = hw;
+      lp.max_iter = b->opts.max_iter;
+      lp.min_tol = b->opts.min_tol;
+      lp.scratch = b->d_scratch;
+      lp.scratch_stride = b->scratch_stride;
+      lp.off_stat = b->off_stat;
+      lp.off_trav = b->off_trav;
+      lp.ctl = b->d_ctl;
+      lp.n_teams = n_teams;
+      lp.allow_drain = (bigger > C) ? 1 : 0;
+      void* args[] = {&lp};
+      SB_CUDA(cudaLaunchKernelExC(&cfg, fn, args));
+      ++launches;
+      ++phases;
+      first_phase = false;
+      if (!lp.allow_drain) break;  // final phase: everything runs to completion
+      // which loci were suspended?
+      SB_CUDA(cudaMemcpyAsync(meta.data(), b->arena + b->metas_off, sizeof(int) * 8 * b->n_probs,
+                              cudaMemcpyDeviceToHost, st));
+      SB_CUDA(cudaStreamSynchronize(st));
+      std::vector<int> rest;
+      for (int id : ids)
+        if (meta[static_cast<size_t>(id) * 8 + 4] != 2) rest.push_back(id);
+      ids.swap(rest);
+      if (ids.empty()) break;
+      const int c_next = next_team_size(ctx, static_cast<int>(ids.size()), C);
+      if (c_next != C) {
+        C = c_next;
+        hw = (C > 1 && C <= 16 && ctx->cluster_ok) ? 1 : 0;
+      }
+    }
   }
   SB_CUDA(cudaEventRecord(ctx->ev[1], st));
   SB_CUDA(cudaStreamSynchronize(st));
   SB_CUDA(cudaGetLastError());
   b->ran = true;
+  b->phases = phases;
   if (stats) {
     std::memset(stats, 0, sizeof(*stats));
     float ms = 0.f;
@@ -863,13 +931,11 @@ extern "C" int sb_batch_run(sb_ctx* ctx, sb_batch* b, sb_run_stats* stats) {
     stats->device_ms = ms;
     stats->prologue_ms = b->prologue_ms;
     stats->n_launches = launches + b->n_launches_create;
-    stats->team_size = C;
+    stats->team_size = b->team_size;
     stats->n_teams = teams_used;
     stats->rows_per_band = b->G_max;
     stats->n_stages = b->NS_max;
     stats->smem_bytes = b->smem_bytes;
-    // iteration / SER counters from the per-problem meta words
-    std::vector<int> meta(static_cast<size_t>(b->n_probs) * 8);
     SB_CUDA(cudaMemcpyAsync(meta.data(), b->arena + b->metas_off, sizeof(int) * 8 * b->n_probs,
                             cudaMemcpyDeviceToHost, st));
     SB_CUDA(cudaStreamSynchronize(st));

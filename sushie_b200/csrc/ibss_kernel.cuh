@@ -76,16 +76,12 @@ struct ProbDev {
   const double* adj_plus;   // [K][K]
   double* r;      // [nrows] current residual (with the current effect added back)
   double* xb;     // [L][nrows] cached X b_l  (summary level: XtX b_l)
-  double* part;   // [team][K][p_pad] per-block partial X^T r   (individual level)
   double* xty;    // [K][p_pad] reduced X^T r                    (individual level)
   double* rfull;  // [nrows] full residual at iteration end      (summary level)
-  double* statA;  // [team][STAT_STRIDE]
-  double* statB;  // [team][STAT_STRIDE]
-  double* statC;  // [team][STAT_STRIDE]
-  double* trav;   // [L][team][TRAV_STRIDE]
   OutBuf out[2];
   double* elbo;   // [max_iter + 1]
   int* meta;      // [0]=n_iter [1]=elbo_increase [2]=final buffer (-1: initial state) [3]=n_ser
+                  // [4]=status: 0 not started, 1 suspended at an iteration boundary, 2 finished
 };
 
 struct LaunchParams {
@@ -99,6 +95,14 @@ struct LaunchParams {
   int hw_cluster;
   int max_iter;
   double min_tol;
+  // per-block scratch (index = blockIdx.x): [part: K*p_pad_max][3 x STAT_STRIDE][trav: L_max*TRAV_STRIDE]
+  double* scratch;
+  long long scratch_stride;  // doubles per block
+  int off_stat, off_trav;    // offsets (doubles) inside a block's scratch
+  // phase control: ctl[0] = teams that found the queue empty, ctl[1] = drain request
+  int* ctl;
+  int n_teams;
+  int allow_drain;  // a later phase with larger teams exists: suspend loci when half the teams idle
 };
 
 // ---------------------------------------------------------------------------------------
@@ -218,7 +222,7 @@ __device__ __forceinline__ double warp_max(double v) {
 struct SmemHdr {
   uint64_t mbar[NSTAGE_MAX];
   ProbDev pb;                // the locus being processed
-  double partsum[2][GMAX];   // sweep-1 partial dot products [band parity][g * nseg + seg]
+  alignas(16) double partsum[2][GMAX];  // sweep-1 partial dot products [band parity][g * nseg + seg]
   double rn[GMAX];           // next residual of the band's rows
   double red[NW][STAT_STRIDE];
   double tot[STAT_STRIDE];   // block / team totals
@@ -411,7 +415,13 @@ __global__ void __launch_bounds__(NT, 1) ibss_kernel(const LaunchParams P) {
     }
     team_sync(team);
     const int qi = __ldcg(&P.team_slot[team.id]);
-    if (qi >= P.n_ids) break;
+    if (qi >= P.n_ids) {
+      if (team.rank == 0 && tid == 0 && P.allow_drain) {
+        const int idle = atomicAdd(&P.ctl[0], 1) + 1;
+        if (2 * idle >= P.n_teams) atomicExch(&P.ctl[1], 1);
+      }
+      break;
+    }
     {
       const int* src = reinterpret_cast<const int*>(&P.probs[P.prob_ids[qi]]);
       int* dst = reinterpret_cast<int*>(&H->pb);
@@ -430,6 +440,12 @@ __global__ void __launch_bounds__(NT, 1) ibss_kernel(const LaunchParams P) {
     const size_t row_bytes = static_cast<size_t>(p_pad) * sizeof(XT);
     const size_t stage_bytes = row_bytes * G;
     const int fast = pb.fast;  // register-tile traversal variant (0 = generic shared-memory path)
+    // scratch of team member c (partials, reduction records, per-traversal scalars)
+    auto scr = [&](int c) -> double* {
+      return P.scratch + static_cast<size_t>(team.id * team.size + c) * static_cast<size_t>(P.scratch_stride);
+    };
+    double* const my_scr = scr(team.rank);
+    const int status0 = __ldcg(&pb.meta[4]);  // 0 fresh, 1 resumed from a suspended state
 
     // dynamic shared-memory carve-up: [header][b (generic path)][acc (generic, individual)][ring]
     double* bsm = reinterpret_cast<double*>(smem_raw + ((sizeof(SmemHdr) + 127) / 128) * 128);
@@ -470,7 +486,7 @@ __global__ void __launch_bounds__(NT, 1) ibss_kernel(const LaunchParams P) {
     };
 
     // ---- locus initialisation (state owned by this block: rows of its bands)
-    for (int pos = 0; pos < nb_own; ++pos) {
+    for (int pos = 0; status0 == 0 && pos < nb_own; ++pos) {
       int k, g0, rows;
       band_of(pos, k, g0, rows);
       for (int t = tid; t < rows; t += NT) {
@@ -517,7 +533,7 @@ __global__ void __launch_bounds__(NT, 1) ibss_kernel(const LaunchParams P) {
             a += H->trow[g][0];
             b += H->trow[g][1];
           }
-          double* dst = pb.trav + (static_cast<size_t>(l) * C + rank) * TRAV_STRIDE;
+          double* dst = my_scr + P.off_trav + l * TRAV_STRIDE;
           __stcg(&dst[k], a);
           __stcg(&dst[KMAX + k], b);
         }
@@ -529,7 +545,7 @@ __global__ void __launch_bounds__(NT, 1) ibss_kernel(const LaunchParams P) {
         const int b0 = pb.band0[k], b1 = pb.band0[k + 1];
         const int first_q = b0 + (((rank - b0) % C) + C) % C;  // first band index == rank (mod C)
         if (!(first_q < b1)) {
-          double* dst = pb.part + (static_cast<size_t>(rank) * K + k) * p_pad;
+          double* dst = my_scr + static_cast<size_t>(k) * p_pad;
           for (int j = tid; j < p_pad; j += NT) __stcg(&dst[j], 0.0);
         }
       }
@@ -570,7 +586,7 @@ __global__ void __launch_bounds__(NT, 1) ibss_kernel(const LaunchParams P) {
       int st = cons_seq % NS;
 
       auto flush_acc = [&](int k) {
-        double* dst = pb.part + (static_cast<size_t>(rank) * K + k) * p_pad;
+        double* dst = my_scr + static_cast<size_t>(k) * p_pad;
 #pragma unroll
         for (int c = 0; c < CPT; ++c) {
           if (vmask & (1u << c)) {
@@ -754,7 +770,7 @@ __global__ void __launch_bounds__(NT, 1) ibss_kernel(const LaunchParams P) {
           // ancestry change: flush X^T r partial, load the new b, clear the accumulator
           __syncthreads();
           if (!SS && cur_k >= 0) {
-            double* dst = pb.part + (static_cast<size_t>(rank) * K + cur_k) * p_pad;
+            double* dst = my_scr + static_cast<size_t>(cur_k) * p_pad;
             for (int j = tid; j < p_pad; j += NT) __stcg(&dst[j], acc[j]);
           }
           if (!first)
@@ -868,7 +884,7 @@ __global__ void __launch_bounds__(NT, 1) ibss_kernel(const LaunchParams P) {
       }
       if (!SS) {
         if (cur_k >= 0) {
-          double* dst = pb.part + (static_cast<size_t>(rank) * K + cur_k) * p_pad;
+          double* dst = my_scr + static_cast<size_t>(cur_k) * p_pad;
           for (int j = tid; j < p_pad; j += NT) __stcg(&dst[j], acc[j]);
         }
         zero_unowned_partials();
@@ -888,21 +904,22 @@ __global__ void __launch_bounds__(NT, 1) ibss_kernel(const LaunchParams P) {
     // ------------------------------------------------------------------------------
     // team combine of per-block (max, scaled sums) records written to `stat`:
     // rec[0] = m, rec[1..nv] = sums scaled by exp(-m).  Result in H->tot[0..nv] (tot[0] = m).
-    auto team_combine = [&](double* stat, int nv) {
+    auto team_combine = [&](int which, int nv) {
       // every block holds its own record in H->tot already (tot[0]=m, tot[1..nv])
       if (C == 1) return;
-      if (tid <= nv) __stcg(&stat[static_cast<size_t>(rank) * STAT_STRIDE + tid], H->tot[tid]);
+      const int so = P.off_stat + which * STAT_STRIDE;
+      if (tid <= nv) __stcg(&my_scr[so + tid], H->tot[tid]);
       team_sync(team);
       if (warp == 0) {
         double m = -CUDART_INF;
-        for (int c = lane; c < C; c += 32) m = fmax(m, __ldcg(&stat[static_cast<size_t>(c) * STAT_STRIDE]));
+        for (int c = lane; c < C; c += 32) m = fmax(m, __ldcg(&scr(c)[so]));
         m = warp_max(m);
         // NaN anywhere must poison the result like the reference's softmax would
         for (int i = 1; i <= nv; ++i) {
           double s = 0.0;
           for (int c = lane; c < C; c += 32) {
-            const double mc = __ldcg(&stat[static_cast<size_t>(c) * STAT_STRIDE]);
-            const double vc = __ldcg(&stat[static_cast<size_t>(c) * STAT_STRIDE + i]);
+            const double mc = __ldcg(&scr(c)[so]);
+            const double vc = __ldcg(&scr(c)[so + i]);
             const double sc = (mc == -CUDART_INF) ? 0.0 : exp(mc - m);
             s += (mc != mc) ? mc : vc * sc;
           }
@@ -918,7 +935,24 @@ __global__ void __launch_bounds__(NT, 1) ibss_kernel(const LaunchParams P) {
     // posterior phases of effect l in iteration `it`: writes the un-normalised rows of out[buf]
     // (alpha slot = log weights, pm = mu_j, pmsq = S_j + mu_j mu_j^T, lbf) and the per-effect
     // scalars; the softmax normaliser (m, sum) is returned through H->tot[0], H->tot[1].
-    auto posterior = [&](int l, int it) {
+    // P1 (individual level): reduce the per-block partial X^T r over the team, own SNP slice
+    auto reduce_partials = [&]() {
+      double* __restrict__ xty_w = pb.xty;
+      for (int j = js + tid; j < je; j += NT) {
+        double s[K];
+#pragma unroll
+        for (int k = 0; k < K; ++k) s[k] = 0.0;
+        for (int c = 0; c < C; ++c) {
+          const double* __restrict__ part = scr(c);
+#pragma unroll
+          for (int k = 0; k < K; ++k) s[k] += __ldcg(&part[static_cast<size_t>(k) * p_pad + j]);
+        }
+#pragma unroll
+        for (int k = 0; k < K; ++k) xty_w[k * p_pad + j] = s[k];
+      }
+    };
+
+    auto posterior = [&](int l, int it, bool have_xty) {
       const int buf = it & 1;
       const OutBuf& ob = pb.out[buf];
       const double* ecov_prev = (it == 0) ? pb.ecov0 : pb.out[buf ^ 1].ecov;
@@ -927,22 +961,7 @@ __global__ void __launch_bounds__(NT, 1) ibss_kernel(const LaunchParams P) {
 #pragma unroll
       for (int k = 0; k < K; ++k) rv[k] = __ldcg(&rv_prev[k]);
 
-      // P1 (individual level): reduce the per-block partial X^T r over the team, own slice
-      if (!SS) {
-        const double* __restrict__ part = pb.part;
-        double* __restrict__ xty_w = pb.xty;
-        for (int j = js + tid; j < je; j += NT) {
-          double s[K];
-#pragma unroll
-          for (int k = 0; k < K; ++k) s[k] = 0.0;
-          for (int c = 0; c < C; ++c) {
-#pragma unroll
-            for (int k = 0; k < K; ++k) s[k] += __ldcg(&part[(static_cast<size_t>(c) * K + k) * p_pad + j]);
-          }
-#pragma unroll
-          for (int k = 0; k < K; ++k) xty_w[k * p_pad + j] = s[k];
-        }
-      }
+      if (!SS && !have_xty) reduce_partials();
       // raw per-SNP inputs (X^T r, XtX, log pi); fetched one SNP ahead of the arithmetic
       constexpr int NRAW = 2 * K + 1;
       const double* __restrict__ xty_r = pb.xty;
@@ -1033,7 +1052,7 @@ __global__ void __launch_bounds__(NT, 1) ibss_kernel(const LaunchParams P) {
           H->tot[0] = mb;
         }
         __syncthreads();
-        team_combine(pb.statA, 1 + NSYM);
+        team_combine(0, 1 + NSYM);
         const double ssum = H->tot[1];
         int t = 2;
 #pragma unroll
@@ -1128,7 +1147,7 @@ __global__ void __launch_bounds__(NT, 1) ibss_kernel(const LaunchParams P) {
           H->tot[0] = mb;
         }
         __syncthreads();
-        team_combine(pb.statB, NVB);
+        team_combine(1, NVB);
       }
       // per-effect scalars (one writer)
       {
@@ -1155,19 +1174,26 @@ __global__ void __launch_bounds__(NT, 1) ibss_kernel(const LaunchParams P) {
 
     // ------------------------------------------------------------------------------
     // the IBSS loop
-    if (!SS) {
-      traverse(0, true, false, 0, 0.0, 0.0);  // X^T y for the first effect
+    int n_iter = 0, inc_flag = 1, final_buf = -1, n_ser = 0, it0 = 0;
+    double elbo_last = -CUDART_INF;
+    bool suspended = false;
+    if (status0 == 0) {
+      if (!SS) traverse(0, true, false, 0, 0.0, 0.0);  // X^T y for the first effect
+      if (rank == 0 && tid == 0) pb.elbo[0] = -CUDART_INF;
+    } else {
+      // resume a locus suspended at an iteration boundary: everything lives in global memory
+      it0 = __ldcg(&pb.meta[0]);
+      n_ser = __ldcg(&pb.meta[3]);
+      elbo_last = __ldcg(&pb.elbo[it0]);
+      n_iter = it0;
+      final_buf = (it0 - 1) & 1;
     }
     team_sync(team);
 
-    int n_iter = 0, inc_flag = 1, final_buf = -1, n_ser = 0;
-    double elbo_last = -CUDART_INF;
-    if (rank == 0 && tid == 0) pb.elbo[0] = -CUDART_INF;
-
-    for (int it = 0; it < P.max_iter; ++it) {
+    for (int it = it0; it < P.max_iter; ++it) {
       const int buf = it & 1;
       for (int l = 0; l < L; ++l) {
-        posterior(l, it);
+        posterior(l, it, status0 != 0 && it == it0 && l == 0);
         const double mt = H->tot[0], inv_s = 1.0 / H->tot[1];
         traverse(l, false, l + 1 == L, buf, mt, inv_s);
         team_sync(team);
@@ -1195,11 +1221,12 @@ __global__ void __launch_bounds__(NT, 1) ibss_kernel(const LaunchParams P) {
         }
         block_sum<2 * K>(H, tv);
         if (C > 1) {
-          if (tid < 2 * K) __stcg(&pb.statC[static_cast<size_t>(rank) * STAT_STRIDE + tid], H->tot[tid]);
+          const int so = P.off_stat + 2 * STAT_STRIDE;
+          if (tid < 2 * K) __stcg(&my_scr[so + tid], H->tot[tid]);
           team_sync(team);
           if (tid < 2 * K) {
             double s = 0.0;
-            for (int c = 0; c < C; ++c) s += __ldcg(&pb.statC[static_cast<size_t>(c) * STAT_STRIDE + tid]);
+            for (int c = 0; c < C; ++c) s += __ldcg(&scr(c)[so + tid]);
             H->tot[tid] = s;
           }
           __syncthreads();
@@ -1213,18 +1240,18 @@ __global__ void __launch_bounds__(NT, 1) ibss_kernel(const LaunchParams P) {
         if (SS) {
           double t4 = 0.0, t5 = 0.0;
           for (int l = 0; l < L; ++l) {
-            for (int c = 0; c < C; ++c) t4 += __ldcg(&pb.trav[(static_cast<size_t>(l) * C + c) * TRAV_STRIDE + k]);
+            for (int c = 0; c < C; ++c) t4 += __ldcg(&scr(c)[P.off_trav + l * TRAV_STRIDE + k]);
             t5 += __ldcg(&ob.xtxb2[l * K + k]);
           }
           e = pb.nsamp[k] - 2.0 * H->tot[k] + H->tot[K + k] - t4 + t5;
         } else {
           double rs = 0.0;
           for (int c = 0; c < C; ++c)
-            rs += __ldcg(&pb.trav[(static_cast<size_t>(L - 1) * C + c) * TRAV_STRIDE + KMAX + k]);
+            rs += __ldcg(&scr(c)[P.off_trav + (L - 1) * TRAV_STRIDE + KMAX + k]);
           double t2 = 0.0;
           for (int l = 0; l < L; ++l) {
             double vs = 0.0;
-            for (int c = 0; c < C; ++c) vs += __ldcg(&pb.trav[(static_cast<size_t>(l) * C + c) * TRAV_STRIDE + k]);
+            for (int c = 0; c < C; ++c) vs += __ldcg(&scr(c)[P.off_trav + l * TRAV_STRIDE + k]);
             t2 += __ldcg(&ob.xtxb2[l * K + k]) - vs;
           }
           e = rs + t2;
@@ -1266,16 +1293,26 @@ __global__ void __launch_bounds__(NT, 1) ibss_kernel(const LaunchParams P) {
       }
       final_buf = buf;
       if (dec == 1) break;
-      team_sync(team);  // new residual variances visible to every block
+      // drain request (half of the teams idle, larger teams available): one consistent read per team
+      if (rank == 0 && tid == 0)
+        __stcg(&P.team_slot[P.n_teams + team.id], (P.allow_drain && it + 1 < P.max_iter) ? atomicAdd(&P.ctl[1], 0) : 0);
+      team_sync(team);  // new residual variances (and the drain decision) visible to every block
+      if (__ldcg(&P.team_slot[P.n_teams + team.id])) {
+        // suspend: reduce the pending X^T r now so the next phase may use any team size
+        if (!SS) reduce_partials();
+        suspended = true;
+        break;
+      }
     }
     if (rank == 0 && tid == 0) {
       pb.meta[0] = n_iter;
       pb.meta[1] = inc_flag;
       pb.meta[2] = final_buf;
       pb.meta[3] = n_ser;
+      pb.meta[4] = suspended ? 1 : 2;
     }
     // ---- normalise the returned buffer once: alpha = softmax(w), alpha-weighted mean / second moment
-    if (final_buf >= 0) {
+    if (!suspended && final_buf >= 0) {
       const OutBuf& ob = pb.out[final_buf];
       for (int l = 0; l < L; ++l) {
         const double mt = __ldcg(&ob.lse[2 * l]), ssum = __ldcg(&ob.lse[2 * l + 1]);

@@ -133,7 +133,7 @@ def _finish(batch: "_capi.Batch", index: int, prep: _Prepared, fit) -> SushieRes
 def _run_prepared(preps: Sequence[_Prepared], device: int = 0) -> List[SushieResult]:
     """Fit a list of prepared problems that share max_iter / min_tol on one GPU."""
     eng = _capi.get_engine(device)
-    opts = eng.make_opts(preps[0].max_iter, preps[0].min_tol, config.storage_code(), config.team_size)
+    opts = eng.make_opts(preps[0].max_iter, preps[0].min_tol, config.storage_code(), config.team_size, config.single_phase)
     with eng.create_batch([p.problem for p in preps], opts) as batch:
         batch.run()
         fits = batch.fetch()

@@ -82,7 +82,7 @@ def _finish_ss(batch, index, prep, fit) -> SushieResult:
 
 def _run_prepared_ss(preps: Sequence["infer._Prepared"], device: int = 0) -> List[SushieResult]:
     eng = _capi.get_engine(device)
-    opts = eng.make_opts(preps[0].max_iter, preps[0].min_tol, config.storage_code(), config.team_size)
+    opts = eng.make_opts(preps[0].max_iter, preps[0].min_tol, config.storage_code(), config.team_size, config.single_phase)
     with eng.create_batch([p.problem for p in preps], opts) as batch:
         batch.run()
         fits = batch.fetch()
