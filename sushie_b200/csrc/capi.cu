@@ -203,7 +203,7 @@ static bool plan_geometry(int p, int n_max, int es, bool ss, int smem_budget, Ge
   const int pv = static_cast<int>(row_bytes / 16);  // 16-byte vectors per row
   // register-tile traversal (individual level): every thread owns CPT vectors of GR rows
   g.fast = 0;
-  if (!ss) {
+  {
     int gr = 0;
     if (pv > sb::NT && pv <= 4 * sb::NT) {
       g.fast = 1;
@@ -211,13 +211,15 @@ static bool plan_geometry(int p, int n_max, int es, bool ss, int smem_budget, Ge
     } else if (pv > 4 * sb::NT && pv <= 8 * sb::NT) {
       g.fast = 2;
       gr = 2;
+    } else if (ss && pv > 8 * sb::NT && pv <= 12 * sb::NT) {
+      g.fast = 3;
+      gr = 1;
     }
     if (g.fast) {
       const int rows_fit = static_cast<int>((smem_budget - hdr) / row_bytes);
       if (rows_fit >= 2 * gr) {
         g.G = gr;
         g.NS = std::min(sb::NSTAGE_MAX, rows_fit / gr);
-        if (g.NS > 3) g.NS = 3;
         g.NSEG = 1;
         g.smem = hdr + static_cast<size_t>(g.NS) * g.G * row_bytes;
         return true;

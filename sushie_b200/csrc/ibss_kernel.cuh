@@ -63,7 +63,7 @@ struct ProbDev {
   int G, nstage, nseg; // rows per band, ring stages, warps per row in sweep 1
   int em;              // 1 = EM prior update, 0 = times/plus adjustor
   int skip_first_pass; // adjustor.times == 0: the first posterior pass cannot matter
-  int fast;            // traversal variant: 0 generic, 1 register tile 4x4, 2 register tile 8x2
+  int fast;            // traversal variant: 0 generic; register tile 1: 4 vec x 4 rows, 2: 8 x 2, 3: 12 x 1
   const void* X[KMAX]; // [n_k][p_pad] storage type
   double nscale[KMAX]; // summary level: n_k (XtX = n LD); individual level: 1
   double nsamp[KMAX];  // n_k as double for the ELBO
@@ -897,6 +897,9 @@ __global__ void __launch_bounds__(NT, 1) ibss_kernel(const LaunchParams P) {
         traverse_fast(IntC<4>{}, IntC<4>{}, l, first, last_effect, buf, mt, inv_s);
       else if (fast == 2)
         traverse_fast(IntC<8>{}, IntC<2>{}, l, first, last_effect, buf, mt, inv_s);
+      else if (SS && fast == 3) {
+        if constexpr (SS) traverse_fast(IntC<12>{}, IntC<1>{}, l, first, last_effect, buf, mt, inv_s);
+      }
       else
         traverse_generic(l, first, last_effect, buf, mt, inv_s);
     };

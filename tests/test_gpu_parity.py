@@ -227,3 +227,26 @@ def test_phased_schedule_matches_single_phase_and_reruns(engine_lib, golden_syn)
             assert a.n_iter == c.n_iter
             np.testing.assert_allclose(a.elbo[1:], c.elbo[1:], rtol=1e-9)
             np.testing.assert_allclose(a.alpha, c.alpha, atol=1e-8)
+
+
+def test_summary_level_large_crop_fp32_storage(engine_lib):
+    """Config 4 crop: k=3, p=2000 AR(1) LD stored fp32 (fp64 arithmetic), co-operative team over
+    many blocks; compared with the fp64 oracle fed the same fp32-rounded LD."""
+    import sys, os
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "scripts"))
+    import bench_ss
+    import sushie_b200
+    from sushie_b200 import config
+    from oracle import ibss
+
+    lds, ns, zs, causal = bench_ss.make_locus(2000, np.float32)
+    old_p, old_t = config.precision, config.team_size
+    config.precision, config.team_size = 32, 40
+    try:
+        res = sushie_b200.infer_sushie_ss(lds, ns, zs, L=10, max_iter=6, min_tol=0.0)
+    finally:
+        config.precision, config.team_size = old_p, old_t
+    ref = ibss.fit_summary([ld.astype(np.float64) for ld in lds], ns, zs, L=10, max_iter=6, min_tol=0.0)
+    assert len(res.elbo) == len(ref.elbo) == 7
+    np.testing.assert_allclose(res.elbo[1:], ref.elbo[1:], rtol=1e-6)
+    assert np.max(np.abs(res.pip_all - ibss.make_pip(ref.posteriors.alpha))) <= 1e-4
