@@ -19,6 +19,8 @@ SB_CENTER, SB_SCALE = 1, 2
 SB_FLAG_SINGLE_PHASE = 1
 
 _LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_lib", "libsushie_b200.so")
+# development: A/B a differently built engine without touching the tree
+_LIB_PATH = os.environ.get("SUSHIE_B200_LIB", _LIB_PATH)
 
 EXPORTED_SYMBOLS = (
     "sb_version",

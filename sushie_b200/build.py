@@ -41,7 +41,9 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not force and up_to_date():
         return OUT
     os.makedirs(os.path.dirname(OUT), exist_ok=True)
-    cmd = [find_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT] + SRC
+    dev = os.environ.get("SUSHIE_B200_ONLY_K")  # development: compile one ancestry count only
+    extra = [f"-DSB_ONLY_K={int(dev)}"] if dev else []
+    cmd = [find_nvcc()] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT] + SRC
     proc = subprocess.run(cmd, capture_output=True, text=True)
     if proc.returncode != 0:
         raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + proc.stdout + proc.stderr)

@@ -104,10 +104,14 @@ static const void* pick_kernel(int K, int storage, bool ss) {
     return ss ? (f32 ? kfn<KK, float, true>() : kfn<KK, double, true>())                      \
               : (f32 ? kfn<KK, float, false>() : kfn<KK, double, false>());
   switch (K) {
+#ifdef SB_ONLY_K  // development builds: instantiate a single ancestry count
+    SB_PICK(SB_ONLY_K)
+#else
     SB_PICK(1)
     SB_PICK(2)
     SB_PICK(3)
     SB_PICK(4)
+#endif
   }
 #undef SB_PICK
   return nullptr;
@@ -216,12 +220,14 @@ static bool plan_geometry(int p, int n_max, int es, bool ss, int smem_budget, Ge
       gr = 1;
     }
     if (g.fast) {
-      const int rows_fit = static_cast<int>((smem_budget - hdr) / row_bytes);
+      // summary level: partial row sums of a chunk are parked behind the ring
+      const size_t park = ss ? sizeof(double) * sb::SS_CHUNK_ROWS * sb::NW : 0;
+      const int rows_fit = static_cast<int>((smem_budget - hdr - park) / row_bytes);
       if (rows_fit >= 2 * gr) {
         g.G = gr;
         g.NS = std::min(sb::NSTAGE_MAX, rows_fit / gr);
         g.NSEG = 1;
-        g.smem = hdr + static_cast<size_t>(g.NS) * g.G * row_bytes;
+        g.smem = hdr + static_cast<size_t>(g.NS) * g.G * row_bytes + park;
         return true;
       }
       g.fast = 0;
@@ -279,7 +285,7 @@ struct Bump {
 };
 
 struct ProbLayout {  // offsets inside the arena
-  size_t X[KMAX], y, logpi, pi_raw, xtx, ecov0, rv0, adjt, adjp, r, xb, xty, rfull, out[2], elbo, meta, z;
+  size_t X[KMAX], y, logpi, pi_raw, xtx, ecov0, rv0, adjt, adjp, r, xb, xty, rfull, bvec, out[2], elbo, meta, z;
   size_t out_fields[2][10];
 };
 
@@ -482,6 +488,7 @@ static int batch_create(sb_ctx* ctx, const std::vector<GenericProblem>& gp, bool
     l.xb = bump.take(sizeof(double) * nrows * g.L);
     l.xty = ss ? 0 : bump.take(sizeof(double) * Kp);
     l.rfull = ss ? bump.take(sizeof(double) * nrows) : 0;
+    l.bvec = bump.take(sizeof(double) * g.L * Kp);
     Kp_max = std::max(Kp_max, Kp);
     L_max = std::max(L_max, g.L);
     for (int q = 0; q < 2; ++q) {
@@ -583,6 +590,8 @@ static int batch_create(sb_ctx* ctx, const std::vector<GenericProblem>& gp, bool
     d.xb = reinterpret_cast<double*>(A + l.xb);
     d.xty = ss ? nullptr : reinterpret_cast<double*>(A + l.xty);
     d.rfull = ss ? reinterpret_cast<double*>(A + l.rfull) : nullptr;
+    d.bvec = reinterpret_cast<double*>(A + l.bvec);
+    SB_CUDA_B(cudaMemsetAsync(A + l.bvec, 0, sizeof(double) * g.L * g.K * ge.p_pad, st));  // pad columns stay 0
     for (int q = 0; q < 2; ++q) {
       OutBuf& o = d.out[q];
       const size_t* f = l.out_fields[q];
@@ -828,8 +837,7 @@ extern "C" int sb_batch_run(sb_ctx* ctx, sb_batch* b, sb_run_stats* stats) {
     std::vector<int> ids(b->ids_host.begin() + g0, b->ids_host.begin() + g1);
     int C = b->team_size;
     int hw = b->hw_cluster;
-    bool first_phase = true;
-    while (!ids.empty()) {
+      while (!ids.empty()) {
       // (re)upload the id list of this phase: a previous run leaves the last phase's list behind
       SB_CUDA(cudaMemcpyAsync(b->d_ids + g0, ids.data(), sizeof(int) * ids.size(), cudaMemcpyHostToDevice, st));
       cudaLaunchConfig_t cfg{};
@@ -903,7 +911,6 @@ extern "C" int sb_batch_run(sb_ctx* ctx, sb_batch* b, sb_run_stats* stats) {
       SB_CUDA(cudaLaunchKernelExC(&cfg, fn, args));
       ++launches;
       ++phases;
-      first_phase = false;
       if (!lp.allow_drain) break;  // final phase: everything runs to completion
       // which loci were suspended?
       SB_CUDA(cudaMemcpyAsync(meta.data(), b->arena + b->metas_off, sizeof(int) * 8 * b->n_probs,

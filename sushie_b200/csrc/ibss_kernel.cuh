@@ -37,7 +37,8 @@ constexpr int KMAX = 4;
 constexpr int NT = 256;  // threads per block
 constexpr int NW = NT / 32;
 constexpr int GMAX = 32;  // max rows per band
-constexpr int NSTAGE_MAX = 4;
+constexpr int NSTAGE_MAX = 6;
+constexpr int SS_CHUNK_ROWS = 256;  // summary-level register-tile path: rows whose partial sums are parked in shared memory
 constexpr int NSYM_MAX = KMAX * (KMAX + 1) / 2;
 constexpr int STAT_STRIDE = 20;  // doubles per team-reduction record (>= 2 + NSYM_MAX + 2 + KMAX)
 constexpr int TRAV_STRIDE = 2 * KMAX;
@@ -78,6 +79,7 @@ struct ProbDev {
   double* xb;     // [L][nrows] cached X b_l  (summary level: XtX b_l)
   double* xty;    // [K][p_pad] reduced X^T r                    (individual level)
   double* rfull;  // [nrows] full residual at iteration end      (summary level)
+  double* bvec;   // [L][K][p_pad] posterior-mean effects b_l = alpha_l * mu_l of the current iteration (pad = 0)
   OutBuf out[2];
   double* elbo;   // [max_iter + 1]
   int* meta;      // [0]=n_iter [1]=elbo_increase [2]=final buffer (-1: initial state) [3]=n_ser
@@ -117,6 +119,9 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
                : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t done;
@@ -194,11 +199,20 @@ struct Vec<double> {
     o[0] = t.x;
     o[1] = t.y;
   }
+  __device__ static __forceinline__ void load_raw(const double* base, int v, double (&o)[2]) { load(base, v, o); }
 };
 template <>
 struct Vec<float> {
   static constexpr int W = 4;
   __device__ static __forceinline__ void load(const float* base, int v, double (&o)[4]) {
+    const float4 t = reinterpret_cast<const float4*>(base)[v];
+    o[0] = t.x;
+    o[1] = t.y;
+    o[2] = t.z;
+    o[3] = t.w;
+  }
+  // storage-typed copy: the register tile keeps fp32 genotypes as fp32 and widens at the FMA
+  __device__ static __forceinline__ void load_raw(const float* base, int v, float (&o)[4]) {
     const float4 t = reinterpret_cast<const float4*>(base)[v];
     o[0] = t.x;
     o[1] = t.y;
@@ -220,7 +234,8 @@ __device__ __forceinline__ double warp_max(double v) {
 
 // Shared-memory header (fixed part of the dynamic allocation).
 struct SmemHdr {
-  uint64_t mbar[NSTAGE_MAX];
+  uint64_t mbar[NSTAGE_MAX];  // "stage filled" (bulk-copy completion)
+  uint64_t ebar[NSTAGE_MAX];  // "stage drained" (one arrival per warp; summary-level register-tile path)
   ProbDev pb;                // the locus being processed
   alignas(16) double partsum[2][GMAX];  // sweep-1 partial dot products [band parity][g * nseg + seg]
   double rn[GMAX];           // next residual of the band's rows
@@ -228,6 +243,7 @@ struct SmemHdr {
   double tot[STAT_STRIDE];   // block / team totals
   double cst[2 * KMAX * KMAX + 8];  // Cinv, misc per-pass constants
   double trow[GMAX][2];      // per-row scalars of a traversal
+  double rstate[2][8];       // register-tile traversal: (r, xb_next) of the band's rows, fetched one band ahead
   int decision;
   int pad_[3];
 };
@@ -399,13 +415,17 @@ __global__ void __launch_bounds__(NT, 1) ibss_kernel(const LaunchParams P) {
   team.bar = P.team_bar + static_cast<size_t>(team.id) * 64;
 
   if (tid == 0) {
-    for (int s = 0; s < NSTAGE_MAX; ++s) mbar_init(&H->mbar[s], 1);
+    for (int s = 0; s < NSTAGE_MAX; ++s) {
+      mbar_init(&H->mbar[s], 1);
+      mbar_init(&H->ebar[s], NW);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
   __syncthreads();
 
-  uint32_t phase_bits = 0;  // bit s = mbarrier parity of the next fill to consume in stage s
+  uint32_t phase_bits = 0;   // bit s = mbarrier parity of the next fill to consume in stage s
+  uint32_t ephase_bits = 0;  // bit s = parity of the next "drained" phase of stage s (producer thread only)
 
   for (;;) {
     // ---- pull the next locus from the device queue
@@ -508,13 +528,10 @@ __global__ void __launch_bounds__(NT, 1) ibss_kernel(const LaunchParams P) {
       }
     }
 
-    // b_l[j] for ancestry k from the un-normalised rows of pass B (alpha slot holds the log
-    // weights, pm the per-SNP posterior means): b = softmax(w)_j * mu_jk  (infer.py:721-723)
-    auto effect_b = [&](const OutBuf& ob, int l, int k, int j, double mt, double inv_s) -> double {
-      if (j >= p) return 0.0;
-      const size_t lj = static_cast<size_t>(l) * p + j;
-      const double w = __ldcg(&ob.alpha[lj]);
-      return exp(w - mt) * inv_s * __ldcg(&ob.pm[lj * K + k]);
+    // b_l = softmax(w) * mu (infer.py:721-723) is materialised once per single-effect update by the
+    // team (end of posterior()); the traversals read it back with coalesced loads.
+    auto effect_vec = [&](int l, int k) -> const double* {
+      return pb.bvec + (static_cast<size_t>(l) * K + k) * p_pad;
     };
 
     // per-traversal scalars: fixed-order serial sum over the designated threads
@@ -559,18 +576,16 @@ __global__ void __launch_bounds__(NT, 1) ibss_kernel(const LaunchParams P) {
     // Register-tile variant: every thread owns CPT 16-byte column vectors and keeps them for
     // all GR rows of the band in registers, so the band is read from shared memory once and
     // both sweeps run from registers; b and the X^T r accumulators live in registers too.
-    auto traverse_fast = [&](auto cpt_c, auto gr_c, int l, bool first, bool last_effect, int buf, double mt,
-                             double inv_s) {
+    auto traverse_fast = [&](auto cpt_c, auto gr_c, int l, bool first, bool last_effect) {
       constexpr int CPT = decltype(cpt_c)::value;
       constexpr int GR = decltype(gr_c)::value;
       constexpr int PRODUCER_TID = NT - 32;  // lane 0 of the last warp issues the bulk copies
-      const OutBuf& ob = pb.out[buf];
       const int lnext = first ? 0 : ((l + 1 == L) ? 0 : l + 1);
       double vsq[K], rsq[K];  // meaningful in threads < GR only
 #pragma unroll
       for (int k = 0; k < K; ++k) vsq[k] = rsq[k] = 0.0;
       double bq[CPT][VW], aq[CPT][VW];
-      double x[GR][CPT][VW];  // the band slice of this thread; columns past the row end stay 0
+      XT x[GR][CPT][VW];  // the band slice of this thread (storage type); columns past the row end stay 0
       uint32_t vmask = 0;     // bit c: this thread owns a c-th column vector
 #pragma unroll
       for (int c = 0; c < CPT; ++c) {
@@ -579,11 +594,22 @@ __global__ void __launch_bounds__(NT, 1) ibss_kernel(const LaunchParams P) {
         for (int u = 0; u < VW; ++u) {
           bq[c][u] = aq[c][u] = 0.0;
 #pragma unroll
-          for (int g = 0; g < GR; ++g) x[g][c][u] = 0.0;
+          for (int g = 0; g < GR; ++g) x[g][c][u] = XT(0);
         }
       }
       int cur_k = -1;
       int st = cons_seq % NS;
+      // row state of band `pos` for thread t < 2*GR: t < GR -> r[row g], else xb[lnext][row g]
+      auto fetch_state = [&](int pos) -> double {
+        int k, g0, rows;
+        band_of(pos, k, g0, rows);
+        const int g = tid % GR;
+        if (g >= rows) return 0.0;
+        const int row = pb.row0[k] + g0 + g;
+        return (tid < GR) ? pb.r[row] : pb.xb[static_cast<size_t>(lnext) * nrows + row];
+      };
+      double pre = 0.0;
+      if (tid < 2 * GR && nb_own > 0) pre = fetch_state(0);
 
       auto flush_acc = [&](int k) {
         double* dst = my_scr + static_cast<size_t>(k) * p_pad;
@@ -603,13 +629,17 @@ __global__ void __launch_bounds__(NT, 1) ibss_kernel(const LaunchParams P) {
         band_of(pos, k, g0, rows);
         if (k != cur_k) {
           if (!SS && cur_k >= 0) flush_acc(cur_k);
+          const double* bl = effect_vec(l, k);
 #pragma unroll
           for (int c = 0; c < CPT; ++c) {
             const int v = tid + c * NT;
+            const bool on = !first && (vmask & (1u << c));
 #pragma unroll
-            for (int u = 0; u < VW; ++u) {
-              aq[c][u] = 0.0;
-              bq[c][u] = (first || !(vmask & (1u << c))) ? 0.0 : effect_b(ob, l, k, v * VW + u, mt, inv_s);
+            for (int u = 0; u < VW; u += 2) {
+              const double2 t2 = on ? __ldcg(reinterpret_cast<const double2*>(bl + v * VW + u)) : make_double2(0.0, 0.0);
+              aq[c][u] = aq[c][u + 1] = 0.0;
+              bq[c][u] = t2.x;
+              bq[c][u + 1] = t2.y;
             }
           }
           cur_k = k;
@@ -619,16 +649,8 @@ __global__ void __launch_bounds__(NT, 1) ibss_kernel(const LaunchParams P) {
         const double nsc = pb.nscale[k];
         const bool full_rows = (rows == GR);
 
-        // per-row state (same addresses for every thread: broadcast loads), in flight while the band lands
-        double r_old[GR], xb_next[GR];
-        const double* rp = pb.r + row_base;
-        const double* xp = pb.xb + static_cast<size_t>(lnext) * nrows + row_base;
-#pragma unroll
-        for (int g = 0; g < GR; ++g) {
-          const bool ok = full_rows || g < rows;
-          r_old[g] = ok ? rp[g] : 0.0;
-          xb_next[g] = ok ? xp[g] : 0.0;
-        }
+        // per-row state (r, xb[lnext]) was fetched one band ahead by threads 0..2*GR-1: publish it
+        if (tid < 2 * GR) H->rstate[pos & 1][tid] = pre;
         mbar_wait(&H->mbar[st], (phase_bits >> st) & 1u);
 
         // the band -> registers (the only shared-memory read of the genotypes)
@@ -637,17 +659,17 @@ __global__ void __launch_bounds__(NT, 1) ibss_kernel(const LaunchParams P) {
           for (int g = 0; g < GR; ++g)
 #pragma unroll
             for (int c = 0; c < CPT; ++c)
-              if (vmask & (1u << c)) Vec<XT>::load(tile + static_cast<size_t>(g) * p_pad, tid + c * NT, x[g][c]);
+              if (vmask & (1u << c)) Vec<XT>::load_raw(tile + static_cast<size_t>(g) * p_pad, tid + c * NT, x[g][c]);
         } else {
 #pragma unroll
           for (int g = 0; g < GR; ++g)
 #pragma unroll
             for (int c = 0; c < CPT; ++c) {
               if (g < rows) {
-                if (vmask & (1u << c)) Vec<XT>::load(tile + static_cast<size_t>(g) * p_pad, tid + c * NT, x[g][c]);
+                if (vmask & (1u << c)) Vec<XT>::load_raw(tile + static_cast<size_t>(g) * p_pad, tid + c * NT, x[g][c]);
               } else {
 #pragma unroll
-                for (int u = 0; u < VW; ++u) x[g][c][u] = 0.0;
+                for (int u = 0; u < VW; ++u) x[g][c][u] = XT(0);
               }
             }
         }
@@ -663,8 +685,8 @@ __global__ void __launch_bounds__(NT, 1) ibss_kernel(const LaunchParams P) {
             for (int c = 0; c < CPT; ++c)
 #pragma unroll
               for (int u = 0; u < VW; u += 2) {
-                s0 = fma(x[g][c][u], bq[c][u], s0);
-                s1 = fma(x[g][c][u + 1], bq[c][u + 1], s1);
+                s0 = fma(static_cast<double>(x[g][c][u]), bq[c][u], s0);
+                s1 = fma(static_cast<double>(x[g][c][u + 1]), bq[c][u + 1], s1);
               }
             ps[g] = s0 + s1;
           }
@@ -702,8 +724,15 @@ __global__ void __launch_bounds__(NT, 1) ibss_kernel(const LaunchParams P) {
           issue_fill(prod_pos, st);
           prod_pos = (prod_pos + 1 == nb_own) ? 0 : prod_pos + 1;
         }
+        if (tid < 2 * GR && pos + 1 < nb_own) pre = fetch_state(pos + 1);  // lands during the rest of this band
         // every thread finishes the row sums itself (no second barrier); fixed pairwise order
         double rn[GR];
+        double r_old[GR], xb_next[GR];
+#pragma unroll
+        for (int g = 0; g < GR; ++g) {
+          r_old[g] = H->rstate[pos & 1][g];
+          xb_next[g] = H->rstate[pos & 1][GR + g];
+        }
 #pragma unroll
         for (int g = 0; g < GR; ++g) {
           double v = 0.0;
@@ -721,7 +750,7 @@ __global__ void __launch_bounds__(NT, 1) ibss_kernel(const LaunchParams P) {
             pb.r[row] = rn[g];
             double vterm = v * v;  // |X b_l|^2 (infer.py:806)
             if (SS) {
-              vterm = effect_b(ob, l, k, g0 + g, mt, inv_s) * v;  // b_l^T XtX b_l (infer_ss.py:572)
+              vterm = __ldcg(&effect_vec(l, k)[g0 + g]) * v;  // b_l^T XtX b_l (infer_ss.py:572)
               if (last_effect) pb.rfull[row] = Rfull;
             }
 #pragma unroll
@@ -739,7 +768,7 @@ __global__ void __launch_bounds__(NT, 1) ibss_kernel(const LaunchParams P) {
 #pragma unroll
             for (int c = 0; c < CPT; ++c)
 #pragma unroll
-              for (int u = 0; u < VW; ++u) aq[c][u] = fma(x[g][c][u], rn[g], aq[c][u]);
+              for (int u = 0; u < VW; ++u) aq[c][u] = fma(static_cast<double>(x[g][c][u]), rn[g], aq[c][u]);
         }
         phase_bits ^= (1u << st);
         cons_seq += 1;
@@ -752,10 +781,165 @@ __global__ void __launch_bounds__(NT, 1) ibss_kernel(const LaunchParams P) {
       store_trav(l, first, vsq, rsq);
     };
 
+    // Summary-level register-tile variant: rows are LD rows, there is no X^T r sweep, so a warp
+    // never needs another warp's result while it streams.  Every thread keeps its CPT column
+    // vectors of b in registers, takes its slice of each row straight from the shared-memory
+    // band, and the per-warp partial dot products of up to SS_CHUNK_ROWS rows are parked in
+    // shared memory.  Warps run free of block-wide barriers; a stage is handed back to the
+    // bulk-copy producer through a "drained" mbarrier (one arrival per warp).  Once per chunk
+    // the block finishes the rows in parallel (row sums in fixed order, residual update,
+    // cached XtX b_l, ERSS terms).
+    auto traverse_ss = [&](auto cpt_c, auto gr_c, int l, bool last_effect) {
+      constexpr int CPT = decltype(cpt_c)::value;
+      constexpr int GR = decltype(gr_c)::value;
+      constexpr int PRODUCER_TID = NT - 32;
+      constexpr int CHUNK_BANDS = SS_CHUNK_ROWS / GR;
+      static_assert(SS_CHUNK_ROWS <= NT, "one finishing thread per parked row");
+      const int lnext = (l + 1 == L) ? 0 : l + 1;
+      double* psum = reinterpret_cast<double*>(ring + static_cast<size_t>(NS) * stage_bytes);  // [rows][NW]
+      double tv[2 * K];  // per-thread ERSS terms: b_l^T XtX b_l, |full residual|^2 per ancestry
+#pragma unroll
+      for (int i = 0; i < 2 * K; ++i) tv[i] = 0.0;
+      double bq[CPT][VW];
+      uint32_t vmask = 0;
+#pragma unroll
+      for (int c = 0; c < CPT; ++c) {
+        if (tid + c * NT < pv) vmask |= (1u << c);
+#pragma unroll
+        for (int u = 0; u < VW; ++u) bq[c][u] = 0.0;
+      }
+      int cur_k = -1;
+      int st = cons_seq % NS;
+
+      for (int pos0 = 0; pos0 < nb_own; pos0 += CHUNK_BANDS) {
+        const int pos1 = min(nb_own, pos0 + CHUNK_BANDS);
+        for (int pos = pos0; pos < pos1; ++pos) {
+          int k, g0, rows;
+          band_of(pos, k, g0, rows);
+          if (k != cur_k) {
+            const double* bl = effect_vec(l, k);
+#pragma unroll
+            for (int c = 0; c < CPT; ++c) {
+              const int v = tid + c * NT;
+              const bool on = vmask & (1u << c);
+#pragma unroll
+              for (int u = 0; u < VW; u += 2) {
+                const double2 t2 = on ? __ldcg(reinterpret_cast<const double2*>(bl + v * VW + u)) : make_double2(0.0, 0.0);
+                bq[c][u] = t2.x;
+                bq[c][u + 1] = t2.y;
+              }
+            }
+            cur_k = k;
+          }
+          const XT* tile = reinterpret_cast<const XT*>(ring + static_cast<size_t>(st) * stage_bytes);
+          mbar_wait(&H->mbar[st], (phase_bits >> st) & 1u);
+          // rows past the end of a short band hold stale (finite or not) data: their sums are never read
+          double ps[GR];
+#pragma unroll
+          for (int g = 0; g < GR; ++g) {
+            double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+#pragma unroll
+            for (int c = 0; c < CPT; ++c) {
+              if (vmask & (1u << c)) {
+                double x[VW];
+                Vec<XT>::load(tile + static_cast<size_t>(g) * p_pad, tid + c * NT, x);
+                if constexpr (VW == 4) {
+                  s0 = fma(x[0], bq[c][0], s0);
+                  s1 = fma(x[1], bq[c][1], s1);
+                  s2 = fma(x[2], bq[c][2], s2);
+                  s3 = fma(x[3], bq[c][3], s3);
+                } else {
+                  if (c & 1) {
+                    s2 = fma(x[0], bq[c][0], s2);
+                    s3 = fma(x[1], bq[c][1], s3);
+                  } else {
+                    s0 = fma(x[0], bq[c][0], s0);
+                    s1 = fma(x[1], bq[c][1], s1);
+                  }
+                }
+              }
+            }
+            ps[g] = (s0 + s1) + (s2 + s3);
+          }
+          double t;
+          if constexpr (GR == 4) {
+            const bool hi = lane & 16;
+            double k0 = hi ? ps[2] : ps[0], k1 = hi ? ps[3] : ps[1];
+            const double q0 = hi ? ps[0] : ps[2], q1 = hi ? ps[1] : ps[3];
+            k0 += __shfl_xor_sync(0xffffffffu, q0, 16);
+            k1 += __shfl_xor_sync(0xffffffffu, q1, 16);
+            const bool hi2 = lane & 8;
+            t = hi2 ? k1 : k0;
+            const double q = hi2 ? k0 : k1;
+            t += __shfl_xor_sync(0xffffffffu, q, 8);
+            t += __shfl_xor_sync(0xffffffffu, t, 4);
+            t += __shfl_xor_sync(0xffffffffu, t, 2);
+            t += __shfl_xor_sync(0xffffffffu, t, 1);
+          } else if constexpr (GR == 2) {
+            const bool hi = lane & 16;
+            t = hi ? ps[1] : ps[0];
+            const double q = hi ? ps[0] : ps[1];
+            t += __shfl_xor_sync(0xffffffffu, q, 16);
+            t += __shfl_xor_sync(0xffffffffu, t, 8);
+            t += __shfl_xor_sync(0xffffffffu, t, 4);
+            t += __shfl_xor_sync(0xffffffffu, t, 2);
+            t += __shfl_xor_sync(0xffffffffu, t, 1);
+          } else {
+            t = warp_sum(ps[0]);
+          }
+          // the shuffles above are a warp-wide convergence point: every lane has finished reading the stage
+          if ((lane & (32 / GR - 1)) == 0) psum[((pos - pos0) * GR + lane / (32 / GR)) * NW + warp] = t;
+          if (lane == 0) mbar_arrive(&H->ebar[st]);
+          if (tid == PRODUCER_TID) {  // refill the stage as soon as all warps have drained it
+            mbar_wait(&H->ebar[st], (ephase_bits >> st) & 1u);
+            ephase_bits ^= (1u << st);
+            issue_fill(prod_pos, st);
+            prod_pos = (prod_pos + 1 == nb_own) ? 0 : prod_pos + 1;
+          }
+          phase_bits ^= (1u << st);
+          cons_seq += 1;
+          st = (st + 1 == NS) ? 0 : st + 1;
+        }
+        __syncthreads();  // partial sums of the chunk visible
+        {
+          const int pos = pos0 + tid / GR, g = tid % GR;
+          if (tid < SS_CHUNK_ROWS && pos < pos1) {
+            int k, g0, rows;
+            band_of(pos, k, g0, rows);
+            if (g < rows) {
+              const int row = pb.row0[k] + g0 + g;
+              const double2* ps2 = reinterpret_cast<const double2*>(&psum[tid * NW]);
+              static_assert(NW == 8, "pairwise tree below assumes 8 warps");
+              const double2 q0 = ps2[0], q1 = ps2[1], q2 = ps2[2], q3 = ps2[3];
+              const double v = (((q0.x + q0.y) + (q1.x + q1.y)) + ((q2.x + q2.y) + (q3.x + q3.y))) * pb.nscale[k];
+              const double Rfull = pb.r[row] - v;
+              pb.r[row] = Rfull + pb.xb[static_cast<size_t>(lnext) * nrows + row];
+              pb.xb[static_cast<size_t>(l) * nrows + row] = v;
+              if (last_effect) pb.rfull[row] = Rfull;
+              const double vterm = __ldcg(&effect_vec(l, k)[g0 + g]) * v;  // b_l^T XtX b_l (infer_ss.py:572)
+#pragma unroll
+              for (int kk = 0; kk < K; ++kk)
+                if (kk == k) {
+                  tv[kk] += vterm;
+                  tv[K + kk] += Rfull * Rfull;
+                }
+            }
+          }
+        }
+        __syncthreads();  // the parking area is reused by the next chunk
+      }
+      block_sum<2 * K>(H, tv);
+      if (tid < K) {
+        double* dst = my_scr + P.off_trav + l * TRAV_STRIDE;
+        __stcg(&dst[tid], H->tot[tid]);
+        __stcg(&dst[KMAX + tid], H->tot[K + tid]);
+      }
+      __syncthreads();
+    };
+
     // Generic variant (any p that fits, any G <= GMAX): b and the accumulators in shared memory,
     // two sweeps over the shared-memory band separated by a barrier.
-    auto traverse_generic = [&](int l, bool first, bool last_effect, int buf, double mt, double inv_s) {
-      const OutBuf& ob = pb.out[buf];
+    auto traverse_generic = [&](int l, bool first, bool last_effect) {
       const int lnext = first ? 0 : ((l + 1 == L) ? 0 : l + 1);
       double vsq[K], rsq[K];  // meaningful in threads < G only
 #pragma unroll
@@ -774,7 +958,7 @@ __global__ void __launch_bounds__(NT, 1) ibss_kernel(const LaunchParams P) {
             for (int j = tid; j < p_pad; j += NT) __stcg(&dst[j], acc[j]);
           }
           if (!first)
-            for (int j = tid; j < p_pad; j += NT) bsm[j] = effect_b(ob, l, k, j, mt, inv_s);
+            for (int j = tid; j < p_pad; j += NT) bsm[j] = __ldcg(&effect_vec(l, k)[j]);
           if (!SS)
             for (int j = tid; j < p_pad; j += NT) acc[j] = 0.0;
           cur_k = k;
@@ -892,44 +1076,57 @@ __global__ void __launch_bounds__(NT, 1) ibss_kernel(const LaunchParams P) {
       store_trav(l, first, vsq, rsq);
     };
 
-    auto traverse = [&](int l, bool first, bool last_effect, int buf, double mt, double inv_s) {
-      if (fast == 1)
-        traverse_fast(IntC<4>{}, IntC<4>{}, l, first, last_effect, buf, mt, inv_s);
-      else if (fast == 2)
-        traverse_fast(IntC<8>{}, IntC<2>{}, l, first, last_effect, buf, mt, inv_s);
-      else if (SS && fast == 3) {
-        if constexpr (SS) traverse_fast(IntC<12>{}, IntC<1>{}, l, first, last_effect, buf, mt, inv_s);
+    auto traverse = [&](int l, bool first, bool last_effect) {
+      if constexpr (SS) {
+        if (fast == 1)
+          traverse_ss(IntC<4>{}, IntC<4>{}, l, last_effect);
+        else if (fast == 2)
+          traverse_ss(IntC<8>{}, IntC<2>{}, l, last_effect);
+        else if (fast == 3)
+          traverse_ss(IntC<12>{}, IntC<1>{}, l, last_effect);
+        else
+          traverse_generic(l, first, last_effect);
+      } else {
+        if (fast == 1)
+          traverse_fast(IntC<4>{}, IntC<4>{}, l, first, last_effect);
+        else if (fast == 2)
+          traverse_fast(IntC<8>{}, IntC<2>{}, l, first, last_effect);
+        else
+          traverse_generic(l, first, last_effect);
       }
-      else
-        traverse_generic(l, first, last_effect, buf, mt, inv_s);
     };
 
     // ------------------------------------------------------------------------------
     // team combine of per-block (max, scaled sums) records written to `stat`:
     // rec[0] = m, rec[1..nv] = sums scaled by exp(-m).  Result in H->tot[0..nv] (tot[0] = m).
-    auto team_combine = [&](int which, int nv) {
-      // every block holds its own record in H->tot already (tot[0]=m, tot[1..nv])
+    auto team_combine = [&](int which, auto nv_c) {
+      constexpr int NV = decltype(nv_c)::value;
+      // every block holds its own record in H->tot already (tot[0]=m, tot[1..NV])
       if (C == 1) return;
       const int so = P.off_stat + which * STAT_STRIDE;
-      if (tid <= nv) __stcg(&my_scr[so + tid], H->tot[tid]);
+      if (tid <= NV) __stcg(&my_scr[so + tid], H->tot[tid]);
       team_sync(team);
-      if (warp == 0) {
-        double m = -CUDART_INF;
-        for (int c = lane; c < C; c += 32) m = fmax(m, __ldcg(&scr(c)[so]));
-        m = warp_max(m);
+      // one thread per team member (C <= NT): all records are fetched in one round trip
+      double mc = -CUDART_INF, v[NV];
+#pragma unroll
+      for (int i = 0; i < NV; ++i) v[i] = 0.0;
+      if (tid < C) {
+        const double* rec = scr(tid) + so;
+        mc = __ldcg(rec);
+#pragma unroll
+        for (int i = 0; i < NV; ++i) v[i] = __ldcg(rec + 1 + i);
+      }
+      const double m = block_max(H, mc);
+      if (tid < C) {
         // NaN anywhere must poison the result like the reference's softmax would
-        for (int i = 1; i <= nv; ++i) {
-          double s = 0.0;
-          for (int c = lane; c < C; c += 32) {
-            const double mc = __ldcg(&scr(c)[so]);
-            const double vc = __ldcg(&scr(c)[so + i]);
-            const double sc = (mc == -CUDART_INF) ? 0.0 : exp(mc - m);
-            s += (mc != mc) ? mc : vc * sc;
-          }
-          s = warp_sum(s);
-          if (lane == 0) H->tot[i] = s;
-        }
-        if (lane == 0) H->tot[0] = m;
+        const double sc = (mc == -CUDART_INF) ? 0.0 : exp(mc - m);
+#pragma unroll
+        for (int i = 0; i < NV; ++i) v[i] = (mc != mc) ? mc : v[i] * sc;
+      }
+      block_sum<NV>(H, v);
+      if (tid == 0) {
+        for (int i = NV - 1; i >= 0; --i) H->tot[i + 1] = H->tot[i];
+        H->tot[0] = m;
       }
       __syncthreads();
     };
@@ -1055,7 +1252,7 @@ __global__ void __launch_bounds__(NT, 1) ibss_kernel(const LaunchParams P) {
           H->tot[0] = mb;
         }
         __syncthreads();
-        team_combine(0, 1 + NSYM);
+        team_combine(0, IntC<1 + NSYM>{});
         const double ssum = H->tot[1];
         int t = 2;
 #pragma unroll
@@ -1150,7 +1347,7 @@ __global__ void __launch_bounds__(NT, 1) ibss_kernel(const LaunchParams P) {
           H->tot[0] = mb;
         }
         __syncthreads();
-        team_combine(1, NVB);
+        team_combine(1, IntC<NVB>{});
       }
       // per-effect scalars (one writer)
       {
@@ -1172,6 +1369,15 @@ __global__ void __launch_bounds__(NT, 1) ibss_kernel(const LaunchParams P) {
           __stcg(&ob.lse[2 * l], mt);
           __stcg(&ob.lse[2 * l + 1], ssum);
         }
+        // b_l = softmax(w) * mu for the own SNP slice (infer.py:721-723), read back by the traversal
+        const double inv_s = 1.0 / ssum;
+        double* bl = pb.bvec + static_cast<size_t>(l) * K * p_pad;
+        for (int j = js + tid; j < je; j += NT) {
+          const size_t lj = static_cast<size_t>(l) * p + j;
+          const double e = exp(__ldcg(&ob.alpha[lj]) - mt) * inv_s;
+#pragma unroll
+          for (int k = 0; k < K; ++k) __stcg(&bl[static_cast<size_t>(k) * p_pad + j], e * __ldcg(&ob.pm[lj * K + k]));
+        }
       }
     };
 
@@ -1181,7 +1387,7 @@ __global__ void __launch_bounds__(NT, 1) ibss_kernel(const LaunchParams P) {
     double elbo_last = -CUDART_INF;
     bool suspended = false;
     if (status0 == 0) {
-      if (!SS) traverse(0, true, false, 0, 0.0, 0.0);  // X^T y for the first effect
+      if (!SS) traverse(0, true, false);  // X^T y for the first effect
       if (rank == 0 && tid == 0) pb.elbo[0] = -CUDART_INF;
     } else {
       // resume a locus suspended at an iteration boundary: everything lives in global memory
@@ -1197,8 +1403,8 @@ __global__ void __launch_bounds__(NT, 1) ibss_kernel(const LaunchParams P) {
       const int buf = it & 1;
       for (int l = 0; l < L; ++l) {
         posterior(l, it, status0 != 0 && it == it0 && l == 0);
-        const double mt = H->tot[0], inv_s = 1.0 / H->tot[1];
-        traverse(l, false, l + 1 == L, buf, mt, inv_s);
+        team_sync(team);  // b_l of every SNP slice visible to the whole team
+        traverse(l, false, l + 1 == L);
         team_sync(team);
         n_ser += 1;
       }
@@ -1215,8 +1421,7 @@ __global__ void __launch_bounds__(NT, 1) ibss_kernel(const LaunchParams P) {
 #pragma unroll
           for (int k = 0; k < K; ++k) {
             double eb = 0.0;
-            for (int l = 0; l < L; ++l)
-              eb += effect_b(ob, l, k, j, __ldcg(&ob.lse[2 * l]), 1.0 / __ldcg(&ob.lse[2 * l + 1]));
+            for (int l = 0; l < L; ++l) eb += __ldcg(&effect_vec(l, k)[j]);
             const double xty = pb.y[pb.row0[k] + j];
             tv[k] += eb * xty;                                         // E[b]^T Xty
             tv[K + k] += eb * (xty - __ldcg(&pb.rfull[pb.row0[k] + j]));  // E[b]^T XtX E[b]
@@ -1227,38 +1432,39 @@ __global__ void __launch_bounds__(NT, 1) ibss_kernel(const LaunchParams P) {
           const int so = P.off_stat + 2 * STAT_STRIDE;
           if (tid < 2 * K) __stcg(&my_scr[so + tid], H->tot[tid]);
           team_sync(team);
-          if (tid < 2 * K) {
-            double s = 0.0;
-            for (int c = 0; c < C; ++c) s += __ldcg(&scr(c)[so + tid]);
-            H->tot[tid] = s;
-          }
-          __syncthreads();
+#pragma unroll
+          for (int i = 0; i < 2 * K; ++i) tv[i] = (tid < C) ? __ldcg(&scr(tid)[so + i]) : 0.0;
+          block_sum<2 * K>(H, tv);
         }
       }
-      // per (l, k) traversal scalars summed over the team in fixed order
-      __syncthreads();
+      double ssv[2 * K];  // summary level: E[b]^T Xty, E[b]^T XtX E[b] per ancestry
+#pragma unroll
+      for (int i = 0; i < 2 * K; ++i) ssv[i] = SS ? H->tot[i] : 0.0;
+      // per (l, k) traversal scalars summed over the team: one thread per team member, fixed order
+      {
+        double tr[2 * K];
+#pragma unroll
+        for (int i = 0; i < 2 * K; ++i) tr[i] = 0.0;
+        if (tid < C) {
+          const double* rec = scr(tid) + P.off_trav;
+          for (int l = 0; l < L; ++l) {
+#pragma unroll
+            for (int k = 0; k < K; ++k) tr[k] += __ldcg(&rec[l * TRAV_STRIDE + k]);
+          }
+#pragma unroll
+          for (int k = 0; k < K; ++k) tr[K + k] = __ldcg(&rec[(L - 1) * TRAV_STRIDE + KMAX + k]);
+        }
+        block_sum<2 * K>(H, tr);
+      }
       if (tid < K) {
         const int k = tid;
+        double t5 = 0.0;  // sum_l sum_p XtX E[b_l^2]
+        for (int l = 0; l < L; ++l) t5 += __ldcg(&ob.xtxb2[l * K + k]);
         double e;
-        if (SS) {
-          double t4 = 0.0, t5 = 0.0;
-          for (int l = 0; l < L; ++l) {
-            for (int c = 0; c < C; ++c) t4 += __ldcg(&scr(c)[P.off_trav + l * TRAV_STRIDE + k]);
-            t5 += __ldcg(&ob.xtxb2[l * K + k]);
-          }
-          e = pb.nsamp[k] - 2.0 * H->tot[k] + H->tot[K + k] - t4 + t5;
-        } else {
-          double rs = 0.0;
-          for (int c = 0; c < C; ++c)
-            rs += __ldcg(&scr(c)[P.off_trav + (L - 1) * TRAV_STRIDE + KMAX + k]);
-          double t2 = 0.0;
-          for (int l = 0; l < L; ++l) {
-            double vs = 0.0;
-            for (int c = 0; c < C; ++c) vs += __ldcg(&scr(c)[P.off_trav + l * TRAV_STRIDE + k]);
-            t2 += __ldcg(&ob.xtxb2[l * K + k]) - vs;
-          }
-          e = rs + t2;
-        }
+        if (SS)
+          e = pb.nsamp[k] - 2.0 * ssv[k] + ssv[K + k] - H->tot[k] + t5;  // infer_ss.py:555-575
+        else
+          e = H->tot[K + k] + (t5 - H->tot[k]);  // infer.py:799-808
         erss_sm[k] = e;
       }
       __syncthreads();
