@@ -50,7 +50,8 @@ extern "C" {
 /* element types of genotype / LD inputs and of their device storage */
 #define SB_F64 0
 #define SB_F32 1
-#define SB_I8 2 /* input only: hard-call genotypes 0/1/2 */
+#define SB_I8 2 /* hard-call genotypes (int8). As sb_opts.storage (individual level, every problem x_dtype ==
+                  SB_I8, p <= 8192): raw bytes stay resident, centring/scaling is folded into the vectors */
 
 /* sb_opts.flags */
 #define SB_FLAG_SINGLE_PHASE 1 /* keep one team size for the whole batch (no suspend / regroup phases) */
@@ -101,7 +102,7 @@ typedef struct {
 typedef struct {
   int32_t max_iter;          /* reference default 500 */
   double min_tol;            /* reference default 1e-4 (CLI 1e-3) */
-  int32_t storage;           /* device storage of X / LD: SB_F64 (parity mode) or SB_F32 */
+  int32_t storage;           /* device storage of X / LD: SB_F64 (parity mode), SB_F32, or SB_I8 (see above) */
   int32_t team_size;         /* thread blocks cooperating on one locus in the first phase; 0 = choose */
   int32_t flags;             /* SB_FLAG_* */
   int32_t reserved[3];

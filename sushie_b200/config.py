@@ -8,6 +8,11 @@ from typing import List, Optional
 
 # 64 -> fp64 storage (parity mode, the reference CLI default); 32 -> fp32 storage.
 precision: int = int(os.environ.get("SUSHIE_B200_PRECISION", "64"))
+# Device storage of individual-level genotypes: "auto" keeps hard calls (integer-valued, int8 range,
+# not residualised on covariates) as one byte per entry and folds centring / scaling into the
+# vectors (8x less HBM traffic than fp64, same fp64 arithmetic); "dense" always stores the
+# standardised matrix at `precision`.
+genotype_storage: str = os.environ.get("SUSHIE_B200_GENO", "auto")
 # GPU ordinals used by the batch entry points; None = device 0 only.
 devices: Optional[List[int]] = None
 # thread blocks cooperating on one locus; 0 lets the engine choose.

@@ -45,6 +45,8 @@ struct HostProb {
   double bytes_per_ser = 0.0;  // algorithmic: one traversal of X / LD at storage precision
   std::vector<double> ecov0, rv0;
   void* d_X[KMAX] = {nullptr, nullptr, nullptr, nullptr};
+  const double* d_cmean[KMAX] = {nullptr, nullptr, nullptr, nullptr};  // hard-call storage: column means, 1/std
+  const double* d_cisd[KMAX] = {nullptr, nullptr, nullptr, nullptr};
 };
 
 struct sb_batch {
@@ -99,8 +101,11 @@ static const void* kfn() {
 }
 static const void* pick_kernel(int K, int storage, bool ss) {
   const bool f32 = storage == SB_F32;
+  const bool i8 = storage == SB_I8;
+  if (i8 && ss) return nullptr;
 #define SB_PICK(KK)                                                                           \
   case KK:                                                                                    \
+    if (i8) return kfn<KK, int8_t, false>();                                                  \
     return ss ? (f32 ? kfn<KK, float, true>() : kfn<KK, double, true>())                      \
               : (f32 ? kfn<KK, float, false>() : kfn<KK, double, false>());
   switch (K) {
@@ -205,8 +210,31 @@ static bool plan_geometry(int p, int n_max, int es, bool ss, int smem_budget, Ge
   const size_t hdr = align_up(sizeof(sb::SmemHdr), 128);
   const size_t row_bytes = static_cast<size_t>(g.p_pad) * es;
   const int pv = static_cast<int>(row_bytes / 16);  // 16-byte vectors per row
-  // register-tile traversal (individual level): every thread owns CPT vectors of GR rows
   g.fast = 0;
+  if (es == 1) {
+    // hard-call storage: every thread owns CPT 8-byte vectors of GR rows (traverse_i8)
+    const int pv8 = g.p_pad / 8;
+    int gr;
+    if (pv8 <= sb::NT) {
+      g.fast = 1;
+      gr = 8;
+    } else if (pv8 <= 2 * sb::NT) {
+      g.fast = 2;
+      gr = 4;
+    } else if (pv8 <= 4 * sb::NT) {
+      g.fast = 3;
+      gr = 2;
+    } else {
+      return false;
+    }
+    const int rows_fit = static_cast<int>((smem_budget - hdr) / row_bytes);
+    g.G = gr;
+    g.NS = std::max(2, std::min(sb::NSTAGE_MAX, rows_fit / gr));
+    g.NSEG = 1;
+    g.smem = hdr + static_cast<size_t>(g.NS) * g.G * row_bytes;
+    return true;
+  }
+  // register-tile traversal (individual level): every thread owns CPT vectors of GR rows
   {
     int gr = 0;
     if (pv > sb::NT && pv <= 4 * sb::NT) {
@@ -285,7 +313,7 @@ struct Bump {
 };
 
 struct ProbLayout {  // offsets inside the arena
-  size_t X[KMAX], y, logpi, pi_raw, xtx, ecov0, rv0, adjt, adjp, r, xb, xty, rfull, bvec, out[2], elbo, meta, z;
+  size_t X[KMAX], y, logpi, pi_raw, xtx, cmean, cisd, ecov0, rv0, adjt, adjp, r, xb, xty, rfull, bvec, out[2], elbo, meta, z;
   size_t out_fields[2][10];
 };
 
@@ -396,9 +424,20 @@ static int batch_create(sb_ctx* ctx, const std::vector<GenericProblem>& gp, bool
     ctx->err = "max_iter must be >= 1";
     return SB_EINVAL;
   }
-  if (opts.storage != SB_F64 && opts.storage != SB_F32) {
-    ctx->err = "storage must be SB_F64 or SB_F32";
+  if (opts.storage != SB_F64 && opts.storage != SB_F32 && opts.storage != SB_I8) {
+    ctx->err = "storage must be SB_F64, SB_F32 or SB_I8";
     return SB_EINVAL;
+  }
+  if (opts.storage == SB_I8) {
+    if (ss) {
+      ctx->err = "SB_I8 storage is for individual-level hard-call genotypes only";
+      return SB_EINVAL;
+    }
+    for (int i = 0; i < n_probs; ++i)
+      if (gp[i].mat_dtype != SB_I8) {
+        ctx->err = "problem " + std::to_string(i) + ": SB_I8 storage needs x_dtype == SB_I8";
+        return SB_EINVAL;
+      }
   }
   const int es = elem_size(opts.storage);
   const int smem_budget = ctx->smem_optin - 1024;  // leave room for static shared memory
@@ -470,7 +509,7 @@ static int batch_create(sb_ctx* ctx, const std::vector<GenericProblem>& gp, bool
       h.n[k] = g.n[k];
       nrows += g.n[k];
       l.X[k] = bump.take(static_cast<size_t>(g.n[k]) * ge.p_pad * es);
-      const bool direct = (g.mat_dtype == opts.storage) && g.standardize == 0;
+      const bool direct = (g.mat_dtype == opts.storage) && g.standardize == 0 && opts.storage != SB_I8;
       if (!direct) staging_bytes = std::max(staging_bytes, static_cast<size_t>(g.n[k]) * g.p * elem_size(g.mat_dtype));
     }
     h.nrows = nrows;
@@ -480,6 +519,8 @@ static int batch_create(sb_ctx* ctx, const std::vector<GenericProblem>& gp, bool
     l.logpi = bump.take(sizeof(double) * g.p);
     l.pi_raw = bump.take(sizeof(double) * g.p);
     l.xtx = bump.take(sizeof(double) * Kp);
+    l.cmean = opts.storage == SB_I8 ? bump.take(sizeof(double) * Kp) : 0;
+    l.cisd = opts.storage == SB_I8 ? bump.take(sizeof(double) * Kp) : 0;
     l.ecov0 = bump.take(sizeof(double) * g.L * g.K * g.K);
     l.rv0 = bump.take(sizeof(double) * g.K);
     l.adjt = bump.take(sizeof(double) * g.K * g.K);
@@ -582,6 +623,8 @@ static int batch_create(sb_ctx* ctx, const std::vector<GenericProblem>& gp, bool
     d.y = reinterpret_cast<double*>(A + l.y);
     d.logpi = reinterpret_cast<double*>(A + l.logpi);
     d.xtx = reinterpret_cast<double*>(A + l.xtx);
+    d.cmean = opts.storage == SB_I8 ? reinterpret_cast<double*>(A + l.cmean) : nullptr;
+    d.cisd = opts.storage == SB_I8 ? reinterpret_cast<double*>(A + l.cisd) : nullptr;
     d.ecov0 = reinterpret_cast<double*>(A + l.ecov0);
     d.rv0 = reinterpret_cast<double*>(A + l.rv0);
     d.adj_times = reinterpret_cast<double*>(A + l.adjt);
@@ -636,8 +679,17 @@ static int batch_create(sb_ctx* ctx, const std::vector<GenericProblem>& gp, bool
     for (int k = 0; k < g.K; ++k) {
       const int n = g.n[k];
       double* xtx_k = reinterpret_cast<double*>(A + l.xtx) + static_cast<size_t>(k) * ge.p_pad;
-      const bool direct = (g.mat_dtype == opts.storage) && g.standardize == 0;
-      if (direct) {
+      const bool direct = (g.mat_dtype == opts.storage) && g.standardize == 0 && opts.storage != SB_I8;
+      if (opts.storage == SB_I8) {
+        double* cmean_k = reinterpret_cast<double*>(A + l.cmean) + static_cast<size_t>(k) * ge.p_pad;
+        double* cisd_k = reinterpret_cast<double*>(A + l.cisd) + static_cast<size_t>(k) * ge.p_pad;
+        h.d_cmean[k] = cmean_k;
+        h.d_cisd[k] = cisd_k;
+        SB_CUDA_B(cudaMemcpyAsync(A + staging_off, g.mat[k], static_cast<size_t>(n) * g.p, cudaMemcpyHostToDevice, st));
+        sb::prep_columns_i8_kernel<int8_t><<<(ge.p_pad + 127) / 128, 128, 0, st>>>(
+            reinterpret_cast<const int8_t*>(A + staging_off), g.p, n, g.p, ge.p_pad, g.standardize,
+            reinterpret_cast<int8_t*>(A + l.X[k]), xtx_k, cmean_k, cisd_k);
+      } else if (direct) {
         SB_CUDA_B(cudaMemcpy2DAsync(A + l.X[k], static_cast<size_t>(ge.p_pad) * es, g.mat[k],
                                     static_cast<size_t>(g.p) * es, static_cast<size_t>(g.p) * es, n,
                                     cudaMemcpyHostToDevice, st));
@@ -1078,6 +1130,16 @@ extern "C" int sb_batch_purity(sb_ctx* ctx, sb_batch* b, int prob, const int32_t
     return bail(e, "purity H2D offsets");
   if ((e = cudaMemcpyAsync(d_ptrs, h.d_X, sizeof(void*) * K, cudaMemcpyHostToDevice, st)) != cudaSuccess)
     return bail(e, "purity H2D ptrs");
+  const bool i8 = b->storage == SB_I8;
+  const double* const* d_cm = nullptr;
+  const double* const* d_cs = nullptr;
+  if (i8) {  // column statistics pointer tables share the 256-byte pointer block
+    if ((e = cudaMemcpyAsync(d_ptrs + 8, h.d_cmean, sizeof(void*) * K, cudaMemcpyHostToDevice, st)) != cudaSuccess ||
+        (e = cudaMemcpyAsync(d_ptrs + 16, h.d_cisd, sizeof(void*) * K, cudaMemcpyHostToDevice, st)) != cudaSuccess)
+      return bail(e, "purity H2D column statistics");
+    d_cm = reinterpret_cast<const double* const*>(d_ptrs + 8);
+    d_cs = reinterpret_cast<const double* const*>(d_ptrs + 16);
+  }
   if ((e = cudaMemcpyAsync(d_n, h.n, sizeof(int) * K, cudaMemcpyHostToDevice, st)) != cudaSuccess)
     return bail(e, "purity H2D n");
   dim3 grid(n_sets, K);
@@ -1086,9 +1148,11 @@ extern "C" int sb_batch_purity(sb_ctx* ctx, sb_batch* b, int prob, const int32_t
     auto kf = sb::purity_kernel<XT, SSV>;                                                                      \
     if (smem > 48 * 1024) cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);    \
     kf<<<grid, 256, smem, st>>>(reinterpret_cast<const XT* const*>(d_ptrs), d_n, h.p_pad, d_idx, d_off, K,     \
-                                d_out);                                                                        \
+                                d_out, d_cm, d_cs);                                                            \
   } while (0)
-  if (b->storage == SB_F64) {
+  if (i8) {
+    SB_PUR(int8_t, false);
+  } else if (b->storage == SB_F64) {
     if (b->ss)
       SB_PUR(double, true);
     else

@@ -79,6 +79,8 @@ struct ProbDev {
   double* xb;     // [L][nrows] cached X b_l  (summary level: XtX b_l)
   double* xty;    // [K][p_pad] reduced X^T r                    (individual level)
   double* rfull;  // [nrows] full residual at iteration end      (summary level)
+  const double* cmean;  // [K][p_pad] column means      (hard-call int8 storage only; pad = 0)
+  const double* cisd;   // [K][p_pad] 1 / column std    (hard-call int8 storage only; pad = 0)
   double* bvec;   // [L][K][p_pad] posterior-mean effects b_l = alpha_l * mu_l of the current iteration (pad = 0)
   OutBuf out[2];
   double* elbo;   // [max_iter + 1]
@@ -221,6 +223,16 @@ struct Vec<float> {
   }
 };
 
+template <>
+struct Vec<int8_t> {  // hard-call storage has its own traversal (traverse_i8); only the width is shared
+  static constexpr int W = 16;
+  // name-lookup stubs for the dense traversals, which are never instantiated for this storage type
+  template <typename A, typename B>
+  __device__ static void load(A, int, B&) {}
+  template <typename A, typename B>
+  __device__ static void load_raw(A, int, B&) {}
+};
+
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -232,18 +244,53 @@ __device__ __forceinline__ double warp_max(double v) {
   return v;
 }
 
+
+// Hard-call genotype bytes -> double without the conversion pipe: sign-extend byte `B` of `w`
+// (prmt, replicate-sign mode), bias into [0, 2^32), splice under the exponent of 2^52 and
+// subtract the bias.  Exact for every int8.
+template <int B>
+__device__ __forceinline__ double i8_to_f64(uint32_t w) {
+  constexpr uint32_t sel = ((8u | B) << 12) | ((8u | B) << 8) | ((8u | B) << 4) | B;
+  uint32_t lo;
+  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(lo) : "r"(w), "r"(0u), "r"(sel));
+  return __hiloint2double(0x43300000, static_cast<int>(lo ^ 0x80000000u)) - 4503601774854144.0;  // 2^52 + 2^31
+}
+
+// Transposed butterfly: every thread brings GR partial sums; afterwards lane l holds the warp total
+// of row l / (32 / GR).  GR + log2(32 / GR) - 1 double shuffles instead of 5 * GR.
+template <int GR>
+__device__ __forceinline__ double warp_rows_sum(double (&ps)[GR], int lane) {
+  static_assert(GR == 1 || GR == 2 || GR == 4 || GR == 8, "rows per band");
+  int off = 16;
+#pragma unroll
+  for (int cnt = GR; cnt > 1; cnt >>= 1) {
+    const bool hi = lane & off;
+#pragma unroll
+    for (int i = 0; i < cnt / 2; ++i) {
+      const double keep = hi ? ps[i + cnt / 2] : ps[i];
+      const double send = hi ? ps[i] : ps[i + cnt / 2];
+      ps[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+    off >>= 1;
+  }
+  double t = ps[0];
+#pragma unroll
+  for (; off > 0; off >>= 1) t += __shfl_xor_sync(0xffffffffu, t, off);
+  return t;
+}
+
 // Shared-memory header (fixed part of the dynamic allocation).
 struct SmemHdr {
   uint64_t mbar[NSTAGE_MAX];  // "stage filled" (bulk-copy completion)
   uint64_t ebar[NSTAGE_MAX];  // "stage drained" (one arrival per warp; summary-level register-tile path)
   ProbDev pb;                // the locus being processed
-  alignas(16) double partsum[2][GMAX];  // sweep-1 partial dot products [band parity][g * nseg + seg]
+  alignas(16) double partsum[2][2 * GMAX];  // sweep-1 partial dot products [band parity][g * nseg + seg]
   double rn[GMAX];           // next residual of the band's rows
   double red[NW][STAT_STRIDE];
   double tot[STAT_STRIDE];   // block / team totals
   double cst[2 * KMAX * KMAX + 8];  // Cinv, misc per-pass constants
   double trow[GMAX][2];      // per-row scalars of a traversal
-  double rstate[2][8];       // register-tile traversal: (r, xb_next) of the band's rows, fetched one band ahead
+  double rstate[2][16];      // register-tile traversal: (r, xb_next) of the band's rows, fetched one band ahead
   int decision;
   int pad_[3];
 };
@@ -650,7 +697,10 @@ __global__ void __launch_bounds__(NT, 1) ibss_kernel(const LaunchParams P) {
         const bool full_rows = (rows == GR);
 
         // per-row state (r, xb[lnext]) was fetched one band ahead by threads 0..2*GR-1: publish it
-        if (tid < 2 * GR) H->rstate[pos & 1][tid] = pre;
+        if (tid < 2 * GR) {
+          H->rstate[pos & 1][tid] = pre;
+          if (pos + 1 < nb_own) pre = fetch_state(pos + 1);  // a whole band of latency cover
+        }
         mbar_wait(&H->mbar[st], (phase_bits >> st) & 1u);
 
         // the band -> registers (the only shared-memory read of the genotypes)
@@ -724,7 +774,6 @@ __global__ void __launch_bounds__(NT, 1) ibss_kernel(const LaunchParams P) {
           issue_fill(prod_pos, st);
           prod_pos = (prod_pos + 1 == nb_own) ? 0 : prod_pos + 1;
         }
-        if (tid < 2 * GR && pos + 1 < nb_own) pre = fetch_state(pos + 1);  // lands during the rest of this band
         // every thread finishes the row sums itself (no second barrier); fixed pairwise order
         double rn[GR];
         double r_old[GR], xb_next[GR];
@@ -778,6 +827,203 @@ __global__ void __launch_bounds__(NT, 1) ibss_kernel(const LaunchParams P) {
         if (cur_k >= 0) flush_acc(cur_k);
         zero_unowned_partials();
       }
+      store_trav(l, first, vsq, rsq);
+    };
+
+    // Hard-call variant (XT = int8_t): the band holds raw genotype bytes (1 byte per entry: an
+    // eighth of the fp64 traffic); centring / scaling is folded into the vectors,
+    //   X_std b = G (b / sd) - sum_j mean_j b_j / sd_j,   X_std^T r = (G^T r - mean * sum_i r_i) / sd,
+    // so the traversal is G-only.  Every thread owns CPT 8-byte column vectors, widens its slice of
+    // the GR band rows to fp64 once (integer splice + one DADD per entry) and runs both sweeps from
+    // registers.
+    auto traverse_i8 = [&](auto cpt_c, auto gr_c, int l, bool first, bool last_effect) {
+      constexpr int CPT = decltype(cpt_c)::value;
+      constexpr int GR = decltype(gr_c)::value;
+      constexpr int PRODUCER_TID = NT - 32;
+      constexpr int LG = 32 / GR;  // lanes sharing one band row after the butterfly
+      const int pv8 = p_pad / 8;   // 8-byte vectors per row
+      const int lnext = first ? 0 : ((l + 1 == L) ? 0 : l + 1);
+      double vsq[K], rsq[K];  // meaningful in the row-writer lanes of warp 0 only
+#pragma unroll
+      for (int k = 0; k < K; ++k) vsq[k] = rsq[k] = 0.0;
+      double bq[CPT][8], aq[CPT][8];
+      double x[GR][CPT][8];
+      uint32_t vmask = 0;
+#pragma unroll
+      for (int c = 0; c < CPT; ++c) {
+        if (tid + c * NT < pv8) vmask |= (1u << c);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          bq[c][u] = aq[c][u] = 0.0;
+#pragma unroll
+          for (int g = 0; g < GR; ++g) x[g][c][u] = 0.0;
+        }
+      }
+      int cur_k = -1;
+      int st = cons_seq % NS;
+      double cshift = 0.0;  // sum_j mean_j b_j / sd_j of the current ancestry
+      double rsum = 0.0;    // sum of r_next over the rows of the current ancestry seen by this block
+      auto fetch_state = [&](int pos) -> double {
+        int k, g0, rows;
+        band_of(pos, k, g0, rows);
+        const int g = tid % GR;
+        if (g >= rows) return 0.0;
+        const int row = pb.row0[k] + g0 + g;
+        return (tid < GR) ? pb.r[row] : pb.xb[static_cast<size_t>(lnext) * nrows + row];
+      };
+      double pre = 0.0;
+      if (tid < 2 * GR && nb_own > 0) pre = fetch_state(0);
+
+      // partial X_std^T r of ancestry k: (G^T r - mean * sum r) / sd
+      auto flush_acc = [&](int k) {
+        double* dst = my_scr + static_cast<size_t>(k) * p_pad;
+        const double* cm = pb.cmean + static_cast<size_t>(k) * p_pad;
+        const double* cs = pb.cisd + static_cast<size_t>(k) * p_pad;
+#pragma unroll
+        for (int c = 0; c < CPT; ++c) {
+          if (vmask & (1u << c)) {
+            const int j0 = (tid + c * NT) * 8;
+#pragma unroll
+            for (int u = 0; u < 8; u += 2) {
+              const double2 m2 = *reinterpret_cast<const double2*>(cm + j0 + u);
+              const double2 s2 = *reinterpret_cast<const double2*>(cs + j0 + u);
+              __stcg(reinterpret_cast<double2*>(dst + j0 + u),
+                     make_double2((aq[c][u] - m2.x * rsum) * s2.x, (aq[c][u + 1] - m2.y * rsum) * s2.y));
+            }
+          }
+        }
+      };
+
+      for (int pos = 0; pos < nb_own; ++pos) {
+        int k, g0, rows;
+        band_of(pos, k, g0, rows);
+        if (k != cur_k) {
+          if (cur_k >= 0) flush_acc(cur_k);
+          const double* bl = effect_vec(l, k);
+          const double* cm = pb.cmean + static_cast<size_t>(k) * p_pad;
+          const double* cs = pb.cisd + static_cast<size_t>(k) * p_pad;
+          double part[1] = {0.0};
+#pragma unroll
+          for (int c = 0; c < CPT; ++c) {
+            const int j0 = (tid + c * NT) * 8;
+            const bool on = !first && (vmask & (1u << c));
+#pragma unroll
+            for (int u = 0; u < 8; u += 2) {
+              double2 b2 = make_double2(0.0, 0.0);
+              if (on) {
+                const double2 t2 = __ldcg(reinterpret_cast<const double2*>(bl + j0 + u));
+                const double2 s2 = *reinterpret_cast<const double2*>(cs + j0 + u);
+                const double2 m2 = *reinterpret_cast<const double2*>(cm + j0 + u);
+                b2 = make_double2(t2.x * s2.x, t2.y * s2.y);
+                part[0] += m2.x * b2.x + m2.y * b2.y;
+              }
+              aq[c][u] = aq[c][u + 1] = 0.0;
+              bq[c][u] = b2.x;
+              bq[c][u + 1] = b2.y;
+            }
+          }
+          block_sum<1>(H, part);
+          cshift = H->tot[0];
+          rsum = 0.0;
+          cur_k = k;
+        }
+        const unsigned char* tile = ring + static_cast<size_t>(st) * stage_bytes;
+        const int row_base = pb.row0[k] + g0;
+        if (tid < 2 * GR) {
+          H->rstate[pos & 1][tid] = pre;
+          if (pos + 1 < nb_own) pre = fetch_state(pos + 1);
+        }
+        mbar_wait(&H->mbar[st], (phase_bits >> st) & 1u);
+
+        // the band -> fp64 registers (the only shared-memory read of the genotypes)
+#pragma unroll
+        for (int g = 0; g < GR; ++g)
+#pragma unroll
+          for (int c = 0; c < CPT; ++c) {
+            uint2 w = make_uint2(0u, 0u);
+            if (g < rows && (vmask & (1u << c)))
+              w = *reinterpret_cast<const uint2*>(tile + static_cast<size_t>(g) * p_pad + (tid + c * NT) * 8);
+            x[g][c][0] = i8_to_f64<0>(w.x);
+            x[g][c][1] = i8_to_f64<1>(w.x);
+            x[g][c][2] = i8_to_f64<2>(w.x);
+            x[g][c][3] = i8_to_f64<3>(w.x);
+            x[g][c][4] = i8_to_f64<0>(w.y);
+            x[g][c][5] = i8_to_f64<1>(w.y);
+            x[g][c][6] = i8_to_f64<2>(w.y);
+            x[g][c][7] = i8_to_f64<3>(w.y);
+          }
+
+        // sweep 1: G b' per row, transposed butterfly over the warp, one partial per (row, warp)
+        const int pbuf = cons_seq & 1;
+        if (!first) {
+          double ps[GR];
+#pragma unroll
+          for (int g = 0; g < GR; ++g) {
+            double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+            for (int c = 0; c < CPT; ++c)
+#pragma unroll
+              for (int u = 0; u < 8; u += 2) {
+                s0 = fma(x[g][c][u], bq[c][u], s0);
+                s1 = fma(x[g][c][u + 1], bq[c][u + 1], s1);
+              }
+            ps[g] = s0 + s1;
+          }
+          const double t = warp_rows_sum<GR>(ps, lane);
+          if ((lane & (LG - 1)) == 0) H->partsum[pbuf][(lane / LG) * NW + warp] = t;
+        }
+        __syncthreads();  // (A) partial sums visible; every thread holds its tile in registers
+        if (tid == PRODUCER_TID) {
+          issue_fill(prod_pos, st);
+          prod_pos = (prod_pos + 1 == nb_own) ? 0 : prod_pos + 1;
+        }
+        // lane group g = lane / LG finishes band row g (fixed order), then the rows are exchanged by shuffle
+        const int g_me = lane / LG, q = lane & (LG - 1);
+        double v = 0.0;
+        if (!first) {
+          double t = 0.0;
+          if constexpr (LG <= NW) {
+            constexpr int PER = NW / LG;
+#pragma unroll
+            for (int i = 0; i < PER; ++i) t += H->partsum[pbuf][g_me * NW + q * PER + i];
+          } else {
+            if (q < NW) t = H->partsum[pbuf][g_me * NW + q];
+          }
+#pragma unroll
+          for (int o = LG / 2; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+          v = t - cshift;
+        }
+        const bool live = g_me < rows;
+        const double Rfull = live ? H->rstate[pos & 1][g_me] - v : 0.0;
+        const double rn_me = live ? Rfull + H->rstate[pos & 1][GR + g_me] : 0.0;
+        if (warp == 0 && q == 0 && live) {  // row writer
+          const int row = row_base + g_me;
+          if (!first) pb.xb[static_cast<size_t>(l) * nrows + row] = v;
+          pb.r[row] = rn_me;
+#pragma unroll
+          for (int kk = 0; kk < K; ++kk)
+            if (kk == k) {
+              vsq[kk] += v * v;          // |X b_l|^2 (infer.py:806)
+              rsq[kk] += Rfull * Rfull;  // |y - X sum_l b_l|^2 at the last effect (infer.py:804)
+            }
+        }
+        // sweep 2: G^T r_next accumulated in registers
+#pragma unroll
+        for (int g = 0; g < GR; ++g) {
+          const double rg = __shfl_sync(0xffffffffu, rn_me, g * LG);
+          rsum += rg;
+#pragma unroll
+          for (int c = 0; c < CPT; ++c)
+#pragma unroll
+            for (int u = 0; u < 8; ++u) aq[c][u] = fma(x[g][c][u], rg, aq[c][u]);
+        }
+        phase_bits ^= (1u << st);
+        cons_seq += 1;
+        st = (st + 1 == NS) ? 0 : st + 1;
+      }
+      if (cur_k >= 0) flush_acc(cur_k);
+      zero_unowned_partials();
+      // store_trav sums trow[0..GMAX): the row writers are lanes 0, LG, 2 LG, ... of warp 0
       store_trav(l, first, vsq, rsq);
     };
 
@@ -939,7 +1185,7 @@ __global__ void __launch_bounds__(NT, 1) ibss_kernel(const LaunchParams P) {
 
     // Generic variant (any p that fits, any G <= GMAX): b and the accumulators in shared memory,
     // two sweeps over the shared-memory band separated by a barrier.
-    auto traverse_generic = [&](int l, bool first, bool last_effect) {
+    auto traverse_generic = [&](auto /*instantiate on use*/, int l, bool first, bool last_effect) {
       const int lnext = first ? 0 : ((l + 1 == L) ? 0 : l + 1);
       double vsq[K], rsq[K];  // meaningful in threads < G only
 #pragma unroll
@@ -1077,7 +1323,14 @@ __global__ void __launch_bounds__(NT, 1) ibss_kernel(const LaunchParams P) {
     };
 
     auto traverse = [&](int l, bool first, bool last_effect) {
-      if constexpr (SS) {
+      if constexpr (std::is_same<XT, int8_t>::value) {
+        if (fast == 1)
+          traverse_i8(IntC<1>{}, IntC<8>{}, l, first, last_effect);
+        else if (fast == 2)
+          traverse_i8(IntC<2>{}, IntC<4>{}, l, first, last_effect);
+        else
+          traverse_i8(IntC<4>{}, IntC<2>{}, l, first, last_effect);
+      } else if constexpr (SS) {
         if (fast == 1)
           traverse_ss(IntC<4>{}, IntC<4>{}, l, last_effect);
         else if (fast == 2)
@@ -1085,14 +1338,14 @@ __global__ void __launch_bounds__(NT, 1) ibss_kernel(const LaunchParams P) {
         else if (fast == 3)
           traverse_ss(IntC<12>{}, IntC<1>{}, l, last_effect);
         else
-          traverse_generic(l, first, last_effect);
+          traverse_generic(IntC<0>{}, l, first, last_effect);
       } else {
         if (fast == 1)
           traverse_fast(IntC<4>{}, IntC<4>{}, l, first, last_effect);
         else if (fast == 2)
           traverse_fast(IntC<8>{}, IntC<2>{}, l, first, last_effect);
         else
-          traverse_generic(l, first, last_effect);
+          traverse_generic(IntC<0>{}, l, first, last_effect);
       }
     };
 
@@ -1597,6 +1850,52 @@ __global__ void prep_columns_kernel(const IT* in, int in_ld, int n, int p, int p
   xtx[j] = ss;
 }
 
+// Hard-call storage prologue: raw genotype bytes into padded storage; the column statistics that
+// fold centring / scaling (infer.py:326-333) into the vectors; xtx[j] = sum_n ((g - mean) / sd)^2
+// exactly as the dense path computes it (infer.py:494).
+template <typename IT>
+__global__ void prep_columns_i8_kernel(const IT* in, int in_ld, int n, int p, int p_pad, int flags, int8_t* out,
+                                       double* __restrict__ xtx, double* __restrict__ cmean,
+                                       double* __restrict__ cisd) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= p_pad) return;
+  if (j >= p) {
+    for (int i = 0; i < n; ++i) out[static_cast<size_t>(i) * p_pad + j] = 0;
+    xtx[j] = 0.0;
+    cmean[j] = 0.0;
+    cisd[j] = 0.0;
+    return;
+  }
+  double mean = 0.0, sd = 1.0;
+  if (flags & 1) {
+    double s = 0.0;
+    for (int i = 0; i < n; ++i) s += static_cast<double>(in[static_cast<size_t>(i) * in_ld + j]);
+    mean = s / n;
+  }
+  if (flags & 2) {
+    double s1 = 0.0;
+    for (int i = 0; i < n; ++i) s1 += static_cast<double>(in[static_cast<size_t>(i) * in_ld + j]) - mean;
+    const double m2 = s1 / n;
+    double s2 = 0.0;
+    for (int i = 0; i < n; ++i) {
+      const double c = (static_cast<double>(in[static_cast<size_t>(i) * in_ld + j]) - mean) - m2;
+      s2 += c * c;
+    }
+    sd = sqrt(s2 / n);
+  }
+  double ss = 0.0;
+  for (int i = 0; i < n; ++i) {
+    const IT g = in[static_cast<size_t>(i) * in_ld + j];
+    double v = static_cast<double>(g) - mean;
+    if (flags & 2) v /= sd;
+    out[static_cast<size_t>(i) * p_pad + j] = static_cast<int8_t>(g);
+    ss += v * v;
+  }
+  xtx[j] = ss;
+  cmean[j] = mean;
+  cisd[j] = 1.0 / sd;
+}
+
 // Summary-level prologue (infer_ss.py:340-344): Xty = sqrt(n) sqrt(n/(n+z^2)) z,
 // diag(XtX) = n * LD_jj, log pi.
 template <typename XT>
@@ -1638,7 +1937,8 @@ __global__ void pad_rows_kernel(const IT* __restrict__ in, int n, int p, int p_p
 template <typename XT, bool SS>
 __global__ void purity_kernel(const XT* const* __restrict__ Xk, const int* __restrict__ nk, int p_pad,
                               const int* __restrict__ idx, const int* __restrict__ offsets, int K,
-                              double* __restrict__ out) {
+                              double* __restrict__ out, const double* const* __restrict__ cmean,
+                              const double* const* __restrict__ cisd) {
   extern __shared__ __align__(16) unsigned char pur_smem[];
   const int set = blockIdx.x, k = blockIdx.y;
   const int o0 = offsets[set], m = offsets[set + 1] - o0;
@@ -1681,7 +1981,9 @@ __global__ void purity_kernel(const XT* const* __restrict__ Xk, const int* __res
         __syncthreads();
         for (int t = threadIdx.x; t < rc * m; t += blockDim.x) {
           const int rr = t / m, c = t % m;
-          tile[rr * m + c] = static_cast<double>(X[static_cast<size_t>(r0 + rr) * p_pad + sel[c]]);
+          double val = static_cast<double>(X[static_cast<size_t>(r0 + rr) * p_pad + sel[c]]);
+          if (cmean) val = (val - cmean[k][sel[c]]) * cisd[k][sel[c]];  // hard-call storage: standardise on the fly
+          tile[rr * m + c] = val;
         }
         __syncthreads();
 #pragma unroll

@@ -97,6 +97,11 @@ def _prepare(
             mats[idx], phen[idx] = utils.regress_covar(
                 np.asarray(mats[idx], dtype=float), phen[idx], np.asarray(covar[idx], dtype=float), no_regress
             )
+    # hard calls that were not residualised stay one byte per entry on the device
+    if config.genotype_storage == "auto" and (covar is None or no_regress):
+        packed = [utils.as_hard_calls(m) for m in mats]
+        if all(m is not None for m in packed):
+            mats = packed
     for idx in range(n_pop):
         y = phen[idx] - np.mean(phen[idx])
         if not no_scale:
@@ -133,7 +138,12 @@ def _finish(batch: "_capi.Batch", index: int, prep: _Prepared, fit) -> SushieRes
 def _run_prepared(preps: Sequence[_Prepared], device: int = 0) -> List[SushieResult]:
     """Fit a list of prepared problems that share max_iter / min_tol on one GPU."""
     eng = _capi.get_engine(device)
-    opts = eng.make_opts(preps[0].max_iter, preps[0].min_tol, config.storage_code(), config.team_size, config.single_phase)
+    storage = config.storage_code()
+    if config.genotype_storage == "auto" and all(
+        p.problem.x_dtype == _capi.SB_I8 and p.problem.p <= _capi.I8_MAX_SNPS for p in preps
+    ):
+        storage = _capi.SB_I8
+    opts = eng.make_opts(preps[0].max_iter, preps[0].min_tol, storage, config.team_size, config.single_phase)
     with eng.create_batch([p.problem for p in preps], opts) as batch:
         batch.run()
         fits = batch.fetch()

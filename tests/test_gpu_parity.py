@@ -20,6 +20,17 @@ SYN_CASES = {
 }
 
 
+@pytest.fixture(params=["dense", "auto"])
+def geno_storage(request):
+    """Run a test with standardised fp64 storage and with one-byte hard-call storage."""
+    from sushie_b200 import config
+
+    old = config.genotype_storage
+    config.genotype_storage = request.param
+    yield request.param
+    config.genotype_storage = old
+
+
 def _syn_inputs(g, tag, k, as_float=True):
     Xs = [g[f"{tag}_X{i}"] for i in range(k)]
     if as_float:
@@ -58,7 +69,7 @@ def test_bundled_summary_example(engine_lib, golden_ss, tag, tol_tag, tol):
 
 
 @pytest.mark.parametrize("tag", sorted(SYN_CASES))
-def test_synthetic_small(engine_lib, golden_syn, tag):
+def test_synthetic_small(engine_lib, golden_syn, tag, geno_storage):
     import sushie_b200
 
     case = SYN_CASES[tag]
@@ -67,7 +78,7 @@ def test_synthetic_small(engine_lib, golden_syn, tag):
     assert_fit_matches(res, golden_syn, tag)
 
 
-def test_int8_genotypes_match_float(engine_lib, golden_syn):
+def test_int8_genotypes_match_float(engine_lib, golden_syn, geno_storage):
     """Hard-call int8 input is standardised on device exactly like float input."""
     import sushie_b200
 
@@ -78,7 +89,7 @@ def test_int8_genotypes_match_float(engine_lib, golden_syn):
 
 
 @pytest.mark.parametrize("team", [1, 2, 4, 8, 16, 24])
-def test_team_sizes_agree_with_oracle(engine_lib, golden_syn, team):
+def test_team_sizes_agree_with_oracle(engine_lib, golden_syn, team, geno_storage):
     """Cluster teams (hardware barrier, 2..16 blocks) and co-operative teams (24 blocks,
     global-memory barrier) all reproduce the oracle."""
     import sushie_b200
@@ -105,7 +116,7 @@ def golden_ss_inputs():
     return g["k2_lds"], g["k2_ns"], g["k2_zs"], g
 
 
-def test_batch_mixed_shapes_matches_single(engine_lib, golden_syn):
+def test_batch_mixed_shapes_matches_single(engine_lib, golden_syn, geno_storage):
     """Ragged p / n and mixed k in one device-resident batch == the same loci one by one."""
     import sushie_b200
 
@@ -250,3 +261,39 @@ def test_summary_level_large_crop_fp32_storage(engine_lib):
     assert len(res.elbo) == len(ref.elbo) == 7
     np.testing.assert_allclose(res.elbo[1:], ref.elbo[1:], rtol=1e-6)
     assert np.max(np.abs(res.pip_all - ibss.make_pip(ref.posteriors.alpha))) <= 1e-4
+
+
+def test_hard_call_storage_is_selected_and_wide_loci_fit(engine_lib):
+    """One-byte storage through the engine API: the 8-row band geometry is reported, loci wider than
+    2048 / 4096 SNPs use the 16- / 32-column register tiles, and all agree with the fp64 storage run."""
+    from sushie_b200 import _capi
+    from sushie_b200._common import build_priors
+
+    rng = np.random.default_rng(11)
+    eng = _capi.get_engine(0)
+    for p, rows in ((300, 8), (2500, 4), (5000, 2)):
+        k, n, L = 2, [90, 70], 3
+        Xs = [rng.binomial(2, 0.3, size=(n[i], p)).astype(np.int8) for i in range(k)]
+        for X in Xs:
+            X[0, X.std(axis=0) == 0] = 1
+        beta = np.zeros(p)
+        beta[[5, p // 2]] = [1.0, -0.8]
+        ys = []
+        for X in Xs:
+            y = ((X - X.mean(0)) / X.std(0)) @ beta + rng.standard_normal(X.shape[0])
+            ys.append((y - y.mean()) / y.std())
+        ec, adj = build_priors(k, L, None, None, False, summary=False)
+        fits = {}
+        for storage in (_capi.SB_F64, _capi.SB_I8):
+            prob = _capi.IndProblem(Xs, ys, L, None, [np.var(y, ddof=1) for y in ys], ec, adj.times, adj.plus, True,
+                                    standardize=_capi.SB_CENTER | _capi.SB_SCALE)
+            with eng.create_batch([prob], eng.make_opts(30, 1e-4, storage, 1)) as b:
+                st = b.run()
+                fits[storage] = b.fetch()[0]
+                if storage == _capi.SB_I8:
+                    assert st["rows_per_band"] == rows
+        a, c = fits[_capi.SB_F64], fits[_capi.SB_I8]
+        assert a.n_iter == c.n_iter
+        np.testing.assert_allclose(a.elbo[1:], c.elbo[1:], rtol=1e-9)
+        np.testing.assert_allclose(a.alpha, c.alpha, atol=1e-8)
+        np.testing.assert_allclose(a.effect_covar, c.effect_covar, rtol=1e-6, atol=1e-12)
