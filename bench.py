@@ -267,7 +267,9 @@ def workload_config(args, genes_per_gpu):
         "k": K_ANC, "n_per_ancestry": N_IND, "p": P_SNP, "L": L_EFF,
         "genes_per_gpu": genes_per_gpu, "max_iter": args.max_iter, "min_tol": args.min_tol,
         "stop_rule": "to convergence (Python API defaults)",
-        "l2": "inputs_larger_than_L2 (24 MB fp64 per locus, batch >> 126 MB)",
+        "genotype_storage": args.storage,
+        "l2": "inputs_larger_than_L2 (%d MB per locus resident, batch of %d loci >> 126 MB)" % (
+            K_ANC * N_IND * P_SNP * {"i8": 1, "f64": 8, "f32": 4}[args.storage] // 1000000, genes_per_gpu),
         "parallelism": f"loci sharded over {args.gpus} GPU(s), no data-path collective",
     }
 
@@ -281,6 +283,9 @@ def main():
     ap.add_argument("--genes", type=int, default=1000, help="loci per GPU per step")
     ap.add_argument("--max-iter", type=int, default=500)
     ap.add_argument("--min-tol", type=float, default=1e-4)
+    ap.add_argument("--storage", default="i8", choices=["i8", "f64", "f32"],
+                    help="device storage of the genotypes: i8 = raw hard calls (1 B/entry, centring/scaling folded "
+                         "into the vectors), f64 / f32 = standardised dense matrix; arithmetic is fp64 in every case")
     ap.add_argument("--team", type=int, default=0)
     ap.add_argument("--single-phase", action="store_true")
     ap.add_argument("--ref-loci", type=int, default=0)
@@ -347,7 +352,9 @@ def main():
                 em_update=True, standardize=_capi.SB_CENTER | _capi.SB_SCALE))
         return probs
 
-    opts = eng.make_opts(args.max_iter, args.min_tol, _capi.SB_F64, args.team, args.single_phase)
+    storage = {"i8": _capi.SB_I8, "f64": _capi.SB_F64, "f32": _capi.SB_F32}[args.storage]
+    elem_bytes = {"i8": 1, "f64": 8, "f32": 4}[args.storage]
+    opts = eng.make_opts(args.max_iter, args.min_tol, storage, args.team, args.single_phase)
 
     def barrier():
         if world > 1:
@@ -457,12 +464,14 @@ def main():
             "mean_iters_per_locus": n_iter / (total_loci * args.steps),
             "wall_ms_per_step": wall_ms / args.steps,
             "gpu_launches": launches,
-            "kernel": dict(geom, name="sb::ibss_kernel<3,double,false>", launches_per_step=1),
+            "kernel": dict(geom, name="sb::ibss_kernel<3,%s,false>" % {"i8": "int8_t", "f64": "double", "f32": "float"}[args.storage],
+                           launches_per_step=1, genotype_storage=args.storage),
             "roofline": {
                 "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": ncu_traffic_per_launch(), "peak_source": peak_src,
-                "algorithmic_bytes_per_ser": K_ANC * N_IND * P_SNP * 8,
-                "note": "achieved = (#single-effect updates x k*n*p*8 B) / CUDA-event time of the launch, per GPU",
+                "algorithmic_bytes_per_ser": K_ANC * N_IND * P_SNP * elem_bytes,
+                "note": "achieved = (#single-effect updates x k*n*p*%d B, one traversal of the stored genotypes) / "
+                        "CUDA-event time of the launch, per GPU" % elem_bytes,
             },
             "clocks": {"sm_mhz": clocks["sm_mhz"], "sm_max_mhz": clocks["sm_max_mhz"], "reasons": clocks["reasons"],
                        "samples": clocks["samples"]},
@@ -474,7 +483,7 @@ def main():
                 "value": total_loci / (e2e["ms"] / 1e3), "unit": "loci/s",
                 "h2d_bytes_per_step": e2e["h2d"] * world, "d2h_bytes_per_step": e2e["d2h"] * world,
                 "ms_per_step": e2e["ms"], "gpu_launches_per_step": e2e["launches"],
-                "path": "sb_ibss_ind (C ABI): pinned int8 genotypes -> device standardise -> IBSS -> posterior tables to pinned host",
+                "path": "sb_ibss_ind (C ABI): pinned int8 genotypes -> device column statistics -> IBSS -> posterior tables to pinned host",
             }
         if cpu_baseline:
             line["cpu_baseline"] = cpu_baseline

@@ -51,7 +51,7 @@ extern "C" {
 #define SB_F64 0
 #define SB_F32 1
 #define SB_I8 2 /* hard-call genotypes (int8). As sb_opts.storage (individual level, every problem x_dtype ==
-                  SB_I8, p <= 8192): raw bytes stay resident, centring/scaling is folded into the vectors */
+                  SB_I8, entries in 0..127, p <= 8192): raw bytes stay resident, centring/scaling is folded into the vectors */
 
 /* sb_opts.flags */
 #define SB_FLAG_SINGLE_PHASE 1 /* keep one team size for the whole batch (no suspend / regroup phases) */

@@ -1,0 +1,6 @@
+for st in f64 i8; do
+python bench.py --storage $st --genes 296 --steps 2 --warmup 1 --no-cpu-baseline --no-e2e --max-iter 50 --min-tol 0 2>&1 | python scripts/bench_line.py "fixed50 $st"
+done
+python bench.py --storage i8 --genes 592 --steps 1 --warmup 1 --no-cpu-baseline --no-e2e 2>&1 | python scripts/bench_line.py "conv592 i8"
+python bench.py --storage i8 --genes 1000 --steps 1 --warmup 1 --no-cpu-baseline 2>&1 | python scripts/bench_line.py "conv1000 i8 e2e"
+ncu --set full --import-source on --clock-control none -k regex:ibss_kernel -s 1 -c 1 -f -o gpurun_out/prof_i8_r1d python bench.py --storage i8 --genes 296 --steps 1 --warmup 1 --no-cpu-baseline --no-e2e --max-iter 4 --min-tol 0 2>&1 | tail -1 | cut -c1-300

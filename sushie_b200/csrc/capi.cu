@@ -585,6 +585,7 @@ static int batch_create(sb_ctx* ctx, const std::vector<GenericProblem>& gp, bool
     }                                                                            \
   } while (0)
 
+  SB_CUDA_B(cudaMemsetAsync(b->d_ctl, 0, sizeof(int) * 64, st));
   SB_CUDA_B(cudaEventRecord(ctx->ev[2], st));
   int launches = 0;
   std::vector<double> tmp;
@@ -688,7 +689,7 @@ static int batch_create(sb_ctx* ctx, const std::vector<GenericProblem>& gp, bool
         SB_CUDA_B(cudaMemcpyAsync(A + staging_off, g.mat[k], static_cast<size_t>(n) * g.p, cudaMemcpyHostToDevice, st));
         sb::prep_columns_i8_kernel<int8_t><<<(ge.p_pad + 127) / 128, 128, 0, st>>>(
             reinterpret_cast<const int8_t*>(A + staging_off), g.p, n, g.p, ge.p_pad, g.standardize,
-            reinterpret_cast<int8_t*>(A + l.X[k]), xtx_k, cmean_k, cisd_k);
+            reinterpret_cast<int8_t*>(A + l.X[k]), xtx_k, cmean_k, cisd_k, b->d_ctl + 32);
       } else if (direct) {
         SB_CUDA_B(cudaMemcpy2DAsync(A + l.X[k], static_cast<size_t>(ge.p_pad) * es, g.mat[k],
                                     static_cast<size_t>(g.p) * es, static_cast<size_t>(g.p) * es, n,
@@ -752,6 +753,14 @@ static int batch_create(sb_ctx* ctx, const std::vector<GenericProblem>& gp, bool
     SB_CUDA_B(cudaMemcpyAsync(b->d_probs, b->pd.data(), sizeof(ProbDev) * n_probs, cudaMemcpyHostToDevice, st));
     SB_CUDA_B(cudaEventRecord(ctx->ev[3], st));
     SB_CUDA_B(cudaStreamSynchronize(st));
+  }
+  if (opts.storage == SB_I8) {
+    int bad = 0;
+    SB_CUDA_B(cudaMemcpy(&bad, b->d_ctl + 32, sizeof(int), cudaMemcpyDeviceToHost));
+    if (bad) {
+      ctx->err = "SB_I8 storage needs hard-call genotypes in 0..127 (negative entry found)";
+      return fail(SB_EINVAL);
+    }
   }
   float ms = 0.f;
   cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[3]);

@@ -31,6 +31,13 @@
 
 #include <type_traits>
 
+#ifndef SB_I8_KEEP
+#define SB_I8_KEEP 1
+#endif
+#ifndef SB_I8_BLOCKS_PER_SM
+#define SB_I8_BLOCKS_PER_SM 1
+#endif
+
 namespace sb {
 
 constexpr int KMAX = 4;
@@ -245,15 +252,15 @@ __device__ __forceinline__ double warp_max(double v) {
 }
 
 
-// Hard-call genotype bytes -> double without the conversion pipe: sign-extend byte `B` of `w`
-// (prmt, replicate-sign mode), bias into [0, 2^32), splice under the exponent of 2^52 and
-// subtract the bias.  Exact for every int8.
+// Hard-call genotype bytes (0..255, in practice 0/1/2) -> double without the conversion pipe: byte `B` of
+// `w` is zero-extended (prmt) into the low word under the exponent of 2^52, then 2^52 is subtracted.
+// Two instructions, exact.
 template <int B>
-__device__ __forceinline__ double i8_to_f64(uint32_t w) {
-  constexpr uint32_t sel = ((8u | B) << 12) | ((8u | B) << 8) | ((8u | B) << 4) | B;
+__device__ __forceinline__ double u8_to_f64(uint32_t w) {
+  constexpr uint32_t sel = 0x4440u | B;  // bytes 1..3 <- byte 0 of the zero operand
   uint32_t lo;
   asm("prmt.b32 %0, %1, %2, %3;" : "=r"(lo) : "r"(w), "r"(0u), "r"(sel));
-  return __hiloint2double(0x43300000, static_cast<int>(lo ^ 0x80000000u)) - 4503601774854144.0;  // 2^52 + 2^31
+  return __hiloint2double(0x43300000, static_cast<int>(lo)) - 4503599627370496.0;  // 2^52
 }
 
 // Transposed butterfly: every thread brings GR partial sums; afterwards lane l holds the warp total
@@ -447,7 +454,7 @@ template <int N>
 using IntC = std::integral_constant<int, N>;
 
 template <int K, typename XT, bool SS>
-__global__ void __launch_bounds__(NT, 1) ibss_kernel(const LaunchParams P) {
+__global__ void __launch_bounds__(NT, (std::is_same<XT, int8_t>::value ? SB_I8_BLOCKS_PER_SM : 1)) ibss_kernel(const LaunchParams P) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   constexpr int NSYM = K * (K + 1) / 2;
   constexpr int VW = Vec<XT>::W;
@@ -836,8 +843,9 @@ __global__ void __launch_bounds__(NT, 1) ibss_kernel(const LaunchParams P) {
     // so the traversal is G-only.  Every thread owns CPT 8-byte column vectors, widens its slice of
     // the GR band rows to fp64 once (integer splice + one DADD per entry) and runs both sweeps from
     // registers.
-    auto traverse_i8 = [&](auto cpt_c, auto gr_c, int l, bool first, bool last_effect) {
+    auto traverse_i8 = [&](auto cpt_c, auto gr_c, auto keep_c, int l, bool first, bool last_effect) {
       constexpr int CPT = decltype(cpt_c)::value;
+      constexpr bool KEEP = decltype(keep_c)::value != 0;  // widen once and keep the fp64 tile in registers
       constexpr int GR = decltype(gr_c)::value;
       constexpr int PRODUCER_TID = NT - 32;
       constexpr int LG = 32 / GR;  // lanes sharing one band row after the butterfly
@@ -847,7 +855,8 @@ __global__ void __launch_bounds__(NT, 1) ibss_kernel(const LaunchParams P) {
 #pragma unroll
       for (int k = 0; k < K; ++k) vsq[k] = rsq[k] = 0.0;
       double bq[CPT][8], aq[CPT][8];
-      double x[GR][CPT][8];
+      uint2 x[GR][CPT];  // raw genotype bytes of the band slice (2 registers per 8 entries)
+      double xk[KEEP ? GR : 1][KEEP ? CPT : 1][8];  // KEEP: the widened tile, shared by both sweeps
       uint32_t vmask = 0;
 #pragma unroll
       for (int c = 0; c < CPT; ++c) {
@@ -855,8 +864,6 @@ __global__ void __launch_bounds__(NT, 1) ibss_kernel(const LaunchParams P) {
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
           bq[c][u] = aq[c][u] = 0.0;
-#pragma unroll
-          for (int g = 0; g < GR; ++g) x[g][c][u] = 0.0;
         }
       }
       int cur_k = -1;
@@ -871,8 +878,13 @@ __global__ void __launch_bounds__(NT, 1) ibss_kernel(const LaunchParams P) {
         const int row = pb.row0[k] + g0 + g;
         return (tid < GR) ? pb.r[row] : pb.xb[static_cast<size_t>(lnext) * nrows + row];
       };
-      double pre = 0.0;
-      if (tid < 2 * GR && nb_own > 0) pre = fetch_state(0);
+      // a band takes well under one L2 round trip here: keep three bands of row state in flight
+      double pre0 = 0.0, pre1 = 0.0, pre2 = 0.0;
+      if (tid < 2 * GR) {
+        if (nb_own > 0) pre0 = fetch_state(0);
+        if (nb_own > 1) pre1 = fetch_state(1);
+        if (nb_own > 2) pre2 = fetch_state(2);
+      }
 
       // partial X_std^T r of ancestry k: (G^T r - mean * sum r) / sd
       auto flush_acc = [&](int k) {
@@ -930,29 +942,39 @@ __global__ void __launch_bounds__(NT, 1) ibss_kernel(const LaunchParams P) {
         const unsigned char* tile = ring + static_cast<size_t>(st) * stage_bytes;
         const int row_base = pb.row0[k] + g0;
         if (tid < 2 * GR) {
-          H->rstate[pos & 1][tid] = pre;
-          if (pos + 1 < nb_own) pre = fetch_state(pos + 1);
+          H->rstate[pos & 1][tid] = pre0;
+          pre0 = pre1;
+          pre1 = pre2;
+          if (pos + 3 < nb_own) pre2 = fetch_state(pos + 3);
         }
         mbar_wait(&H->mbar[st], (phase_bits >> st) & 1u);
 
-        // the band -> fp64 registers (the only shared-memory read of the genotypes)
+        // the band -> registers (the only shared-memory read of the genotypes)
 #pragma unroll
         for (int g = 0; g < GR; ++g)
 #pragma unroll
           for (int c = 0; c < CPT; ++c) {
-            uint2 w = make_uint2(0u, 0u);
+            x[g][c] = make_uint2(0u, 0u);
             if (g < rows && (vmask & (1u << c)))
-              w = *reinterpret_cast<const uint2*>(tile + static_cast<size_t>(g) * p_pad + (tid + c * NT) * 8);
-            x[g][c][0] = i8_to_f64<0>(w.x);
-            x[g][c][1] = i8_to_f64<1>(w.x);
-            x[g][c][2] = i8_to_f64<2>(w.x);
-            x[g][c][3] = i8_to_f64<3>(w.x);
-            x[g][c][4] = i8_to_f64<0>(w.y);
-            x[g][c][5] = i8_to_f64<1>(w.y);
-            x[g][c][6] = i8_to_f64<2>(w.y);
-            x[g][c][7] = i8_to_f64<3>(w.y);
+              x[g][c] = *reinterpret_cast<const uint2*>(tile + static_cast<size_t>(g) * p_pad + (tid + c * NT) * 8);
           }
+        auto widen = [](const uint2& w, double (&o)[8]) {
+          o[0] = u8_to_f64<0>(w.x);
+          o[1] = u8_to_f64<1>(w.x);
+          o[2] = u8_to_f64<2>(w.x);
+          o[3] = u8_to_f64<3>(w.x);
+          o[4] = u8_to_f64<0>(w.y);
+          o[5] = u8_to_f64<1>(w.y);
+          o[6] = u8_to_f64<2>(w.y);
+          o[7] = u8_to_f64<3>(w.y);
+        };
 
+        if constexpr (KEEP) {
+#pragma unroll
+          for (int g = 0; g < GR; ++g)
+#pragma unroll
+            for (int c = 0; c < CPT; ++c) widen(x[g][c], xk[g][c]);
+        }
         // sweep 1: G b' per row, transposed butterfly over the warp, one partial per (row, warp)
         const int pbuf = cons_seq & 1;
         if (!first) {
@@ -961,12 +983,16 @@ __global__ void __launch_bounds__(NT, 1) ibss_kernel(const LaunchParams P) {
           for (int g = 0; g < GR; ++g) {
             double s0 = 0.0, s1 = 0.0;
 #pragma unroll
-            for (int c = 0; c < CPT; ++c)
+            for (int c = 0; c < CPT; ++c) {
+              double xd[8];
+              if constexpr (!KEEP) widen(x[g][c], xd);
+              const double(&xv)[8] = *(KEEP ? &xk[KEEP ? g : 0][KEEP ? c : 0] : &xd);
 #pragma unroll
               for (int u = 0; u < 8; u += 2) {
-                s0 = fma(x[g][c][u], bq[c][u], s0);
-                s1 = fma(x[g][c][u + 1], bq[c][u + 1], s1);
+                s0 = fma(xv[u], bq[c][u], s0);
+                s1 = fma(xv[u + 1], bq[c][u + 1], s1);
               }
+            }
             ps[g] = s0 + s1;
           }
           const double t = warp_rows_sum<GR>(ps, lane);
@@ -1007,15 +1033,27 @@ __global__ void __launch_bounds__(NT, 1) ibss_kernel(const LaunchParams P) {
               rsq[kk] += Rfull * Rfull;  // |y - X sum_l b_l|^2 at the last effect (infer.py:804)
             }
         }
-        // sweep 2: G^T r_next accumulated in registers
+        // sweep 2: G^T r_next accumulated in registers.  The raw bytes are laundered through an empty
+        // asm so the compiler widens them again here instead of keeping 8 * GR * CPT doubles alive
+        // across the barrier (which spills).
+        if constexpr (!KEEP) {
+#pragma unroll
+          for (int g = 0; g < GR; ++g)
+#pragma unroll
+            for (int c = 0; c < CPT; ++c) asm volatile("" : "+r"(x[g][c].x), "+r"(x[g][c].y));
+        }
 #pragma unroll
         for (int g = 0; g < GR; ++g) {
           const double rg = __shfl_sync(0xffffffffu, rn_me, g * LG);
           rsum += rg;
 #pragma unroll
-          for (int c = 0; c < CPT; ++c)
+          for (int c = 0; c < CPT; ++c) {
+            double xd[8];
+            if constexpr (!KEEP) widen(x[g][c], xd);
+            const double(&xv)[8] = *(KEEP ? &xk[KEEP ? g : 0][KEEP ? c : 0] : &xd);
 #pragma unroll
-            for (int u = 0; u < 8; ++u) aq[c][u] = fma(x[g][c][u], rg, aq[c][u]);
+            for (int u = 0; u < 8; ++u) aq[c][u] = fma(xv[u], rg, aq[c][u]);
+          }
         }
         phase_bits ^= (1u << st);
         cons_seq += 1;
@@ -1325,11 +1363,11 @@ __global__ void __launch_bounds__(NT, 1) ibss_kernel(const LaunchParams P) {
     auto traverse = [&](int l, bool first, bool last_effect) {
       if constexpr (std::is_same<XT, int8_t>::value) {
         if (fast == 1)
-          traverse_i8(IntC<1>{}, IntC<8>{}, l, first, last_effect);
+          traverse_i8(IntC<1>{}, IntC<8>{}, IntC<SB_I8_KEEP>{}, l, first, last_effect);
         else if (fast == 2)
-          traverse_i8(IntC<2>{}, IntC<4>{}, l, first, last_effect);
+          traverse_i8(IntC<2>{}, IntC<4>{}, IntC<0>{}, l, first, last_effect);
         else
-          traverse_i8(IntC<4>{}, IntC<2>{}, l, first, last_effect);
+          traverse_i8(IntC<4>{}, IntC<2>{}, IntC<0>{}, l, first, last_effect);
       } else if constexpr (SS) {
         if (fast == 1)
           traverse_ss(IntC<4>{}, IntC<4>{}, l, last_effect);
@@ -1856,7 +1894,7 @@ __global__ void prep_columns_kernel(const IT* in, int in_ld, int n, int p, int p
 template <typename IT>
 __global__ void prep_columns_i8_kernel(const IT* in, int in_ld, int n, int p, int p_pad, int flags, int8_t* out,
                                        double* __restrict__ xtx, double* __restrict__ cmean,
-                                       double* __restrict__ cisd) {
+                                       double* __restrict__ cisd, int* __restrict__ bad_flag) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= p_pad) return;
   if (j >= p) {
@@ -1884,13 +1922,16 @@ __global__ void prep_columns_i8_kernel(const IT* in, int in_ld, int n, int p, in
     sd = sqrt(s2 / n);
   }
   double ss = 0.0;
+  bool bad = false;
   for (int i = 0; i < n; ++i) {
     const IT g = in[static_cast<size_t>(i) * in_ld + j];
     double v = static_cast<double>(g) - mean;
     if (flags & 2) v /= sd;
     out[static_cast<size_t>(i) * p_pad + j] = static_cast<int8_t>(g);
+    if (g < IT(0)) bad = true;  // the traversal widens the bytes as unsigned
     ss += v * v;
   }
+  if (bad) atomicOr(bad_flag, 1);
   xtx[j] = ss;
   cmean[j] = mean;
   cisd[j] = 1.0 / sd;

@@ -49,8 +49,9 @@ __all__ = [
 class _Prepared:
     """One validated problem: engine arguments + what the epilogue needs."""
 
-    def __init__(self, problem, pi, sample_size, max_iter, min_tol, cs_args, no_reorder):
+    def __init__(self, problem, pi, sample_size, max_iter, min_tol, cs_args, no_reorder, hard_calls=False):
         self.problem = problem
+        self.hard_calls = hard_calls  # genotypes verified to be integers in 0..127, not residualised
         self.pi = pi
         self.sample_size = sample_size
         self.max_iter = max_iter
@@ -98,10 +99,12 @@ def _prepare(
                 np.asarray(mats[idx], dtype=float), phen[idx], np.asarray(covar[idx], dtype=float), no_regress
             )
     # hard calls that were not residualised stay one byte per entry on the device
+    hard_calls = False
     if config.genotype_storage == "auto" and (covar is None or no_regress):
         packed = [utils.as_hard_calls(m) for m in mats]
         if all(m is not None for m in packed):
             mats = packed
+            hard_calls = True
     for idx in range(n_pop):
         y = phen[idx] - np.mean(phen[idx])
         if not no_scale:
@@ -121,7 +124,7 @@ def _prepare(
     )
     sample_size = np.asarray([m.shape[0] for m in mats])[:, np.newaxis]
     cs_args = dict(threshold=threshold, purity=purity, purity_method=purity_method, max_select=max_select, seed=seed)
-    return _Prepared(problem, pi, sample_size, max_iter, min_tol, cs_args, no_reorder)
+    return _Prepared(problem, pi, sample_size, max_iter, min_tol, cs_args, no_reorder, hard_calls)
 
 
 def _finish(batch: "_capi.Batch", index: int, prep: _Prepared, fit) -> SushieResult:
@@ -140,7 +143,7 @@ def _run_prepared(preps: Sequence[_Prepared], device: int = 0) -> List[SushieRes
     eng = _capi.get_engine(device)
     storage = config.storage_code()
     if config.genotype_storage == "auto" and all(
-        p.problem.x_dtype == _capi.SB_I8 and p.problem.p <= _capi.I8_MAX_SNPS for p in preps
+        p.hard_calls and p.problem.x_dtype == _capi.SB_I8 and p.problem.p <= _capi.I8_MAX_SNPS for p in preps
     ):
         storage = _capi.SB_I8
     opts = eng.make_opts(preps[0].max_iter, preps[0].min_tol, storage, config.team_size, config.single_phase)

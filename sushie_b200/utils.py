@@ -70,21 +70,19 @@ def regress_covar(X: np.ndarray, y: np.ndarray, covar: np.ndarray, no_regress: b
 
 
 def as_hard_calls(X) -> "np.ndarray | None":
-    """``X`` as a C-contiguous int8 matrix when every entry is an integer in the int8 range
-    (hard-call genotypes 0/1/2), else ``None``.  Used to pick the one-byte device storage."""
+    """``X`` as a C-contiguous int8 matrix when every entry is an integer in 0..127 (hard-call
+    genotypes 0/1/2), else ``None``.  Used to pick the one-byte device storage."""
     X = np.asarray(X)
     if X.ndim != 2 or X.size == 0:
         return None
-    if X.dtype == np.int8:
-        return np.ascontiguousarray(X)
     if X.dtype.kind in "iu":
-        if X.min() < -128 or X.max() > 127:
+        if X.min() < 0 or X.max() > 127:
             return None
         return np.ascontiguousarray(X, dtype=np.int8)
     if X.dtype.kind != "f":
         return None
     lo, hi = X.min(), X.max()
-    if not (np.isfinite(lo) and np.isfinite(hi)) or lo < -128 or hi > 127:
+    if not (np.isfinite(lo) and np.isfinite(hi)) or lo < 0 or hi > 127:
         return None
     Xi = X.astype(np.int8)
     if not np.array_equal(Xi, X):
