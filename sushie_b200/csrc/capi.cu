@@ -7,6 +7,8 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <chrono>
+#include <cstdlib>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -969,7 +971,20 @@ extern "C" int sb_batch_run(sb_ctx* ctx, sb_batch* b, sb_run_stats* stats) {
       lp.n_teams = n_teams;
       lp.allow_drain = (bigger > C) ? 1 : 0;
       void* args[] = {&lp};
+      static const bool trace = std::getenv("SUSHIE_B200_TRACE_PHASES") != nullptr;
+      if (trace) {  // development aid: wall time of the previous phase ends where this line is printed
+        cudaStreamSynchronize(st);
+        std::fprintf(stderr, "[sushie_b200] phase %d: team_size=%d hw=%d teams=%d loci=%d\n", phases, C, hw, n_teams, n_ids);
+      }
       SB_CUDA(cudaLaunchKernelExC(&cfg, fn, args));
+      if (trace) {
+        cudaEvent_t e0 = ctx->ev[2];
+        (void)e0;
+        auto t0 = std::chrono::steady_clock::now();
+        cudaStreamSynchronize(st);
+        const double ms_phase = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        std::fprintf(stderr, "[sushie_b200] phase %d took %.1f ms\n", phases, ms_phase);
+      }
       ++launches;
       ++phases;
       if (!lp.allow_drain) break;  // final phase: everything runs to completion
