@@ -55,15 +55,30 @@ def _split2(key: Tuple[int, int]):
     return (int(w[0]), int(w[1])), (int(w[2]), int(w[3]))
 
 
-def jax_choice_no_replace(seed: int, values: np.ndarray, n_draws: int) -> np.ndarray:
-    """First ``n_draws`` entries of JAX's sort-based shuffle of ``values``."""
-    key = ((int(seed) >> 32) & 0xFFFFFFFF, int(seed) & 0xFFFFFFFF)
+def prng_key(seed: int) -> Tuple[int, int]:
+    """``jax.random.PRNGKey(seed)`` as a pair of 32-bit words."""
+    return ((int(seed) >> 32) & 0xFFFFFFFF, int(seed) & 0xFFFFFFFF)
+
+
+def split_key(key: Tuple[int, int]):
+    """``jax.random.split(key, 2)`` -> (first, second)."""
+    return _split2(key)
+
+
+def shuffle_with_key(key: Tuple[int, int], values: np.ndarray) -> np.ndarray:
+    """JAX's sort-based shuffle of ``values`` (``jax.random.permutation`` /
+    ``choice(..., replace=False)``): rounds of stable sorts by fresh 32-bit words."""
     out = np.array(values, copy=True)
     rounds = int(np.ceil(3 * np.log(max(1, out.size)) / np.log(np.iinfo(np.uint32).max)))
     for _ in range(rounds):
         key, sub = _split2(key)
         out = out[np.argsort(_threefry_stream(sub, out.size), kind="stable")]
-    return out[:n_draws]
+    return out
+
+
+def jax_choice_no_replace(seed: int, values: np.ndarray, n_draws: int) -> np.ndarray:
+    """First ``n_draws`` entries of JAX's sort-based shuffle of ``values``."""
+    return shuffle_with_key(prng_key(seed), values)[:n_draws]
 
 
 # ---- credible sets ----------------------------------------------------------------------
