@@ -65,7 +65,7 @@ struct sb_batch {
   size_t arena_bytes = 0;
   ProbDev* d_probs = nullptr;
   int* d_ids = nullptr;     // problem ids grouped by K
-  int* d_queue = nullptr;   // [KMAX] one queue head per K group
+  int* d_queue = nullptr;   // device work-queue head of the running launch
   int* d_slots = nullptr;
   unsigned* d_bar = nullptr;
   size_t metas_off = 0;
@@ -74,8 +74,11 @@ struct sb_batch {
   long long scratch_stride = 0;
   int off_stat = 0, off_trav = 0;
   int phases = 0;
-  std::vector<int> ids_host;
-  int group_start[KMAX + 2] = {0};
+  std::vector<int> ids_host;  // problem ids ordered by launch group
+  struct Group {
+    int K, variant, start, count;
+  };
+  std::vector<Group> groups;  // one kernel (K, traversal variant) per group
   std::vector<HostProb> hp;
   std::vector<ProbDev> pd;
   double prologue_ms = 0.0;
@@ -97,17 +100,20 @@ static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; 
 // ------------------------------------------------------------------------------------------
 // kernel table
 
-template <int K, typename XT, bool SS>
+template <int K, typename XT, bool SS, int V = 0>
 static const void* kfn() {
-  return reinterpret_cast<const void*>(&sb::ibss_kernel<K, XT, SS>);
+  return reinterpret_cast<const void*>(&sb::ibss_kernel<K, XT, SS, V>);
 }
-static const void* pick_kernel(int K, int storage, bool ss) {
+// variant: traversal variant compiled into the kernel (hard-call storage only: Geometry::fast), else 0
+static const void* pick_kernel(int K, int storage, bool ss, int variant) {
   const bool f32 = storage == SB_F32;
   const bool i8 = storage == SB_I8;
   if (i8 && ss) return nullptr;
 #define SB_PICK(KK)                                                                           \
   case KK:                                                                                    \
-    if (i8) return kfn<KK, int8_t, false>();                                                  \
+    if (i8)                                                                                   \
+      return variant == 1 ? kfn<KK, int8_t, false, 1>()                                       \
+                          : (variant == 2 ? kfn<KK, int8_t, false, 2>() : kfn<KK, int8_t, false, 3>()); \
     return ss ? (f32 ? kfn<KK, float, true>() : kfn<KK, double, true>())                      \
               : (f32 ? kfn<KK, float, false>() : kfn<KK, double, false>());
   switch (K) {
@@ -229,11 +235,12 @@ static bool plan_geometry(int p, int n_max, int es, bool ss, int smem_budget, Ge
     } else {
       return false;
     }
-    const int rows_fit = static_cast<int>((smem_budget - hdr) / row_bytes);
+    const size_t state = 2 * sizeof(double) * sb::I8_STATE_ROWS;  // staged (r, xb) rows behind the ring
+    const int rows_fit = static_cast<int>((smem_budget - hdr - state) / row_bytes);
     g.G = gr;
     g.NS = std::max(2, std::min(sb::NSTAGE_MAX, rows_fit / gr));
     g.NSEG = 1;
-    g.smem = hdr + static_cast<size_t>(g.NS) * g.G * row_bytes;
+    g.smem = hdr + static_cast<size_t>(g.NS) * g.G * row_bytes + state;
     return true;
   }
   // register-tile traversal (individual level): every thread owns CPT vectors of GR rows
@@ -489,9 +496,9 @@ static int batch_create(sb_ctx* ctx, const std::vector<GenericProblem>& gp, bool
   const size_t probs_off = bump.take(sizeof(ProbDev) * n_probs);
   const size_t ids_off = bump.take(sizeof(int) * n_probs);
   const size_t queue_off = bump.take(sizeof(int) * 64);
-  const size_t slots_off = bump.take(sizeof(int) * 2 * (ctx->num_sms + 8));
+  const size_t slots_off = bump.take(sizeof(int) * 2 * (2 * ctx->num_sms + 8));
   const size_t ctl_off = bump.take(sizeof(int) * 64);
-  const size_t bar_off = bump.take(sizeof(unsigned) * 64 * (ctx->num_sms + 8));
+  const size_t bar_off = bump.take(sizeof(unsigned) * 64 * (2 * ctx->num_sms + 8));
   const size_t metas_off = bump.take(sizeof(int) * 8 * n_probs);
   const size_t elbos_off = bump.take(sizeof(double) * (opts.max_iter + 1) * static_cast<size_t>(n_probs));
   size_t staging_bytes = 0;
@@ -549,7 +556,7 @@ static int batch_create(sb_ctx* ctx, const std::vector<GenericProblem>& gp, bool
   const int off_stat = static_cast<int>(align_up(Kp_max, 16));
   const int off_trav = off_stat + 3 * sb::STAT_STRIDE + 4;
   const size_t scratch_stride = align_up(static_cast<size_t>(off_trav) + static_cast<size_t>(L_max) * sb::TRAV_STRIDE, 32);
-  const size_t scratch_off = bump.take(sizeof(double) * scratch_stride * (ctx->num_sms + 8));
+  const size_t scratch_off = bump.take(sizeof(double) * scratch_stride * (2 * ctx->num_sms + 8));
   b->arena_bytes = align_up(bump.off, 256);
   {
     cudaError_t e = cudaMalloc(&b->arena, b->arena_bytes);
@@ -744,12 +751,14 @@ static int batch_create(sb_ctx* ctx, const std::vector<GenericProblem>& gp, bool
   {
     std::vector<int> ids;
     ids.reserve(n_probs);
-    for (int K = 1; K <= KMAX; ++K) {
-      b->group_start[K] = static_cast<int>(ids.size());
-      for (int i = 0; i < n_probs; ++i)
-        if (gp[i].K == K) ids.push_back(i);
-    }
-    b->group_start[KMAX + 1] = static_cast<int>(ids.size());
+    for (int K = 1; K <= KMAX; ++K)
+      for (int variant = 0; variant <= 3; ++variant) {
+        const int start = static_cast<int>(ids.size());
+        for (int i = 0; i < n_probs; ++i)
+          if (gp[i].K == K && (opts.storage == SB_I8 ? geo[i].fast : 0) == variant) ids.push_back(i);
+        const int count = static_cast<int>(ids.size()) - start;
+        if (count > 0) b->groups.push_back({K, variant, start, count});
+      }
     b->ids_host = ids;
     SB_CUDA_B(cudaMemcpyAsync(b->d_ids, ids.data(), sizeof(int) * n_probs, cudaMemcpyHostToDevice, st));
     SB_CUDA_B(cudaMemcpyAsync(b->d_probs, b->pd.data(), sizeof(ProbDev) * n_probs, cudaMemcpyHostToDevice, st));
@@ -883,10 +892,9 @@ extern "C" int sb_batch_run(sb_ctx* ctx, sb_batch* b, sb_run_stats* stats) {
   int launches = 0, teams_used = 0, phases = 0;
   std::vector<int> meta(static_cast<size_t>(b->n_probs) * 8);
   SB_CUDA(cudaEventRecord(ctx->ev[0], st));
-  for (int K = 1; K <= KMAX; ++K) {
-    const int g0 = b->group_start[K], g1 = b->group_start[K + 1];
-    if (g1 == g0) continue;
-    const void* fn = pick_kernel(K, b->storage, b->ss);
+  for (const sb_batch::Group& grp : b->groups) {
+    const int K = grp.K, g0 = grp.start, g1 = grp.start + grp.count;
+    const void* fn = pick_kernel(K, b->storage, b->ss, grp.variant);
     if (!fn) {
       ctx->err = "no kernel for K=" + std::to_string(K);
       return SB_EINVAL;
@@ -934,7 +942,10 @@ extern "C" int sb_batch_run(sb_ctx* ctx, sb_batch* b, sb_run_stats* stats) {
         attrs[na].val.cooperative = 1;
         ++na;
       }
-      max_teams = std::min(max_teams, ctx->num_sms / C);
+      // one block per SM, except single-block teams of the hard-call kernel, which is built to
+      // co-reside (two loci per SM overlap each other's barriers and posterior phases)
+      const int per_sm_cap = (b->storage == SB_I8 && C == 1) ? SB_I8_BLOCKS_PER_SM : 1;
+      max_teams = std::min(max_teams, per_sm_cap * ctx->num_sms / C);
       if (max_teams < 1) {
         ctx->err = "kernel does not fit on the device (team_size=" + std::to_string(C) + ", smem=" +
                    std::to_string(b->smem_bytes) + ")";
@@ -950,13 +961,13 @@ extern "C" int sb_batch_run(sb_ctx* ctx, sb_batch* b, sb_run_stats* stats) {
       const int bigger = (b->opts.flags & SB_FLAG_SINGLE_PHASE) ? C : next_team_size(ctx, 1, C);
       SB_CUDA(cudaMemsetAsync(b->d_queue, 0, sizeof(int) * 64, st));
       SB_CUDA(cudaMemsetAsync(b->d_ctl, 0, sizeof(int) * 64, st));
-      SB_CUDA(cudaMemsetAsync(b->d_bar, 0, sizeof(unsigned) * 64 * (ctx->num_sms + 8), st));
+      SB_CUDA(cudaMemsetAsync(b->d_bar, 0, sizeof(unsigned) * 64 * (2 * ctx->num_sms + 8), st));
 
       LaunchParams lp{};
       lp.probs = b->d_probs;
       lp.prob_ids = b->d_ids + g0;
       lp.n_ids = n_ids;
-      lp.queue = b->d_queue + (K - 1) * 8;
+      lp.queue = b->d_queue;  // reset before every launch
       lp.team_slot = b->d_slots;
       lp.team_bar = b->d_bar;
       lp.team_size = C;

@@ -45,6 +45,7 @@ constexpr int NT = 256;  // threads per block
 constexpr int NW = NT / 32;
 constexpr int GMAX = 32;  // max rows per band
 constexpr int NSTAGE_MAX = 6;
+constexpr int I8_STATE_ROWS = 2048;  // hard-call path: band rows whose (r, xb) state is staged in shared memory at a time
 constexpr int SS_CHUNK_ROWS = 256;  // summary-level register-tile path: rows whose partial sums are parked in shared memory
 constexpr int NSYM_MAX = KMAX * (KMAX + 1) / 2;
 constexpr int STAT_STRIDE = 20;  // doubles per team-reduction record (>= 2 + NSYM_MAX + 2 + KMAX)
@@ -453,7 +454,9 @@ constexpr double LOG_2PI = 1.8378770664093454835606594728112;
 template <int N>
 using IntC = std::integral_constant<int, N>;
 
-template <int K, typename XT, bool SS>
+// V: traversal variant fixed at compile time (hard-call storage: 1 = 8 columns x 8 rows per thread, 2 = 16 x 4,
+// 3 = 32 x 2, so each variant gets its own register allocation); 0 = chosen per locus at run time.
+template <int K, typename XT, bool SS, int V = 0>
 __global__ void __launch_bounds__(NT, (std::is_same<XT, int8_t>::value ? SB_I8_BLOCKS_PER_SM : 1)) ibss_kernel(const LaunchParams P) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   constexpr int NSYM = K * (K + 1) / 2;
@@ -870,21 +873,29 @@ __global__ void __launch_bounds__(NT, (std::is_same<XT, int8_t>::value ? SB_I8_B
       int st = cons_seq % NS;
       double cshift = 0.0;  // sum_j mean_j b_j / sd_j of the current ancestry
       double rsum = 0.0;    // sum of r_next over the rows of the current ancestry seen by this block
-      auto fetch_state = [&](int pos) -> double {
-        int k, g0, rows;
-        band_of(pos, k, g0, rows);
-        const int g = tid % GR;
-        if (g >= rows) return 0.0;
-        const int row = pb.row0[k] + g0 + g;
-        return (tid < GR) ? pb.r[row] : pb.xb[static_cast<size_t>(lnext) * nrows + row];
+      // row state (r, xb[lnext]) of up to I8_STATE_ROWS band rows is staged in shared memory ahead of the
+      // bands that use it: a band lasts well under one L2 round trip here, so per-band global loads would
+      // sit on the critical path of the block barrier
+      double* rs_sm = reinterpret_cast<double*>(ring + static_cast<size_t>(NS) * stage_bytes);
+      double* xs_sm = rs_sm + I8_STATE_ROWS;
+      constexpr int CHUNK_BANDS = I8_STATE_ROWS / GR;
+      auto stage_rows = [&](int pos0, int pos1) {
+        __syncthreads();  // previous chunk fully consumed
+        for (int i = tid; i < (pos1 - pos0) * GR; i += NT) {
+          int k, g0, rows;
+          band_of(pos0 + i / GR, k, g0, rows);
+          const int g = i % GR;
+          double rv = 0.0, xv = 0.0;
+          if (g < rows) {
+            const int row = pb.row0[k] + g0 + g;
+            rv = pb.r[row];
+            xv = pb.xb[static_cast<size_t>(lnext) * nrows + row];
+          }
+          rs_sm[i] = rv;
+          xs_sm[i] = xv;
+        }
+        __syncthreads();
       };
-      // a band takes well under one L2 round trip here: keep three bands of row state in flight
-      double pre0 = 0.0, pre1 = 0.0, pre2 = 0.0;
-      if (tid < 2 * GR) {
-        if (nb_own > 0) pre0 = fetch_state(0);
-        if (nb_own > 1) pre1 = fetch_state(1);
-        if (nb_own > 2) pre2 = fetch_state(2);
-      }
 
       // partial X_std^T r of ancestry k: (G^T r - mean * sum r) / sd
       auto flush_acc = [&](int k) {
@@ -906,7 +917,12 @@ __global__ void __launch_bounds__(NT, (std::is_same<XT, int8_t>::value ? SB_I8_B
         }
       };
 
+      int chunk0 = 0;
       for (int pos = 0; pos < nb_own; ++pos) {
+        if (pos == 0 || pos == chunk0 + CHUNK_BANDS) {
+          chunk0 = pos;
+          stage_rows(chunk0, min(nb_own, chunk0 + CHUNK_BANDS));
+        }
         int k, g0, rows;
         band_of(pos, k, g0, rows);
         if (k != cur_k) {
@@ -941,12 +957,6 @@ __global__ void __launch_bounds__(NT, (std::is_same<XT, int8_t>::value ? SB_I8_B
         }
         const unsigned char* tile = ring + static_cast<size_t>(st) * stage_bytes;
         const int row_base = pb.row0[k] + g0;
-        if (tid < 2 * GR) {
-          H->rstate[pos & 1][tid] = pre0;
-          pre0 = pre1;
-          pre1 = pre2;
-          if (pos + 3 < nb_own) pre2 = fetch_state(pos + 3);
-        }
         mbar_wait(&H->mbar[st], (phase_bits >> st) & 1u);
 
         // the band -> registers (the only shared-memory read of the genotypes)
@@ -1020,8 +1030,9 @@ __global__ void __launch_bounds__(NT, (std::is_same<XT, int8_t>::value ? SB_I8_B
           v = t - cshift;
         }
         const bool live = g_me < rows;
-        const double Rfull = live ? H->rstate[pos & 1][g_me] - v : 0.0;
-        const double rn_me = live ? Rfull + H->rstate[pos & 1][GR + g_me] : 0.0;
+        const int srow = (pos - chunk0) * GR + g_me;
+        const double Rfull = live ? rs_sm[srow] - v : 0.0;
+        const double rn_me = live ? Rfull + xs_sm[srow] : 0.0;
         if (warp == 0 && q == 0 && live) {  // row writer
           const int row = row_base + g_me;
           if (!first) pb.xb[static_cast<size_t>(l) * nrows + row] = v;
@@ -1362,9 +1373,9 @@ __global__ void __launch_bounds__(NT, (std::is_same<XT, int8_t>::value ? SB_I8_B
 
     auto traverse = [&](int l, bool first, bool last_effect) {
       if constexpr (std::is_same<XT, int8_t>::value) {
-        if (fast == 1)
+        if constexpr (V == 1)
           traverse_i8(IntC<1>{}, IntC<8>{}, IntC<SB_I8_KEEP>{}, l, first, last_effect);
-        else if (fast == 2)
+        else if constexpr (V == 2)
           traverse_i8(IntC<2>{}, IntC<4>{}, IntC<0>{}, l, first, last_effect);
         else
           traverse_i8(IntC<4>{}, IntC<2>{}, IntC<0>{}, l, first, last_effect);
