@@ -384,7 +384,7 @@ def main():
         n_ser += st["n_ser"]
         n_iter += st["n_iter"]
         alg_bytes += st["algorithmic_bytes"]
-        launches += 1
+        launches += st["n_run_launches"]
     barrier()
     wall_ms = 1e3 * (time.perf_counter() - t_wall0)
     clocks = sampler.stop()
@@ -492,12 +492,13 @@ def main():
             "wall_ms_per_step": wall_ms / args.steps,
             "gpu_launches": launches,
             "kernel": dict(geom, name="sb::ibss_kernel<3,%s,false>" % {"i8": "int8_t", "f64": "double", "f32": "float"}[args.storage],
-                           launches_per_step=1, genotype_storage=args.storage),
+                           launches_per_step=launches / args.steps, genotype_storage=args.storage),
             "roofline": {
                 "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": (traffic_per_ser * (n_ser / world) / launches) if traffic_per_ser else None,
+                "traffic": (traffic_per_ser * (n_ser / world) / args.steps) if traffic_per_ser else None,
                 "traffic_source": (f"{traffic_src}: ncu dram read+write bytes per single-effect update "
-                                   f"({traffic_per_ser:.0f} B) x updates per launch") if traffic_per_ser else None,
+                                   f"({traffic_per_ser:.0f} B) x updates per step (one persistent launch "
+                                   f"plus its short tail phases)") if traffic_per_ser else None,
                 "peak_source": peak_src,
                 "algorithmic_bytes_per_ser": K_ANC * N_IND * P_SNP * elem_bytes,
                 "note": "achieved = (#single-effect updates x k*n*p*%d B, one traversal of the stored genotypes) / "

@@ -137,6 +137,7 @@ typedef struct {
   int32_t rows_per_band;
   int32_t n_stages;
   int32_t smem_bytes;
+  int32_t n_run_launches;    /* IBSS kernel launches (phases of the team-size ladder) of the last sb_batch_run */
 } sb_run_stats;
 
 int sb_version(void);

@@ -123,6 +123,7 @@ class SbRunStats(C.Structure):
         ("rows_per_band", C.c_int32),
         ("n_stages", C.c_int32),
         ("smem_bytes", C.c_int32),
+        ("n_run_launches", C.c_int32),
     ]
 
     def as_dict(self):

@@ -1032,6 +1032,7 @@ extern "C" int sb_batch_run(sb_ctx* ctx, sb_batch* b, sb_run_stats* stats) {
     stats->rows_per_band = b->G_max;
     stats->n_stages = b->NS_max;
     stats->smem_bytes = b->smem_bytes;
+    stats->n_run_launches = launches;
     SB_CUDA(cudaMemcpyAsync(meta.data(), b->arena + b->metas_off, sizeof(int) * 8 * b->n_probs,
                             cudaMemcpyDeviceToHost, st));
     SB_CUDA(cudaStreamSynchronize(st));
