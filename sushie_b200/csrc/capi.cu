@@ -255,6 +255,9 @@ static bool plan_geometry(int p, int n_max, int es, bool ss, int smem_budget, Ge
     } else if (ss && pv > 8 * sb::NT && pv <= 12 * sb::NT) {
       g.fast = 3;
       gr = 1;
+    } else if (ss && pv > 12 * sb::NT && pv <= 16 * sb::NT) {
+      g.fast = 4;
+      gr = 1;
     }
     if (g.fast) {
       // summary level: partial row sums of a chunk are parked behind the ring

@@ -72,7 +72,7 @@ struct ProbDev {
   int G, nstage, nseg; // rows per band, ring stages, warps per row in sweep 1
   int em;              // 1 = EM prior update, 0 = times/plus adjustor
   int skip_first_pass; // adjustor.times == 0: the first posterior pass cannot matter
-  int fast;            // traversal variant: 0 generic; register tile 1: 4 vec x 4 rows, 2: 8 x 2, 3: 12 x 1
+  int fast;            // traversal variant: 0 generic; register tile 1: 4 vec x 4 rows, 2: 8 x 2, 3: 12 x 1, 4: 16 x 1 (summary level)
   const void* X[KMAX]; // [n_k][p_pad] storage type
   double nscale[KMAX]; // summary level: n_k (XtX = n LD); individual level: 1
   double nsamp[KMAX];  // n_k as double for the ELBO
@@ -638,6 +638,7 @@ __global__ void __launch_bounds__(NT, (std::is_same<XT, int8_t>::value ? SB_I8_B
       constexpr int GR = decltype(gr_c)::value;
       constexpr int PRODUCER_TID = NT - 32;  // lane 0 of the last warp issues the bulk copies
       const int lnext = first ? 0 : ((l + 1 == L) ? 0 : l + 1);
+      const bool self_next = !first && lnext == l;
       double vsq[K], rsq[K];  // meaningful in threads < GR only
 #pragma unroll
       for (int k = 0; k < K; ++k) vsq[k] = rsq[k] = 0.0;
@@ -802,7 +803,7 @@ __global__ void __launch_bounds__(NT, (std::is_same<XT, int8_t>::value ? SB_I8_B
             v = (((q0.x + q0.y) + (q1.x + q1.y)) + ((q2.x + q2.y) + (q3.x + q3.y))) * nsc;
           }
           const double Rfull = r_old[g] - v;
-          rn[g] = Rfull + xb_next[g];
+          rn[g] = Rfull + (self_next ? v : xb_next[g]);  // L == 1: the effect added back is the one just computed
           if (tid == g && g < rows) {  // designated thread of row g: publish the row state
             const int row = row_base + g;
             if (!first) pb.xb[static_cast<size_t>(l) * nrows + row] = v;
@@ -854,6 +855,7 @@ __global__ void __launch_bounds__(NT, (std::is_same<XT, int8_t>::value ? SB_I8_B
       constexpr int LG = 32 / GR;  // lanes sharing one band row after the butterfly
       const int pv8 = p_pad / 8;   // 8-byte vectors per row
       const int lnext = first ? 0 : ((l + 1 == L) ? 0 : l + 1);
+      const bool self_next = !first && lnext == l;
       double vsq[K], rsq[K];  // meaningful in the row-writer lanes of warp 0 only
 #pragma unroll
       for (int k = 0; k < K; ++k) vsq[k] = rsq[k] = 0.0;
@@ -1032,7 +1034,7 @@ __global__ void __launch_bounds__(NT, (std::is_same<XT, int8_t>::value ? SB_I8_B
         const bool live = g_me < rows;
         const int srow = (pos - chunk0) * GR + g_me;
         const double Rfull = live ? rs_sm[srow] - v : 0.0;
-        const double rn_me = live ? Rfull + xs_sm[srow] : 0.0;
+        const double rn_me = live ? Rfull + (self_next ? v : xs_sm[srow]) : 0.0;  // L == 1: add back the new effect
         if (warp == 0 && q == 0 && live) {  // row writer
           const int row = row_base + g_me;
           if (!first) pb.xb[static_cast<size_t>(l) * nrows + row] = v;
@@ -1208,7 +1210,7 @@ __global__ void __launch_bounds__(NT, (std::is_same<XT, int8_t>::value ? SB_I8_B
               const double2 q0 = ps2[0], q1 = ps2[1], q2 = ps2[2], q3 = ps2[3];
               const double v = (((q0.x + q0.y) + (q1.x + q1.y)) + ((q2.x + q2.y) + (q3.x + q3.y))) * pb.nscale[k];
               const double Rfull = pb.r[row] - v;
-              pb.r[row] = Rfull + pb.xb[static_cast<size_t>(lnext) * nrows + row];
+              pb.r[row] = Rfull + (lnext == l ? v : pb.xb[static_cast<size_t>(lnext) * nrows + row]);  // L == 1
               pb.xb[static_cast<size_t>(l) * nrows + row] = v;
               if (last_effect) pb.rfull[row] = Rfull;
               const double vterm = __ldcg(&effect_vec(l, k)[g0 + g]) * v;  // b_l^T XtX b_l (infer_ss.py:572)
@@ -1308,7 +1310,7 @@ __global__ void __launch_bounds__(NT, (std::is_same<XT, int8_t>::value ? SB_I8_B
             pb.xb[static_cast<size_t>(l) * nrows + row] = v;
           }
           const double Rfull = r_old - v;
-          const double rnext = Rfull + xb_next;
+          const double rnext = Rfull + ((lnext == l && !first) ? v : xb_next);  // L == 1: add back the new effect
           pb.r[row] = rnext;
           H->rn[tid] = rnext;
           // b_l^T XtX b_l (infer_ss.py:572)  |  |X b_l|^2 (infer.py:806)
@@ -1386,6 +1388,8 @@ __global__ void __launch_bounds__(NT, (std::is_same<XT, int8_t>::value ? SB_I8_B
           traverse_ss(IntC<8>{}, IntC<2>{}, l, last_effect);
         else if (fast == 3)
           traverse_ss(IntC<12>{}, IntC<1>{}, l, last_effect);
+        else if (fast == 4)
+          traverse_ss(IntC<16>{}, IntC<1>{}, l, last_effect);
         else
           traverse_generic(IntC<0>{}, l, first, last_effect);
       } else {

@@ -1,0 +1,143 @@
+"""GPU parity for option combinations and edge shapes, against the oracle run in the test itself
+(small loci, so the numpy oracle takes well under a second each).
+
+Tolerances as in tests/parity.py: same n_iter, |dELBO| <= 1e-6 |ELBO|, |dPIP| <= 1e-4, prior covariance
+within 1e-4 relative (order-free when the effect order is fragile)."""
+import numpy as np
+import pytest
+
+from parity import COV_RTOL, ELBO_RTOL, PIP_TOL
+
+pytestmark = pytest.mark.gpu
+
+
+def _locus(seed, k, n, p, causal=(3, 40), h=0.9):
+    rng = np.random.default_rng(seed)
+    maf = rng.uniform(0.1, 0.5, size=p)
+    Xs, ys = [], []
+    beta = np.zeros(p)
+    beta[list(causal)] = rng.choice([-1.0, 1.0], size=len(causal)) * h
+    for a in range(k):
+        g = rng.binomial(2, maf, size=(n[a], p)).astype(float)
+        for j in np.nonzero(g.std(axis=0) == 0)[0]:
+            g[0, j] = 1.0 if g[0, j] != 1.0 else 0.0
+        gs = (g - g.mean(0)) / g.std(0)
+        ys.append(gs @ beta + rng.standard_normal(n[a]))
+        Xs.append(g)
+    return Xs, ys
+
+
+def _check(res, ref):
+    from oracle import ibss
+
+    assert len(res.elbo) - 1 == ref.n_iter
+    assert bool(res.elbo_increase) == bool(ref.elbo_increase)
+    fin = np.isfinite(ref.elbo[1:])
+    np.testing.assert_allclose(res.elbo[1:][fin], np.asarray(ref.elbo)[1:][fin], rtol=ELBO_RTOL)
+    assert np.max(np.abs(res.pip_all - ibss.make_pip(ref.posteriors.alpha))) <= PIP_TOL
+    np.testing.assert_allclose(np.sum(res.posteriors.alpha, axis=1), 1.0, atol=1e-9)
+    np.testing.assert_allclose(np.ravel(res.priors.resid_var), np.ravel(ref.priors.resid_var), rtol=1e-8)
+    tr_ref = np.sort(np.trace(ref.priors.effect_covar, axis1=1, axis2=2))
+    tr_got = np.sort(np.trace(res.priors.effect_covar, axis1=1, axis2=2))
+    np.testing.assert_allclose(tr_got, tr_ref, rtol=COV_RTOL)
+
+
+CASES = {
+    "pi_vector": dict(k=2, n=(90, 110), p=120, kw=dict(L=3), pi=True),
+    "resid_var": dict(k=2, n=(90, 110), p=120, kw=dict(L=3, resid_var=[0.8, 1.3])),
+    "single_effect": dict(k=3, n=(70, 80, 60), p=101, kw=dict(L=1)),
+    "not_converged": dict(k=2, n=(90, 110), p=120, kw=dict(L=4, max_iter=3)),
+    "odd_p_k1": dict(k=1, n=(257,), p=333, kw=dict(L=2)),
+    "many_effects": dict(k=2, n=(64, 64), p=128, kw=dict(L=12)),
+    "no_update_rho": dict(k=3, n=(70, 80, 60), p=150, kw=dict(L=3, no_update=True, rho=[0.3, 0.2, 0.1])),
+    "wide_dense": dict(k=2, n=(60, 50), p=2300, kw=dict(L=2)),
+}
+
+
+@pytest.mark.parametrize("storage", ["dense", "auto"])
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_individual_options_match_oracle(engine_lib, name, storage):
+    import sushie_b200
+    from oracle import ibss
+    from sushie_b200 import config
+
+    case = CASES[name]
+    Xs, ys = _locus(abs(hash(name)) % 1000, case["k"], case["n"], case["p"])
+    kw = dict(case["kw"], min_tol=1e-4)
+    if case.get("pi"):
+        pi = np.random.default_rng(5).uniform(0.5, 2.0, size=case["p"])
+        kw["pi"] = pi / pi.sum()
+    old = config.genotype_storage
+    config.genotype_storage = storage
+    try:
+        res = sushie_b200.infer_sushie([x.copy() for x in Xs], [y.copy() for y in ys], min_snps=50, **kw)
+    finally:
+        config.genotype_storage = old
+    ref = ibss.fit_individual(Xs, ys, **kw)
+    _check(res, ref)
+
+
+def test_covariates_with_and_without_genotype_regression(engine_lib):
+    import sushie_b200
+    from oracle import ibss
+
+    Xs, ys = _locus(11, 2, (100, 120), 110)
+    rng = np.random.default_rng(2)
+    covar = [np.column_stack([rng.standard_normal(x.shape[0]), rng.integers(0, 2, x.shape[0])]).astype(float) for x in Xs]
+    for no_regress in (False, True):
+        res = sushie_b200.infer_sushie([x.copy() for x in Xs], [y.copy() for y in ys], covar, L=3,
+                                       no_regress=no_regress, min_tol=1e-4)
+        ref = ibss.fit_individual(Xs, ys, covar=covar, L=3, no_regress=no_regress, min_tol=1e-4)
+        _check(res, ref)
+
+
+@pytest.mark.parametrize("kw", [dict(L=3), dict(L=2, no_update=True, effect_var=[0.02, 0.01]), dict(L=1),
+                                dict(L=3, pi=True), dict(L=4, max_iter=2)])
+def test_summary_options_match_oracle(engine_lib, kw):
+    import sushie_b200
+    from oracle import ibss
+
+    kw = dict(kw)
+    Xs, ys = _locus(21, 2, (150, 170), 140)
+    lds, zs = [], []
+    for X, y in zip(Xs, ys):
+        Xs_ = (X - X.mean(0)) / X.std(0)
+        lds.append(Xs_.T @ Xs_ / X.shape[0])
+        zs.append(Xs_.T @ ((y - y.mean()) / y.std()) / np.sqrt(X.shape[0]))
+    ns = np.array([[150], [170]])
+    if kw.pop("pi", False):
+        pi = np.random.default_rng(6).uniform(0.5, 2.0, size=140)
+        kw["pi"] = pi / pi.sum()
+    res = sushie_b200.infer_sushie_ss(np.stack(lds), ns, np.stack(zs), min_tol=1e-4, **kw)
+    ref = ibss.fit_summary(np.stack(lds), ns, np.stack(zs), min_tol=1e-4, **kw)
+    _check(res, ref)
+
+
+def test_summary_level_very_wide_locus_fits(engine_lib):
+    """p = 13 000 with fp32 LD storage uses the 16-vector register tile; a few iterations vs the oracle on a
+    banded LD (cheap to build) to make sure the wide geometry computes the same thing."""
+    import sushie_b200
+    from oracle import ibss
+    from sushie_b200 import config
+
+    p = 13000
+    idx = np.arange(p)
+    rng = np.random.default_rng(3)
+    lds, zs = [], []
+    for rho in (0.6, 0.4):
+        d = np.abs(idx[:, None] - idx[None, :])
+        ld = np.where(d < 12, rho ** d, 0.0).astype(np.float32)
+        z = rng.standard_normal(p)
+        z[[500, 9000]] += (7.0, -6.0)
+        lds.append(ld)
+        zs.append(z)
+    ns = np.array([[5000], [4000]])
+    old = config.precision
+    config.precision = 32
+    try:
+        res = sushie_b200.infer_sushie_ss(lds, ns, zs, L=2, max_iter=3, min_tol=0.0)
+    finally:
+        config.precision = old
+    ref = ibss.fit_summary([ld.astype(np.float64) for ld in lds], ns, zs, L=2, max_iter=3, min_tol=0.0)
+    np.testing.assert_allclose(res.elbo[1:], np.asarray(ref.elbo)[1:], rtol=1e-6)
+    assert np.max(np.abs(res.pip_all - ibss.make_pip(ref.posteriors.alpha))) <= PIP_TOL
