@@ -202,7 +202,7 @@ def test_c_abi_exports_every_declared_symbol(engine_lib):
     # struct layouts on the Python side must match the C side (sizes are a cheap proxy)
     assert ctypes.sizeof(_capi.SbOpts) == 40
     assert ctypes.sizeof(_capi.SbResult) == 9 * 8 + 16
-    assert ctypes.sizeof(_capi.SbRunStats) == 64
+    assert ctypes.sizeof(_capi.SbRunStats) == 72  # 5 x 8 + 7 x int32, padded to 8
     assert ctypes.sizeof(_capi.SbIndProblem) == 96
     assert ctypes.sizeof(_capi.SbSsProblem) == 96
 
