@@ -146,12 +146,22 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
   } while (!done);
 }
-// Bulk asynchronous global->shared copy (TMA engine), completion counted on an mbarrier.
-__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                   smem_u32(dst_smem)),
-               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
-               : "memory");
+// Bulk asynchronous global->shared copy (TMA engine), completion counted on an mbarrier.  The genotype /
+// LD stream is read once per single-effect update and the per-SM working set (one locus per block) is far
+// larger than L2, so it is tagged evict-first: the small per-locus vectors (residual, cached X b, effect
+// vectors, partial X^T r, priors) then stay L2-resident instead of being flushed every ~20 us.
+__device__ __forceinline__ uint64_t l2_evict_first_policy() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar,
+                                         uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+          smem_u32(dst_smem)),
+      "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
+      : "memory");
 }
 __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
   unsigned v;
@@ -481,6 +491,7 @@ __global__ void __launch_bounds__(NT, (std::is_same<XT, int8_t>::value ? SB_I8_B
   }
   __syncthreads();
 
+  const uint64_t stream_policy = l2_evict_first_policy();
   uint32_t phase_bits = 0;   // bit s = mbarrier parity of the next fill to consume in stage s
   uint32_t ephase_bits = 0;  // bit s = parity of the next "drained" phase of stage s (producer thread only)
 
@@ -559,7 +570,7 @@ __global__ void __launch_bounds__(NT, (std::is_same<XT, int8_t>::value ? SB_I8_B
       unsigned char* dst = ring + static_cast<size_t>(st) * stage_bytes;
       const uint32_t bytes = static_cast<uint32_t>(row_bytes * rows);
       mbar_expect_tx(&H->mbar[st], bytes);
-      bulk_g2s(dst, src, bytes, &H->mbar[st]);
+      bulk_g2s(dst, src, bytes, &H->mbar[st], stream_policy);
     };
 
     // ---- locus initialisation (state owned by this block: rows of its bands)
@@ -657,18 +668,6 @@ __global__ void __launch_bounds__(NT, (std::is_same<XT, int8_t>::value ? SB_I8_B
       }
       int cur_k = -1;
       int st = cons_seq % NS;
-      // row state of band `pos` for thread t < 2*GR: t < GR -> r[row g], else xb[lnext][row g]
-      auto fetch_state = [&](int pos) -> double {
-        int k, g0, rows;
-        band_of(pos, k, g0, rows);
-        const int g = tid % GR;
-        if (g >= rows) return 0.0;
-        const int row = pb.row0[k] + g0 + g;
-        return (tid < GR) ? pb.r[row] : pb.xb[static_cast<size_t>(lnext) * nrows + row];
-      };
-      double pre = 0.0;
-      if (tid < 2 * GR && nb_own > 0) pre = fetch_state(0);
-
       auto flush_acc = [&](int k) {
         double* dst = my_scr + static_cast<size_t>(k) * p_pad;
 #pragma unroll
@@ -707,10 +706,17 @@ __global__ void __launch_bounds__(NT, (std::is_same<XT, int8_t>::value ? SB_I8_B
         const double nsc = pb.nscale[k];
         const bool full_rows = (rows == GR);
 
-        // per-row state (r, xb[lnext]) was fetched one band ahead by threads 0..2*GR-1: publish it
-        if (tid < 2 * GR) {
-          H->rstate[pos & 1][tid] = pre;
-          if (pos + 1 < nb_own) pre = fetch_state(pos + 1);  // a whole band of latency cover
+        // per-row state (same addresses for every thread: broadcast loads), in flight while the band lands
+        double r_old[GR], xb_next[GR];
+        {
+          const double* rp = pb.r + row_base;
+          const double* xp = pb.xb + static_cast<size_t>(lnext) * nrows + row_base;
+#pragma unroll
+          for (int g = 0; g < GR; ++g) {
+            const bool ok = full_rows || g < rows;
+            r_old[g] = ok ? rp[g] : 0.0;
+            xb_next[g] = ok ? xp[g] : 0.0;
+          }
         }
         mbar_wait(&H->mbar[st], (phase_bits >> st) & 1u);
 
@@ -787,12 +793,6 @@ __global__ void __launch_bounds__(NT, (std::is_same<XT, int8_t>::value ? SB_I8_B
         }
         // every thread finishes the row sums itself (no second barrier); fixed pairwise order
         double rn[GR];
-        double r_old[GR], xb_next[GR];
-#pragma unroll
-        for (int g = 0; g < GR; ++g) {
-          r_old[g] = H->rstate[pos & 1][g];
-          xb_next[g] = H->rstate[pos & 1][GR + g];
-        }
 #pragma unroll
         for (int g = 0; g < GR; ++g) {
           double v = 0.0;
