@@ -472,6 +472,30 @@ def main():
         # per-GPU achieved bandwidth of the single persistent launch
         achieved = (alg_bytes / world) / (dev_ms / 1e3) / 1e9
         traffic_per_ser, traffic_src = ncu_traffic(args.storage)
+        # algorithmic bytes = one traversal of the genotype tensor per single-effect update at the
+        # precision under test (fp64 arithmetic: k*n*p*8 B; fp32 storage run: *4).  Hard-call storage keeps the same
+        # fp64 computation but reads 1 B per genotype, so its fraction is > 1 by compression -- stated here with the
+        # stored-bytes figure and the ncu DRAM traffic next to it; the dense arm below is the <= 1 roofline run.
+        alg_elem = 4 if args.storage == "f32" else 8
+        ser_per_gpu_s = (n_ser / world) / (dev_ms / 1e3)
+        achieved_alg = ser_per_gpu_s * K_ANC * N_IND * P_SNP * alg_elem / 1e9
+        roofline = {
+            "bound": "hbm", "achieved": achieved_alg, "peak": peak, "unit": "GB/s", "frac": achieved_alg / peak,
+            "traffic": (traffic_per_ser * (n_ser / world) / args.steps) if traffic_per_ser else None,
+            "traffic_source": (f"{traffic_src}: ncu dram read+write bytes per single-effect update "
+                               f"({traffic_per_ser:.0f} B) x updates per step (one persistent launch "
+                               f"plus its short tail phases)") if traffic_per_ser else None,
+            "peak_source": peak_src,
+            "algorithmic_bytes_per_ser": K_ANC * N_IND * P_SNP * alg_elem,
+            "stored_bytes_per_ser": K_ANC * N_IND * P_SNP * elem_bytes,
+            "achieved_stored_bytes": achieved, "frac_stored_bytes": achieved / peak,
+            "note": ("achieved = #single-effect updates x k*n*p*%d B (one traversal of the genotype tensor at the "
+                     "precision under test) / CUDA-event time, per GPU" % alg_elem)
+                    + ("; genotypes are stored as 1-byte hard calls (compressed), so frac > 1 is expected: DRAM "
+                       "traffic is `traffic`, the kernel is instruction/latency bound (fp64 pipe ~32 %, issue ~44 % "
+                       "busy, profiles/r01_ncu_full_ind_i8.json); the HBM-roofline claim is roofline_dense_fp64"
+                       if args.storage == "i8" else ""),
+        }
         line = {
             "metric": "loci_per_sec",
             "value": value,
@@ -493,17 +517,7 @@ def main():
             "gpu_launches": launches,
             "kernel": dict(geom, name="sb::ibss_kernel<3,%s,false>" % {"i8": "int8_t", "f64": "double", "f32": "float"}[args.storage],
                            launches_per_step=launches / args.steps, genotype_storage=args.storage),
-            "roofline": {
-                "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": (traffic_per_ser * (n_ser / world) / args.steps) if traffic_per_ser else None,
-                "traffic_source": (f"{traffic_src}: ncu dram read+write bytes per single-effect update "
-                                   f"({traffic_per_ser:.0f} B) x updates per step (one persistent launch "
-                                   f"plus its short tail phases)") if traffic_per_ser else None,
-                "peak_source": peak_src,
-                "algorithmic_bytes_per_ser": K_ANC * N_IND * P_SNP * elem_bytes,
-                "note": "achieved = (#single-effect updates x k*n*p*%d B, one traversal of the stored genotypes) / "
-                        "CUDA-event time of the launch, per GPU" % elem_bytes,
-            },
+            "roofline": roofline,
             "clocks": {"sm_mhz": clocks["sm_mhz"], "sm_max_mhz": clocks["sm_max_mhz"], "reasons": clocks["reasons"],
                        "samples": clocks["samples"]},
             "datagen_s": t_gen,

@@ -160,22 +160,21 @@ def build_tables(
         columns[f"log_bf_{tag}"] = log_bf[ldx]
         if kept[ldx]:
             sel = order[:size]
-            cs_parts.append(
-                pd.DataFrame(
-                    {
-                        "CSIndex": np.full(size, ldx + 1, dtype=np.int64),
-                        "SNPIndex": sel.astype(np.int64),
-                        "alpha": alpha[ldx][sel],
-                        "c_alpha": csum[:size],
-                    }
-                )
-            )
+            cs_parts.append((np.full(size, ldx + 1, dtype=np.int64), sel.astype(np.int64), alpha[ldx][sel], csum[:size]))
     columns["pip_all"] = pip_all
     columns["pip_cs"] = pip_cs
     full_alphas = pd.DataFrame(columns)
 
+    # one frame for all kept sets (a frame per effect costs more than the fit at batch throughput)
     if cs_parts:
-        cs = pd.concat(cs_parts, ignore_index=True)
+        cs = pd.DataFrame(
+            {
+                "CSIndex": np.concatenate([c[0] for c in cs_parts]),
+                "SNPIndex": np.concatenate([c[1] for c in cs_parts]),
+                "alpha": np.concatenate([c[2] for c in cs_parts]),
+                "c_alpha": np.concatenate([c[3] for c in cs_parts]),
+            }
+        )
     else:
         cs = pd.DataFrame(
             {
