@@ -236,7 +236,8 @@ static bool plan_geometry(int p, int n_max, int es, bool ss, int smem_budget, Ge
       return false;
     }
     const size_t state = 2 * sizeof(double) * sb::I8_STATE_ROWS;  // staged (r, xb) rows behind the ring
-    const int rows_fit = static_cast<int>((smem_budget - hdr - state) / row_bytes);
+    const int budget = smem_budget / SB_I8_BLOCKS_PER_SM - (SB_I8_BLOCKS_PER_SM > 1 ? 1024 : 0);  // co-resident blocks
+    const int rows_fit = static_cast<int>((budget - hdr - state) / row_bytes);
     g.G = gr;
     g.NS = std::max(2, std::min(sb::NSTAGE_MAX, rows_fit / gr));
     g.NSEG = 1;
@@ -554,7 +555,14 @@ static int batch_create(sb_ctx* ctx, const std::vector<GenericProblem>& gp, bool
     h.elbo_off = l.elbo;
     h.meta_off = l.meta;
   }
-  const size_t staging_off = bump.take(staging_bytes ? staging_bytes : 16);
+  // staging for the batched column prologue: as many input matrices as fit under the cap share one launch
+  size_t staging_total = 0;
+  for (int i = 0; i < n_probs; ++i)
+    for (int k = 0; k < gp[i].K; ++k)
+      staging_total += align_up(static_cast<size_t>(gp[i].n[k]) * gp[i].p * elem_size(gp[i].mat_dtype), 256);
+  const size_t staging_cap = std::max(staging_bytes + 256, std::min<size_t>(staging_total, size_t(1) << 30));
+  const size_t staging_off = bump.take(staging_bytes ? staging_cap : 16);
+  const size_t descs_off = bump.take(sizeof(sb::PrepDesc) * static_cast<size_t>(n_probs) * KMAX);
   // per-block scratch: partial X^T r, three reduction records, per-traversal scalars
   const int off_stat = static_cast<int>(align_up(Kp_max, 16));
   const int off_trav = off_stat + 3 * sb::STAT_STRIDE + 4;
@@ -601,6 +609,65 @@ static int batch_create(sb_ctx* ctx, const std::vector<GenericProblem>& gp, bool
   SB_CUDA_B(cudaEventRecord(ctx->ev[2], st));
   int launches = 0;
   std::vector<double> tmp;
+  // batched column prologue: matrices are staged back to back, described, and standardised by one launch per
+  // staging fill (and per input type)
+  std::vector<sb::PrepDesc> pending;
+  size_t staged = 0, descs_used = 0;
+  int pending_dtype = -1, pending_pmax = 0;
+  auto flush_prep = [&]() -> cudaError_t {
+    if (pending.empty()) return cudaSuccess;
+    sb::PrepDesc* d_descs = reinterpret_cast<sb::PrepDesc*>(A + descs_off) + descs_used;
+    cudaError_t e = cudaMemcpyAsync(d_descs, pending.data(), sizeof(sb::PrepDesc) * pending.size(),
+                                    cudaMemcpyHostToDevice, st);
+    if (e != cudaSuccess) return e;
+    const dim3 grid((pending_pmax + 127) / 128, static_cast<unsigned>(pending.size()));
+    int* flag = b->d_ctl + 32;
+#define SB_PREP(IT, XT) sb::prep_columns_batched_kernel<IT, XT><<<grid, 128, 0, st>>>(d_descs, flag)
+    if (opts.storage == SB_I8) {
+      SB_PREP(int8_t, int8_t);
+    } else if (opts.storage == SB_F64) {
+      if (pending_dtype == SB_F64) SB_PREP(double, double);
+      if (pending_dtype == SB_F32) SB_PREP(float, double);
+      if (pending_dtype == SB_I8) SB_PREP(int8_t, double);
+    } else {
+      if (pending_dtype == SB_F64) SB_PREP(double, float);
+      if (pending_dtype == SB_F32) SB_PREP(float, float);
+      if (pending_dtype == SB_I8) SB_PREP(int8_t, float);
+    }
+#undef SB_PREP
+    ++launches;
+    descs_used += pending.size();
+    pending.clear();
+    staged = 0;
+    pending_pmax = 0;
+    return cudaGetLastError();
+  };
+  auto enqueue_prep = [&](const void* host_mat, int dtype, int n, int p, int p_pad, int flags, void* out, double* xtx,
+                          double* cmean, double* cisd) -> cudaError_t {
+    const size_t bytes = static_cast<size_t>(n) * p * elem_size(dtype);
+    if (!pending.empty() && (dtype != pending_dtype || staged + bytes > staging_cap)) {
+      cudaError_t e = flush_prep();
+      if (e != cudaSuccess) return e;
+    }
+    cudaError_t e = cudaMemcpyAsync(A + staging_off + staged, host_mat, bytes, cudaMemcpyHostToDevice, st);
+    if (e != cudaSuccess) return e;
+    sb::PrepDesc pd{};
+    pd.in = A + staging_off + staged;
+    pd.out = out;
+    pd.xtx = xtx;
+    pd.cmean = cmean;
+    pd.cisd = cisd;
+    pd.in_ld = p;
+    pd.n = n;
+    pd.p = p;
+    pd.p_pad = p_pad;
+    pd.flags = flags;
+    pending.push_back(pd);
+    pending_dtype = dtype;
+    pending_pmax = std::max(pending_pmax, p_pad);
+    staged += align_up(bytes, 256);
+    return cudaSuccess;
+  };
   for (int i = 0; i < n_probs; ++i) {
     const GenericProblem& g = gp[i];
     const Geometry& ge = geo[i];
@@ -698,10 +765,7 @@ static int batch_create(sb_ctx* ctx, const std::vector<GenericProblem>& gp, bool
         double* cisd_k = reinterpret_cast<double*>(A + l.cisd) + static_cast<size_t>(k) * ge.p_pad;
         h.d_cmean[k] = cmean_k;
         h.d_cisd[k] = cisd_k;
-        SB_CUDA_B(cudaMemcpyAsync(A + staging_off, g.mat[k], static_cast<size_t>(n) * g.p, cudaMemcpyHostToDevice, st));
-        sb::prep_columns_i8_kernel<int8_t><<<(ge.p_pad + 127) / 128, 128, 0, st>>>(
-            reinterpret_cast<const int8_t*>(A + staging_off), g.p, n, g.p, ge.p_pad, g.standardize,
-            reinterpret_cast<int8_t*>(A + l.X[k]), xtx_k, cmean_k, cisd_k, b->d_ctl + 32);
+        SB_CUDA_B(enqueue_prep(g.mat[k], SB_I8, n, g.p, ge.p_pad, g.standardize, A + l.X[k], xtx_k, cmean_k, cisd_k));
       } else if (direct) {
         SB_CUDA_B(cudaMemcpy2DAsync(A + l.X[k], static_cast<size_t>(ge.p_pad) * es, g.mat[k],
                                     static_cast<size_t>(g.p) * es, static_cast<size_t>(g.p) * es, n,
@@ -714,12 +778,12 @@ static int batch_create(sb_ctx* ctx, const std::vector<GenericProblem>& gp, bool
                                       0, static_cast<size_t>(ge.p_pad - g.p) * es, n, st));
         }
       } else {
-        SB_CUDA_B(cudaMemcpyAsync(A + staging_off, g.mat[k], static_cast<size_t>(n) * g.p * elem_size(g.mat_dtype),
-                                  cudaMemcpyHostToDevice, st));
         if (!ss) {
-          prep_columns_dispatch(g.mat_dtype, opts.storage, A + staging_off, g.p, n, g.p, ge.p_pad, g.standardize,
-                                A + l.X[k], xtx_k, st);
+          SB_CUDA_B(enqueue_prep(g.mat[k], g.mat_dtype, n, g.p, ge.p_pad, g.standardize, A + l.X[k], xtx_k, nullptr,
+                                 nullptr));
         } else {
+          SB_CUDA_B(cudaMemcpyAsync(A + staging_off, g.mat[k], static_cast<size_t>(n) * g.p * elem_size(g.mat_dtype),
+                                    cudaMemcpyHostToDevice, st));
           if (g.mat_dtype == SB_F64 && opts.storage == SB_F32)
             launch_pad_rows<double, float>(A + staging_off, n, g.p, ge.p_pad, A + l.X[k], st);
           else if (g.mat_dtype == SB_F32 && opts.storage == SB_F64)
@@ -730,7 +794,7 @@ static int batch_create(sb_ctx* ctx, const std::vector<GenericProblem>& gp, bool
           }
         }
       }
-      ++launches;
+      if (ss || direct) ++launches;
       if (!ss) {
         SB_CUDA_B(cudaMemcpyAsync(A + l.y + sizeof(double) * d.row0[k], g.vec[k], sizeof(double) * n,
                                   cudaMemcpyHostToDevice, st));
@@ -749,6 +813,7 @@ static int batch_create(sb_ctx* ctx, const std::vector<GenericProblem>& gp, bool
       }
     }
   }
+  SB_CUDA_B(flush_prep());
   SB_CUDA_B(cudaGetLastError());
   // problem table, ids grouped by K
   {
