@@ -34,14 +34,15 @@ def plan_chunks(preps: Sequence, chunk_bytes: Optional[int] = None, chunk_loci: 
     """Group problem indices into chunks.
 
     Problems that cannot share a launch configuration (different ``max_iter`` /
-    ``min_tol``) never share a chunk.  Within a group, indices are sorted by descending
+    ``min_tol``, or hard-call vs dense genotype storage) never share a chunk.  Within a group, indices are sorted by descending
     cost (longest-processing-time first) and cut where the memory budget or the locus
     cap is reached."""
     chunk_bytes = config.chunk_bytes if chunk_bytes is None else chunk_bytes
     chunk_loci = config.chunk_loci if chunk_loci is None else chunk_loci
     groups: Dict[Tuple, List[int]] = {}
     for i, p in enumerate(preps):
-        groups.setdefault((p.max_iter, p.min_tol), []).append(i)
+        # loci eligible for one-byte hard-call storage get chunks of their own (storage is per batch)
+        groups.setdefault((p.max_iter, p.min_tol, bool(getattr(p, "hard_calls", False))), []).append(i)
     chunks: List[List[int]] = []
     for ids in groups.values():
         ids = sorted(ids, key=lambda i: (-preps[i].problem.cost, i))

@@ -297,3 +297,31 @@ def test_hard_call_storage_is_selected_and_wide_loci_fit(engine_lib):
         np.testing.assert_allclose(a.elbo[1:], c.elbo[1:], rtol=1e-9)
         np.testing.assert_allclose(a.alpha, c.alpha, atol=1e-8)
         np.testing.assert_allclose(a.effect_covar, c.effect_covar, rtol=1e-6, atol=1e-12)
+
+
+def test_batch_sharded_over_all_visible_gpus(engine_lib, golden_syn):
+    """The host work queue with one worker (own sb_ctx) per visible GPU returns the same fits, in input order,
+    as a single-GPU run -- also with hard-call and dense loci mixed in one call (they get separate chunks)."""
+    import sushie_b200
+    from sushie_b200 import _capi, config
+
+    n_dev = _capi.device_count()
+    assert n_dev >= 1
+    problems, tags = [], []
+    for rep in range(3):
+        for tag in ("k2", "k3", "k3null", "k2noscale"):
+            case = SYN_CASES[tag]
+            Xs, ys = _syn_inputs(golden_syn, tag, case["k"])
+            if rep == 1:
+                Xs = [x + 0.5 for x in Xs]  # not hard calls any more (same standardised matrix): dense chunk
+            problems.append(dict(Xs=Xs, ys=ys, **case["kw"]))
+            tags.append(tag)
+    old = config.chunk_loci
+    config.chunk_loci = 2  # many chunks so every worker pulls several
+    try:
+        out = sushie_b200.infer_sushie_batch(problems, devices=list(range(n_dev)), min_tol=1e-4)
+    finally:
+        config.chunk_loci = old
+    assert len(out) == len(problems)
+    for tag, res in zip(tags, out):
+        assert_fit_matches(res, golden_syn, tag)
