@@ -25,7 +25,7 @@ from . import config, cs as _cs, infer, infer_ss, io, log, utils
 
 __all__ = [
     "parameter_check", "parameter_check_ss", "process_raw", "process_raw_ss", "sushie_wrapper",
-    "sushie_wrapper_ss", "run_finemap", "build_finemap_parser", "run_cli",
+    "sushie_wrapper_ss", "run_finemap", "run_finemap_batch", "build_finemap_parser", "build_batch_parser", "run_cli",
 ]
 
 _AMBIGUOUS = ("AT", "TA", "CG", "GC")
@@ -223,17 +223,20 @@ def _prepare_cv(geno: List[np.ndarray], pheno: List[np.ndarray], cv_num: int, se
     return folds
 
 
-def _run_cv(args, cv_data: List[io.CVData], pi) -> List[List[float]]:
-    """All folds are fitted as one device-resident batch; predictions use the un-standardised
-    validation genotypes, as the reference does (``cli.py:378-419``)."""
+def _cv_specs(args, cv_data: List[io.CVData], pi) -> List[dict]:
+    """One ``infer_sushie`` keyword set per fold (``cli.py:378-402``: no covariates, default
+    ``purity_method`` / ``min_snps`` / ``no_reorder``)."""
+    kw = dict(covar=None, L=args.L, no_scale=args.no_scale, no_regress=args.no_regress, no_update=args.no_update, pi=pi,
+              resid_var=args.resid_var, effect_var=args.effect_var, rho=args.rho, max_iter=args.max_iter,
+              min_tol=args.min_tol, threshold=args.threshold, purity=args.purity, max_select=args.max_select,
+              seed=args.seed)
+    return [dict(kw, Xs=fold.train_geno, ys=fold.train_pheno) for fold in cv_data[: args.cv_num]]
+
+
+def _cv_scores(cv_data: List[io.CVData], fits) -> List[List[float]]:
+    """Out-of-fold predictions with the un-standardised validation genotypes, then adjusted r-squared and
+    p-value per ancestry, as the reference does (``cli.py:404-419``)."""
     n_pop = len(cv_data[0].train_geno)
-    fits = infer.infer_sushie_batch(
-        [dict(Xs=fold.train_geno, ys=fold.train_pheno) for fold in cv_data[: args.cv_num]],
-        covar=None, L=args.L, no_scale=args.no_scale, no_regress=args.no_regress, no_update=args.no_update, pi=pi,
-        resid_var=args.resid_var, effect_var=args.effect_var, rho=args.rho, max_iter=args.max_iter,
-        min_tol=args.min_tol, threshold=args.threshold, purity=args.purity, max_select=args.max_select,
-        seed=args.seed,
-    )
     est = [[] for _ in range(n_pop)]
     obs = [[] for _ in range(n_pop)]
     for fold, fit in zip(cv_data, fits):
@@ -246,6 +249,11 @@ def _run_cv(args, cv_data: List[io.CVData], pi) -> List[List[float]]:
         _, adj_r2, p_value = utils.ols(np.concatenate(est[idx])[:, np.newaxis], np.concatenate(obs[idx])[:, np.newaxis])
         out.append([adj_r2[0], p_value[1][0]])
     return out
+
+
+def _run_cv(args, cv_data: List[io.CVData], pi) -> List[List[float]]:
+    """All folds are fitted as one device-resident batch (``cli.py:378-419``)."""
+    return _cv_scores(cv_data, infer.infer_sushie_batch(_cv_specs(args, cv_data, pi)))
 
 
 # ------------------------------------------------------------------------------------------
@@ -782,36 +790,24 @@ def _meta_pips(result) -> List[np.ndarray]:
     return [utils.make_pip(np.stack([r.pip_all for r in result])), utils.make_pip(np.stack([r.pip_cs for r in result]))]
 
 
-def sushie_wrapper(data: io.CleanData, cv_data, args, snps: pd.DataFrame, meta: bool = False, mega: bool = False) -> None:
-    """Regular, per-ancestry (``--meta``) or stacked (``--mega``) individual-level fine-mapping + outputs."""
+def _ind_specs(data: io.CleanData, args, meta: bool, mega: bool) -> List[dict]:
+    """``infer_sushie`` keyword sets of one wrapper call: one joint fit, or one per ancestry for ``--meta``."""
     n_pop = len(data.geno)
-    method_type = "meta" if meta else ("mega" if mega else "sushie")
-    output = f"{args.output}.{method_type}"
     kw = dict(_shared_kw(args), no_scale=args.no_scale, no_regress=args.no_regress, pi=data.pi)
     if meta:
-        for idx in range(n_pop):
-            log.logger.info(
-                f"Start fine-mapping using SuSiE on ancestry {idx + 1} with {args.L} effects because --meta is specified."
-            )
-        # the single-ancestry fits are independent: one device-resident batch
-        result = infer.infer_sushie_batch(
-            [dict(Xs=[data.geno[i]], ys=[data.pheno[i]], covar=None if data.covar is None else [data.covar[i]],
-                  resid_var=_one(args.resid_var, i), effect_var=_one(args.effect_var, i), rho=None)
-             for i in range(n_pop)],
-            **kw,
-        )
-        pips = _meta_pips(result)
-    else:
-        if mega:
-            log.logger.info(f"Start fine-mapping using Mega SuSiE with {args.L} effects because --mega is specified.")
-        else:
-            log.logger.info(f"Start fine-mapping using SuShiE with {args.L} effects.")
-        fit = infer.infer_sushie(
-            data.geno, data.pheno, data.covar,
-            resid_var=None if mega else args.resid_var, effect_var=None if mega else args.effect_var,
-            rho=None if mega else args.rho, **kw,
-        )
-        result, pips = [fit], None
+        return [dict(kw, Xs=[data.geno[i]], ys=[data.pheno[i]], covar=None if data.covar is None else [data.covar[i]],
+                     resid_var=_one(args.resid_var, i), effect_var=_one(args.effect_var, i), rho=None)
+                for i in range(n_pop)]
+    return [dict(kw, Xs=data.geno, ys=data.pheno, covar=data.covar,
+                 resid_var=None if mega else args.resid_var, effect_var=None if mega else args.effect_var,
+                 rho=None if mega else args.rho)]
+
+
+def _ind_emit(result, cv_fits, data: io.CleanData, cv_data, args, snps: pd.DataFrame, meta: bool, mega: bool) -> None:
+    """Write the output files of one wrapper call from its fits (and the fold fits for ``--cv``)."""
+    method_type = "meta" if meta else ("mega" if mega else "sushie")
+    output = f"{args.output}.{method_type}"
+    pips = _meta_pips(result) if meta else None
     _write_common(result, pips, snps, output, args, method_type)
     if not (mega or meta):
         io.output_corr(result, output, args.trait, args.compress)
@@ -820,9 +816,31 @@ def sushie_wrapper(data: io.CleanData, cv_data, args, snps: pd.DataFrame, meta: 
                 "Skip heritability estimation (--her): the LMM estimator is a third-party stack outside this build."
             )
         if args.cv:
-            log.logger.info(f"Start {args.cv_num}-fold cross validation as --cv is specified ")
-            cv_res = _run_cv(args, cv_data, data.pi)
-            io.output_cv(cv_res, np.squeeze(result[0].sample_size), output, args.trait, args.compress)
+            io.output_cv(_cv_scores(cv_data, cv_fits), np.squeeze(result[0].sample_size), output, args.trait,
+                         args.compress)
+
+
+def sushie_wrapper(data: io.CleanData, cv_data, args, snps: pd.DataFrame, meta: bool = False, mega: bool = False) -> None:
+    """Regular, per-ancestry (``--meta``) or stacked (``--mega``) individual-level fine-mapping + outputs.
+    The fits of one call (per-ancestry fits, cross-validation folds) run as one device-resident batch."""
+    n_pop = len(data.geno)
+    if meta:
+        for idx in range(n_pop):
+            log.logger.info(
+                f"Start fine-mapping using SuSiE on ancestry {idx + 1} with {args.L} effects because --meta is specified."
+            )
+    elif mega:
+        log.logger.info(f"Start fine-mapping using Mega SuSiE with {args.L} effects because --mega is specified.")
+    else:
+        log.logger.info(f"Start fine-mapping using SuShiE with {args.L} effects.")
+    specs = _ind_specs(data, args, meta, mega)
+    with_cv = args.cv and not (meta or mega)
+    if with_cv:
+        log.logger.info(f"Start {args.cv_num}-fold cross validation as --cv is specified ")
+        specs = specs + _cv_specs(args, cv_data, data.pi)
+    fits = infer.infer_sushie_batch(specs) if len(specs) > 1 else [infer.infer_sushie(**specs[0])]
+    n_main = n_pop if meta else 1
+    _ind_emit(fits[:n_main], fits[n_main:] if with_cv else None, data, cv_data, args, snps, meta, mega)
     return None
 
 
@@ -893,6 +911,148 @@ def run_finemap(args) -> int:
             + " For bug reporting, suggestions, and comments, please go to https://github.com/mancusolab/sushie."
         )
     return 0
+
+
+# ------------------------------------------------------------------------------------------
+# many genes in one process (replaces the reference's one-process-per-gene driver, misc/run_sushie.sh)
+
+
+class _Gene:
+    """One manifest line: parsed arguments, cleaned data, and where its fits sit in the window's batch."""
+
+    def __init__(self, line_no: int, args):
+        self.line_no, self.args = line_no, args
+        self.error: Optional[str] = None
+        self.parts: List[tuple] = []   # (label, first index, count) into the window's spec list
+        self.snps = self.data = self.cv_data = self.mega_data = None
+        self.n_pop = 0
+
+
+def _prepare_gene(gene: _Gene, specs: List[dict], ss_specs: List[dict]) -> None:
+    """Read + QC one gene and append its fits (regular, --meta, --mega, --cv folds) to the window."""
+    args = gene.args
+    if args.summary:
+        n_pop, pi, geno_path, geno_func, ld_file = parameter_check_ss(args)
+        gene.snps, data = process_raw_ss(geno_path, geno_func, ld_file, pi, args)
+        gene.data, gene.n_pop = data, n_pop
+        kw = dict(_shared_kw(args), pi=data.pi)
+        gene.parts.append(("sushie", len(ss_specs), 1))
+        ss_specs.append(dict(kw, lds=data.lds, ns=data.ns, zs=data.zs, resid_var=args.resid_var,
+                             effect_var=args.effect_var, rho=args.rho))
+        if n_pop != 1 and args.meta:
+            gene.parts.append(("meta", len(ss_specs), n_pop))
+            ss_specs.extend(
+                dict(kw, lds=[data.lds[i]], ns=np.asarray(data.ns[i])[:, np.newaxis], zs=[data.zs[i]],
+                     resid_var=_one(args.resid_var, i), effect_var=_one(args.effect_var, i), rho=None)
+                for i in range(n_pop))
+        return
+    n_pop, ancestry_index, keep_subject, pi, geno_path, geno_func = parameter_check(args)
+    raw = io.read_data(n_pop, ancestry_index, args.pheno, args.covar, geno_path, geno_func)
+    gene.snps, gene.data, gene.mega_data, gene.cv_data = process_raw(
+        raw, keep_subject, pi, args.keep_ambiguous, args.maf, args.rint, args.no_regress, args.mega, args.cv,
+        args.cv_num, args.seed, args.chrom, args.start, args.end,
+    )
+    gene.n_pop = n_pop
+    gene.parts.append(("sushie", len(specs), 1))
+    specs.extend(_ind_specs(gene.data, args, False, False))
+    if args.cv:
+        folds = _cv_specs(args, gene.cv_data, gene.data.pi)
+        gene.parts.append(("cv", len(specs), len(folds)))
+        specs.extend(folds)
+    if n_pop != 1 and args.meta:
+        gene.parts.append(("meta", len(specs), n_pop))
+        specs.extend(_ind_specs(gene.data, args, True, False))
+    if n_pop != 1 and args.mega:
+        gene.parts.append(("mega", len(specs), 1))
+        specs.extend(_ind_specs(gene.mega_data, args, False, True))
+
+
+def _emit_gene(gene: _Gene, fits: list, ss_fits: list) -> None:
+    args = gene.args
+    got = {label: (ss_fits if args.summary else fits)[first:first + count] for label, first, count in gene.parts}
+    if args.summary:
+        for label in ("sushie", "meta"):
+            if label in got:
+                output = f"{args.output}.{label}"
+                pips = _meta_pips(got[label]) if label == "meta" else None
+                _write_common(got[label], pips, gene.snps, output, args, label)
+                if label == "sushie":
+                    io.output_corr(got[label], output, args.trait, args.compress)
+        return
+    _ind_emit(got["sushie"], got.get("cv"), gene.data, gene.cv_data, args, gene.snps, False, False)
+    if "meta" in got:
+        _ind_emit(got["meta"], None, gene.data, None, args, gene.snps, True, False)
+    if "mega" in got:
+        _ind_emit(got["mega"], None, gene.mega_data, None, args, gene.snps, False, True)
+
+
+def run_finemap_batch(bargs) -> int:
+    """``finemap-batch``: every non-comment line of the manifest holds the arguments of one ``finemap`` run.
+    Genes are read and cleaned on the host, all their fits (joint, per-ancestry, stacked, cross-validation
+    folds) go through the device work queue together -- sharded over ``--devices`` -- and each gene gets the
+    same output files a separate ``finemap`` run would write.  A gene that fails is reported and skipped."""
+    import shlex
+
+    parser = argparse.ArgumentParser(prog="finemap", add_help=False)
+    for flag, kw in _FINEMAP_ARGS:
+        parser.add_argument(flag, **kw)
+    with open(bargs.manifest) as fh:
+        lines = [(no + 1, ln.strip()) for no, ln in enumerate(fh)]
+    lines = [(no, ln) for no, ln in lines if ln and not ln.startswith("#")]
+    devices = bargs.devices if bargs.devices else None
+    config.precision = int(bargs.jax_precision)
+    n_ok = n_bad = 0
+    for w0 in range(0, len(lines), bargs.window):
+        genes: List[_Gene] = []
+        specs: List[dict] = []
+        ss_specs: List[dict] = []
+        for no, ln in lines[w0:w0 + bargs.window]:
+            try:
+                gene = _Gene(no, parser.parse_args(shlex.split(ln)))
+            except SystemExit:
+                log.logger.error(f"Manifest line {no}: arguments could not be parsed; gene skipped.")
+                n_bad += 1
+                continue
+            mark, ss_mark = len(specs), len(ss_specs)
+            try:
+                _prepare_gene(gene, specs, ss_specs)
+            except Exception as err:  # keep the batch going, like one failed process among many
+                del specs[mark:], ss_specs[ss_mark:]
+                gene.error = str(err)
+                log.logger.error(f"Manifest line {no} ({gene.args.trait}): {err}")
+                n_bad += 1
+                continue
+            genes.append(gene)
+        log.logger.info(
+            f"Window of {len(genes)} genes: {len(specs)} individual-level and {len(ss_specs)} summary-level fits."
+        )
+        fits = infer.infer_sushie_batch(specs, devices=devices) if specs else []
+        ss_fits = infer_ss.infer_sushie_ss_batch(ss_specs, devices=devices) if ss_specs else []
+        for gene in genes:
+            try:
+                _emit_gene(gene, fits, ss_fits)
+                n_ok += 1
+            except Exception as err:
+                log.logger.error(f"Manifest line {gene.line_no} ({gene.args.trait}): {err}")
+                n_bad += 1
+    log.logger.info(f"Batch fine-mapping finishes: {n_ok} genes written, {n_bad} failed.")
+    return 0
+
+
+def build_batch_parser(subp):
+    batch = subp.add_parser(
+        "finemap-batch",
+        description="Fine-map many genes in one process: one line of `finemap` arguments per gene in a manifest file.",
+    )
+    batch.add_argument("--manifest", required=True, type=str, help="Text file, one gene per line (finemap arguments).")
+    batch.add_argument("--devices", nargs="+", type=int, default=None, help="GPU ordinals to shard over (default: 0).")
+    batch.add_argument("--window", type=int, default=256, help="Genes read, fitted and written per pass.")
+    batch.add_argument("--jax-precision", default=64, type=int, choices=[32, 64],
+                       help="64: fp64 device storage of dense matrices; 32: fp32 storage.")
+    batch.add_argument("--quiet", **_FLAG)
+    batch.add_argument("--verbose", **_FLAG)
+    batch.add_argument("--output", default="sushie_finemap_batch", help="Prefix of the batch log file.")
+    return batch
 
 
 # ------------------------------------------------------------------------------------------
@@ -997,6 +1157,7 @@ def _main(argv: List[str]) -> int:
     argp.add_argument("--version", action="version", version=__version__)
     subp = argp.add_subparsers(help="Subcommands: finemap to perform gene expression fine-mapping using SuShiE")
     build_finemap_parser(subp).set_defaults(func=run_finemap)
+    build_batch_parser(subp).set_defaults(func=run_finemap_batch)
     args = argp.parse_args(argv)
     if not hasattr(args, "func"):
         argp.print_help()
