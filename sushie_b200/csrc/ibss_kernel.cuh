@@ -308,7 +308,6 @@ struct SmemHdr {
   double tot[STAT_STRIDE];   // block / team totals
   double cst[2 * KMAX * KMAX + 8];  // Cinv, misc per-pass constants
   double trow[GMAX][2];      // per-row scalars of a traversal
-  double rstate[2][16];      // register-tile traversal: (r, xb_next) of the band's rows, fetched one band ahead
   int decision;
   int pad_[3];
 };

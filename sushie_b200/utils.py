@@ -81,6 +81,9 @@ def as_hard_calls(X) -> "np.ndarray | None":
         return np.ascontiguousarray(X, dtype=np.int8)
     if X.dtype.kind != "f":
         return None
+    head = X[: min(4, X.shape[0])]
+    if not np.array_equal(head, np.rint(head)):  # residualised / dosage data: reject without a full pass
+        return None
     lo, hi = X.min(), X.max()
     if not (np.isfinite(lo) and np.isfinite(hi)) or lo < 0 or hi > 127:
         return None
