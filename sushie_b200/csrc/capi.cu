@@ -104,7 +104,13 @@ template <int K, typename XT, bool SS, int V = 0>
 static const void* kfn() {
   return reinterpret_cast<const void*>(&sb::ibss_kernel<K, XT, SS, V>);
 }
-// variant: traversal variant compiled into the kernel (hard-call storage only: Geometry::fast), else 0
+// variant: traversal variant compiled into the kernel -- hard-call storage: Geometry::fast (1..4); dense fp64
+// individual level: 3 for the wide 12 x 1 tile; everything else 0 (variant chosen per locus at run time)
+static int launch_variant(int storage, bool ss, int fast) {
+  if (storage == SB_I8) return fast;
+  if (storage == SB_F64 && !ss && fast == 3) return 3;
+  return 0;
+}
 static const void* pick_kernel(int K, int storage, bool ss, int variant) {
   const bool f32 = storage == SB_F32;
   const bool i8 = storage == SB_I8;
@@ -113,7 +119,9 @@ static const void* pick_kernel(int K, int storage, bool ss, int variant) {
   case KK:                                                                                    \
     if (i8)                                                                                   \
       return variant == 1 ? kfn<KK, int8_t, false, 1>()                                       \
-                          : (variant == 2 ? kfn<KK, int8_t, false, 2>() : kfn<KK, int8_t, false, 3>()); \
+             : variant == 2 ? kfn<KK, int8_t, false, 2>()                                     \
+             : variant == 3 ? kfn<KK, int8_t, false, 3>() : kfn<KK, int8_t, false, 4>();      \
+    if (!ss && !f32 && variant == 3) return kfn<KK, double, false, 3>();                      \
     return ss ? (f32 ? kfn<KK, float, true>() : kfn<KK, double, true>())                      \
               : (f32 ? kfn<KK, float, false>() : kfn<KK, double, false>());
   switch (K) {
@@ -223,7 +231,10 @@ static bool plan_geometry(int p, int n_max, int es, bool ss, int smem_budget, Ge
     // hard-call storage: every thread owns CPT 8-byte vectors of GR rows (traverse_i8)
     const int pv8 = g.p_pad / 8;
     int gr;
-    if (pv8 <= sb::NT) {
+    if (g.p_pad / 4 <= sb::NT) {  // narrow locus: 4-byte vectors keep every thread busy
+      g.fast = 4;
+      gr = 8;
+    } else if (pv8 <= sb::NT) {
       g.fast = 1;
       gr = 8;
     } else if (pv8 <= 2 * sb::NT) {
@@ -253,7 +264,7 @@ static bool plan_geometry(int p, int n_max, int es, bool ss, int smem_budget, Ge
     } else if (pv > 4 * sb::NT && pv <= 8 * sb::NT) {
       g.fast = 2;
       gr = 2;
-    } else if (ss && pv > 8 * sb::NT && pv <= 12 * sb::NT) {
+    } else if ((ss || es == 8) && pv > 8 * sb::NT && pv <= 12 * sb::NT) {  // (fp32 individual level: generic path)
       g.fast = 3;
       gr = 1;
     } else if (ss && pv > 12 * sb::NT && pv <= 16 * sb::NT) {
@@ -820,10 +831,10 @@ static int batch_create(sb_ctx* ctx, const std::vector<GenericProblem>& gp, bool
     std::vector<int> ids;
     ids.reserve(n_probs);
     for (int K = 1; K <= KMAX; ++K)
-      for (int variant = 0; variant <= 3; ++variant) {
+      for (int variant = 0; variant <= 4; ++variant) {
         const int start = static_cast<int>(ids.size());
         for (int i = 0; i < n_probs; ++i)
-          if (gp[i].K == K && (opts.storage == SB_I8 ? geo[i].fast : 0) == variant) ids.push_back(i);
+          if (gp[i].K == K && launch_variant(opts.storage, ss, geo[i].fast) == variant) ids.push_back(i);
         const int count = static_cast<int>(ids.size()) - start;
         if (count > 0) b->groups.push_back({K, variant, start, count});
       }

@@ -464,7 +464,8 @@ template <int N>
 using IntC = std::integral_constant<int, N>;
 
 // V: traversal variant fixed at compile time (hard-call storage: 1 = 8 columns x 8 rows per thread, 2 = 16 x 4,
-// 3 = 32 x 2, so each variant gets its own register allocation); 0 = chosen per locus at run time.
+// 3 = 32 x 2, 4 = 4 x 8 for narrow loci, so each variant gets its own register allocation); 0 = chosen per
+// locus at run time.
 template <int K, typename XT, bool SS, int V = 0>
 __global__ void __launch_bounds__(NT, (std::is_same<XT, int8_t>::value ? SB_I8_BLOCKS_PER_SM : 1)) ibss_kernel(const LaunchParams P) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -846,27 +847,29 @@ __global__ void __launch_bounds__(NT, (std::is_same<XT, int8_t>::value ? SB_I8_B
     // so the traversal is G-only.  Every thread owns CPT 8-byte column vectors, widens its slice of
     // the GR band rows to fp64 once (integer splice + one DADD per entry) and runs both sweeps from
     // registers.
-    auto traverse_i8 = [&](auto cpt_c, auto gr_c, auto keep_c, int l, bool first, bool last_effect) {
+    auto traverse_i8 = [&](auto cpt_c, auto gr_c, auto keep_c, auto vb_c, int l, bool first, bool last_effect) {
       constexpr int CPT = decltype(cpt_c)::value;
+      constexpr int VB = decltype(vb_c)::value;  // genotype bytes (= columns) per vector: 8, or 4 for narrow loci
+      constexpr int VWD = VB / 4;                // 32-bit words per vector
       constexpr bool KEEP = decltype(keep_c)::value != 0;  // widen once and keep the fp64 tile in registers
       constexpr int GR = decltype(gr_c)::value;
       constexpr int PRODUCER_TID = NT - 32;
       constexpr int LG = 32 / GR;  // lanes sharing one band row after the butterfly
-      const int pv8 = p_pad / 8;   // 8-byte vectors per row
+      const int pv8 = p_pad / VB;  // vectors per row
       const int lnext = first ? 0 : ((l + 1 == L) ? 0 : l + 1);
       const bool self_next = !first && lnext == l;
       double vsq[K], rsq[K];  // meaningful in the row-writer lanes of warp 0 only
 #pragma unroll
       for (int k = 0; k < K; ++k) vsq[k] = rsq[k] = 0.0;
-      double bq[CPT][8], aq[CPT][8];
-      uint2 x[GR][CPT];  // raw genotype bytes of the band slice (2 registers per 8 entries)
-      double xk[KEEP ? GR : 1][KEEP ? CPT : 1][8];  // KEEP: the widened tile, shared by both sweeps
+      double bq[CPT][VB], aq[CPT][VB];
+      uint32_t x[GR][CPT][VWD];  // raw genotype bytes of the band slice (1 register per 4 entries)
+      double xk[KEEP ? GR : 1][KEEP ? CPT : 1][VB];  // KEEP: the widened tile, shared by both sweeps
       uint32_t vmask = 0;
 #pragma unroll
       for (int c = 0; c < CPT; ++c) {
         if (tid + c * NT < pv8) vmask |= (1u << c);
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
+        for (int u = 0; u < VB; ++u) {
           bq[c][u] = aq[c][u] = 0.0;
         }
       }
@@ -906,9 +909,9 @@ __global__ void __launch_bounds__(NT, (std::is_same<XT, int8_t>::value ? SB_I8_B
 #pragma unroll
         for (int c = 0; c < CPT; ++c) {
           if (vmask & (1u << c)) {
-            const int j0 = (tid + c * NT) * 8;
+            const int j0 = (tid + c * NT) * VB;
 #pragma unroll
-            for (int u = 0; u < 8; u += 2) {
+            for (int u = 0; u < VB; u += 2) {
               const double2 m2 = *reinterpret_cast<const double2*>(cm + j0 + u);
               const double2 s2 = *reinterpret_cast<const double2*>(cs + j0 + u);
               __stcg(reinterpret_cast<double2*>(dst + j0 + u),
@@ -934,10 +937,10 @@ __global__ void __launch_bounds__(NT, (std::is_same<XT, int8_t>::value ? SB_I8_B
           double part[1] = {0.0};
 #pragma unroll
           for (int c = 0; c < CPT; ++c) {
-            const int j0 = (tid + c * NT) * 8;
+            const int j0 = (tid + c * NT) * VB;
             const bool on = !first && (vmask & (1u << c));
 #pragma unroll
-            for (int u = 0; u < 8; u += 2) {
+            for (int u = 0; u < VB; u += 2) {
               double2 b2 = make_double2(0.0, 0.0);
               if (on) {
                 const double2 t2 = __ldcg(reinterpret_cast<const double2*>(bl + j0 + u));
@@ -965,19 +968,27 @@ __global__ void __launch_bounds__(NT, (std::is_same<XT, int8_t>::value ? SB_I8_B
         for (int g = 0; g < GR; ++g)
 #pragma unroll
           for (int c = 0; c < CPT; ++c) {
-            x[g][c] = make_uint2(0u, 0u);
-            if (g < rows && (vmask & (1u << c)))
-              x[g][c] = *reinterpret_cast<const uint2*>(tile + static_cast<size_t>(g) * p_pad + (tid + c * NT) * 8);
+#pragma unroll
+            for (int w = 0; w < VWD; ++w) x[g][c][w] = 0u;
+            if (g < rows && (vmask & (1u << c))) {
+              const unsigned char* src = tile + static_cast<size_t>(g) * p_pad + (tid + c * NT) * VB;
+              if constexpr (VB == 8) {
+                const uint2 t2 = *reinterpret_cast<const uint2*>(src);
+                x[g][c][0] = t2.x;
+                x[g][c][1] = t2.y;
+              } else {
+                x[g][c][0] = *reinterpret_cast<const uint32_t*>(src);
+              }
+            }
           }
-        auto widen = [](const uint2& w, double (&o)[8]) {
-          o[0] = u8_to_f64<0>(w.x);
-          o[1] = u8_to_f64<1>(w.x);
-          o[2] = u8_to_f64<2>(w.x);
-          o[3] = u8_to_f64<3>(w.x);
-          o[4] = u8_to_f64<0>(w.y);
-          o[5] = u8_to_f64<1>(w.y);
-          o[6] = u8_to_f64<2>(w.y);
-          o[7] = u8_to_f64<3>(w.y);
+        auto widen = [](const uint32_t (&w)[VWD], double (&o)[VB]) {
+#pragma unroll
+          for (int q4 = 0; q4 < VWD; ++q4) {
+            o[4 * q4 + 0] = u8_to_f64<0>(w[q4]);
+            o[4 * q4 + 1] = u8_to_f64<1>(w[q4]);
+            o[4 * q4 + 2] = u8_to_f64<2>(w[q4]);
+            o[4 * q4 + 3] = u8_to_f64<3>(w[q4]);
+          }
         };
 
         if constexpr (KEEP) {
@@ -995,11 +1006,11 @@ __global__ void __launch_bounds__(NT, (std::is_same<XT, int8_t>::value ? SB_I8_B
             double s0 = 0.0, s1 = 0.0;
 #pragma unroll
             for (int c = 0; c < CPT; ++c) {
-              double xd[8];
+              double xd[VB];
               if constexpr (!KEEP) widen(x[g][c], xd);
-              const double(&xv)[8] = *(KEEP ? &xk[KEEP ? g : 0][KEEP ? c : 0] : &xd);
+              const double(&xv)[VB] = *(KEEP ? &xk[KEEP ? g : 0][KEEP ? c : 0] : &xd);
 #pragma unroll
-              for (int u = 0; u < 8; u += 2) {
+              for (int u = 0; u < VB; u += 2) {
                 s0 = fma(xv[u], bq[c][u], s0);
                 s1 = fma(xv[u + 1], bq[c][u + 1], s1);
               }
@@ -1052,7 +1063,9 @@ __global__ void __launch_bounds__(NT, (std::is_same<XT, int8_t>::value ? SB_I8_B
 #pragma unroll
           for (int g = 0; g < GR; ++g)
 #pragma unroll
-            for (int c = 0; c < CPT; ++c) asm volatile("" : "+r"(x[g][c].x), "+r"(x[g][c].y));
+            for (int c = 0; c < CPT; ++c)
+#pragma unroll
+              for (int w = 0; w < VWD; ++w) asm volatile("" : "+r"(x[g][c][w]));
         }
 #pragma unroll
         for (int g = 0; g < GR; ++g) {
@@ -1060,11 +1073,11 @@ __global__ void __launch_bounds__(NT, (std::is_same<XT, int8_t>::value ? SB_I8_B
           rsum += rg;
 #pragma unroll
           for (int c = 0; c < CPT; ++c) {
-            double xd[8];
+            double xd[VB];
             if constexpr (!KEEP) widen(x[g][c], xd);
-            const double(&xv)[8] = *(KEEP ? &xk[KEEP ? g : 0][KEEP ? c : 0] : &xd);
+            const double(&xv)[VB] = *(KEEP ? &xk[KEEP ? g : 0][KEEP ? c : 0] : &xd);
 #pragma unroll
-            for (int u = 0; u < 8; ++u) aq[c][u] = fma(xv[u], rg, aq[c][u]);
+            for (int u = 0; u < VB; ++u) aq[c][u] = fma(xv[u], rg, aq[c][u]);
           }
         }
         phase_bits ^= (1u << st);
@@ -1375,11 +1388,13 @@ __global__ void __launch_bounds__(NT, (std::is_same<XT, int8_t>::value ? SB_I8_B
     auto traverse = [&](int l, bool first, bool last_effect) {
       if constexpr (std::is_same<XT, int8_t>::value) {
         if constexpr (V == 1)
-          traverse_i8(IntC<1>{}, IntC<8>{}, IntC<SB_I8_KEEP>{}, l, first, last_effect);
+          traverse_i8(IntC<1>{}, IntC<8>{}, IntC<SB_I8_KEEP>{}, IntC<8>{}, l, first, last_effect);
         else if constexpr (V == 2)
-          traverse_i8(IntC<2>{}, IntC<4>{}, IntC<0>{}, l, first, last_effect);
-        else
-          traverse_i8(IntC<4>{}, IntC<2>{}, IntC<0>{}, l, first, last_effect);
+          traverse_i8(IntC<2>{}, IntC<4>{}, IntC<0>{}, IntC<8>{}, l, first, last_effect);
+        else if constexpr (V == 3)
+          traverse_i8(IntC<4>{}, IntC<2>{}, IntC<0>{}, IntC<8>{}, l, first, last_effect);
+        else  // narrow loci (p_pad <= 1024): 4 columns per thread so every thread has work
+          traverse_i8(IntC<1>{}, IntC<8>{}, IntC<1>{}, IntC<4>{}, l, first, last_effect);
       } else if constexpr (SS) {
         if (fast == 1)
           traverse_ss(IntC<4>{}, IntC<4>{}, l, last_effect);
@@ -1392,12 +1407,18 @@ __global__ void __launch_bounds__(NT, (std::is_same<XT, int8_t>::value ? SB_I8_B
         else
           traverse_generic(IntC<0>{}, l, first, last_effect);
       } else {
-        if (fast == 1)
-          traverse_fast(IntC<4>{}, IntC<4>{}, l, first, last_effect);
-        else if (fast == 2)
-          traverse_fast(IntC<8>{}, IntC<2>{}, l, first, last_effect);
-        else
-          traverse_generic(IntC<0>{}, l, first, last_effect);
+        // the wide fp64 tile (12 vectors x 1 row) lives in its own kernel (V == 3): compiled next to the
+        // others it wrecks the code generated for the common 4 x 4 tile (3x slower, measured)
+        if constexpr (V == 3 && sizeof(XT) == 8) {
+          traverse_fast(IntC<12>{}, IntC<1>{}, l, first, last_effect);
+        } else {
+          if (fast == 1)
+            traverse_fast(IntC<4>{}, IntC<4>{}, l, first, last_effect);
+          else if (fast == 2)
+            traverse_fast(IntC<8>{}, IntC<2>{}, l, first, last_effect);
+          else
+            traverse_generic(IntC<0>{}, l, first, last_effect);
+        }
       }
     };
 

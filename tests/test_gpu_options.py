@@ -51,6 +51,8 @@ CASES = {
     "many_effects": dict(k=2, n=(64, 64), p=128, kw=dict(L=12)),
     "no_update_rho": dict(k=3, n=(70, 80, 60), p=150, kw=dict(L=3, no_update=True, rho=[0.3, 0.2, 0.1])),
     "wide_dense": dict(k=2, n=(60, 50), p=2300, kw=dict(L=2)),
+    "very_wide": dict(k=2, n=(60, 50), p=5000, kw=dict(L=2, max_iter=6)),   # 12 x 1 fp64 tile / 32 x 2 int8 tile
+    "narrow": dict(k=3, n=(120, 90, 70), p=700, kw=dict(L=3)),              # 4-byte int8 vectors
 }
 
 
