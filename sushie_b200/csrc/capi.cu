@@ -108,7 +108,7 @@ static const void* kfn() {
 // individual level: 3 for the wide 12 x 1 tile; everything else 0 (variant chosen per locus at run time)
 static int launch_variant(int storage, bool ss, int fast) {
   if (storage == SB_I8) return fast;
-  if (storage == SB_F64 && !ss && fast == 3) return 3;
+  if (storage == SB_F64 && !ss && (fast == 3 || fast == 1)) return fast;
   return 0;
 }
 static const void* pick_kernel(int K, int storage, bool ss, int variant) {
@@ -122,6 +122,7 @@ static const void* pick_kernel(int K, int storage, bool ss, int variant) {
              : variant == 2 ? kfn<KK, int8_t, false, 2>()                                     \
              : variant == 3 ? kfn<KK, int8_t, false, 3>() : kfn<KK, int8_t, false, 4>();      \
     if (!ss && !f32 && variant == 3) return kfn<KK, double, false, 3>();                      \
+    if (!ss && !f32 && variant == 1) return kfn<KK, double, false, 1>();                      \
     return ss ? (f32 ? kfn<KK, float, true>() : kfn<KK, double, true>())                      \
               : (f32 ? kfn<KK, float, false>() : kfn<KK, double, false>());
   switch (K) {

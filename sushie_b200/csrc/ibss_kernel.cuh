@@ -1411,6 +1411,8 @@ __global__ void __launch_bounds__(NT, (std::is_same<XT, int8_t>::value ? SB_I8_B
         // others it wrecks the code generated for the common 4 x 4 tile (3x slower, measured)
         if constexpr (V == 3 && sizeof(XT) == 8) {
           traverse_fast(IntC<12>{}, IntC<1>{}, l, first, last_effect);
+        } else if constexpr (V == 1 && sizeof(XT) == 8) {
+          traverse_fast(IntC<4>{}, IntC<4>{}, l, first, last_effect);
         } else {
           if (fast == 1)
             traverse_fast(IntC<4>{}, IntC<4>{}, l, first, last_effect);
