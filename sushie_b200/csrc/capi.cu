@@ -286,8 +286,13 @@ static bool plan_geometry(int p, int n_max, int es, bool ss, int smem_budget, Ge
       g.fast = 0;
     }
   }
-  const size_t fixed = hdr + static_cast<size_t>(g.p_pad) * sizeof(double) * (ss ? 1 : 2);
-  if (fixed + 2 * row_bytes > static_cast<size_t>(smem_budget)) return false;
+  size_t fixed = hdr + static_cast<size_t>(g.p_pad) * sizeof(double) * (ss ? 1 : 2);
+  if (fixed + 2 * row_bytes > static_cast<size_t>(smem_budget)) {
+    // very wide locus: keep b / the accumulator in global memory, all shared memory goes to the ring
+    fixed = hdr;
+    if (fixed + 2 * row_bytes > static_cast<size_t>(smem_budget)) return false;
+    g.fast = sb::FAST_GLOBAL_VECTORS;
+  }
   const int rows_fit = static_cast<int>((smem_budget - fixed) / row_bytes);
   g.NS = rows_fit >= 3 ? 3 : 2;
   g.G = std::max(1, std::min({sb::GMAX, rows_fit / g.NS, std::max(1, n_max)}));

@@ -48,6 +48,7 @@ constexpr int NSTAGE_MAX = 6;
 constexpr int I8_STATE_ROWS = 2048;  // hard-call path: band rows whose (r, xb) state is staged in shared memory at a time
 constexpr int SS_CHUNK_ROWS = 256;  // summary-level register-tile path: rows whose partial sums are parked in shared memory
 constexpr int NSYM_MAX = KMAX * (KMAX + 1) / 2;
+constexpr int FAST_GLOBAL_VECTORS = 9;  // ProbDev::fast: generic traversal with b / accumulator in global memory
 constexpr int STAT_STRIDE = 20;  // doubles per team-reduction record (>= 2 + NSYM_MAX + 2 + KMAX)
 constexpr int TRAV_STRIDE = 2 * KMAX;
 
@@ -536,11 +537,11 @@ __global__ void __launch_bounds__(NT, (std::is_same<XT, int8_t>::value ? SB_I8_B
     const int status0 = __ldcg(&pb.meta[4]);  // 0 fresh, 1 resumed from a suspended state
 
     // dynamic shared-memory carve-up: [header][b (generic path)][acc (generic, individual)][ring]
-    double* bsm = reinterpret_cast<double*>(smem_raw + ((sizeof(SmemHdr) + 127) / 128) * 128);
-    double* acc = bsm + p_pad;
+    double* bsm_sm = reinterpret_cast<double*>(smem_raw + ((sizeof(SmemHdr) + 127) / 128) * 128);
+    double* acc_sm = bsm_sm + p_pad;
     unsigned char* ring =
-        fast ? reinterpret_cast<unsigned char*>(bsm)
-             : reinterpret_cast<unsigned char*>(SS ? (bsm + p_pad) : (acc + p_pad));
+        fast ? reinterpret_cast<unsigned char*>(bsm_sm)
+             : reinterpret_cast<unsigned char*>(SS ? (bsm_sm + p_pad) : (acc_sm + p_pad));
 
     // SNP slice of this block for the posterior phases
     const int js = static_cast<int>((static_cast<long long>(p) * rank) / C);
@@ -585,7 +586,9 @@ __global__ void __launch_bounds__(NT, (std::is_same<XT, int8_t>::value ? SB_I8_B
     }
 
     // ring prologue: keep NS fills in flight; positions wrap (the traversal order is static)
-    const int producer_tid = fast ? NT - 32 : 0;  // the thread that issues bulk copies (owns prod_pos)
+    // the thread that issues bulk copies (owns prod_pos): lane 0 of the last warp in the register-tile
+    // traversals, thread 0 in the generic one (also when its vectors live in global memory)
+    const int producer_tid = (fast && fast != FAST_GLOBAL_VECTORS) ? NT - 32 : 0;
     int prod_pos = 0;  // next own band position to issue (producer thread only)
     int cons_seq = 0;  // bands consumed so far in this locus (stage = cons_seq % NS)
     __syncthreads();
@@ -1255,6 +1258,12 @@ __global__ void __launch_bounds__(NT, (std::is_same<XT, int8_t>::value ? SB_I8_B
       for (int k = 0; k < K; ++k) vsq[k] = rsq[k] = 0.0;
       int cur_k = -1;
       int pending_refill = -1;  // stage to refill once every thread has left its sweep 2
+      // loci too wide for b / the X^T r accumulator to sit in shared memory next to two band stages keep both
+      // in global memory (b is read from the materialised effect vector, the accumulator is the block's
+      // partial X^T r itself); slower (L2 traffic per row) but any row that fits the ring twice works
+      const bool big = (fast == FAST_GLOBAL_VECTORS);
+      double* bsm = big ? nullptr : bsm_sm;
+      double* acc = big ? nullptr : acc_sm;
 
       for (int pos = 0; pos < nb_own; ++pos) {
         int k, g0, rows;
@@ -1262,12 +1271,16 @@ __global__ void __launch_bounds__(NT, (std::is_same<XT, int8_t>::value ? SB_I8_B
         if (k != cur_k) {
           // ancestry change: flush X^T r partial, load the new b, clear the accumulator
           __syncthreads();
-          if (!SS && cur_k >= 0) {
+          if (!SS && cur_k >= 0 && !big) {
             double* dst = my_scr + static_cast<size_t>(cur_k) * p_pad;
             for (int j = tid; j < p_pad; j += NT) __stcg(&dst[j], acc[j]);
           }
-          if (!first)
+          if (big) {
+            bsm = const_cast<double*>(effect_vec(l, k));  // read-only; not touched when first
+            acc = my_scr + static_cast<size_t>(k) * p_pad;
+          } else if (!first) {
             for (int j = tid; j < p_pad; j += NT) bsm[j] = __ldcg(&effect_vec(l, k)[j]);
+          }
           if (!SS)
             for (int j = tid; j < p_pad; j += NT) acc[j] = 0.0;
           cur_k = k;
@@ -1299,7 +1312,9 @@ __global__ void __launch_bounds__(NT, (std::is_same<XT, int8_t>::value ? SB_I8_B
                 const double* bb = bsm + v * VW;
 #pragma unroll
                 for (int u = 0; u < VW; u += 2) {
-                  const double2 b2 = *reinterpret_cast<const double2*>(bb + u);
+                  // (global-memory b is rewritten every iteration: read it past L1)
+                  const double2 b2 = big ? __ldcg(reinterpret_cast<const double2*>(bb + u))
+                                         : *reinterpret_cast<const double2*>(bb + u);
                   a0 = fma(x[u], b2.x, a0);
                   a1 = fma(x[u + 1], b2.y, a1);
                 }
@@ -1326,7 +1341,7 @@ __global__ void __launch_bounds__(NT, (std::is_same<XT, int8_t>::value ? SB_I8_B
           pb.r[row] = rnext;
           H->rn[tid] = rnext;
           // b_l^T XtX b_l (infer_ss.py:572)  |  |X b_l|^2 (infer.py:806)
-          const double vterm = SS ? bsm[g0 + tid] * v : v * v;
+          const double vterm = SS ? (big ? __ldcg(&bsm[g0 + tid]) : bsm[g0 + tid]) * v : v * v;
           if (SS && last_effect) pb.rfull[row] = Rfull;
 #pragma unroll
           for (int kk = 0; kk < K; ++kk)
@@ -1376,7 +1391,7 @@ __global__ void __launch_bounds__(NT, (std::is_same<XT, int8_t>::value ? SB_I8_B
         prod_pos = (prod_pos + 1 == nb_own) ? 0 : prod_pos + 1;
       }
       if (!SS) {
-        if (cur_k >= 0) {
+        if (cur_k >= 0 && !big) {
           double* dst = my_scr + static_cast<size_t>(cur_k) * p_pad;
           for (int j = tid; j < p_pad; j += NT) __stcg(&dst[j], acc[j]);
         }

@@ -143,3 +143,39 @@ def test_summary_level_very_wide_locus_fits(engine_lib):
     ref = ibss.fit_summary([ld.astype(np.float64) for ld in lds], ns, zs, L=2, max_iter=3, min_tol=0.0)
     np.testing.assert_allclose(res.elbo[1:], np.asarray(ref.elbo)[1:], rtol=1e-6)
     assert np.max(np.abs(res.pip_all - ibss.make_pip(ref.posteriors.alpha))) <= PIP_TOL
+
+
+def test_loci_too_wide_for_shared_memory_vectors(engine_lib):
+    """p = 9000 at fp64: neither the register tiles nor the shared-memory generic path fit, so b and the X^T r
+    accumulator live in global memory (individual level) / b is read from the effect vector (summary level)."""
+    import sushie_b200
+    from oracle import ibss
+    from sushie_b200 import config
+
+    p = 9000
+    rng = np.random.default_rng(8)
+    X = rng.standard_normal((40, p))          # not hard calls: dense storage
+    beta = np.zeros(p)
+    beta[[100, 7000]] = (1.0, -1.0)
+    y = X @ beta + rng.standard_normal(40)
+    old = config.team_size
+    try:
+        for team in (1, 4):
+            config.team_size = team
+            res = sushie_b200.infer_sushie([X.copy()], [y.copy()], L=2, max_iter=4, min_tol=0.0)
+            ref = ibss.fit_individual([X], [y], L=2, max_iter=4, min_tol=0.0)
+            np.testing.assert_allclose(res.elbo[1:], np.asarray(ref.elbo)[1:], rtol=1e-6)
+            assert np.max(np.abs(res.pip_all - ibss.make_pip(ref.posteriors.alpha))) <= PIP_TOL
+        config.team_size = 8
+        idx = np.arange(p)
+        d = np.abs(idx[:, None] - idx[None, :])
+        ld = np.where(d < 6, 0.5 ** d, 0.0)
+        z = rng.standard_normal(p)
+        z[[300, 8000]] += (8.0, -7.0)
+        ns = np.array([[3000]])
+        res = sushie_b200.infer_sushie_ss([ld], ns, [z], L=2, max_iter=3, min_tol=0.0)
+        ref = ibss.fit_summary([ld], ns, [z], L=2, max_iter=3, min_tol=0.0)
+        np.testing.assert_allclose(res.elbo[1:], np.asarray(ref.elbo)[1:], rtol=1e-6)
+        assert np.max(np.abs(res.pip_all - ibss.make_pip(ref.posteriors.alpha))) <= PIP_TOL
+    finally:
+        config.team_size = old
