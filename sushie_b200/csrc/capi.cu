@@ -108,7 +108,7 @@ static const void* kfn() {
 // individual level: 3 for the wide 12 x 1 tile; everything else 0 (variant chosen per locus at run time)
 static int launch_variant(int storage, bool ss, int fast) {
   if (storage == SB_I8) return fast;
-  if (storage == SB_F64 && !ss && (fast == 3 || fast == 1)) return fast;
+  if (storage == SB_F64 && !ss && (fast == 1 || fast == 3 || fast == 5 || fast == 6)) return fast;
   return 0;
 }
 static const void* pick_kernel(int K, int storage, bool ss, int variant) {
@@ -123,6 +123,8 @@ static const void* pick_kernel(int K, int storage, bool ss, int variant) {
              : variant == 3 ? kfn<KK, int8_t, false, 3>() : kfn<KK, int8_t, false, 4>();      \
     if (!ss && !f32 && variant == 3) return kfn<KK, double, false, 3>();                      \
     if (!ss && !f32 && variant == 1) return kfn<KK, double, false, 1>();                      \
+    if (!ss && !f32 && variant == 5) return kfn<KK, double, false, 5>();                      \
+    if (!ss && !f32 && variant == 6) return kfn<KK, double, false, 6>();                      \
     return ss ? (f32 ? kfn<KK, float, true>() : kfn<KK, double, true>())                      \
               : (f32 ? kfn<KK, float, false>() : kfn<KK, double, false>());
   switch (K) {
@@ -259,7 +261,13 @@ static bool plan_geometry(int p, int n_max, int es, bool ss, int smem_budget, Ge
   // register-tile traversal (individual level): every thread owns CPT vectors of GR rows
   {
     int gr = 0;
-    if (pv > sb::NT && pv <= 4 * sb::NT) {
+    if (!ss && es == 8 && pv >= sb::NT / 2 && pv <= sb::NT) {  // narrow fp64 loci: 1 or 2 vectors x 8 rows (own kernels)
+      g.fast = 5;
+      gr = 8;
+    } else if (!ss && es == 8 && pv > sb::NT && pv <= 2 * sb::NT) {
+      g.fast = 6;
+      gr = 8;
+    } else if (pv > sb::NT && pv <= 4 * sb::NT) {
       g.fast = 1;
       gr = 4;
     } else if (pv > 4 * sb::NT && pv <= 8 * sb::NT) {
@@ -837,7 +845,7 @@ static int batch_create(sb_ctx* ctx, const std::vector<GenericProblem>& gp, bool
     std::vector<int> ids;
     ids.reserve(n_probs);
     for (int K = 1; K <= KMAX; ++K)
-      for (int variant = 0; variant <= 4; ++variant) {
+      for (int variant = 0; variant <= 6; ++variant) {
         const int start = static_cast<int>(ids.size());
         for (int i = 0; i < n_probs; ++i)
           if (gp[i].K == K && launch_variant(opts.storage, ss, geo[i].fast) == variant) ids.push_back(i);

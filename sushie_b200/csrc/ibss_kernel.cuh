@@ -784,6 +784,8 @@ __global__ void __launch_bounds__(NT, (std::is_same<XT, int8_t>::value ? SB_I8_B
             t += __shfl_xor_sync(0xffffffffu, t, 4);
             t += __shfl_xor_sync(0xffffffffu, t, 2);
             t += __shfl_xor_sync(0xffffffffu, t, 1);
+          } else if constexpr (GR == 8) {
+            t = warp_rows_sum<8>(ps, lane);
           } else {
             t = warp_sum(ps[0]);
           }
@@ -1428,6 +1430,10 @@ __global__ void __launch_bounds__(NT, (std::is_same<XT, int8_t>::value ? SB_I8_B
           traverse_fast(IntC<12>{}, IntC<1>{}, l, first, last_effect);
         } else if constexpr (V == 1 && sizeof(XT) == 8) {
           traverse_fast(IntC<4>{}, IntC<4>{}, l, first, last_effect);
+        } else if constexpr (V == 5 && sizeof(XT) == 8) {
+          traverse_fast(IntC<1>{}, IntC<8>{}, l, first, last_effect);  // narrow loci: p_pad <= 512
+        } else if constexpr (V == 6 && sizeof(XT) == 8) {
+          traverse_fast(IntC<2>{}, IntC<8>{}, l, first, last_effect);  // p_pad <= 1024
         } else {
           if (fast == 1)
             traverse_fast(IntC<4>{}, IntC<4>{}, l, first, last_effect);
