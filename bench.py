@@ -406,7 +406,7 @@ def main():
         d_ach = d_st["algorithmic_bytes"] / (d_st["device_ms"] / 1e3) / 1e9
         d_traffic, d_src = ncu_traffic("f64")
         dense = {
-            "kernel": "sb::ibss_kernel<3,double,false>", "bound": "hbm", "achieved": d_ach, "unit": "GB/s",
+            "kernel": "sb::ibss_kernel<3,double,false,1>", "bound": "hbm", "achieved": d_ach, "unit": "GB/s",
             "loci_per_sec": B / (d_st["device_ms"] / 1e3), "ms_per_step": d_st["device_ms"],
             "algorithmic_bytes_per_ser": K_ANC * N_IND * P_SNP * 8,
             "traffic": d_traffic * d_st["n_ser"] if d_traffic else None, "traffic_source": d_src,
@@ -515,7 +515,7 @@ def main():
             "mean_iters_per_locus": n_iter / (total_loci * args.steps),
             "wall_ms_per_step": wall_ms / args.steps,
             "gpu_launches": launches,
-            "kernel": dict(geom, name="sb::ibss_kernel<3,%s,false>" % {"i8": "int8_t", "f64": "double", "f32": "float"}[args.storage],
+            "kernel": dict(geom, name="sb::ibss_kernel<3,%s>" % {"i8": "int8_t,false,1", "f64": "double,false,1", "f32": "float,false,0"}[args.storage],
                            launches_per_step=launches / args.steps, genotype_storage=args.storage),
             "roofline": roofline,
             "clocks": {"sm_mhz": clocks["sm_mhz"], "sm_max_mhz": clocks["sm_max_mhz"], "reasons": clocks["reasons"],
