@@ -236,7 +236,7 @@ static bool plan_geometry(int p, int n_max, int es, bool ss, int smem_budget, Ge
     int gr;
     if (g.p_pad / 4 <= sb::NT) {  // narrow locus: 4-byte vectors keep every thread busy
       g.fast = 4;
-      gr = 8;
+      gr = 16;
     } else if (pv8 <= sb::NT) {
       g.fast = 1;
       gr = 8;

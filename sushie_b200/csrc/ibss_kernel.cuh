@@ -279,7 +279,7 @@ __device__ __forceinline__ double u8_to_f64(uint32_t w) {
 // of row l / (32 / GR).  GR + log2(32 / GR) - 1 double shuffles instead of 5 * GR.
 template <int GR>
 __device__ __forceinline__ double warp_rows_sum(double (&ps)[GR], int lane) {
-  static_assert(GR == 1 || GR == 2 || GR == 4 || GR == 8, "rows per band");
+  static_assert(GR == 1 || GR == 2 || GR == 4 || GR == 8 || GR == 16, "rows per band");
   int off = 16;
 #pragma unroll
   for (int cnt = GR; cnt > 1; cnt >>= 1) {
@@ -303,7 +303,7 @@ struct SmemHdr {
   uint64_t mbar[NSTAGE_MAX];  // "stage filled" (bulk-copy completion)
   uint64_t ebar[NSTAGE_MAX];  // "stage drained" (one arrival per warp; summary-level register-tile path)
   ProbDev pb;                // the locus being processed
-  alignas(16) double partsum[2][2 * GMAX];  // sweep-1 partial dot products [band parity][g * nseg + seg]
+  alignas(16) double partsum[2][4 * GMAX];  // sweep-1 partial dot products [band parity][g * nseg + seg]
   double rn[GMAX];           // next residual of the band's rows
   double red[NW][STAT_STRIDE];
   double tot[STAT_STRIDE];   // block / team totals
@@ -1410,8 +1410,8 @@ __global__ void __launch_bounds__(NT, (std::is_same<XT, int8_t>::value ? SB_I8_B
           traverse_i8(IntC<2>{}, IntC<4>{}, IntC<0>{}, IntC<8>{}, l, first, last_effect);
         else if constexpr (V == 3)
           traverse_i8(IntC<4>{}, IntC<2>{}, IntC<0>{}, IntC<8>{}, l, first, last_effect);
-        else  // narrow loci (p_pad <= 1024): 4 columns per thread so every thread has work
-          traverse_i8(IntC<1>{}, IntC<8>{}, IntC<1>{}, IntC<4>{}, l, first, last_effect);
+        else  // narrow loci (p_pad <= 1024): 4 columns x 16 rows per thread so every thread has work and bands are tall
+          traverse_i8(IntC<1>{}, IntC<16>{}, IntC<1>{}, IntC<4>{}, l, first, last_effect);
       } else if constexpr (SS) {
         if (fast == 1)
           traverse_ss(IntC<4>{}, IntC<4>{}, l, last_effect);

@@ -271,7 +271,7 @@ def test_hard_call_storage_is_selected_and_wide_loci_fit(engine_lib):
 
     rng = np.random.default_rng(11)
     eng = _capi.get_engine(0)
-    for p, rows in ((300, 8), (2500, 4), (5000, 2)):
+    for p, rows in ((300, 16), (1500, 8), (2500, 4), (5000, 2)):
         k, n, L = 2, [90, 70], 3
         Xs = [rng.binomial(2, 0.3, size=(n[i], p)).astype(np.int8) for i in range(k)]
         for X in Xs:
