@@ -1153,7 +1153,7 @@ def _get_command_string(argv: List[str]) -> str:
 def _main(argv: List[str]) -> int:
     from . import __version__
 
-    argp = argparse.ArgumentParser(formatter_class=argparse.ArgumentDefaultsHelpFormatter)
+    argp = argparse.ArgumentParser(prog="sushie", formatter_class=argparse.ArgumentDefaultsHelpFormatter)
     argp.add_argument("--version", action="version", version=__version__)
     subp = argp.add_subparsers(help="Subcommands: finemap to perform gene expression fine-mapping using SuShiE")
     build_finemap_parser(subp).set_defaults(func=run_finemap)
