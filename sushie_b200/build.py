@@ -30,11 +30,33 @@ def find_nvcc() -> str:
     return nvcc
 
 
+STAMP = OUT + ".srchash"
+
+
+def _source_hash() -> str:
+    """Hash of everything the library is built from (sources, header, flags, development switches)."""
+    import hashlib
+
+    h = hashlib.sha256()
+    for path in DEPS:
+        with open(path, "rb") as fh:
+            h.update(fh.read())
+    h.update(" ".join(NVCC_FLAGS).encode())
+    h.update(os.environ.get("SUSHIE_B200_ONLY_K", "").encode())
+    return h.hexdigest()
+
+
 def up_to_date() -> bool:
+    """True when the library was built from exactly these sources.  Content hash, not mtimes: a snapshot
+    copied to another machine (the GPU box) must not trigger a multi-minute rebuild."""
     if not os.path.exists(OUT):
         return False
-    t = os.path.getmtime(OUT)
-    return all(os.path.getmtime(d) <= t for d in DEPS)
+    try:
+        with open(STAMP) as fh:
+            return fh.read().strip() == _source_hash()
+    except OSError:
+        t = os.path.getmtime(OUT)
+        return all(os.path.getmtime(d) <= t for d in DEPS)
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
@@ -49,6 +71,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
         raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + proc.stdout + proc.stderr)
     if verbose:
         sys.stderr.write(proc.stderr)
+    with open(STAMP, "w") as fh:
+        fh.write(_source_hash() + "\n")
     return OUT
 
 
