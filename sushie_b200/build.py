@@ -11,16 +11,18 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
-SRC = [os.path.join(HERE, "csrc", "capi.cu")]
-DEPS = SRC + [os.path.join(HERE, "csrc", "ibss_kernel.cuh"), os.path.join(ROOT, "include", "sushie_b200.h")]
+CAPI = os.path.join(HERE, "csrc", "capi.cu")            # host side of the C ABI + small kernels
+KERNELS = os.path.join(HERE, "csrc", "ibss_kernels.cu")  # IBSS kernel instantiations, compiled once per ancestry count
+DEPS = [CAPI, KERNELS, os.path.join(HERE, "csrc", "ibss_kernel.cuh"), os.path.join(ROOT, "include", "sushie_b200.h")]
 OUT = os.path.join(HERE, "_lib", "libsushie_b200.so")
+OBJ = os.path.join(HERE, "_lib", "obj")
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-lineinfo", "-O3", "-std=c++17",
-    "-Xcompiler", "-fPIC", "-shared",
-    "-cudart", "static",
+    "-Xcompiler", "-fPIC",
 ]
+LINK_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-cudart", "static"]
 
 
 def find_nvcc() -> str:
@@ -60,17 +62,35 @@ def up_to_date() -> bool:
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
+    """Compile capi.cu and the four per-ancestry-count kernel units in parallel, then link the shared library."""
     if not force and up_to_date():
         return OUT
-    os.makedirs(os.path.dirname(OUT), exist_ok=True)
+    os.makedirs(OBJ, exist_ok=True)
+    nvcc = find_nvcc()
     dev = os.environ.get("SUSHIE_B200_ONLY_K")  # development: compile one ancestry count only
-    extra = [f"-DSB_ONLY_K={int(dev)}"] if dev else []
-    cmd = [find_nvcc()] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT] + SRC
-    proc = subprocess.run(cmd, capture_output=True, text=True)
+    ks = [int(dev)] if dev else [1, 2, 3, 4]
+    vflags = ["-Xptxas", "-v"] if verbose else []
+    jobs = [([nvcc] + NVCC_FLAGS + ([f"-DSB_ONLY_K={int(dev)}"] if dev else []) + ["-c", "-o", os.path.join(OBJ, "capi.o"), CAPI],
+             os.path.join(OBJ, "capi.o"))]
+    for k in ks:
+        obj = os.path.join(OBJ, f"ibss_k{k}.o")
+        jobs.append(([nvcc] + NVCC_FLAGS + vflags + [f"-DSB_K={k}", "-c", "-o", obj, KERNELS], obj))
+    procs = [(cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)) for cmd, _ in jobs]
+    logs = []
+    for cmd, proc in procs:
+        out, _ = proc.communicate()
+        logs.append(out)
+        if proc.returncode != 0:
+            for _, other in procs:
+                if other.poll() is None:
+                    other.kill()
+            raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + out)
+    link = [nvcc] + LINK_FLAGS + ["-o", OUT] + [obj for _, obj in jobs]
+    proc = subprocess.run(link, capture_output=True, text=True)
     if proc.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + proc.stdout + proc.stderr)
+        raise RuntimeError("nvcc link failed:\n" + " ".join(link) + "\n" + proc.stdout + proc.stderr)
     if verbose:
-        sys.stderr.write(proc.stderr)
+        sys.stderr.write("".join(logs))
     with open(STAMP, "w") as fh:
         fh.write(_source_hash() + "\n")
     return OUT

@@ -100,10 +100,12 @@ static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; 
 // ------------------------------------------------------------------------------------------
 // kernel table
 
-template <int K, typename XT, bool SS, int V = 0>
-static const void* kfn() {
-  return reinterpret_cast<const void*>(&sb::ibss_kernel<K, XT, SS, V>);
-}
+// The kernel instantiations live in ibss_kernels.cu, one translation unit per ancestry count (built in parallel).
+extern "C" const void* sb_kernel_table_k1(int storage, int ss, int variant);
+extern "C" const void* sb_kernel_table_k2(int storage, int ss, int variant);
+extern "C" const void* sb_kernel_table_k3(int storage, int ss, int variant);
+extern "C" const void* sb_kernel_table_k4(int storage, int ss, int variant);
+
 // variant: traversal variant compiled into the kernel -- hard-call storage: Geometry::fast (1..4); dense fp64
 // individual level: 3 for the wide 12 x 1 tile; everything else 0 (variant chosen per locus at run time)
 static int launch_variant(int storage, bool ss, int fast) {
@@ -112,33 +114,20 @@ static int launch_variant(int storage, bool ss, int fast) {
   return 0;
 }
 static const void* pick_kernel(int K, int storage, bool ss, int variant) {
-  const bool f32 = storage == SB_F32;
-  const bool i8 = storage == SB_I8;
-  if (i8 && ss) return nullptr;
-#define SB_PICK(KK)                                                                           \
-  case KK:                                                                                    \
-    if (i8)                                                                                   \
-      return variant == 1 ? kfn<KK, int8_t, false, 1>()                                       \
-             : variant == 2 ? kfn<KK, int8_t, false, 2>()                                     \
-             : variant == 3 ? kfn<KK, int8_t, false, 3>() : kfn<KK, int8_t, false, 4>();      \
-    if (!ss && !f32 && variant == 3) return kfn<KK, double, false, 3>();                      \
-    if (!ss && !f32 && variant == 1) return kfn<KK, double, false, 1>();                      \
-    if (!ss && !f32 && variant == 5) return kfn<KK, double, false, 5>();                      \
-    if (!ss && !f32 && variant == 6) return kfn<KK, double, false, 6>();                      \
-    return ss ? (f32 ? kfn<KK, float, true>() : kfn<KK, double, true>())                      \
-              : (f32 ? kfn<KK, float, false>() : kfn<KK, double, false>());
-  switch (K) {
-#ifdef SB_ONLY_K  // development builds: instantiate a single ancestry count
-    SB_PICK(SB_ONLY_K)
+#ifdef SB_ONLY_K  // development builds: a single ancestry count is compiled and linked
+  if (K != SB_ONLY_K) return nullptr;
+#define SB_TABLE2(k) sb_kernel_table_k##k
+#define SB_TABLE(k) SB_TABLE2(k)
+  return SB_TABLE(SB_ONLY_K)(storage, ss ? 1 : 0, variant);
 #else
-    SB_PICK(1)
-    SB_PICK(2)
-    SB_PICK(3)
-    SB_PICK(4)
-#endif
+  switch (K) {
+    case 1: return sb_kernel_table_k1(storage, ss ? 1 : 0, variant);
+    case 2: return sb_kernel_table_k2(storage, ss ? 1 : 0, variant);
+    case 3: return sb_kernel_table_k3(storage, ss ? 1 : 0, variant);
+    case 4: return sb_kernel_table_k4(storage, ss ? 1 : 0, variant);
   }
-#undef SB_PICK
   return nullptr;
+#endif
 }
 
 // ------------------------------------------------------------------------------------------

@@ -2037,7 +2037,7 @@ __global__ void prep_ss_kernel(const XT* __restrict__ ld, const double* __restri
 }
 
 // log pi (infer.py:721); in == nullptr means the uniform default 1/p (infer.py:302-303)
-__global__ void log_kernel(const double* __restrict__ in, double uniform, double* __restrict__ out, int n) {
+static __global__ void log_kernel(const double* __restrict__ in, double uniform, double* __restrict__ out, int n) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) out[i] = log(in ? in[i] : uniform);
 }
