@@ -234,8 +234,7 @@ def log_convergence(n_iter: int, max_iter: int, min_tol: float, elbo: np.ndarray
         )
 
 
-def assemble_result(fit, pi, sample_size, no_reorder, cs_builder) -> SushieResult:
-    """RawFit (engine output) -> SushieResult: re-order effects, then credible sets."""
+def _reordered(fit, pi, no_reorder):
     k = fit.resid_var.shape[0]
     L, p = fit.alpha.shape
     if pi is None:
@@ -253,9 +252,41 @@ def assemble_result(fit, pi, sample_size, no_reorder, cs_builder) -> SushieResul
     if not no_reorder:
         log.logger.debug("Reordering effects based on Frobenius norm of effect size covariance prior.")
         priors, posteriors, l_order = _reorder_l(priors, posteriors)
+    return priors, posteriors, l_order
+
+
+def assemble_result(fit, pi, sample_size, no_reorder, cs_builder) -> SushieResult:
+    """RawFit (engine output) -> SushieResult: re-order effects, then credible sets."""
+    priors, posteriors, l_order = _reordered(fit, pi, no_reorder)
     log.logger.debug("Computing credible sets.")
     cs, full_alphas, pip_all, pip_cs = cs_builder(posteriors.alpha, posteriors.log_bf)
     log.logger.debug("Inference and credible set computation complete. Beginning to write results.")
     return SushieResult(
         priors, posteriors, pip_all, pip_cs, cs, full_alphas, sample_size, fit.elbo, fit.elbo_increase, l_order
     )
+
+
+def stage_result(fit, pi, sample_size, no_reorder, min_abs_corr, threshold, purity, purity_method, max_select, seed):
+    """Epilogue in two halves.  This call does the half that needs the device-resident batch (effect
+    re-ordering, credible-set selection, purity Gram matrices through ``min_abs_corr``) and returns the
+    host-only half (output tables) as a zero-argument callable, so a batch entry point can release the
+    device batch -- and start the next chunk of loci -- before the tables are assembled."""
+    from . import cs as _cs
+
+    if purity_method not in ("weighted", "max", "min"):
+        raise ValueError(f"Invalid purity method {purity_method}. Choose from 'weighted', 'max', or 'min'.")
+    priors, posteriors, l_order = _reordered(fit, pi, no_reorder)
+    log.logger.debug("Computing credible sets.")
+    selection = _cs.select_sets(posteriors.alpha, threshold, max_select, seed)
+    min_abs = np.asarray(min_abs_corr(selection[3]), dtype=float)
+
+    def finish() -> SushieResult:
+        cs, full_alphas, pip_all, pip_cs = _cs.finish_tables(
+            posteriors.alpha, posteriors.log_bf, sample_size, selection, min_abs, purity, purity_method
+        )
+        log.logger.debug("Inference and credible set computation complete. Beginning to write results.")
+        return SushieResult(
+            priors, posteriors, pip_all, pip_cs, cs, full_alphas, sample_size, fit.elbo, fit.elbo_increase, l_order
+        )
+
+    return finish

@@ -21,6 +21,12 @@ team_size: int = int(os.environ.get("SUSHIE_B200_TEAM", "0"))
 single_phase: bool = bool(int(os.environ.get("SUSHIE_B200_SINGLE_PHASE", "0")))
 # loci per device-resident chunk in the batch entry points (0 = size by memory budget).
 chunk_loci: int = int(os.environ.get("SUSHIE_B200_CHUNK", "0"))
+# automatic chunking with several GPU workers (chunk_loci = 0): at least one chunk per worker, up to
+# `chunks_per_worker` per worker while a chunk keeps `min_chunk_loci` loci (two per SM)
+chunks_per_worker: int = int(os.environ.get("SUSHIE_B200_CHUNKS_PER_WORKER", "3"))
+min_chunk_loci: int = int(os.environ.get("SUSHIE_B200_MIN_CHUNK", "296"))
+# print the wall time of the host-side phases of every chunk (upload, run, download, purity, tables) to stderr
+trace_host: bool = bool(int(os.environ.get("SUSHIE_B200_TRACE_HOST", "0")))
 # device memory budget per chunk, bytes
 chunk_bytes: int = int(float(os.environ.get("SUSHIE_B200_CHUNK_GB", "24")) * (1 << 30))
 

@@ -9,6 +9,7 @@ same un-split key for every effect, ``infer.py:894,940-943``).
 """
 from __future__ import annotations
 
+import functools
 from typing import Callable, List, Optional, Sequence, Tuple
 
 import numpy as np
@@ -65,15 +66,25 @@ def split_key(key: Tuple[int, int]):
     return _split2(key)
 
 
-def shuffle_with_key(key: Tuple[int, int], values: np.ndarray) -> np.ndarray:
-    """JAX's sort-based shuffle of ``values`` (``jax.random.permutation`` /
-    ``choice(..., replace=False)``): rounds of stable sorts by fresh 32-bit words."""
-    out = np.array(values, copy=True)
-    rounds = int(np.ceil(3 * np.log(max(1, out.size)) / np.log(np.iinfo(np.uint32).max)))
+@functools.lru_cache(maxsize=256)
+def _shuffle_order(key: Tuple[int, int], n: int) -> np.ndarray:
+    """Positions picked by JAX's sort-based shuffle of ``n`` items under ``key``: rounds of stable sorts by
+    fresh 32-bit words.  It does not depend on the values, and ``make_cs`` re-uses one key for every effect
+    of every locus (``infer.py:894,940-943``), so the orders are cached per (key, n)."""
+    order = np.arange(n)
+    rounds = int(np.ceil(3 * np.log(max(1, n)) / np.log(np.iinfo(np.uint32).max)))
     for _ in range(rounds):
         key, sub = _split2(key)
-        out = out[np.argsort(_threefry_stream(sub, out.size), kind="stable")]
-    return out
+        order = order[np.argsort(_threefry_stream(sub, n), kind="stable")]
+    order.setflags(write=False)
+    return order
+
+
+def shuffle_with_key(key: Tuple[int, int], values: np.ndarray) -> np.ndarray:
+    """JAX's sort-based shuffle of ``values`` (``jax.random.permutation`` /
+    ``choice(..., replace=False)``)."""
+    values = np.asarray(values)
+    return values[_shuffle_order((int(key[0]), int(key[1])), int(values.size))]
 
 
 def jax_choice_no_replace(seed: int, values: np.ndarray, n_draws: int) -> np.ndarray:
@@ -134,13 +145,25 @@ def build_tables(
 
     ``min_abs_corr(list_of_index_arrays) -> [n_sets, k]`` supplies the purity raw material
     (device kernel)."""
+    if purity_method not in ("weighted", "max", "min"):
+        raise ValueError(f"Invalid purity method {purity_method}. Choose from 'weighted', 'max', or 'min'.")
+    alpha = np.asarray(alpha, dtype=float)
+    selection = select_sets(alpha, threshold, max_select, seed)
+    min_abs = min_abs_corr(selection[3])
+    return finish_tables(alpha, log_bf, ns, selection, min_abs, purity, purity_method)
+
+
+def finish_tables(alpha, log_bf, ns, selection, min_abs, purity: float, purity_method: str):
+    """Host-only second half of :func:`build_tables`: from the selected sets (``select_sets``) and their
+    min |corr| per ancestry to the output tables.  The batch entry points run this half on a finisher
+    thread while the GPU works on the next chunk of loci."""
     alpha = np.asarray(alpha, dtype=float)
     log_bf = np.asarray(log_bf, dtype=float)
     if purity_method not in ("weighted", "max", "min"):
         raise ValueError(f"Invalid purity method {purity_method}. Choose from 'weighted', 'max', or 'min'.")
     n_l, p = alpha.shape
-    orders, csums, sizes, purity_idx = select_sets(alpha, threshold, max_select, seed)
-    purities = combine_purity(np.asarray(min_abs_corr(purity_idx), dtype=float).reshape(n_l, -1), ns, purity_method)
+    orders, csums, sizes, _ = selection
+    purities = combine_purity(np.asarray(min_abs, dtype=float).reshape(n_l, -1), ns, purity_method)
     kept = purities > purity
 
     pip_all = make_pip(alpha)

@@ -14,6 +14,8 @@ Deliberate differences from the reference:
 """
 from __future__ import annotations
 
+import sys
+import time
 from typing import List, Optional, Sequence
 
 import numpy as np
@@ -25,13 +27,13 @@ from ._common import (
     SushieResult,
     _PriorAdjustor,
     _reorder_l,
-    assemble_result,
     build_priors,
     check_scalar_options,
     check_snp_counts,
     log_convergence,
     resolve_pi,
     resolve_resid_var,
+    stage_result,
 )
 
 __all__ = [
@@ -127,19 +129,19 @@ def _prepare(
     return _Prepared(problem, pi, sample_size, max_iter, min_tol, cs_args, no_reorder, hard_calls)
 
 
-def _finish(batch: "_capi.Batch", index: int, prep: _Prepared, fit) -> SushieResult:
+def _stage(batch: "_capi.Batch", index: int, prep: _Prepared, fit):
+    """Device-dependent half of the epilogue of one fit; returns the host-only half as a callable."""
     log_convergence(fit.n_iter, prep.max_iter, prep.min_tol, fit.elbo, fit.elbo_increase)
-
-    def builder(alpha, log_bf):
-        return _cs.build_tables(
-            alpha, log_bf, prep.sample_size, lambda sets: batch.purity(index, sets), **prep.cs_args
-        )
-
-    return assemble_result(fit, prep.pi, prep.sample_size, prep.no_reorder, builder)
+    return stage_result(
+        fit, prep.pi, prep.sample_size, prep.no_reorder, lambda sets: batch.purity(index, sets), **prep.cs_args
+    )
 
 
-def _run_prepared(preps: Sequence[_Prepared], device: int = 0) -> List[SushieResult]:
-    """Fit a list of prepared problems that share max_iter / min_tol on one GPU."""
+def _run_prepared(preps: Sequence[_Prepared], device: int = 0, defer: bool = False) -> list:
+    """Fit a list of prepared problems that share max_iter / min_tol on one GPU.
+
+    ``defer=True`` returns one zero-argument callable per problem (the host-only table assembly) instead of
+    the finished ``SushieResult`` -- the work queue runs them while the GPU is busy with the next chunk."""
     eng = _capi.get_engine(device)
     storage = config.storage_code()
     if config.genotype_storage == "auto" and all(
@@ -147,10 +149,39 @@ def _run_prepared(preps: Sequence[_Prepared], device: int = 0) -> List[SushieRes
     ):
         storage = _capi.SB_I8
     opts = eng.make_opts(preps[0].max_iter, preps[0].min_tol, storage, config.team_size, config.single_phase)
+    return run_chunk(eng, preps, opts, _stage, defer)
+
+
+def run_chunk(eng, preps, opts, stage, defer: bool) -> list:
+    """Upload -> IBSS -> download -> device half of the epilogue (`stage`) for one chunk, then the host-only
+    half of every fit, now or deferred.  ``config.trace_host`` prints the wall time of each phase."""
+    t = [time.perf_counter()]
+
+    def lap():
+        t.append(time.perf_counter())
+
     with eng.create_batch([p.problem for p in preps], opts) as batch:
+        lap()
         batch.run()
+        lap()
         fits = batch.fetch()
-        return [_finish(batch, i, p, f) for i, (p, f) in enumerate(zip(preps, fits))]
+        lap()
+        staged = [stage(batch, i, p, f) for i, (p, f) in enumerate(zip(preps, fits))]
+        lap()
+    if config.trace_host:
+        d = np.diff(t) * 1e3
+        print(
+            f"[sushie_b200] chunk of {len(preps)} fits: upload+column statistics {d[0]:.0f} ms, IBSS {d[1]:.0f} ms, "
+            f"download {d[2]:.0f} ms, reorder+set selection+purity {d[3]:.0f} ms", file=sys.stderr, flush=True,
+        )
+    if defer:
+        return staged
+    t0 = time.perf_counter()
+    out = [finish() for finish in staged]
+    if config.trace_host:
+        print(f"[sushie_b200] chunk of {len(preps)} fits: output tables {1e3 * (time.perf_counter() - t0):.0f} ms",
+              file=sys.stderr, flush=True)
+    return out
 
 
 def infer_sushie(
@@ -193,11 +224,15 @@ def infer_sushie_batch(problems: Sequence[dict], devices: Optional[Sequence[int]
     results come back in input order."""
     from . import batch as _batch
 
+    t0 = time.perf_counter()
     preps = []
     for pr in problems:
         kw = dict(common)
         kw.update(pr)
         preps.append(_prepare_kw(**kw))
+    if config.trace_host:
+        print(f"[sushie_b200] host prologue of {len(preps)} fits: {1e3 * (time.perf_counter() - t0):.0f} ms",
+              file=sys.stderr, flush=True)
     return _batch.run_sharded(preps, _run_prepared, devices)
 
 

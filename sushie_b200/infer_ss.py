@@ -11,16 +11,16 @@ from typing import List, Optional, Sequence
 
 import numpy as np
 
-from . import _capi, config, cs as _cs, infer, utils
+from . import _capi, config, infer, utils
 from ._common import (
     SushieResult,
-    assemble_result,
     build_priors,
     check_scalar_options,
     check_snp_counts,
     log_convergence,
     resolve_pi,
     resolve_resid_var,
+    stage_result,
 )
 
 __all__ = ["infer_sushie_ss", "infer_sushie_ss_batch"]
@@ -69,24 +69,18 @@ def _prepare_ss(
     return infer._Prepared(problem, pi, ns, max_iter, min_tol, cs_args, no_reorder)
 
 
-def _finish_ss(batch, index, prep, fit) -> SushieResult:
+def _stage_ss(batch, index, prep, fit):
     log_convergence(fit.n_iter, prep.max_iter, prep.min_tol, fit.elbo, fit.elbo_increase)
-
-    def builder(alpha, log_bf):
-        return _cs.build_tables(
-            alpha, log_bf, prep.sample_size, lambda sets: batch.purity(index, sets), **prep.cs_args
-        )
-
-    return assemble_result(fit, prep.pi, prep.sample_size, prep.no_reorder, builder)
+    return stage_result(
+        fit, prep.pi, prep.sample_size, prep.no_reorder, lambda sets: batch.purity(index, sets), **prep.cs_args
+    )
 
 
-def _run_prepared_ss(preps: Sequence["infer._Prepared"], device: int = 0) -> List[SushieResult]:
+def _run_prepared_ss(preps: Sequence["infer._Prepared"], device: int = 0, defer: bool = False) -> list:
+    """Summary-level twin of ``infer._run_prepared`` (``defer``: see there)."""
     eng = _capi.get_engine(device)
     opts = eng.make_opts(preps[0].max_iter, preps[0].min_tol, config.storage_code(), config.team_size, config.single_phase)
-    with eng.create_batch([p.problem for p in preps], opts) as batch:
-        batch.run()
-        fits = batch.fetch()
-        return [_finish_ss(batch, i, p, f) for i, (p, f) in enumerate(zip(preps, fits))]
+    return infer.run_chunk(eng, preps, opts, _stage_ss, defer)
 
 
 def infer_sushie_ss(

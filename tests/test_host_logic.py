@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 
 import sushie_b200
-from sushie_b200 import _capi, _common, batch, cs as cs_mod, utils
+from sushie_b200 import _capi, _common, batch, config, cs as cs_mod, utils
 from oracle import credible_sets, ibss, threefry
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -190,6 +190,64 @@ def test_plan_chunks_covers_everything_once():
     while (c := q.next()) is not None:
         got.append(c)
     assert sorted(got) == list(range(len(chunks)))
+
+
+def test_plan_chunks_memory_budget_beyond_int32():
+    """Sample counts arrive as an int32 array (`IndProblem.n`); the running byte total of a chunk must not wrap at
+    2 GiB, or the memory budget would never cut a chunk."""
+    class P:
+        def __init__(self):
+            self.problem = type("X", (), dict(n=np.asarray([500, 500, 500], dtype=np.int32), p=4000, L=10, k=3,
+                                              cost=1500.0 * 4000 * 10))()
+            self.max_iter, self.min_tol = 500, 1e-4
+    preps = [P() for _ in range(120)]
+    one = batch.estimate_bytes(preps[0])
+    assert type(one) is int and one > 60_000_000
+    chunks = batch.plan_chunks(preps, chunk_bytes=3 << 30, chunk_loci=0)
+    assert len(chunks) >= 2 and sorted(i for c in chunks for i in c) == list(range(120))
+    for c in chunks:
+        assert len(c) * one <= 3 << 30
+
+
+class _FakePrep:
+    def __init__(self, p=200):
+        self.problem = type("X", (), dict(n=np.asarray([100, 100], dtype=np.int32), p=p, L=10, k=2, cost=200.0 * p * 10))()
+        self.max_iter, self.min_tol = 500, 1e-4
+
+
+def test_auto_chunking_gives_every_worker_a_chunk(monkeypatch):
+    monkeypatch.setattr(config, "chunk_loci", 0)
+    preps = [_FakePrep(200 + i % 17) for i in range(1300)]
+    assert len(batch.plan_chunks(preps, n_workers=1)) == 1       # one worker: nothing to balance
+    two = batch.plan_chunks(preps, n_workers=2)                  # 1300 // 296 = 4 chunks of 325
+    assert sorted(len(c) for c in two) == [325, 325, 325, 325]
+    eight = batch.plan_chunks(preps, n_workers=8)                # small chunks rather than idle GPUs
+    assert len(eight) == 8 and sorted(i for c in eight for i in c) == list(range(1300))
+    assert len(batch.plan_chunks(preps[:5], n_workers=8)) == 5
+
+
+@pytest.mark.parametrize("devices", [[0], [0, 1, 2]])
+def test_run_sharded_defers_table_assembly_and_keeps_input_order(monkeypatch, devices):
+    monkeypatch.setattr(config, "chunk_loci", 7)
+    preps = [_FakePrep(100 + i) for i in range(40)]
+    seen = []
+
+    def runner(chunk, device, defer=False):
+        seen.append((device, len(chunk), defer))
+        done = [lambda p=p: ("fit", p.problem.p) for p in chunk]
+        return done if defer else [f() for f in done]
+
+    out = batch.run_sharded(preps, runner, devices)
+    assert out == [("fit", 100 + i) for i in range(40)]
+    assert all(d for _, _, d in seen) and sum(n for _, n, _ in seen) == 40
+
+    def bad_runner(chunk, device, defer=False):
+        def boom():
+            raise RuntimeError("table assembly failed")
+        return [boom for _ in chunk]
+
+    with pytest.raises(RuntimeError, match="table assembly failed"):
+        batch.run_sharded(preps, bad_runner, devices)
 
 
 def test_c_abi_exports_every_declared_symbol(engine_lib):
