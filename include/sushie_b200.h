@@ -173,6 +173,11 @@ int sb_batch_storage(sb_batch *batch, int prob, int ancestry, void **d_ptr, int6
  * LD sub-matrix. */
 int sb_batch_purity(sb_ctx *ctx, sb_batch *batch, int prob, const int32_t *idx,
                     const int32_t *offsets, int n_sets, double *out_min_abs);
+/* The same for the sets of many problems of the batch in one launch (one call per chunk of loci instead of
+ * one per locus): set s belongs to problem set_prob[s] and lists idx[offsets[s] .. offsets[s+1]);
+ * out[n_sets][SB_MAX_ANCESTRIES], entries of ancestries a problem does not have are 0. */
+int sb_batch_purity_many(sb_ctx *ctx, sb_batch *batch, int n_sets, const int32_t *set_prob,
+                         const int32_t *idx, const int32_t *offsets, double *out_min_abs);
 
 #ifdef __cplusplus
 }

@@ -133,9 +133,8 @@ def main():
         api = {
             "fits_per_sec": n_fits / (t_fit + t_cv), "genes_per_sec": args.genes / (t_fit + t_cv),
             "wall_s_fits": t_fit, "wall_s_cv_scores": t_cv, "devices": args.devices,
-            "chunk_loci": config.chunk_loci or "auto (about %d chunks per GPU worker, >= %d loci each; table assembly of "
-                                               "one chunk overlaps the device time of the next)" % (
-                                                   config.chunks_per_worker, config.min_chunk_loci),
+            "chunk_loci": config.chunk_loci or "auto (memory budget %.0f GiB per chunk at fp64 size; with several GPU "
+                                               "workers at least one chunk per worker)" % (config.chunk_bytes / 2**30),
             "mean_cv_adj_r2_ancestry0": float(np.mean([r[0][0] for r in r2])),
             "n_credible_sets": int(sum(len(set(f.cs["CSIndex"])) if len(f.cs) else 0 for f in fits[:: 1 + CV_NUM])),
         }

@@ -39,6 +39,7 @@ EXPORTED_SYMBOLS = (
     "sb_batch_destroy",
     "sb_batch_storage",
     "sb_batch_purity",
+    "sb_batch_purity_many",
 )
 
 _pd = C.POINTER(C.c_double)
@@ -167,6 +168,8 @@ def load_library():
         lib.sb_batch_destroy.argtypes = [vp, vp]
         lib.sb_batch_storage.argtypes = [vp, C.c_int, C.c_int, C.POINTER(vp), C.POINTER(C.c_int64)]
         lib.sb_batch_purity.argtypes = [vp, vp, C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_int, _pd]
+        lib.sb_batch_purity_many.argtypes = [vp, vp, C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_int32),
+                                             C.POINTER(C.c_int32), _pd]
         for name in EXPORTED_SYMBOLS:
             fn = getattr(lib, name)
             if name not in ("sb_last_error",):
@@ -429,6 +432,33 @@ class Batch:
             "sb_batch_purity",
         )
         return out
+
+    def purity_many(self, index_sets_per_problem: Sequence[Sequence[np.ndarray]]) -> List[np.ndarray]:
+        """``purity`` for the sets of every problem of the batch in one launch: entry i lists the index sets of
+        problem i (may be empty); returns one ``[n_sets_i, k_i]`` array per problem."""
+        counts = [len(sets) for sets in index_sets_per_problem]
+        flat = [np.asarray(s, dtype=np.int32) for sets in index_sets_per_problem for s in sets]
+        ks = [pr.k for pr in self.problems]
+        if not flat:
+            return [np.zeros((0, k)) for k in ks]
+        i32 = C.POINTER(C.c_int32)
+        set_prob = np.repeat(np.arange(len(counts), dtype=np.int32), counts)
+        offs = np.zeros(len(flat) + 1, dtype=np.int64)
+        offs[1:] = np.cumsum([s.size for s in flat])
+        if offs[-1] >= 2**31:
+            raise EngineError("too many credible-set members for one purity call")
+        offs = offs.astype(np.int32)
+        idx = np.ascontiguousarray(np.concatenate(flat), dtype=np.int32)
+        out = np.empty((len(flat), SB_MAX_ANCESTRIES))
+        self.engine._check(
+            self.engine.lib.sb_batch_purity_many(
+                self.engine._ctx, self._h, len(flat), set_prob.ctypes.data_as(i32), idx.ctypes.data_as(i32),
+                offs.ctypes.data_as(i32), _dptr(out),
+            ),
+            "sb_batch_purity_many",
+        )
+        bounds = np.concatenate([[0], np.cumsum(counts)])
+        return [out[bounds[i]:bounds[i + 1], :k].copy() for i, k in enumerate(ks)]
 
     def storage_ptr(self, prob: int, ancestry: int):
         ptr, ld = C.c_void_p(), C.c_int64()

@@ -266,27 +266,39 @@ def assemble_result(fit, pi, sample_size, no_reorder, cs_builder) -> SushieResul
     )
 
 
-def stage_result(fit, pi, sample_size, no_reorder, min_abs_corr, threshold, purity, purity_method, max_select, seed):
-    """Epilogue in two halves.  This call does the half that needs the device-resident batch (effect
-    re-ordering, credible-set selection, purity Gram matrices through ``min_abs_corr``) and returns the
-    host-only half (output tables) as a zero-argument callable, so a batch entry point can release the
-    device batch -- and start the next chunk of loci -- before the tables are assembled."""
-    from . import cs as _cs
+class StagedResult:
+    """Epilogue of one fit in two halves.  Construction does the effect re-ordering and the credible-set
+    selection; ``purity_sets`` is what the device has to look at (one index list per effect).  ``finisher``
+    takes the min |corr| per (effect, ancestry) and returns the host-only rest (output tables) as a
+    zero-argument callable, so a batch entry point can ask for the purity of a whole chunk of loci in one
+    launch, release the device batch and start the next chunk before the tables are assembled."""
 
-    if purity_method not in ("weighted", "max", "min"):
-        raise ValueError(f"Invalid purity method {purity_method}. Choose from 'weighted', 'max', or 'min'.")
-    priors, posteriors, l_order = _reordered(fit, pi, no_reorder)
-    log.logger.debug("Computing credible sets.")
-    selection = _cs.select_sets(posteriors.alpha, threshold, max_select, seed)
-    min_abs = np.asarray(min_abs_corr(selection[3]), dtype=float)
+    def __init__(self, fit, pi, sample_size, no_reorder, threshold, purity, purity_method, max_select, seed):
+        from . import cs as _cs
 
-    def finish() -> SushieResult:
-        cs, full_alphas, pip_all, pip_cs = _cs.finish_tables(
-            posteriors.alpha, posteriors.log_bf, sample_size, selection, min_abs, purity, purity_method
-        )
-        log.logger.debug("Inference and credible set computation complete. Beginning to write results.")
-        return SushieResult(
-            priors, posteriors, pip_all, pip_cs, cs, full_alphas, sample_size, fit.elbo, fit.elbo_increase, l_order
-        )
+        if purity_method not in ("weighted", "max", "min"):
+            raise ValueError(f"Invalid purity method {purity_method}. Choose from 'weighted', 'max', or 'min'.")
+        self._fit, self._sample_size = fit, sample_size
+        self._purity, self._purity_method = purity, purity_method
+        self._priors, self._posteriors, self._l_order = _reordered(fit, pi, no_reorder)
+        log.logger.debug("Computing credible sets.")
+        self._selection = _cs.select_sets(self._posteriors.alpha, threshold, max_select, seed)
+        self.purity_sets = self._selection[3]
 
-    return finish
+    def finisher(self, min_abs):
+        from . import cs as _cs
+
+        min_abs = np.asarray(min_abs, dtype=float)
+
+        def finish() -> SushieResult:
+            cs, full_alphas, pip_all, pip_cs = _cs.finish_tables(
+                self._posteriors.alpha, self._posteriors.log_bf, self._sample_size, self._selection, min_abs,
+                self._purity, self._purity_method,
+            )
+            log.logger.debug("Inference and credible set computation complete. Beginning to write results.")
+            return SushieResult(
+                self._priors, self._posteriors, pip_all, pip_cs, cs, full_alphas, self._sample_size, self._fit.elbo,
+                self._fit.elbo_increase, self._l_order,
+            )
+
+        return finish

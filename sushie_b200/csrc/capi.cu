@@ -1197,15 +1197,16 @@ extern "C" int sb_batch_storage(sb_batch* b, int prob, int ancestry, void** d_pt
   return SB_OK;
 }
 
-extern "C" int sb_batch_purity(sb_ctx* ctx, sb_batch* b, int prob, const int32_t* idx, const int32_t* offsets,
-                               int n_sets, double* out_min_abs) {
-  if (!ctx || !b || !idx || !offsets || !out_min_abs || prob < 0 || prob >= b->n_probs || n_sets < 0)
-    return SB_EINVAL;
+extern "C" int sb_batch_purity_many(sb_ctx* ctx, sb_batch* b, int n_sets, const int32_t* set_prob,
+                                    const int32_t* idx, const int32_t* offsets, double* out_min_abs) {
+  if (!ctx || !b || n_sets < 0 || (n_sets > 0 && (!set_prob || !idx || !offsets || !out_min_abs))) return SB_EINVAL;
   if (n_sets == 0) return SB_OK;
   cudaSetDevice(ctx->device);
   cudaStream_t st = ctx->stream;
-  const HostProb& h = b->hp[prob];
-  const int K = h.K;
+  if (offsets[0] != 0) {
+    ctx->err = "offsets must start at 0";
+    return SB_EINVAL;
+  }
   const int total = offsets[n_sets];
   int m_max = 0;
   for (int s = 0; s < n_sets; ++s) {
@@ -1214,27 +1215,33 @@ extern "C" int sb_batch_purity(sb_ctx* ctx, sb_batch* b, int prob, const int32_t
       ctx->err = "empty index set";
       return SB_EINVAL;
     }
-    m_max = std::max(m_max, m);
-  }
-  for (int t = 0; t < total; ++t)
-    if (idx[t] < 0 || idx[t] >= h.p) {
-      ctx->err = "SNP index out of range";
+    if (set_prob[s] < 0 || set_prob[s] >= b->n_probs) {
+      ctx->err = "problem index out of range";
       return SB_EINVAL;
     }
-  const size_t smem = b->ss ? 0 : sizeof(double) * 32 * m_max;
+    const int p = b->hp[set_prob[s]].p;
+    for (int t = offsets[s]; t < offsets[s + 1]; ++t)
+      if (idx[t] < 0 || idx[t] >= p) {
+        ctx->err = "SNP index out of range";
+        return SB_EINVAL;
+      }
+    m_max = std::max(m_max, m);
+  }
+  const int m_pad_max = (m_max + 3) / 4 * 4;
+  const size_t smem = b->ss ? 0 : sb::purity_smem_bytes(m_max);
   if (smem > static_cast<size_t>(ctx->smem_optin) - 1024) {
     ctx->err = "credible set too large for the purity kernel";
     return SB_EINVAL;
   }
   unsigned char* d_buf = nullptr;
   const size_t idx_b = align_up(sizeof(int) * total, 256), off_b = align_up(sizeof(int) * (n_sets + 1), 256);
-  const size_t ptr_b = 256, n_b = 256, out_b = align_up(sizeof(double) * n_sets * K, 256);
-  SB_CUDA(cudaMalloc(&d_buf, idx_b + off_b + ptr_b + n_b + out_b));
+  const size_t prob_b = align_up(sizeof(int) * n_sets, 256);
+  const size_t out_n = static_cast<size_t>(n_sets) * sb::KMAX;
+  SB_CUDA(cudaMalloc(&d_buf, idx_b + off_b + prob_b + align_up(sizeof(double) * out_n, 256)));
   int* d_idx = reinterpret_cast<int*>(d_buf);
   int* d_off = reinterpret_cast<int*>(d_buf + idx_b);
-  void** d_ptrs = reinterpret_cast<void**>(d_buf + idx_b + off_b);
-  int* d_n = reinterpret_cast<int*>(d_buf + idx_b + off_b + ptr_b);
-  double* d_out = reinterpret_cast<double*>(d_buf + idx_b + off_b + ptr_b + n_b);
+  int* d_prob = reinterpret_cast<int*>(d_buf + idx_b + off_b);
+  double* d_out = reinterpret_cast<double*>(d_buf + idx_b + off_b + prob_b);
   auto bail = [&](cudaError_t e, const char* what) {
     ctx->err = std::string(what) + ": " + cudaGetErrorString(e);
     cudaStreamSynchronize(st);
@@ -1246,29 +1253,18 @@ extern "C" int sb_batch_purity(sb_ctx* ctx, sb_batch* b, int prob, const int32_t
     return bail(e, "purity H2D idx");
   if ((e = cudaMemcpyAsync(d_off, offsets, sizeof(int) * (n_sets + 1), cudaMemcpyHostToDevice, st)) != cudaSuccess)
     return bail(e, "purity H2D offsets");
-  if ((e = cudaMemcpyAsync(d_ptrs, h.d_X, sizeof(void*) * K, cudaMemcpyHostToDevice, st)) != cudaSuccess)
-    return bail(e, "purity H2D ptrs");
-  const bool i8 = b->storage == SB_I8;
-  const double* const* d_cm = nullptr;
-  const double* const* d_cs = nullptr;
-  if (i8) {  // column statistics pointer tables share the 256-byte pointer block
-    if ((e = cudaMemcpyAsync(d_ptrs + 8, h.d_cmean, sizeof(void*) * K, cudaMemcpyHostToDevice, st)) != cudaSuccess ||
-        (e = cudaMemcpyAsync(d_ptrs + 16, h.d_cisd, sizeof(void*) * K, cudaMemcpyHostToDevice, st)) != cudaSuccess)
-      return bail(e, "purity H2D column statistics");
-    d_cm = reinterpret_cast<const double* const*>(d_ptrs + 8);
-    d_cs = reinterpret_cast<const double* const*>(d_ptrs + 16);
-  }
-  if ((e = cudaMemcpyAsync(d_n, h.n, sizeof(int) * K, cudaMemcpyHostToDevice, st)) != cudaSuccess)
-    return bail(e, "purity H2D n");
-  dim3 grid(n_sets, K);
+  if ((e = cudaMemcpyAsync(d_prob, set_prob, sizeof(int) * n_sets, cudaMemcpyHostToDevice, st)) != cudaSuccess)
+    return bail(e, "purity H2D problem ids");
+  if ((e = cudaMemsetAsync(d_out, 0, sizeof(double) * out_n, st)) != cudaSuccess) return bail(e, "purity memset");
+  // grid.x is limited only by 2^31 - 1; blocks of ancestries a problem does not have exit at once
+  dim3 grid(n_sets, sb::KMAX);
 #define SB_PUR(XT, SSV)                                                                                        \
   do {                                                                                                         \
     auto kf = sb::purity_kernel<XT, SSV>;                                                                      \
     if (smem > 48 * 1024) cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);    \
-    kf<<<grid, 256, smem, st>>>(reinterpret_cast<const XT* const*>(d_ptrs), d_n, h.p_pad, d_idx, d_off, K,     \
-                                d_out, d_cm, d_cs);                                                            \
+    kf<<<grid, 256, smem, st>>>(b->d_probs, d_prob, d_idx, d_off, m_pad_max, d_out);                           \
   } while (0)
-  if (i8) {
+  if (b->storage == SB_I8) {
     SB_PUR(int8_t, false);
   } else if (b->storage == SB_F64) {
     if (b->ss)
@@ -1283,11 +1279,25 @@ extern "C" int sb_batch_purity(sb_ctx* ctx, sb_batch* b, int prob, const int32_t
   }
 #undef SB_PUR
   if ((e = cudaGetLastError()) != cudaSuccess) return bail(e, "purity launch");
-  if ((e = cudaMemcpyAsync(out_min_abs, d_out, sizeof(double) * n_sets * K, cudaMemcpyDeviceToHost, st)) !=
-      cudaSuccess)
+  if ((e = cudaMemcpyAsync(out_min_abs, d_out, sizeof(double) * out_n, cudaMemcpyDeviceToHost, st)) != cudaSuccess)
     return bail(e, "purity D2H");
   if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return bail(e, "purity sync");
   cudaFree(d_buf);
+  return SB_OK;
+}
+
+extern "C" int sb_batch_purity(sb_ctx* ctx, sb_batch* b, int prob, const int32_t* idx, const int32_t* offsets,
+                               int n_sets, double* out_min_abs) {
+  if (!ctx || !b || !idx || !offsets || !out_min_abs || prob < 0 || prob >= b->n_probs || n_sets < 0)
+    return SB_EINVAL;
+  if (n_sets == 0) return SB_OK;
+  const int K = b->hp[prob].K;
+  std::vector<int32_t> set_prob(static_cast<size_t>(n_sets), prob);
+  std::vector<double> wide(static_cast<size_t>(n_sets) * sb::KMAX);
+  const int rc = sb_batch_purity_many(ctx, b, n_sets, set_prob.data(), idx, offsets, wide.data());
+  if (rc != SB_OK) return rc;
+  for (int s = 0; s < n_sets; ++s)
+    for (int k = 0; k < K; ++k) out_min_abs[s * K + k] = wide[static_cast<size_t>(s) * sb::KMAX + k];
   return SB_OK;
 }
 

@@ -2055,19 +2055,31 @@ __global__ void pad_rows_kernel(const IT* __restrict__ in, int n, int p, int p_p
 }
 
 // Purity (infer.py:946-956): min |X_sel^T X_sel| / n over all pairs of a credible set.
-// One block per (set, ancestry); the selected columns are gathered into shared memory in
-// row chunks and the m x m Gram entries are accumulated by the threads that own them.
+// Credible-set purity (infer.py:936-965) for the sets of many loci in one launch: block (set, ancestry) returns
+// min |X_sel^T X_sel| / n over the m x m Gram matrix of the set's columns (summary level: min |LD_sel|).
+// The selected columns are gathered -- and, for hard-call storage, standardised -- into shared memory 32 rows
+// at a time; every thread owns 4 x 4 tiles of the upper triangle and accumulates them in registers over the
+// rows in row order (so the sums do not depend on the tiling).
+constexpr int PUR_ROWS = 32;
+
+__host__ __device__ inline size_t purity_smem_bytes(int m) {
+  const size_t m_pad = static_cast<size_t>((m + 3) / 4) * 4;
+  return m_pad * (sizeof(double) * (PUR_ROWS + 2) + sizeof(int));
+}
+
 template <typename XT, bool SS>
-__global__ void purity_kernel(const XT* const* __restrict__ Xk, const int* __restrict__ nk, int p_pad,
-                              const int* __restrict__ idx, const int* __restrict__ offsets, int K,
-                              double* __restrict__ out, const double* const* __restrict__ cmean,
-                              const double* const* __restrict__ cisd) {
+__global__ void __launch_bounds__(256) purity_kernel(const ProbDev* __restrict__ probs,
+                                                     const int* __restrict__ set_prob,
+                                                     const int* __restrict__ idx, const int* __restrict__ offsets,
+                                                     int m_pad_max, double* __restrict__ out) {
   extern __shared__ __align__(16) unsigned char pur_smem[];
   const int set = blockIdx.x, k = blockIdx.y;
+  const ProbDev& P = probs[set_prob[set]];
+  if (k >= P.K) return;
   const int o0 = offsets[set], m = offsets[set + 1] - o0;
   const int* sel = idx + o0;
-  const XT* X = Xk[k];
-  const int n = nk[k];
+  const XT* X = reinterpret_cast<const XT*>(P.X[k]);
+  const int n = P.n[k], p_pad = P.p_pad;
   double best = CUDART_INF;
   if (SS) {
     for (int e = threadIdx.x; e < m * m; e += blockDim.x) {
@@ -2075,54 +2087,69 @@ __global__ void purity_kernel(const XT* const* __restrict__ Xk, const int* __res
       best = fmin(best, fabs(static_cast<double>(X[static_cast<size_t>(sel[a]) * p_pad + sel[b]])));
     }
   } else {
-    constexpr int RC = 32;  // rows per chunk
-    double* tile = reinterpret_cast<double*>(pur_smem);  // [RC][m]
-    // each thread owns pairs e = tid, tid + T, ... of the upper triangle (incl. diagonal);
-    // to keep registers bounded we process pairs in rounds of PR per thread.
-    constexpr int PR = 8;
-    const int npairs = m * (m + 1) / 2;
-    for (int base = 0; base < npairs; base += PR * blockDim.x) {
-      double accv[PR];
-      int pa[PR], pb2[PR];
-#pragma unroll
-      for (int u = 0; u < PR; ++u) {
-        accv[u] = 0.0;
-        const int e = base + u * blockDim.x + threadIdx.x;
-        int a = 0, b = 0;
-        if (e < npairs) {
-          // row a of the upper triangle: first index with a*(2m-a+1)/2 <= e
-          a = static_cast<int>((2.0 * m + 1.0 - sqrt((2.0 * m + 1.0) * (2.0 * m + 1.0) - 8.0 * e)) * 0.5);
-          while (a * (2 * m - a + 1) / 2 > e) --a;
-          while ((a + 1) * (2 * m - a) / 2 <= e) ++a;
-          b = a + (e - a * (2 * m - a + 1) / 2);
-        }
-        pa[u] = a;
-        pb2[u] = b;
+    constexpr bool I8 = sizeof(XT) == 1;
+    const int m4 = (m + 3) / 4, m_pad = m4 * 4;
+    double* tile = reinterpret_cast<double*>(pur_smem);           // [PUR_ROWS][m_pad]
+    double* c_mean = tile + static_cast<size_t>(PUR_ROWS) * m_pad_max;  // [m_pad]
+    double* c_isd = c_mean + m_pad_max;                            // [m_pad]
+    int* c_sel = reinterpret_cast<int*>(c_isd + m_pad_max);        // [m_pad]
+    for (int c = threadIdx.x; c < m_pad; c += blockDim.x) {
+      const int j = c < m ? sel[c] : 0;
+      c_sel[c] = j;
+      c_mean[c] = (I8 && c < m) ? P.cmean[static_cast<size_t>(k) * p_pad + j] : 0.0;
+      c_isd[c] = (I8 && c < m) ? P.cisd[static_cast<size_t>(k) * p_pad + j] : (c < m ? 1.0 : 0.0);
+    }
+    const int ntiles = m4 * (m4 + 1) / 2;
+    for (int base = 0; base < ntiles; base += blockDim.x) {
+      const int t = base + threadIdx.x;
+      const bool valid = t < ntiles;
+      int ta = 0, tb = 0;
+      if (valid) {
+        // row ta of the upper triangle of the m4 x m4 tile grid: first index with ta*(2*m4-ta+1)/2 <= t
+        ta = static_cast<int>((2.0 * m4 + 1.0 - sqrt((2.0 * m4 + 1.0) * (2.0 * m4 + 1.0) - 8.0 * t)) * 0.5);
+        while (ta * (2 * m4 - ta + 1) / 2 > t) --ta;
+        while ((ta + 1) * (2 * m4 - ta) / 2 <= t) ++ta;
+        tb = ta + (t - ta * (2 * m4 - ta + 1) / 2);
       }
-      for (int r0 = 0; r0 < n; r0 += RC) {
-        const int rc = min(RC, n - r0);
+      double acc[4][4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
+      for (int r0 = 0; r0 < n; r0 += PUR_ROWS) {
+        const int rc = min(PUR_ROWS, n - r0);
         __syncthreads();
-        for (int t = threadIdx.x; t < rc * m; t += blockDim.x) {
-          const int rr = t / m, c = t % m;
-          double val = static_cast<double>(X[static_cast<size_t>(r0 + rr) * p_pad + sel[c]]);
-          if (cmean) val = (val - cmean[k][sel[c]]) * cisd[k][sel[c]];  // hard-call storage: standardise on the fly
-          tile[rr * m + c] = val;
+        for (int e = threadIdx.x; e < rc * m_pad; e += blockDim.x) {
+          const int rr = e / m_pad, c = e - rr * m_pad;
+          double val = static_cast<double>(X[static_cast<size_t>(r0 + rr) * p_pad + c_sel[c]]);
+          if (I8) val = (val - c_mean[c]) * c_isd[c];  // hard-call storage: standardise on the fly
+          else val *= c_isd[c];                        // zero for the padding columns
+          tile[rr * m_pad + c] = val;
         }
         __syncthreads();
+        if (valid) {
+          const double* ra = tile + 4 * ta;
+          const double* rb = tile + 4 * tb;
+          for (int rr = 0; rr < rc; ++rr) {
+            const double2 a01 = *reinterpret_cast<const double2*>(ra + rr * m_pad);
+            const double2 a23 = *reinterpret_cast<const double2*>(ra + rr * m_pad + 2);
+            const double2 b01 = *reinterpret_cast<const double2*>(rb + rr * m_pad);
+            const double2 b23 = *reinterpret_cast<const double2*>(rb + rr * m_pad + 2);
+            const double av[4] = {a01.x, a01.y, a23.x, a23.y};
+            const double bv[4] = {b01.x, b01.y, b23.x, b23.y};
 #pragma unroll
-        for (int u = 0; u < PR; ++u) {
-          const int e = base + u * blockDim.x + threadIdx.x;
-          if (e < npairs) {
-            double s = accv[u];
-            for (int rr = 0; rr < rc; ++rr) s = fma(tile[rr * m + pa[u]], tile[rr * m + pb2[u]], s);
-            accv[u] = s;
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+              for (int j = 0; j < 4; ++j) acc[i][j] = fma(av[i], bv[j], acc[i][j]);
           }
         }
       }
+      if (valid) {
 #pragma unroll
-      for (int u = 0; u < PR; ++u) {
-        const int e = base + u * blockDim.x + threadIdx.x;
-        if (e < npairs) best = fmin(best, fabs(accv[u] / n));
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if (4 * ta + i < m && 4 * tb + j < m) best = fmin(best, fabs(acc[i][j] / n));
       }
     }
   }
@@ -2134,7 +2161,7 @@ __global__ void purity_kernel(const XT* const* __restrict__ Xk, const int* __res
   if (threadIdx.x == 0) {
     double b = red[0];
     for (int w = 1; w < static_cast<int>(blockDim.x >> 5); ++w) b = fmin(b, red[w]);
-    out[set * K + k] = b;
+    out[set * KMAX + k] = b;
   }
 }
 

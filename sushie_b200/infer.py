@@ -24,6 +24,7 @@ from . import _capi, config, cs as _cs, log, utils
 from ._common import (
     Posterior,
     Prior,
+    StagedResult,
     SushieResult,
     _PriorAdjustor,
     _reorder_l,
@@ -33,7 +34,6 @@ from ._common import (
     log_convergence,
     resolve_pi,
     resolve_resid_var,
-    stage_result,
 )
 
 __all__ = [
@@ -129,12 +129,10 @@ def _prepare(
     return _Prepared(problem, pi, sample_size, max_iter, min_tol, cs_args, no_reorder, hard_calls)
 
 
-def _stage(batch: "_capi.Batch", index: int, prep: _Prepared, fit):
-    """Device-dependent half of the epilogue of one fit; returns the host-only half as a callable."""
+def _stage(prep: _Prepared, fit) -> StagedResult:
+    """Host half of the epilogue of one fit before the purity launch: convergence log, re-order, set selection."""
     log_convergence(fit.n_iter, prep.max_iter, prep.min_tol, fit.elbo, fit.elbo_increase)
-    return stage_result(
-        fit, prep.pi, prep.sample_size, prep.no_reorder, lambda sets: batch.purity(index, sets), **prep.cs_args
-    )
+    return StagedResult(fit, prep.pi, prep.sample_size, prep.no_reorder, **prep.cs_args)
 
 
 def _run_prepared(preps: Sequence[_Prepared], device: int = 0, defer: bool = False) -> list:
@@ -153,8 +151,8 @@ def _run_prepared(preps: Sequence[_Prepared], device: int = 0, defer: bool = Fal
 
 
 def run_chunk(eng, preps, opts, stage, defer: bool) -> list:
-    """Upload -> IBSS -> download -> device half of the epilogue (`stage`) for one chunk, then the host-only
-    half of every fit, now or deferred.  ``config.trace_host`` prints the wall time of each phase."""
+    """Upload -> IBSS -> download -> credible-set selection (`stage`, per fit) -> purity of every set of the
+    chunk in one launch, then the output tables of every fit, now or deferred.  ``config.trace_host`` prints the wall time of each phase."""
     t = [time.perf_counter()]
 
     def lap():
@@ -166,18 +164,22 @@ def run_chunk(eng, preps, opts, stage, defer: bool) -> list:
         lap()
         fits = batch.fetch()
         lap()
-        staged = [stage(batch, i, p, f) for i, (p, f) in enumerate(zip(preps, fits))]
+        staged = [stage(p, f) for p, f in zip(preps, fits)]
         lap()
+        min_abs = batch.purity_many([s.purity_sets for s in staged])  # one launch for the whole chunk
+        lap()
+    finishers = [s.finisher(m) for s, m in zip(staged, min_abs)]
     if config.trace_host:
         d = np.diff(t) * 1e3
         print(
             f"[sushie_b200] chunk of {len(preps)} fits: upload+column statistics {d[0]:.0f} ms, IBSS {d[1]:.0f} ms, "
-            f"download {d[2]:.0f} ms, reorder+set selection+purity {d[3]:.0f} ms", file=sys.stderr, flush=True,
+            f"download {d[2]:.0f} ms, reorder+set selection {d[3]:.0f} ms, purity {d[4]:.0f} ms",
+            file=sys.stderr, flush=True,
         )
     if defer:
-        return staged
+        return finishers
     t0 = time.perf_counter()
-    out = [finish() for finish in staged]
+    out = [finish() for finish in finishers]
     if config.trace_host:
         print(f"[sushie_b200] chunk of {len(preps)} fits: output tables {1e3 * (time.perf_counter() - t0):.0f} ms",
               file=sys.stderr, flush=True)

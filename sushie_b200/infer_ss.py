@@ -13,6 +13,7 @@ import numpy as np
 
 from . import _capi, config, infer, utils
 from ._common import (
+    StagedResult,
     SushieResult,
     build_priors,
     check_scalar_options,
@@ -20,7 +21,6 @@ from ._common import (
     log_convergence,
     resolve_pi,
     resolve_resid_var,
-    stage_result,
 )
 
 __all__ = ["infer_sushie_ss", "infer_sushie_ss_batch"]
@@ -69,11 +69,9 @@ def _prepare_ss(
     return infer._Prepared(problem, pi, ns, max_iter, min_tol, cs_args, no_reorder)
 
 
-def _stage_ss(batch, index, prep, fit):
+def _stage_ss(prep, fit) -> StagedResult:
     log_convergence(fit.n_iter, prep.max_iter, prep.min_tol, fit.elbo, fit.elbo_increase)
-    return stage_result(
-        fit, prep.pi, prep.sample_size, prep.no_reorder, lambda sets: batch.purity(index, sets), **prep.cs_args
-    )
+    return StagedResult(fit, prep.pi, prep.sample_size, prep.no_reorder, **prep.cs_args)
 
 
 def _run_prepared_ss(preps: Sequence["infer._Prepared"], device: int = 0, defer: bool = False) -> list:

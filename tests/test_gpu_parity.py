@@ -325,3 +325,37 @@ def test_batch_sharded_over_all_visible_gpus(engine_lib, golden_syn):
     assert len(out) == len(problems)
     for tag, res in zip(tags, out):
         assert_fit_matches(res, golden_syn, tag)
+
+
+@pytest.mark.parametrize("storage", ["dense", "i8"])
+def test_purity_of_a_whole_chunk_in_one_launch(engine_lib, storage):
+    """`sb_batch_purity_many`: ragged index sets (1 ... 300 SNPs, not multiples of the 4 x 4 tile) of loci with
+    different ancestry counts and widths, against numpy on the standardised genotypes."""
+    from sushie_b200 import _capi
+    from sushie_b200._common import build_priors
+
+    rng = np.random.default_rng(99)
+    eng = _capi.get_engine(0)
+    probs, Xstd, sets = [], [], []
+    for k, n, p in ((1, [90], 330), (3, [64, 33, 120], 517), (4, [50, 70, 31, 32], 300), (2, [200, 150], 1100)):
+        G = [rng.binomial(2, rng.uniform(0.1, 0.5, size=p), size=(ni, p)).astype(np.int8) for ni in n]
+        for g in G:
+            g[0, g.std(axis=0) == 0] += 1
+        Xstd.append([(g - g.mean(0)) / g.std(0) for g in G])
+        ec, adj = build_priors(k, 2, None, None, False, summary=False)
+        mats = G if storage == "i8" else [g.astype(np.float64) for g in G]
+        probs.append(_capi.IndProblem(mats, [rng.standard_normal(ni) for ni in n], 2, None, np.ones(k), ec, adj.times,
+                                      adj.plus, True, standardize=_capi.SB_CENTER | _capi.SB_SCALE))
+        sizes = [1, 3, 4, 5, 37, 250, min(p, 300)]
+        sets.append([rng.choice(p, size=m, replace=False) for m in sizes])
+    sets[2] = []  # a locus without sets
+    opts = eng.make_opts(2, 1e-4, _capi.SB_I8 if storage == "i8" else _capi.SB_F64, 1)
+    with eng.create_batch(probs, opts) as b:
+        got = b.purity_many(sets)
+        one = b.purity(1, sets[1])
+    assert [g.shape for g in got] == [(len(s), len(x)) for s, x in zip(sets, Xstd)]
+    for g, ss, xs in zip(got, sets, Xstd):
+        for row, idx in zip(g, ss):
+            want = [np.min(np.abs(x[:, idx].T @ x[:, idx] / x.shape[0])) for x in xs]
+            np.testing.assert_allclose(row, want, rtol=1e-10, atol=1e-12)
+    np.testing.assert_array_equal(one, got[1])
