@@ -51,6 +51,7 @@ def _threefry_stream(key: Tuple[int, int], n: int) -> np.ndarray:
     return np.concatenate([a, b])[:n]
 
 
+@functools.lru_cache(maxsize=1024)
 def _split2(key: Tuple[int, int]):
     w = _threefry_stream(key, 4)
     return (int(w[0]), int(w[1])), (int(w[2]), int(w[3]))
@@ -66,12 +67,13 @@ def split_key(key: Tuple[int, int]):
     return _split2(key)
 
 
-@functools.lru_cache(maxsize=256)
+@functools.lru_cache(maxsize=4096)
 def _shuffle_order(key: Tuple[int, int], n: int) -> np.ndarray:
     """Positions picked by JAX's sort-based shuffle of ``n`` items under ``key``: rounds of stable sorts by
     fresh 32-bit words.  It does not depend on the values, and ``make_cs`` re-uses one key for every effect
-    of every locus (``infer.py:894,940-943``), so the orders are cached per (key, n)."""
-    order = np.arange(n)
+    of every locus (``infer.py:894,940-943``), so the orders are cached per (key, n) -- a genome-wide batch
+    asks for the same few thousand sizes over and over (int32 entries: at most ~50 MB for 4096 sizes)."""
+    order = np.arange(n, dtype=np.int32)
     rounds = int(np.ceil(3 * np.log(max(1, n)) / np.log(np.iinfo(np.uint32).max)))
     for _ in range(rounds):
         key, sub = _split2(key)

@@ -1228,9 +1228,13 @@ extern "C" int sb_batch_purity_many(sb_ctx* ctx, sb_batch* b, int n_sets, const 
     m_max = std::max(m_max, m);
   }
   const int m_pad_max = (m_max + 3) / 4 * 4;
-  const size_t smem = b->ss ? 0 : sb::purity_smem_bytes(m_max);
-  if (smem > static_cast<size_t>(ctx->smem_optin) - 1024) {
-    ctx->err = "credible set too large for the purity kernel";
+  // rows of the set's columns staged per pass: 32, halved until the largest set fits in shared memory
+  int rows = sb::PUR_ROWS;
+  const size_t smem_cap = static_cast<size_t>(ctx->smem_optin) - 1024;
+  while (!b->ss && rows > 1 && sb::purity_smem_bytes(m_max, rows) > smem_cap) rows >>= 1;
+  const size_t smem = b->ss ? 0 : sb::purity_smem_bytes(m_max, rows);
+  if (smem > smem_cap) {
+    ctx->err = "credible set too large for the purity kernel (" + std::to_string(m_max) + " SNPs)";
     return SB_EINVAL;
   }
   unsigned char* d_buf = nullptr;
@@ -1262,7 +1266,7 @@ extern "C" int sb_batch_purity_many(sb_ctx* ctx, sb_batch* b, int n_sets, const 
   do {                                                                                                         \
     auto kf = sb::purity_kernel<XT, SSV>;                                                                      \
     if (smem > 48 * 1024) cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);    \
-    kf<<<grid, 256, smem, st>>>(b->d_probs, d_prob, d_idx, d_off, m_pad_max, d_out);                           \
+    kf<<<grid, 256, smem, st>>>(b->d_probs, d_prob, d_idx, d_off, m_pad_max, rows, d_out);                     \
   } while (0)
   if (b->storage == SB_I8) {
     SB_PUR(int8_t, false);

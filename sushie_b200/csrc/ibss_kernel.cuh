@@ -2057,21 +2057,21 @@ __global__ void pad_rows_kernel(const IT* __restrict__ in, int n, int p, int p_p
 // Purity (infer.py:946-956): min |X_sel^T X_sel| / n over all pairs of a credible set.
 // Credible-set purity (infer.py:936-965) for the sets of many loci in one launch: block (set, ancestry) returns
 // min |X_sel^T X_sel| / n over the m x m Gram matrix of the set's columns (summary level: min |LD_sel|).
-// The selected columns are gathered -- and, for hard-call storage, standardised -- into shared memory 32 rows
-// at a time; every thread owns 4 x 4 tiles of the upper triangle and accumulates them in registers over the
-// rows in row order (so the sums do not depend on the tiling).
+// The selected columns are gathered -- and, for hard-call storage, standardised -- into shared memory `rows`
+// rows at a time (32, fewer for sets too large for that); every thread owns 4 x 4 tiles of the upper triangle
+// and accumulates them in registers over the rows in row order (so the sums do not depend on the tiling).
 constexpr int PUR_ROWS = 32;
 
-__host__ __device__ inline size_t purity_smem_bytes(int m) {
+__host__ __device__ inline size_t purity_smem_bytes(int m, int rows) {
   const size_t m_pad = static_cast<size_t>((m + 3) / 4) * 4;
-  return m_pad * (sizeof(double) * (PUR_ROWS + 2) + sizeof(int));
+  return m_pad * (sizeof(double) * (rows + 2) + sizeof(int));
 }
 
 template <typename XT, bool SS>
 __global__ void __launch_bounds__(256) purity_kernel(const ProbDev* __restrict__ probs,
                                                      const int* __restrict__ set_prob,
                                                      const int* __restrict__ idx, const int* __restrict__ offsets,
-                                                     int m_pad_max, double* __restrict__ out) {
+                                                     int m_pad_max, int rows, double* __restrict__ out) {
   extern __shared__ __align__(16) unsigned char pur_smem[];
   const int set = blockIdx.x, k = blockIdx.y;
   const ProbDev& P = probs[set_prob[set]];
@@ -2089,8 +2089,8 @@ __global__ void __launch_bounds__(256) purity_kernel(const ProbDev* __restrict__
   } else {
     constexpr bool I8 = sizeof(XT) == 1;
     const int m4 = (m + 3) / 4, m_pad = m4 * 4;
-    double* tile = reinterpret_cast<double*>(pur_smem);           // [PUR_ROWS][m_pad]
-    double* c_mean = tile + static_cast<size_t>(PUR_ROWS) * m_pad_max;  // [m_pad]
+    double* tile = reinterpret_cast<double*>(pur_smem);           // [rows][m_pad]
+    double* c_mean = tile + static_cast<size_t>(rows) * m_pad_max;  // [m_pad]
     double* c_isd = c_mean + m_pad_max;                            // [m_pad]
     int* c_sel = reinterpret_cast<int*>(c_isd + m_pad_max);        // [m_pad]
     for (int c = threadIdx.x; c < m_pad; c += blockDim.x) {
@@ -2116,8 +2116,8 @@ __global__ void __launch_bounds__(256) purity_kernel(const ProbDev* __restrict__
       for (int i = 0; i < 4; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
-      for (int r0 = 0; r0 < n; r0 += PUR_ROWS) {
-        const int rc = min(PUR_ROWS, n - r0);
+      for (int r0 = 0; r0 < n; r0 += rows) {
+        const int rc = min(rows, n - r0);
         __syncthreads();
         for (int e = threadIdx.x; e < rc * m_pad; e += blockDim.x) {
           const int rr = e / m_pad, c = e - rr * m_pad;

@@ -346,7 +346,7 @@ def test_purity_of_a_whole_chunk_in_one_launch(engine_lib, storage):
         mats = G if storage == "i8" else [g.astype(np.float64) for g in G]
         probs.append(_capi.IndProblem(mats, [rng.standard_normal(ni) for ni in n], 2, None, np.ones(k), ec, adj.times,
                                       adj.plus, True, standardize=_capi.SB_CENTER | _capi.SB_SCALE))
-        sizes = [1, 3, 4, 5, 37, 250, min(p, 300)]
+        sizes = [1, 3, 4, 5, 37, 250, min(p, 300)] + ([1000] if p > 1000 else [])  # 1000: fewer rows per pass
         sets.append([rng.choice(p, size=m, replace=False) for m in sizes])
     sets[2] = []  # a locus without sets
     opts = eng.make_opts(2, 1e-4, _capi.SB_I8 if storage == "i8" else _capi.SB_F64, 1)
