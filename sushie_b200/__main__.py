@@ -3,4 +3,5 @@ import sys
 
 from .cli import run_cli
 
-sys.exit(run_cli())
+if __name__ == "__main__":  # worker processes of `finemap-batch` re-import this module
+    sys.exit(run_cli())

@@ -986,55 +986,145 @@ def _emit_gene(gene: _Gene, fits: list, ss_fits: list) -> None:
         _ind_emit(got["mega"], None, gene.mega_data, None, args, gene.snps, False, True)
 
 
-def run_finemap_batch(bargs) -> int:
-    """``finemap-batch``: every non-comment line of the manifest holds the arguments of one ``finemap`` run.
-    Genes are read and cleaned on the host, all their fits (joint, per-ancestry, stacked, cross-validation
-    folds) go through the device work queue together -- sharded over ``--devices`` -- and each gene gets the
-    same output files a separate ``finemap`` run would write.  A gene that fails is reported and skipped."""
-    import shlex
-
+def _finemap_line_parser() -> argparse.ArgumentParser:
     parser = argparse.ArgumentParser(prog="finemap", add_help=False)
     for flag, kw in _FINEMAP_ARGS:
         parser.add_argument(flag, **kw)
+    return parser
+
+
+def _run_window(parser, lines: List[Tuple[int, str]], devices) -> Tuple[int, int]:
+    """Read, fit and write the genes of one window of manifest lines; returns (written, failed)."""
+    import shlex
+
+    n_ok = n_bad = 0
+    genes: List[_Gene] = []
+    specs: List[dict] = []
+    ss_specs: List[dict] = []
+    for no, ln in lines:
+        try:
+            gene = _Gene(no, parser.parse_args(shlex.split(ln)))
+        except SystemExit:
+            log.logger.error(f"Manifest line {no}: arguments could not be parsed; gene skipped.")
+            n_bad += 1
+            continue
+        mark, ss_mark = len(specs), len(ss_specs)
+        try:
+            _prepare_gene(gene, specs, ss_specs)
+        except Exception as err:  # keep the batch going, like one failed process among many
+            del specs[mark:], ss_specs[ss_mark:]
+            gene.error = str(err)
+            log.logger.error(f"Manifest line {no} ({gene.args.trait}): {err}")
+            n_bad += 1
+            continue
+        genes.append(gene)
+    log.logger.info(
+        f"Window of {len(genes)} genes: {len(specs)} individual-level and {len(ss_specs)} summary-level fits."
+    )
+    fits = infer.infer_sushie_batch(specs, devices=devices) if specs else []
+    ss_fits = infer_ss.infer_sushie_ss_batch(ss_specs, devices=devices) if ss_specs else []
+    for gene in genes:
+        try:
+            _emit_gene(gene, fits, ss_fits)
+            n_ok += 1
+        except Exception as err:
+            log.logger.error(f"Manifest line {gene.line_no} ({gene.args.trait}): {err}")
+            n_bad += 1
+    return n_ok, n_bad
+
+
+def _batch_worker(device: int, work_q, done_q, log_q, precision: int, level: int) -> None:
+    """Body of one `finemap-batch` worker process: owns one GPU, pulls windows of manifest lines until the
+    queue is drained, reads / fits / writes its genes itself (no data goes through the parent) and sends its log
+    records to the parent's log."""
+    import logging.handlers
+
+    log.logger.setLevel(level)
+    log.logger.propagate = False
+    for handler in list(log.logger.handlers):
+        log.logger.removeHandler(handler)
+    log.logger.addHandler(logging.handlers.QueueHandler(log_q))
+    config.precision = precision
+    parser = _finemap_line_parser()
+    while True:
+        lines = work_q.get()
+        if lines is None:
+            return
+        try:
+            done_q.put((device, *_run_window(parser, lines, [device]), None))
+        except BaseException as err:  # a window that fails as a whole (e.g. no usable GPU) ends the worker
+            done_q.put((device, 0, len(lines), f"{type(err).__name__}: {err}"))
+            return
+
+
+def _run_windows_in_processes(lines, devices: List[int], window: int, precision: int) -> Tuple[int, int]:
+    """One worker process per GPU (``spawn``): per-fit host work (readers, QC, credible-set tables, output
+    files) is Python and would serialise on one interpreter lock, so beyond one GPU the genes are sharded over
+    processes, dynamically, in windows of manifest lines."""
+    import logging.handlers
+    import multiprocessing as mp
+    import queue as _queue
+
+    ctx = mp.get_context("spawn")
+    window = max(1, min(window, -(-len(lines) // (4 * len(devices)))))
+    windows = [lines[w0:w0 + window] for w0 in range(0, len(lines), window)]
+    work_q, done_q, log_q = ctx.Queue(), ctx.Queue(), ctx.Queue()
+    for w in windows:
+        work_q.put(w)
+    for _ in devices:
+        work_q.put(None)
+    listener = logging.handlers.QueueListener(log_q, *log.logger.handlers, respect_handler_level=True)
+    listener.start()
+    procs = [ctx.Process(target=_batch_worker, args=(d, work_q, done_q, log_q, precision, log.logger.level), daemon=True)
+             for d in devices]
+    for p in procs:
+        p.start()
+    n_ok = n_bad = 0
+    pending, failed = len(windows), []
+    try:
+        while pending > 0:
+            try:
+                device, ok, bad, err = done_q.get(timeout=1.0)
+            except _queue.Empty:
+                if not any(p.is_alive() for p in procs):
+                    raise RuntimeError(f"finemap-batch workers exited with {pending} windows left")
+                continue
+            pending -= 1
+            n_ok, n_bad = n_ok + ok, n_bad + bad
+            if err is not None:
+                failed.append((device, err))
+                log.logger.error(f"Worker of GPU {device} stopped: {err}")
+                if len(failed) == len(devices):
+                    raise RuntimeError(f"every finemap-batch worker failed; first error: {failed[0][1]}")
+    finally:
+        for p in procs:
+            p.join(timeout=30)
+            if p.is_alive():
+                p.terminate()
+        listener.stop()
+    return n_ok, n_bad
+
+
+def run_finemap_batch(bargs) -> int:
+    """``finemap-batch``: every non-comment line of the manifest holds the arguments of one ``finemap`` run.
+    Genes are read and cleaned on the host, all their fits (joint, per-ancestry, stacked, cross-validation
+    folds) go through the device work queue together and each gene gets the same output files a separate
+    ``finemap`` run would write.  A gene that fails is reported and skipped.  With several ``--devices`` the
+    genes are sharded over one worker process per GPU (``--threads`` keeps one process with one worker thread
+    per GPU)."""
     with open(bargs.manifest) as fh:
         lines = [(no + 1, ln.strip()) for no, ln in enumerate(fh)]
     lines = [(no, ln) for no, ln in lines if ln and not ln.startswith("#")]
     devices = bargs.devices if bargs.devices else None
     config.precision = int(bargs.jax_precision)
     n_ok = n_bad = 0
-    for w0 in range(0, len(lines), bargs.window):
-        genes: List[_Gene] = []
-        specs: List[dict] = []
-        ss_specs: List[dict] = []
-        for no, ln in lines[w0:w0 + bargs.window]:
-            try:
-                gene = _Gene(no, parser.parse_args(shlex.split(ln)))
-            except SystemExit:
-                log.logger.error(f"Manifest line {no}: arguments could not be parsed; gene skipped.")
-                n_bad += 1
-                continue
-            mark, ss_mark = len(specs), len(ss_specs)
-            try:
-                _prepare_gene(gene, specs, ss_specs)
-            except Exception as err:  # keep the batch going, like one failed process among many
-                del specs[mark:], ss_specs[ss_mark:]
-                gene.error = str(err)
-                log.logger.error(f"Manifest line {no} ({gene.args.trait}): {err}")
-                n_bad += 1
-                continue
-            genes.append(gene)
-        log.logger.info(
-            f"Window of {len(genes)} genes: {len(specs)} individual-level and {len(ss_specs)} summary-level fits."
-        )
-        fits = infer.infer_sushie_batch(specs, devices=devices) if specs else []
-        ss_fits = infer_ss.infer_sushie_ss_batch(ss_specs, devices=devices) if ss_specs else []
-        for gene in genes:
-            try:
-                _emit_gene(gene, fits, ss_fits)
-                n_ok += 1
-            except Exception as err:
-                log.logger.error(f"Manifest line {gene.line_no} ({gene.args.trait}): {err}")
-                n_bad += 1
+    if devices and len(devices) > 1 and not bargs.threads and len(lines) > 1:
+        n_ok, n_bad = _run_windows_in_processes(lines, list(devices), bargs.window, config.precision)
+    else:
+        parser = _finemap_line_parser()
+        for w0 in range(0, len(lines), bargs.window):
+            ok, bad = _run_window(parser, lines[w0:w0 + bargs.window], devices)
+            n_ok, n_bad = n_ok + ok, n_bad + bad
     log.logger.info(f"Batch fine-mapping finishes: {n_ok} genes written, {n_bad} failed.")
     return 0
 
@@ -1042,11 +1132,13 @@ def run_finemap_batch(bargs) -> int:
 def build_batch_parser(subp):
     batch = subp.add_parser(
         "finemap-batch",
-        description="Fine-map many genes in one process: one line of `finemap` arguments per gene in a manifest file.",
+        description="Fine-map many genes in one run: one line of `finemap` arguments per gene in a manifest file.",
     )
     batch.add_argument("--manifest", required=True, type=str, help="Text file, one gene per line (finemap arguments).")
     batch.add_argument("--devices", nargs="+", type=int, default=None, help="GPU ordinals to shard over (default: 0).")
     batch.add_argument("--window", type=int, default=256, help="Genes read, fitted and written per pass.")
+    batch.add_argument("--threads", **_FLAG, help="With several --devices: one process with a worker thread per GPU "
+                                                  "instead of one worker process per GPU.")
     batch.add_argument("--jax-precision", default=64, type=int, choices=[32, 64],
                        help="64: fp64 device storage of dense matrices; 32: fp32 storage.")
     batch.add_argument("--quiet", **_FLAG)

@@ -192,3 +192,24 @@ def test_output_tables_follow_the_reference_schema(tmp_path):
     one = _fake_result(k=1)
     meta = io.output_weights([one, one], [one.pip_all, one.pip_cs], snps, out, "GENE", False, "meta")
     assert {"ancestry1_single_weight", "ancestry2_single_pip_all", "ancestry2_cs_index", "meta_pip_all"} <= set(meta.columns)
+
+
+def test_finemap_batch_worker_processes_plumbing(tmp_path):
+    """Several `--devices`: one spawned worker process per GPU pulls windows of manifest lines and logs through
+    the parent.  Every line here fails before any fit (missing files / bad arguments), so no GPU is needed:
+    the test covers the spawn, the window queue, the log forwarding and the counts."""
+    from sushie_b200 import cli
+
+    manifest = tmp_path / "genes.txt"
+    with open(manifest, "w") as fh:
+        fh.write("# comment\n\n")
+        for g in range(5):
+            fh.write(f"--pheno /nonexistent/p{g} --vcf /nonexistent/v{g}.vcf --trait GENE{g} --output {tmp_path}/o{g}\n")
+        fh.write("--no-such-flag 1\n")
+    out = str(tmp_path / "batch")
+    assert cli._main(["finemap-batch", "--manifest", str(manifest), "--devices", "0", "1", "--quiet", "--output", out]) == 0
+    text = open(out + ".log").read()
+    assert "0 genes written, 6 failed" in text
+    for g in range(5):
+        assert f"GENE{g}" in text
+    assert "arguments could not be parsed" in text
