@@ -190,36 +190,34 @@ def finish_tables(alpha, log_bf, ns, selection, min_abs, purity: float, purity_m
     columns["pip_cs"] = pip_cs
     full_alphas = pd.DataFrame(columns)
 
-    # one frame for all kept sets (a frame per effect costs more than the fit at batch throughput)
+    # one frame for all kept sets, built in one go (a frame per effect, or adding columns afterwards, costs
+    # more than the fit at batch throughput)
     if cs_parts:
-        cs = pd.DataFrame(
-            {
-                "CSIndex": np.concatenate([c[0] for c in cs_parts]),
-                "SNPIndex": np.concatenate([c[1] for c in cs_parts]),
-                "alpha": np.concatenate([c[2] for c in cs_parts]),
-                "c_alpha": np.concatenate([c[3] for c in cs_parts]),
-            }
-        )
+        cs_index = np.concatenate([c[0] for c in cs_parts])
+        snp_in_cs = np.concatenate([c[1] for c in cs_parts])
+        cs_alpha = np.concatenate([c[2] for c in cs_parts])
+        cs_c_alpha = np.concatenate([c[3] for c in cs_parts])
     else:
-        cs = pd.DataFrame(
-            {
-                "CSIndex": np.zeros(0, dtype=np.int64),
-                "SNPIndex": np.zeros(0, dtype=np.int64),
-                "alpha": np.zeros(0),
-                "c_alpha": np.zeros(0),
-            }
-        )
-    snp_in_cs = cs.SNPIndex.values.astype(int)
+        cs_index = snp_in_cs = np.zeros(0, dtype=np.int64)
+        cs_alpha = cs_c_alpha = np.zeros(0)
     if len(snp_in_cs) != len(np.unique(snp_in_cs)):
         log.logger.warning(
             "Same SNPs appear in different credible set, which is very unusual."
             + " You may want to check this gene in details."
         )
-    cs["pip_all"] = pip_all[snp_in_cs]
-    cs["pip_cs"] = pip_cs[snp_in_cs]
+    cs = pd.DataFrame(
+        {
+            "CSIndex": cs_index,
+            "SNPIndex": snp_in_cs,
+            "alpha": cs_alpha,
+            "c_alpha": cs_c_alpha,
+            "pip_all": pip_all[snp_in_cs],
+            "pip_cs": pip_cs[snp_in_cs],
+        }
+    )
 
     log.logger.info(
-        f"{len(cs.CSIndex.unique())} out of {n_l} credible sets remain after pruning based on purity ({purity})."
+        f"{len(cs_parts)} out of {n_l} credible sets remain after pruning based on purity ({purity})."
         + " For detailed results, specify --alphas."
     )
     return cs, full_alphas, pip_all, pip_cs

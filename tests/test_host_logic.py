@@ -273,3 +273,44 @@ def test_product_never_imports_the_oracle():
             if fn.endswith((".py", ".cu", ".cuh", ".h")):
                 text = open(os.path.join(dirpath, fn)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", text, re.M), fn
+
+
+@pytest.mark.parametrize("no_reorder", [True, False])
+def test_staged_epilogue_equals_one_shot_assembly(no_reorder):
+    """`StagedResult` (set selection -> purity for the whole chunk -> deferred tables) must give exactly what the
+    one-shot `assemble_result` + `build_tables` path gives."""
+    import types
+
+    rng = np.random.default_rng(3)
+    L, p, k = 4, 400, 3
+    alpha = rng.dirichlet(np.ones(p) * 0.02, size=L)
+    alpha[3] = rng.dirichlet(np.ones(p) * 5.0)  # a diffuse effect: its set is sub-sampled to max_select
+    fit = types.SimpleNamespace(
+        alpha=alpha, post_mean=rng.standard_normal((L, p, k)), post_mean_sq=rng.random((L, p, k, k)),
+        weighted_sum_covar=np.stack([np.eye(k) * w for w in (0.3, 2.0, 1.0, 0.1)]), kl=rng.random(L),
+        log_bf=rng.standard_normal((L, p)), effect_covar=np.stack([np.eye(k) * w for w in (0.3, 2.0, 1.0, 0.1)]),
+        resid_var=np.ones(k), elbo=np.array([-np.inf, -3.0, -2.0]), elbo_increase=True,
+    )
+    ns = np.array([[100], [120], [90]])
+    seen = []
+
+    def min_abs(sets):
+        seen.append([np.asarray(s).copy() for s in sets])
+        return np.array([[0.2 + 0.1 * i + 0.01 * a for a in range(k)] for i in range(len(sets))])
+
+    cs_args = dict(threshold=0.9, purity=0.35, purity_method="weighted", max_select=50, seed=7)
+    one = _common.assemble_result(
+        fit, None, ns, no_reorder, lambda a, lbf: cs_mod.build_tables(a, lbf, ns, min_abs, **cs_args))
+    staged = _common.StagedResult(fit, None, ns, no_reorder, **cs_args)
+    assert max(len(s) for s in staged.purity_sets) == 50
+    two = staged.finisher(min_abs(staged.purity_sets))()
+    assert all(np.array_equal(a, b) for a, b in zip(seen[0], seen[1]))
+    pd_testing = pytest.importorskip("pandas.testing")
+    pd_testing.assert_frame_equal(one.cs, two.cs)
+    pd_testing.assert_frame_equal(one.alphas, two.alphas)
+    np.testing.assert_array_equal(one.pip_all, two.pip_all)
+    np.testing.assert_array_equal(one.pip_cs, two.pip_cs)
+    np.testing.assert_array_equal(one.l_order, two.l_order)
+    np.testing.assert_array_equal(one.posteriors.alpha, two.posteriors.alpha)
+    with pytest.raises(ValueError, match="Invalid purity method"):
+        _common.StagedResult(fit, None, ns, True, 0.9, 0.5, "median", 50, 7)
