@@ -51,18 +51,25 @@ def plan_chunks(preps: Sequence, chunk_bytes: Optional[int] = None, chunk_loci: 
     chunks: List[List[int]] = []
     for ids in groups.values():
         ids = sorted(ids, key=lambda i: (-preps[i].problem.cost, i))
-        cap = chunk_loci
-        if not cap and n_workers > 1:
-            # at least one chunk per worker; more (for balance) only while the chunks stay large enough
+        # target chunk sizes: an explicit cap, or -- several workers, no cap -- at least one chunk per worker,
+        # more (for balance) only while the chunks stay large enough; sizes differ by at most one locus
+        caps: List[int] = []
+        if chunk_loci:
+            caps = [chunk_loci]
+        elif n_workers > 1:
             n_cut = max(n_workers, min(config.chunks_per_worker * n_workers, len(ids) // max(1, config.min_chunk_loci)))
-            cap = -(-len(ids) // n_cut)
+            n_cut = min(n_cut, len(ids))
+            caps = [len(ids) // n_cut + (1 if c < len(ids) % n_cut else 0) for c in range(n_cut)]
         cur: List[int] = []
         cur_bytes = 0
+        n_done = 0  # chunks closed in this group (indexes the target sizes)
         for i in ids:
             b = estimate_bytes(preps[i])
+            cap = caps[min(n_done, len(caps) - 1)] if caps else 0
             if cur and (cur_bytes + b > chunk_bytes or (cap and len(cur) >= cap)):
                 chunks.append(cur)
                 cur, cur_bytes = [], 0
+                n_done += 1
             cur.append(i)
             cur_bytes += b
         if cur:

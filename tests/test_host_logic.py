@@ -314,3 +314,37 @@ def test_staged_epilogue_equals_one_shot_assembly(no_reorder):
     np.testing.assert_array_equal(one.posteriors.alpha, two.posteriors.alpha)
     with pytest.raises(ValueError, match="Invalid purity method"):
         _common.StagedResult(fit, None, ns, True, 0.9, 0.5, "median", 50, 7)
+
+
+def test_plan_chunks_properties_under_random_inputs():
+    """Property check (hypothesis): every problem lands in exactly one chunk, chunks never mix launch
+    configurations or storage kinds, and explicit caps are respected, for any worker count."""
+    hyp = pytest.importorskip("hypothesis")
+    st = pytest.importorskip("hypothesis.strategies")
+
+    class P:
+        def __init__(self, p, tol, hard):
+            self.problem = type("X", (), dict(n=np.asarray([50, 60], dtype=np.int32), p=p, L=5, k=2, cost=110.0 * p * 5))()
+            self.max_iter, self.min_tol, self.hard_calls = 500, tol, hard
+
+    @hyp.settings(max_examples=300, deadline=None)
+    @hyp.given(
+        st.lists(st.tuples(st.integers(100, 3000), st.sampled_from([1e-3, 1e-4]), st.booleans()), min_size=1, max_size=80),
+        st.integers(1, 8), st.integers(0, 9),
+    )
+    def check(items, n_workers, cap):
+        preps = [P(*it) for it in items]
+        chunks = batch.plan_chunks(preps, chunk_bytes=1 << 40, chunk_loci=cap, n_workers=n_workers)
+        assert sorted(i for c in chunks for i in c) == list(range(len(preps)))
+        for c in chunks:
+            assert len({(preps[i].min_tol, preps[i].hard_calls) for i in c}) == 1
+            if cap:
+                assert len(c) <= cap
+        if not cap:
+            groups = {(p.min_tol, p.hard_calls) for p in preps}
+            sizes = {g: sum(1 for p in preps if (p.min_tol, p.hard_calls) == g) for g in groups}
+            for g, n in sizes.items():  # with several workers every group is cut into at least min(n, workers) chunks
+                n_chunks = sum(1 for c in chunks if (preps[c[0]].min_tol, preps[c[0]].hard_calls) == g)
+                assert n_chunks >= (min(n, n_workers) if n_workers > 1 else 1)
+
+    check()
