@@ -10,7 +10,7 @@ same un-split key for every effect, ``infer.py:894,940-943``).
 from __future__ import annotations
 
 import functools
-from typing import Callable, List, Optional, Sequence, Tuple
+from typing import Callable, List, Tuple
 
 import numpy as np
 import pandas as pd

@@ -20,7 +20,7 @@ from typing import List, Optional, Sequence
 
 import numpy as np
 
-from . import _capi, config, cs as _cs, log, utils
+from . import _capi, config, cs as _cs, utils
 from ._common import (
     Posterior,
     Prior,

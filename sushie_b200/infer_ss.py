@@ -7,7 +7,7 @@ sample-size factor in the kernel; ``Xty`` follows ``infer_ss.py:342-343`` on dev
 """
 from __future__ import annotations
 
-from typing import List, Optional, Sequence
+from typing import Optional, Sequence
 
 import numpy as np
 

@@ -19,7 +19,7 @@ from typing import Callable, List, NamedTuple, Optional, Tuple
 import numpy as np
 import pandas as pd
 
-from . import log, utils
+from . import log
 
 __all__ = [
     "CVData", "CleanData", "RawData", "ssData", "read_data", "read_triplet", "read_bgen", "read_vcf",
