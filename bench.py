@@ -272,7 +272,9 @@ def workload_config(args, genes_per_gpu):
         "workload": "config 3: synthetic 3-ancestry individual-level loci (AR(1) haplotypes, h2=0.2, 0-3 causal)",
         "k": K_ANC, "n_per_ancestry": N_IND, "p": P_SNP, "L": L_EFF,
         "genes_per_gpu": genes_per_gpu, "max_iter": args.max_iter, "min_tol": args.min_tol,
-        "stop_rule": "to convergence (Python API defaults)",
+        "stop_rule": ("to convergence (Python API defaults)" if (args.max_iter, args.min_tol) == (500, 1e-4) else
+                      f"fixed {args.max_iter} iterations (min_tol = 0 disables the stop, infer.py:537)" if args.min_tol == 0
+                      else f"to convergence (max_iter = {args.max_iter}, min_tol = {args.min_tol})"),
         "genotype_storage": args.storage,
         "l2": "inputs_larger_than_L2 (%d MB per locus resident, batch of %d loci >> 126 MB)" % (
             K_ANC * N_IND * P_SNP * {"i8": 1, "f64": 8, "f32": 4}[args.storage] // 1000000, genes_per_gpu),
