@@ -113,25 +113,71 @@ def _oracle_fit(args):
         threadpool_limits(1)
     except Exception:
         pass
-    from oracle import ibss
+    from oracle import ibss_fast
 
-    g, max_iter, min_tol, n, p = args
+    g, max_iter, min_tol, n, p, keep = args
     Xs, ys = make_gene(g, n, p)
     t0 = time.perf_counter()
-    fit = ibss.fit_individual([x.astype(np.float64) for x in Xs], ys, L=L_EFF, max_iter=max_iter, min_tol=min_tol)
-    return time.perf_counter() - t0, fit.n_iter
+    fit = ibss_fast.fit_individual([x.astype(np.float64) for x in Xs], ys, L=L_EFF, max_iter=max_iter, min_tol=min_tol)
+    out = {"seconds": time.perf_counter() - t0, "n_iter": fit.n_iter}
+    if keep:  # what the in-bench parity check compares (effects in IBSS order, before the re-ordering)
+        out.update(alpha=fit.alpha, effect_covar=fit.effect_covar, elbo_last=float(fit.elbo[-1]))
+    return out
 
 
-def cpu_pass(first_gene: int, n_loci: int, cores: int, max_iter: int, min_tol: float, n=N_IND, p=P_SNP):
-    """Fit n_loci genes with the numpy oracle, one process per core.  Returns (seconds, iters)."""
+def cpu_pass(first_gene: int, n_loci: int, cores: int, max_iter: int, min_tol: float, n=N_IND, p=P_SNP, keep=False):
+    """Fit n_loci genes with the numpy port of the reference (oracle/ibss_fast.py: same quantities as the literal
+    restatement oracle/ibss.py, two traversals of X per single-effect update), one single-threaded process per core.
+    Returns (wall seconds, total iterations, per-locus records)."""
     import multiprocessing as mp
 
-    jobs = [(first_gene + i, max_iter, min_tol, n, p) for i in range(n_loci)]
+    jobs = [(first_gene + i, max_iter, min_tol, n, p, keep) for i in range(n_loci)]
     t0 = time.perf_counter()
     with mp.get_context("fork").Pool(min(cores, n_loci)) as pool:
         out = pool.map(_oracle_fit, jobs, chunksize=1)
     wall = time.perf_counter() - t0
-    return wall, int(sum(o[1] for o in out))
+    return wall, int(sum(o["n_iter"] for o in out)), out
+
+
+def credible_members(alpha, threshold=0.95, max_size=250):
+    """Per effect: the SNPs of the `threshold` credible set (descending alpha, cumulative cut, infer.py:903-915), or
+    None when the set is larger than max_size (a null effect: its membership is decided by rounding)."""
+    out = []
+    for a in alpha:
+        order = np.argsort(-a, kind="stable")
+        size = int(np.count_nonzero(np.cumsum(a[order]) < threshold)) + 1
+        out.append(frozenset(order[:size].tolist()) if size <= max_size else None)
+    return out
+
+
+def parity_record(gpu_fits, cpu_records):
+    """GPU fits vs the CPU port on the SAME loci (the cpu_baseline sample), effect by effect in IBSS order:
+    north_star tolerances |dPIP| <= 1e-4, identical credible-set membership, prior covariance within 1e-4 relative."""
+    n_same_iter, d_pip, d_cov, d_elbo, sets_total, sets_same = 0, 0.0, 0.0, 0.0, 0, 0
+    for fit, rec in zip(gpu_fits, cpu_records):
+        n_same_iter += int(fit.n_iter == rec["n_iter"])
+        pip_g = -np.expm1(np.log1p(-fit.alpha).sum(axis=0))
+        pip_c = -np.expm1(np.log1p(-rec["alpha"]).sum(axis=0))
+        d_pip = max(d_pip, float(np.max(np.abs(pip_g - pip_c))))
+        for cg, cc in zip(fit.effect_covar, rec["effect_covar"]):
+            d_cov = max(d_cov, float(np.linalg.norm(cg - cc) / np.linalg.norm(cc)))
+        d_elbo = max(d_elbo, abs(float(fit.elbo[-1]) - rec["elbo_last"]) / abs(rec["elbo_last"]))
+        for sg, sc in zip(credible_members(fit.alpha), credible_members(rec["alpha"])):
+            if sg is None and sc is None:
+                continue
+            sets_total += 1
+            sets_same += int(sg == sc)
+    n = len(cpu_records)
+    ok = n_same_iter == n and d_pip <= 1e-4 and d_cov <= 1e-4 and sets_same == sets_total
+    return {
+        "loci_compared": n, "same_n_iter": n_same_iter, "max_abs_dpip": d_pip, "max_rel_dcov": d_cov,
+        "max_rel_delbo": d_elbo, "credible_sets_compared": sets_total, "credible_sets_identical": sets_same,
+        "within_tolerance": bool(ok),
+        "tolerance": "same n_iter; |dPIP| <= 1e-4; identical 95% credible-set membership (sets <= 250 SNPs); "
+                     "|dC|/|C| <= 1e-4 per effect",
+        "against": "oracle/ibss_fast.py on the cpu_baseline loci (numpy port; held to the literal restatement and, "
+                   "through tests/refshim, to the reference's own source by the test-suite)",
+    }
 
 
 # ----------------------------------------------------------------------------------------
@@ -202,15 +248,19 @@ def hbm_peak():
         return HBM_FALLBACK_GBS, "fallback (B200_PROFILING.md)"
 
 
-def ncu_traffic(storage: str):
-    """DRAM read+write bytes per single-effect update of the IBSS kernel, from the committed
-    `ncu --set full` summary of the same kernel (profiles/r01_ncu_full_ind_<storage>.json)."""
-    path = os.path.join(ROOT, "profiles", f"r01_ncu_full_ind_{storage}.json")
-    try:
-        with open(path) as fh:
-            return float(json.load(fh)["dram_bytes_per_ser"]), os.path.relpath(path, ROOT)
-    except Exception:
-        return None, None
+def ncu_traffic(which: str):
+    """DRAM read+write bytes per single-effect update of an IBSS kernel, from the newest committed `ncu --set full`
+    summary of the same kernel (profiles/rNN_ncu_full_<ind_i8|ind_f64|ss_f32>.json)."""
+    import glob
+
+    name = which if which.startswith("ss_") else f"ind_{which}"
+    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", f"r*_ncu_full_{name}.json")), reverse=True):
+        try:
+            with open(path) as fh:
+                return float(json.load(fh)["dram_bytes_per_ser"]), os.path.relpath(path, ROOT)
+        except Exception:
+            continue
+    return None, None
 
 
 def prep_y(ys):
@@ -231,12 +281,12 @@ def run_reference(args):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    sample = max(1, min(cores, args.ref_loci or cores))
+    sample = max(1, args.ref_loci or cores)
     times, iters = [], 0
-    for _ in range(args.warmup):  # warm-up passes are bounded: 2 loci x 10 iterations (imports, page-in)
-        cpu_pass(0, min(2, sample), cores, 10, 0.0)
+    for _ in range(args.warmup):  # warm-up passes are bounded: 2 loci x 5 iterations (imports, page-in)
+        cpu_pass(0, min(2, sample), cores, 5, 0.0)
     for _ in range(args.steps):
-        wall, it = cpu_pass(0, sample, cores, args.max_iter, args.min_tol)
+        wall, it, _ = cpu_pass(0, sample, cores, args.max_iter, args.min_tol)
         times.append(wall)
         iters += it
     ms = 1e3 * float(np.mean(times))
@@ -255,11 +305,12 @@ def run_reference(args):
         "vs_baseline": None,
         "dtype": "f64",
         "data": "synthetic",
-        "config": workload_config(args, sample),
+        "config": workload_config(args),
         "cpu_baseline": {
             "value": value, "unit": "loci/s", "cores": min(cores, sample), "kind": "port",
-            "sample": f"first {sample} loci of the workload per step, one numpy-oracle process per core "
-                      f"(reference JAX path not installable: no jax/equinox wheels)",
+            "sample": f"each step: the first {sample} loci of the workload fitted to convergence, one single-threaded "
+                      f"process per core (numpy port oracle/ibss_fast.py; the reference's JAX path is not "
+                      f"installable: no jax/equinox wheels)",
         },
         "e2e": {"value": value, "unit": "loci/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "iters_per_sec": iters / (sum(times)),
@@ -267,17 +318,18 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
-def workload_config(args, genes_per_gpu):
+def workload_config(args):
+    """The workload, identical for both arms (`--impl reference` fits a bounded sample of it per step, described in
+    its `cpu_baseline.sample`)."""
     return {
         "workload": "config 3: synthetic 3-ancestry individual-level loci (AR(1) haplotypes, h2=0.2, 0-3 causal)",
         "k": K_ANC, "n_per_ancestry": N_IND, "p": P_SNP, "L": L_EFF,
-        "genes_per_gpu": genes_per_gpu, "max_iter": args.max_iter, "min_tol": args.min_tol,
+        "genes_per_gpu": args.genes, "max_iter": args.max_iter, "min_tol": args.min_tol,
         "stop_rule": ("to convergence (Python API defaults)" if (args.max_iter, args.min_tol) == (500, 1e-4) else
                       f"fixed {args.max_iter} iterations (min_tol = 0 disables the stop, infer.py:537)" if args.min_tol == 0
                       else f"to convergence (max_iter = {args.max_iter}, min_tol = {args.min_tol})"),
-        "genotype_storage": args.storage,
-        "l2": "inputs_larger_than_L2 (%d MB per locus resident, batch of %d loci >> 126 MB)" % (
-            K_ANC * N_IND * P_SNP * {"i8": 1, "f64": 8, "f32": 4}[args.storage] // 1000000, genes_per_gpu),
+        "l2": "inputs_larger_than_L2 (>= %d MB of genotypes per locus resident, batch of %d loci >> 126 MB)" % (
+            K_ANC * N_IND * P_SNP // 1000000, args.genes),
         "parallelism": f"loci sharded over {args.gpus} GPU(s), no data-path collective",
     }
 
@@ -302,6 +354,12 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-dense-arm", action="store_true", help="skip the extra fp64-storage roofline run (N=1 only)")
     ap.add_argument("--e2e-steps", type=int, default=1)
+    ap.add_argument("--dense-steps", type=int, default=3)
+    ap.add_argument("--no-ss-arm", action="store_true", help="skip the summary-level (config 4) roofline run (N=1 only)")
+    ap.add_argument("--ss-p", type=int, default=10000)
+    ap.add_argument("--ss-iters", type=int, default=20)
+    ap.add_argument("--no-api-arm", action="store_true", help="skip the public-API end-to-end run")
+    ap.add_argument("--api-genes", type=int, default=0, help="loci of the public-API end-to-end run (0 = --genes)")
     args = ap.parse_args()
 
     if args.impl == "reference":
@@ -320,13 +378,14 @@ def main():
     genes = generate_genes(rank * B, B, gen_workers)
     t_gen = time.time() - t0
 
-    cpu_baseline = None
+    cpu_baseline, cpu_records = None, None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         sample = args.cpu_loci or min(cores, B)
-        wall, it = cpu_pass(0, sample, cores, args.max_iter, args.min_tol)
+        wall, it, cpu_records = cpu_pass(0, sample, cores, args.max_iter, args.min_tol, keep=True)
         cpu_baseline = {
             "value": sample / wall, "unit": "loci/s", "cores": min(cores, sample), "kind": "port",
-            "sample": f"first {sample} loci of the workload, numpy oracle, one process per core, {wall:.1f} s wall",
+            "sample": f"first {sample} loci of the workload to convergence, numpy port (oracle/ibss_fast.py), one "
+                      f"single-threaded process per core, {wall:.1f} s wall",
             "iters_per_sec": it / wall,
         }
 
@@ -392,6 +451,9 @@ def main():
     clocks = sampler.stop()
     fits = batch.fetch()
     pip_sum = float(sum(np.sum(-np.expm1(np.log1p(-f.alpha).sum(axis=0))) for f in fits[:8]))
+    # the GPU fits of the loci the CPU port has just fitted in this very run: compared, not just printed
+    parity = parity_record(fits[: len(cpu_records)], cpu_records) if cpu_records else None
+    n_nonfinite = int(sum(f.status != 0 for f in fits))
     geom = {k: st[k] for k in ("team_size", "n_teams", "rows_per_band", "n_stages", "smem_bytes")}
     batch.close()
     del fits
@@ -403,16 +465,60 @@ def main():
         d_opts = eng.make_opts(args.max_iter, args.min_tol, _capi.SB_F64, args.team, args.single_phase)
         d_batch = eng.create_batch(build_problems(), d_opts)
         d_batch.run()
-        d_st = d_batch.run()
+        d_sampler = ClockSampler(local_rank)
+        d_sampler.start()
+        d_ms, d_alg, d_ser, d_steps = 0.0, 0.0, 0, max(3, args.dense_steps)
+        for _ in range(d_steps):
+            d_st = d_batch.run()
+            d_ms += d_st["device_ms"]
+            d_alg += d_st["algorithmic_bytes"]
+            d_ser += d_st["n_ser"]
+        d_clocks = d_sampler.stop()
         d_batch.close()
-        d_ach = d_st["algorithmic_bytes"] / (d_st["device_ms"] / 1e3) / 1e9
+        d_ach = d_alg / (d_ms / 1e3) / 1e9
         d_traffic, d_src = ncu_traffic("f64")
         dense = {
             "kernel": "sb::ibss_kernel<3,double,false,1>", "bound": "hbm", "achieved": d_ach, "unit": "GB/s",
-            "loci_per_sec": B / (d_st["device_ms"] / 1e3), "ms_per_step": d_st["device_ms"],
+            "loci_per_sec": B * d_steps / (d_ms / 1e3), "ms_per_step": d_ms / d_steps,
             "algorithmic_bytes_per_ser": K_ANC * N_IND * P_SNP * 8,
-            "traffic": d_traffic * d_st["n_ser"] if d_traffic else None, "traffic_source": d_src,
-            "steps": 1, "warmup": 1,
+            "traffic": d_traffic * d_ser / d_steps if d_traffic else None, "traffic_source": d_src,
+            "steps": d_steps, "warmup": 1, "clocks": d_clocks,
+        }
+
+    # ---- summary-level arm (N=1): BASELINE.json config 4, one k=3, p=10 000 locus, LD stored fp32 (1.2 GB read per
+    # single-effect update), L=10, EM on, fixed iterations, co-operative team over the whole device
+    ss_arm = None
+    if world == 1 and not args.no_ss_arm:
+        import scripts.bench_ss as bench_ss
+
+        lds, ns, zs, _ = bench_ss.make_locus(args.ss_p, np.float32)
+        ec, adj_ss = build_priors(K_ANC, L_EFF, None, None, False, summary=True)
+        prob = _capi.SsProblem(lds, ns.reshape(-1), zs, L_EFF, None, [1.0] * K_ANC, ec, adj_ss.times, adj_ss.plus, True)
+        s_opts = eng.make_opts(args.ss_iters, 0.0, _capi.SB_F32, 0, True)
+        s_batch = eng.create_batch([prob], s_opts)
+        del lds
+        for _ in range(3):
+            s_batch.run()
+        s_sampler = ClockSampler(local_rank)
+        s_sampler.start()
+        s_ms, s_ser, s_steps = 0.0, 0, 5
+        for _ in range(s_steps):
+            s_st = s_batch.run()
+            s_ms += s_st["device_ms"]
+            s_ser += s_st["n_ser"]
+        s_clocks = s_sampler.stop()
+        s_batch.close()
+        s_bytes = float(K_ANC) * args.ss_p * args.ss_p * 4
+        s_traffic, s_src = ncu_traffic("ss_f32")
+        ss_arm = {
+            "workload": f"config 4: summary-level, k={K_ANC}, p={args.ss_p}, L={L_EFF}, fp32 LD storage, EM on, "
+                        f"{args.ss_iters} fixed iterations",
+            "kernel": "sb::ibss_kernel<3,float,true,0>", "team_size": s_st["team_size"], "bound": "hbm",
+            "achieved": s_ser * s_bytes / (s_ms / 1e3) / 1e9, "unit": "GB/s", "us_per_ser": 1e3 * s_ms / s_ser,
+            "ms_per_iteration": s_ms / s_ser * L_EFF, "algorithmic_bytes_per_ser": s_bytes,
+            "traffic": s_traffic * s_ser / s_steps if s_traffic else None, "traffic_source": s_src,
+            "steps": s_steps, "warmup": 3, "clocks": s_clocks,
+            "l2": "1.2 GB of LD per single-effect update >> 126 MB L2",
         }
 
     # ---- end-to-end arm: host buffers through the C ABI, copies in the timed region
@@ -452,13 +558,34 @@ def main():
         d2h = B * 8 * (per - (args.max_iter + 1)) + 8 * int(stats.n_iter) + 8 * B
         e2e = {"ms": e2e_step, "h2d": h2d, "d2h": d2h, "launches": int(stats.n_launches)}
 
+    # ---- public-API arm: numpy arrays in -> list of SushieResult out (host prologue, upload, IBSS, download, effect
+    # re-ordering, credible sets + purity, output tables) -- what a user of `infer_sushie` gets, per locus
+    api = None
+    if not args.no_api_arm:
+        import sushie_b200
+
+        n_api = min(B, args.api_genes or B)
+        api_probs = [dict(Xs=[x_np[i, a] for a in range(K_ANC)], ys=ys_all[i]) for i in range(n_api)]
+        kw = dict(L=L_EFF, max_iter=args.max_iter, min_tol=args.min_tol, devices=[local_rank])
+        sushie_b200.infer_sushie_batch(api_probs[: min(n_api, 64)], **kw)  # warm-up (imports, pandas, shuffle cache)
+        barrier()
+        t0 = time.perf_counter()
+        results = sushie_b200.infer_sushie_batch(api_probs, **kw)
+        barrier()
+        api = {"ms": 1e3 * (time.perf_counter() - t0), "loci": n_api,
+               "n_cs": int(sum(len(set(r.cs.CSIndex.values.tolist())) for r in results))}
+        del results
+
     # ---- reduce over ranks (max time), gather a small result record with NCCL
     if world > 1:
-        t = torch.tensor([dev_ms, wall_ms, e2e["ms"] if e2e else 0.0], device="cuda", dtype=torch.float64)
+        t = torch.tensor([dev_ms, wall_ms, e2e["ms"] if e2e else 0.0, api["ms"] if api else 0.0], device="cuda",
+                         dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dev_ms, wall_ms = float(t[0]), float(t[1])
         if e2e:
             e2e["ms"] = float(t[2])
+        if api:
+            api["ms"] = float(t[3])
         cnt = torch.tensor([n_ser, n_iter, alg_bytes, pip_sum], device="cuda", dtype=torch.float64)
         gathered = [torch.zeros_like(cnt) for _ in range(world)]
         dist.all_gather(gathered, cnt)
@@ -491,12 +618,17 @@ def main():
             "algorithmic_bytes_per_ser": K_ANC * N_IND * P_SNP * alg_elem,
             "stored_bytes_per_ser": K_ANC * N_IND * P_SNP * elem_bytes,
             "achieved_stored_bytes": achieved, "frac_stored_bytes": achieved / peak,
+            # DRAM view: ncu read+write bytes per update x updates / time -- what the memory system actually moves
+            "achieved_dram": (traffic_per_ser * ser_per_gpu_s / 1e9) if traffic_per_ser else None,
+            "frac_dram": (traffic_per_ser * ser_per_gpu_s / 1e9 / peak) if traffic_per_ser else None,
+            "limiter": ("fp64 issue" if args.storage == "i8" else "hbm"),
             "note": ("achieved = #single-effect updates x k*n*p*%d B (one traversal of the genotype tensor at the "
                      "precision under test) / CUDA-event time, per GPU" % alg_elem)
-                    + ("; genotypes are stored as 1-byte hard calls (compressed), so frac > 1 is expected: DRAM "
-                       "traffic is `traffic`, the kernel is instruction/latency bound (fp64 pipe ~32 %, issue ~44 % "
-                       "busy, profiles/r01_ncu_full_ind_i8.json); the HBM-roofline claim is roofline_dense_fp64"
-                       if args.storage == "i8" else ""),
+                    + ("; genotypes are stored as 1-byte hard calls (compressed), so `frac` counts fp64-equivalent "
+                       "bytes and is NOT a fraction of HBM bandwidth: the memory system moves `achieved_dram` "
+                       "(`frac_dram` of peak) and the kernel is bound by fp64 / issue slots (`limiter`); the "
+                       "HBM-roofline claims are roofline_dense_fp64 and roofline_ss_f32, where DRAM traffic equals "
+                       "the algorithmic bytes" if args.storage == "i8" else ""),
         }
         line = {
             "metric": "loci_per_sec",
@@ -511,14 +643,15 @@ def main():
             "vs_baseline": None,
             "dtype": "f64",
             "data": "synthetic",
-            "config": workload_config(args, B),
+            "config": workload_config(args),
             "iters_per_sec": n_iter / (dev_ms / 1e3),
             "ser_per_sec": n_ser / (dev_ms / 1e3),
             "mean_iters_per_locus": n_iter / (total_loci * args.steps),
             "wall_ms_per_step": wall_ms / args.steps,
             "gpu_launches": launches,
             "kernel": dict(geom, name="sb::ibss_kernel<3,%s>" % {"i8": "int8_t,false,1", "f64": "double,false,1", "f32": "float,false,0"}[args.storage],
-                           launches_per_step=launches / args.steps, genotype_storage=args.storage),
+                           launches_per_step=launches / args.steps, genotype_storage=args.storage,
+                           stored_mb_per_locus=K_ANC * N_IND * P_SNP * elem_bytes / 1e6),
             "roofline": roofline,
             "clocks": {"sm_mhz": clocks["sm_mhz"], "sm_max_mhz": clocks["sm_max_mhz"], "reasons": clocks["reasons"],
                        "samples": clocks["samples"]},
@@ -532,10 +665,24 @@ def main():
                 "ms_per_step": e2e["ms"], "gpu_launches_per_step": e2e["launches"],
                 "path": "sb_ibss_ind (C ABI): pinned int8 genotypes -> device column statistics -> IBSS -> posterior tables to pinned host",
             }
+        if api:
+            line["e2e_api"] = {
+                "value": api["loci"] * world / (api["ms"] / 1e3), "unit": "loci/s", "ms_per_step": api["ms"],
+                "loci_per_gpu": api["loci"], "steps": 1, "warmup": 1, "credible_sets_rank0": api["n_cs"],
+                "path": "sushie_b200.infer_sushie_batch: numpy genotypes / phenotypes in -> SushieResult (priors, "
+                        "posteriors, PIPs, credible-set and alpha tables) out, one call for the whole batch",
+            }
         if dense:
             dense["peak"] = peak
             dense["frac"] = dense["achieved"] / peak
             line["roofline_dense_fp64"] = dense
+        if ss_arm:
+            ss_arm["peak"] = peak
+            ss_arm["frac"] = ss_arm["achieved"] / peak
+            line["roofline_ss_f32"] = ss_arm
+        if parity:
+            line["parity"] = parity
+        line["nonfinite_loci_rank0"] = n_nonfinite
         if cpu_baseline:
             line["cpu_baseline"] = cpu_baseline
         print(json.dumps(line), flush=True)

@@ -47,6 +47,12 @@ extern "C" {
 #define SB_ENOMEM (-3)   /* device or host allocation failed */
 #define SB_ENODEV (-4)   /* no usable CUDA device */
 
+/* sb_result.status */
+#define SB_STATUS_OK 0
+#define SB_STATUS_NONFINITE 1 /* the ELBO became NaN (posterior precision not positive definite, non-finite input):
+                                 the reference's "ELBO decreased" branch ran -- previous iteration returned,
+                                 elbo_increase == 0 (infer.py:523-533) */
+
 /* element types of genotype / LD inputs and of their device storage */
 #define SB_F64 0
 #define SB_F32 1
@@ -121,7 +127,7 @@ typedef struct {
   double *elbo;              /* [max_iter + 1], elbo[0] = -inf, entries past n_iter untouched */
   int32_t n_iter;            /* outer iterations executed */
   int32_t elbo_increase;     /* 0 => ELBO decreased, previous iteration returned */
-  int32_t status;            /* 0 ok */
+  int32_t status;            /* SB_STATUS_* */
   int32_t reserved;
 } sb_result;
 

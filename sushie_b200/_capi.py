@@ -305,6 +305,7 @@ class RawFit:
         self._elbo = np.full(max_iter + 1, np.nan)
         self.n_iter = 0
         self.elbo_increase = True
+        self.status = 0  # SB_STATUS_*: 1 = the run stopped on a NaN ELBO
 
     def fill(self, s: SbResult):
         for name in ("alpha", "post_mean", "post_mean_sq", "weighted_sum_covar", "kl", "log_bf", "effect_covar", "resid_var"):
@@ -314,6 +315,7 @@ class RawFit:
     def finish(self, s: SbResult):
         self.n_iter = int(s.n_iter)
         self.elbo_increase = bool(s.elbo_increase)
+        self.status = int(s.status)
         self.elbo = self._elbo[: self.n_iter + 1].copy()
 
 
@@ -498,6 +500,17 @@ def get_engine(device: int = 0) -> Engine:
             eng = Engine(device)
             _engines[key] = eng
         return eng
+
+
+def release_thread_engines() -> None:
+    """Close and forget the engines of the calling thread.  Short-lived worker threads (``batch.run_sharded``
+    starts one per GPU and call) must not leave their ``sb_ctx`` -- a stream and events -- behind."""
+    me = threading.get_ident()
+    with _engines_lock:
+        mine = [key for key in _engines if key[0] == me]
+        engines = [_engines.pop(key) for key in mine]
+    for eng in engines:
+        eng.close()
 
 
 def device_count() -> int:

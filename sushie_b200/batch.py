@@ -5,8 +5,9 @@ independent IBSS problem -- the reference parallelises only by running one proce
 (``misc/run_sushie.sh``) -- so there is no data-path collective: problems are cut into
 chunks (cost-sorted, longest first), one worker per GPU pulls chunks from a shared queue
 until it is empty, and results are put back in input order.  A locus is never split across
-GPUs.  The same planner is used by ``bench.py`` under ``torchrun`` (one process per GPU),
-where the queue head is a ``torch.distributed`` store counter instead of a thread lock.
+GPUs.  Under ``torchrun`` (one process per GPU: ``run_distributed``, used by ``bench.py``'s config-5 arm and
+``scripts/bench_cv.py``) every rank plans the same global chunk list and the queue head is an atomic counter in
+the ``torch.distributed`` store (``StoreQueue``) instead of a thread lock.
 """
 from __future__ import annotations
 
@@ -189,6 +190,8 @@ def run_sharded(preps: Sequence, runner: Callable, devices: Optional[Sequence[in
             drain(q, chunks, preps, runner, dev, results, trace, defer)
         except BaseException as exc:  # surfaced after join
             errors.append(exc)
+        finally:
+            _capi.release_thread_engines()  # this thread ends here: do not leak its sb_ctx
 
     threads = [threading.Thread(target=work, args=(d,), daemon=True) for d in devices]
     for t in threads:

@@ -838,10 +838,28 @@ def sushie_wrapper(data: io.CleanData, cv_data, args, snps: pd.DataFrame, meta: 
     if with_cv:
         log.logger.info(f"Start {args.cv_num}-fold cross validation as --cv is specified ")
         specs = specs + _cv_specs(args, cv_data, data.pi)
-    fits = infer.infer_sushie_batch(specs) if len(specs) > 1 else [infer.infer_sushie(**specs[0])]
     n_main = n_pop if meta else 1
+    try:
+        fits = infer.infer_sushie_batch(specs) if len(specs) > 1 else [infer.infer_sushie(**specs[0])]
+    except Exception:
+        if not with_cv:
+            raise
+        # The reference writes the fine-mapping outputs before it starts cross validation (cli.py:1863-1906), so a
+        # failing fold (validation, memory of the larger batch) must not cost them: fit and write the main
+        # problem on its own, then let the error surface as the reference's `_run_cv` would.
+        log.logger.warning("The batch holding the cross-validation folds failed; writing the fine-mapping outputs first.")
+        main = [infer.infer_sushie(**specs[0])]
+        _ind_emit(main, None, data, None, _without_cv(args), snps, meta, mega)
+        raise
     _ind_emit(fits[:n_main], fits[n_main:] if with_cv else None, data, cv_data, args, snps, meta, mega)
     return None
+
+
+def _without_cv(args):
+    """A copy of the parsed arguments with ``--cv`` switched off (outputs of the main fit only)."""
+    out = copy.copy(args)
+    out.cv = False
+    return out
 
 
 def sushie_wrapper_ss(data: io.ssData, args, snps: pd.DataFrame, meta: bool = False) -> None:

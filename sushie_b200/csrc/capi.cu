@@ -509,7 +509,7 @@ static int batch_create(sb_ctx* ctx, const std::vector<GenericProblem>& gp, bool
   const int C = b->team_size;
 
   // arena layout
-  Bump bump;
+  Bump bump, small;
   std::vector<ProbLayout> lay(n_probs);
   const size_t probs_off = bump.take(sizeof(ProbDev) * n_probs);
   const size_t ids_off = bump.take(sizeof(int) * n_probs);
@@ -541,17 +541,19 @@ static int batch_create(sb_ctx* ctx, const std::vector<GenericProblem>& gp, bool
     }
     h.nrows = nrows;
     const size_t Kp = static_cast<size_t>(g.K) * ge.p_pad;
-    l.y = bump.take(sizeof(double) * nrows);
-    l.z = ss ? bump.take(sizeof(double) * nrows) : 0;
+    // host-filled small vectors live in one contiguous region (offsets relative to its base for now): the whole
+    // batch's priors, phenotypes / z-scores and prior weights go up in ONE copy instead of ~10 per locus
+    (ss ? l.z : l.y) = small.take(sizeof(double) * nrows, 16);
+    if (ss) l.y = bump.take(sizeof(double) * nrows);  // Xty, formed on device from z
+    l.pi_raw = g.pi ? small.take(sizeof(double) * g.p, 16) : 0;
+    l.ecov0 = small.take(sizeof(double) * g.L * g.K * g.K, 16);
+    l.rv0 = small.take(sizeof(double) * g.K, 16);
+    l.adjt = small.take(sizeof(double) * g.K * g.K, 16);
+    l.adjp = small.take(sizeof(double) * g.K * g.K, 16);
     l.logpi = bump.take(sizeof(double) * g.p);
-    l.pi_raw = bump.take(sizeof(double) * g.p);
     l.xtx = bump.take(sizeof(double) * Kp);
     l.cmean = opts.storage == SB_I8 ? bump.take(sizeof(double) * Kp) : 0;
     l.cisd = opts.storage == SB_I8 ? bump.take(sizeof(double) * Kp) : 0;
-    l.ecov0 = bump.take(sizeof(double) * g.L * g.K * g.K);
-    l.rv0 = bump.take(sizeof(double) * g.K);
-    l.adjt = bump.take(sizeof(double) * g.K * g.K);
-    l.adjp = bump.take(sizeof(double) * g.K * g.K);
     l.r = bump.take(sizeof(double) * nrows);
     l.xb = bump.take(sizeof(double) * nrows * g.L);
     l.xty = ss ? 0 : bump.take(sizeof(double) * Kp);
@@ -568,6 +570,17 @@ static int batch_create(sb_ctx* ctx, const std::vector<GenericProblem>& gp, bool
     l.meta = metas_off + sizeof(int) * 8 * static_cast<size_t>(i);
     h.elbo_off = l.elbo;
     h.meta_off = l.meta;
+  }
+  const size_t small_bytes = align_up(small.off, 256);
+  const size_t small_base = bump.take(small_bytes);
+  for (int i = 0; i < n_probs; ++i) {
+    ProbLayout& l = lay[i];
+    (ss ? l.z : l.y) += small_base;
+    if (gp[i].pi) l.pi_raw += small_base;
+    l.ecov0 += small_base;
+    l.rv0 += small_base;
+    l.adjt += small_base;
+    l.adjp += small_base;
   }
   // staging for the batched column prologue: as many input matrices as fit under the cap share one launch
   size_t staging_total = 0;
@@ -622,7 +635,16 @@ static int batch_create(sb_ctx* ctx, const std::vector<GenericProblem>& gp, bool
   SB_CUDA_B(cudaMemsetAsync(b->d_ctl, 0, sizeof(int) * 64, st));
   SB_CUDA_B(cudaEventRecord(ctx->ev[2], st));
   int launches = 0;
-  std::vector<double> tmp;
+  std::vector<unsigned char> small_host(small_bytes, 0);
+  struct SsPrep {
+    const void* ld;
+    const double* z;
+    double ns;
+    int p, p_pad;
+    double *xty, *xtx;
+  };
+  std::vector<SsPrep> ss_prep;
+  int p_max_all = 0;
   // batched column prologue: matrices are staged back to back, described, and standardised by one launch per
   // staging fill (and per input type)
   std::vector<sb::PrepDesc> pending;
@@ -750,24 +772,19 @@ static int batch_create(sb_ctx* ctx, const std::vector<GenericProblem>& gp, bool
     const int KK = g.K * g.K;
     h.ecov0.assign(g.effect_covar, g.effect_covar + static_cast<size_t>(g.L) * KK);
     h.rv0.assign(g.resid_var, g.resid_var + g.K);
-    SB_CUDA_B(cudaMemcpyAsync(A + l.ecov0, g.effect_covar, sizeof(double) * g.L * KK, cudaMemcpyHostToDevice, st));
-    SB_CUDA_B(cudaMemcpyAsync(A + l.rv0, g.resid_var, sizeof(double) * g.K, cudaMemcpyHostToDevice, st));
-    tmp.assign(2 * KK, 0.0);
+    auto host_at = [&](size_t arena_off) { return reinterpret_cast<double*>(small_host.data() + (arena_off - small_base)); };
+    std::memcpy(host_at(l.ecov0), g.effect_covar, sizeof(double) * g.L * KK);
+    std::memcpy(host_at(l.rv0), g.resid_var, sizeof(double) * g.K);
     bool times_zero = true;
     for (int t = 0; t < KK; ++t) {
-      tmp[t] = g.em ? 1.0 : g.adj_times[t];
-      tmp[KK + t] = g.em ? 0.0 : g.adj_plus[t];
-      if (tmp[t] != 0.0) times_zero = false;
+      host_at(l.adjt)[t] = g.em ? 1.0 : g.adj_times[t];
+      host_at(l.adjp)[t] = g.em ? 0.0 : g.adj_plus[t];
+      if (host_at(l.adjt)[t] != 0.0) times_zero = false;
     }
     d.skip_first_pass = (!g.em && times_zero) ? 1 : 0;
-    SB_CUDA_B(cudaMemcpyAsync(A + l.adjt, tmp.data(), sizeof(double) * KK, cudaMemcpyHostToDevice, st));
-    SB_CUDA_B(cudaMemcpyAsync(A + l.adjp, tmp.data() + KK, sizeof(double) * KK, cudaMemcpyHostToDevice, st));
-    // (pageable-source cudaMemcpyAsync returns once the source has been staged, so tmp may be reused)
-    if (g.pi) SB_CUDA_B(cudaMemcpyAsync(A + l.pi_raw, g.pi, sizeof(double) * g.p, cudaMemcpyHostToDevice, st));
-    sb::log_kernel<<<(g.p + 255) / 256, 256, 0, st>>>(
-        g.pi ? reinterpret_cast<const double*>(A + l.pi_raw) : nullptr, 1.0 / static_cast<double>(g.p),
-        reinterpret_cast<double*>(A + l.logpi), g.p);
-    ++launches;
+    if (g.pi) std::memcpy(host_at(l.pi_raw), g.pi, sizeof(double) * g.p);
+    d.pi_raw = g.pi ? reinterpret_cast<const double*>(A + l.pi_raw) : nullptr;
+    p_max_all = std::max(p_max_all, g.p);
 
     // matrices and per-row vectors
     for (int k = 0; k < g.K; ++k) {
@@ -809,25 +826,26 @@ static int batch_create(sb_ctx* ctx, const std::vector<GenericProblem>& gp, bool
         }
       }
       if (ss || direct) ++launches;
-      if (!ss) {
-        SB_CUDA_B(cudaMemcpyAsync(A + l.y + sizeof(double) * d.row0[k], g.vec[k], sizeof(double) * n,
-                                  cudaMemcpyHostToDevice, st));
-      } else {
-        SB_CUDA_B(cudaMemcpyAsync(A + l.z + sizeof(double) * d.row0[k], g.vec[k], sizeof(double) * n,
-                                  cudaMemcpyHostToDevice, st));
+      std::memcpy(host_at((ss ? l.z : l.y) + sizeof(double) * d.row0[k]), g.vec[k], sizeof(double) * n);
+      if (ss) {
         double* xty_k = reinterpret_cast<double*>(A + l.y) + d.row0[k];
         const double* z_k = reinterpret_cast<const double*>(A + l.z) + d.row0[k];
-        if (opts.storage == SB_F64)
-          sb::prep_ss_kernel<double><<<(ge.p_pad + 127) / 128, 128, 0, st>>>(
-              reinterpret_cast<const double*>(A + l.X[k]), z_k, g.ns[k], g.p, ge.p_pad, xty_k, xtx_k);
-        else
-          sb::prep_ss_kernel<float><<<(ge.p_pad + 127) / 128, 128, 0, st>>>(
-              reinterpret_cast<const float*>(A + l.X[k]), z_k, g.ns[k], g.p, ge.p_pad, xty_k, xtx_k);
-        ++launches;
+        ss_prep.push_back({A + l.X[k], z_k, g.ns[k], g.p, ge.p_pad, xty_k, xtx_k});
       }
     }
   }
   SB_CUDA_B(flush_prep());
+  // the batch's small vectors: one copy (pageable source: staged by the runtime before the call returns)
+  SB_CUDA_B(cudaMemcpyAsync(A + small_base, small_host.data(), small_bytes, cudaMemcpyHostToDevice, st));
+  for (const SsPrep& sp : ss_prep) {  // Xty / diag(XtX) need the z-scores just uploaded
+    if (opts.storage == SB_F64)
+      sb::prep_ss_kernel<double><<<(sp.p_pad + 127) / 128, 128, 0, st>>>(static_cast<const double*>(sp.ld), sp.z, sp.ns, sp.p,
+                                                                       sp.p_pad, sp.xty, sp.xtx);
+    else
+      sb::prep_ss_kernel<float><<<(sp.p_pad + 127) / 128, 128, 0, st>>>(static_cast<const float*>(sp.ld), sp.z, sp.ns, sp.p,
+                                                                      sp.p_pad, sp.xty, sp.xtx);
+    ++launches;
+  }
   SB_CUDA_B(cudaGetLastError());
   // problem table, ids grouped by K
   {
@@ -844,6 +862,10 @@ static int batch_create(sb_ctx* ctx, const std::vector<GenericProblem>& gp, bool
     b->ids_host = ids;
     SB_CUDA_B(cudaMemcpyAsync(b->d_ids, ids.data(), sizeof(int) * n_probs, cudaMemcpyHostToDevice, st));
     SB_CUDA_B(cudaMemcpyAsync(b->d_probs, b->pd.data(), sizeof(ProbDev) * n_probs, cudaMemcpyHostToDevice, st));
+    // log pi of every problem in one launch (was one launch per locus)
+    sb::log_pi_batched_kernel<<<dim3((p_max_all + 255) / 256, n_probs), 256, 0, st>>>(b->d_probs);
+    ++launches;
+    SB_CUDA_B(cudaGetLastError());
     SB_CUDA_B(cudaEventRecord(ctx->ev[3], st));
     SB_CUDA_B(cudaStreamSynchronize(st));
   }
@@ -1145,7 +1167,7 @@ extern "C" int sb_batch_fetch(sb_ctx* ctx, sb_batch* b, sb_result* results) {
     const int n_iter = meta[i * 8 + 0], inc = meta[i * 8 + 1], fb = meta[i * 8 + 2];
     r.n_iter = n_iter;
     r.elbo_increase = inc;
-    r.status = 0;
+    r.status = meta[i * 8 + 5] ? SB_STATUS_NONFINITE : SB_STATUS_OK;
     const size_t Lp = static_cast<size_t>(h.L) * h.p;
     const int K = h.K, KK = K * K;
     if (r.elbo)

@@ -78,7 +78,8 @@ struct ProbDev {
   double nscale[KMAX]; // summary level: n_k (XtX = n LD); individual level: 1
   double nsamp[KMAX];  // n_k as double for the ELBO
   const double* y;     // [nrows]   (summary level: Xty [K][p] concatenated)
-  const double* logpi; // [p]
+  double* logpi;       // [p]
+  const double* pi_raw; // [p] user prior weights, nullptr = uniform 1/p (only read by the prologue)
   const double* xtx;   // [K][p_pad] diagonal of XtX
   const double* ecov0; // [L][K][K]
   const double* rv0;   // [K]
@@ -95,6 +96,7 @@ struct ProbDev {
   double* elbo;   // [max_iter + 1]
   int* meta;      // [0]=n_iter [1]=elbo_increase [2]=final buffer (-1: initial state) [3]=n_ser
                   // [4]=status: 0 not started, 1 suspended at an iteration boundary, 2 finished
+                  // [5]=1 when the run stopped on a NaN ELBO (reported as sb_result.status)
 };
 
 struct LaunchParams {
@@ -1868,6 +1870,7 @@ __global__ void __launch_bounds__(NT, (std::is_same<XT, int8_t>::value ? SB_I8_B
       pb.meta[2] = final_buf;
       pb.meta[3] = n_ser;
       pb.meta[4] = suspended ? 1 : 2;
+      pb.meta[5] = (!inc_flag && !(elbo_last == elbo_last)) ? 1 : 0;  // SB_STATUS_NONFINITE: the ELBO became NaN
     }
     // ---- normalise the returned buffer once: alpha = softmax(w), alpha-weighted mean / second moment
     if (!suspended && final_buf >= 0) {
@@ -2036,10 +2039,12 @@ __global__ void prep_ss_kernel(const XT* __restrict__ ld, const double* __restri
   xtx[j] = ns * static_cast<double>(ld[static_cast<size_t>(j) * p_pad + j]);
 }
 
-// log pi (infer.py:721); in == nullptr means the uniform default 1/p (infer.py:302-303)
-static __global__ void log_kernel(const double* __restrict__ in, double uniform, double* __restrict__ out, int n) {
+// log pi (infer.py:721) of every problem of a batch (blockIdx.y = problem); no user weights means the uniform
+// default 1/p (infer.py:302-303)
+static __global__ void log_pi_batched_kernel(const ProbDev* __restrict__ probs) {
+  const ProbDev& P = probs[blockIdx.y];
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) out[i] = log(in ? in[i] : uniform);
+  if (i < P.p) P.logpi[i] = log(P.pi_raw ? P.pi_raw[i] : 1.0 / static_cast<double>(P.p));
 }
 
 // Pad-copy rows: in [n][p] -> out [n][p_pad] with zero tail, optional type conversion.
@@ -2061,6 +2066,10 @@ __global__ void pad_rows_kernel(const IT* __restrict__ in, int n, int p, int p_p
 // rows at a time (32, fewer for sets too large for that); every thread owns 4 x 4 tiles of the upper triangle
 // and accumulates them in registers over the rows in row order (so the sums do not depend on the tiling).
 constexpr int PUR_ROWS = 32;
+
+// min that propagates NaN like jnp.min (infer.py:954-963): a NaN correlation (monomorphic column, NaN LD entry)
+// must make the purity NaN so that `purity > threshold` is false and the set is dropped, as in the reference.
+__device__ __forceinline__ double nan_min(double a, double b) { return (a != a || b != b) ? CUDART_NAN : fmin(a, b); }
 
 __host__ __device__ inline size_t purity_smem_bytes(int m, int rows) {
   const size_t m_pad = static_cast<size_t>((m + 3) / 4) * 4;
@@ -2084,7 +2093,7 @@ __global__ void __launch_bounds__(256) purity_kernel(const ProbDev* __restrict__
   if (SS) {
     for (int e = threadIdx.x; e < m * m; e += blockDim.x) {
       const int a = e / m, b = e % m;
-      best = fmin(best, fabs(static_cast<double>(X[static_cast<size_t>(sel[a]) * p_pad + sel[b]])));
+      best = nan_min(best, fabs(static_cast<double>(X[static_cast<size_t>(sel[a]) * p_pad + sel[b]])));
     }
   } else {
     constexpr bool I8 = sizeof(XT) == 1;
@@ -2149,18 +2158,18 @@ __global__ void __launch_bounds__(256) purity_kernel(const ProbDev* __restrict__
         for (int i = 0; i < 4; ++i)
 #pragma unroll
           for (int j = 0; j < 4; ++j)
-            if (4 * ta + i < m && 4 * tb + j < m) best = fmin(best, fabs(acc[i][j] / n));
+            if (4 * ta + i < m && 4 * tb + j < m) best = nan_min(best, fabs(acc[i][j] / n));
       }
     }
   }
   // block min
   __shared__ double red[32];
-  for (int o = 16; o > 0; o >>= 1) best = fmin(best, __shfl_xor_sync(0xffffffffu, best, o));
+  for (int o = 16; o > 0; o >>= 1) best = nan_min(best, __shfl_xor_sync(0xffffffffu, best, o));
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = best;
   __syncthreads();
   if (threadIdx.x == 0) {
     double b = red[0];
-    for (int w = 1; w < static_cast<int>(blockDim.x >> 5); ++w) b = fmin(b, red[w]);
+    for (int w = 1; w < static_cast<int>(blockDim.x >> 5); ++w) b = nan_min(b, red[w]);
     out[set * KMAX + k] = b;
   }
 }

@@ -146,23 +146,29 @@ def read_triplet(path: str) -> Tuple[pd.DataFrame, pd.DataFrame, np.ndarray]:
 
 
 def _vcf_dosage(field: str, gt_pos: int, cache: dict) -> float:
-    """``2 - gt_type`` of one sample column (cyvcf2 ``gts012``: 0 hom-ref, 1 het, 2 hom-alt, 3 unknown)."""
+    """``2 - gt_type`` of one sample column, with cyvcf2's ``gts012`` genotype classes (``VCF(path, gts012=True)``,
+    default ``strict_gt=False``; ``io.py:243-255`` of the reference): 0 hom-ref, 1 het, 2 hom-alt, 3 unknown -> NaN.
+
+    Diploid ``a/b``: both alleles missing -> unknown; ``0/0`` -> hom-ref; ``a == b != 0`` (``1/1``, ``2/2``) -> hom-alt;
+    ``a != b`` -> het, where a missing allele counts as different (``0/.``, ``./1``) and so does a second ALT
+    (``1/2``).  Haploid ``a``: ``0`` -> hom-ref, ``1`` -> hom-alt, anything else unknown."""
     hit = cache.get(field)
     if hit is not None:
         return hit
     gt = field.split(":")[gt_pos] if gt_pos >= 0 else "."
-    alleles = [a for a in gt.replace("|", "/").split("/")]
-    known = [a for a in alleles if a not in (".", "")]
-    if not known:
+    alleles = [-1 if a in (".", "") else int(a) for a in gt.replace("|", "/").split("/")]
+    if all(a < 0 for a in alleles):
         val = float("nan")
+    elif len(alleles) == 1:
+        val = 2.0 if alleles[0] == 0 else (0.0 if alleles[0] == 1 else float("nan"))
     else:
-        n_alt = sum(1 for a in known if a != "0")
-        if n_alt == 0:
+        a, b = alleles[0], alleles[1]
+        if a == 0 and b == 0:
             val = 2.0
-        elif n_alt == len(known) and len(known) == len(alleles):
-            val = 0.0
-        else:
+        elif a != b:
             val = 1.0
+        else:
+            val = 0.0
     cache[field] = val
     return val
 

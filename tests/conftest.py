@@ -9,10 +9,14 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 GOLDEN = os.path.join(ROOT, "tests", "golden")
+SCRIPTS = os.path.join(ROOT, "scripts")
+if SCRIPTS not in sys.path:
+    sys.path.append(SCRIPTS)  # bench_cv / bench_ss: generators of the BASELINE.json config 4 / 5 inputs
 
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+    config.addinivalue_line("markers", "slow: full-size BASELINE.json configuration (tens of seconds)")
 
 
 @pytest.fixture(scope="session")
@@ -37,3 +41,25 @@ def engine_lib():
 
     build.build()
     return _capi.load_library()
+
+
+def _load_golden(name):
+    path = os.path.join(GOLDEN, name)
+    if not os.path.exists(path):
+        pytest.fail(f"{path} missing: run tests/golden/make_golden.py in the build container")
+    return np.load(path)
+
+
+@pytest.fixture(scope="session")
+def golden_headline():
+    return _load_golden("headline_genes.npz")
+
+
+@pytest.fixture(scope="session")
+def golden_config5():
+    return _load_golden("config5_gene.npz")
+
+
+@pytest.fixture(scope="session")
+def golden_config4():
+    return _load_golden("config4_summary.npz")

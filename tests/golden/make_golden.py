@@ -1,24 +1,29 @@
 #!/usr/bin/env python
 """Generate the committed golden fixtures under ``tests/golden/``.
 
-Run in the build container only (it reads ``/root/reference/data``, which does not
-exist on the GPU box):
+Run in the build container only (it reads ``/root/reference``, which does not exist on the GPU box):
 
-    python tests/golden/make_golden.py
+    python tests/golden/make_golden.py [ind] [ss] [syn] [headline] [config5] [config4]   (default: all)
+    python tests/golden/make_golden.py --oracle ...      (outputs of oracle/ instead; for diffing only)
+
+**What produces the numbers.**  By default every expected output below comes from the REFERENCE'S OWN SOURCE --
+``/root/reference/sushie/infer.py`` / ``infer_ss.py`` / ``utils.py`` / ``cli.py`` imported unmodified and executed
+through ``tests/refshim`` (stand-in ``jax`` / ``equinox`` modules backed by numpy fp64; see its docstring for the
+primitive-by-primitive substitution).  The real jax wheels are not installable here, so this is the strongest pin
+available: the reference's algorithm text runs line by line; only the array library underneath differs.
 
 Outputs
-  * ``example_ind.npz``  -- config 1: bundled EUR+AFR VCF + phenotypes + covariates after
-    the CLI's QC order (``cli.py:897-1231``: impute, MAF 0.01, de-dup, common subjects,
-    common SNPs, allele match/flip, drop ambiguous), as raw int8 REF-allele counts
-    (``io.py:243-255``: ``bed = 2 - gt_types``) plus oracle outputs at ``min_tol`` 1e-3
-    (CLI default) and 1e-4 (API default).
-  * ``example_ss.npz``   -- config 2: bundled ``*.ld`` + ``*.gwas`` z-scores for EUR+AFR and
-    EUR+AFR+EAS with ns = 489/639/481, plus oracle outputs.
-  * ``synthetic_small.npz`` -- seeded synthetic loci (k in 1..3) with oracle outputs.
-
-The oracle (``oracle/``) is a numpy restatement of the reference; the reference itself
-cannot be executed here (no jax), so these are *oracle* goldens, anchored externally
-only by the documented causal SNPs rs1886340 / rs10914958 (``docs/manual.rst:88``).
+  * ``example_ind.npz``  -- config 1: bundled EUR+AFR VCF + phenotypes + covariates after the CLI's QC order
+    (``cli.py:897-1231``), as raw int8 REF-allele counts (``io.py:243-255``) plus ``infer_sushie`` outputs at
+    ``min_tol`` 1e-3 (CLI default) and 1e-4 (API default).
+  * ``example_ss.npz``   -- config 2: bundled ``*.ld`` + ``*.gwas`` z-scores for EUR+AFR and EUR+AFR+EAS with
+    ns = 489/639/481, plus ``infer_sushie_ss`` outputs.
+  * ``synthetic_small.npz`` -- seeded synthetic loci (k in 1..4, option mixes) with outputs.
+  * ``headline_genes.npz`` -- config 3: genes 0..3 of ``bench.make_gene`` (k=3, n=500, p=2000, L=10; 0/1/2/3 causal
+    SNPs) fitted TO CONVERGENCE at ``min_tol`` 1e-4 and 1e-3 (inputs are regenerated from the seed by the tests).
+  * ``config5_gene.npz`` -- config 5: gene 7 of ``scripts/bench_cv`` (ragged p = 1138): the reference's
+    ``cli._prepare_cv`` row shuffles / folds, the full fit, the 5 fold fits and ``cli._run_cv``'s scores.
+  * ``config4_summary.npz`` -- config 4: ``scripts/bench_ss.make_locus`` (k=3, p=10 000 LD), 3 fixed iterations.
 """
 from __future__ import annotations
 
@@ -31,9 +36,37 @@ import pandas as pd
 HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.abspath(os.path.join(HERE, "..", "..")))
 
+sys.path.insert(0, os.path.abspath(os.path.join(HERE, "..")))
+sys.path.insert(0, os.path.abspath(os.path.join(HERE, "..", "..", "scripts")))
+
 from oracle import credible_sets, ibss  # noqa: E402
 
 DATA = "/root/reference/data"
+USE_ORACLE = "--oracle" in sys.argv
+_REF = None
+
+
+def reference():
+    """The reference's modules, executed through the numpy-backed jax stand-in (tests/refshim)."""
+    global _REF
+    if _REF is None:
+        import refshim
+
+        _REF = refshim.load_reference(("log", "utils", "infer", "infer_ss", "io", "cli"))
+    return _REF
+
+
+class _RefFit:
+    """Adapter: the reference's ``SushieResult`` under the attribute names ``pack_fit`` reads."""
+
+    def __init__(self, res):
+        self.n_iter = len(res.elbo) - 1
+        self.elbo = np.asarray(res.elbo, dtype=float)
+        self.elbo_increase = bool(res.elbo_increase)
+        self.l_order = np.asarray(res.l_order)
+        self.posteriors = res.posteriors
+        self.priors = res.priors
+        self.sample_size = np.asarray(res.sample_size)
 
 
 def read_vcf_text(path):
@@ -110,21 +143,24 @@ def qc_individual(ancestries):
     return np.asarray(snps.snp.tolist(), dtype=str), Xs, ys, cvs
 
 
-def pack_fit(prefix, fit, cs_out, out):
+def pack_fit(prefix, fit, cs_out, out, slim=False):
+    """``slim``: large loci keep alpha and the summed weights only (no per-effect means / log Bayes factors)."""
     cs, alphas, pip_all, pip_cs = cs_out
     out[f"{prefix}_n_iter"] = fit.n_iter
-    out[f"{prefix}_elbo"] = fit.elbo
-    out[f"{prefix}_elbo_increase"] = fit.elbo_increase
-    out[f"{prefix}_l_order"] = fit.l_order
-    out[f"{prefix}_alpha"] = fit.posteriors.alpha
-    out[f"{prefix}_post_mean"] = fit.posteriors.post_mean
-    out[f"{prefix}_wsc"] = fit.posteriors.weighted_sum_covar
-    out[f"{prefix}_kl"] = fit.posteriors.kl
-    out[f"{prefix}_log_bf"] = fit.posteriors.log_bf
-    out[f"{prefix}_effect_covar"] = fit.priors.effect_covar
-    out[f"{prefix}_resid_var"] = fit.priors.resid_var
-    out[f"{prefix}_pip_all"] = pip_all
-    out[f"{prefix}_pip_cs"] = pip_cs
+    out[f"{prefix}_elbo"] = np.asarray(fit.elbo, dtype=float)
+    out[f"{prefix}_elbo_increase"] = bool(fit.elbo_increase)
+    out[f"{prefix}_l_order"] = np.asarray(fit.l_order)
+    out[f"{prefix}_alpha"] = np.asarray(fit.posteriors.alpha)
+    out[f"{prefix}_weights"] = np.asarray(fit.posteriors.post_mean).sum(axis=0)
+    if not slim:
+        out[f"{prefix}_post_mean"] = np.asarray(fit.posteriors.post_mean)
+        out[f"{prefix}_log_bf"] = np.asarray(fit.posteriors.log_bf)
+    out[f"{prefix}_wsc"] = np.asarray(fit.posteriors.weighted_sum_covar)
+    out[f"{prefix}_kl"] = np.asarray(fit.posteriors.kl)
+    out[f"{prefix}_effect_covar"] = np.asarray(fit.priors.effect_covar)
+    out[f"{prefix}_resid_var"] = np.asarray(fit.priors.resid_var)
+    out[f"{prefix}_pip_all"] = np.asarray(pip_all)
+    out[f"{prefix}_pip_cs"] = np.asarray(pip_cs)
     out[f"{prefix}_cs_index"] = cs.CSIndex.values.astype(np.int64)
     out[f"{prefix}_cs_snp"] = cs.SNPIndex.values.astype(np.int64)
     purity_cols = [c for c in alphas.columns if c.startswith("purity_l")]
@@ -134,6 +170,11 @@ def pack_fit(prefix, fit, cs_out, out):
 
 
 def fit_and_cs_ind(Xs, ys, covar, **kw):
+    if not USE_ORACLE:
+        res = reference().infer.infer_sushie(
+            [np.array(x, dtype=float) for x in Xs], [np.array(y, dtype=float) for y in ys],
+            None if covar is None else [np.array(c, dtype=float) for c in covar], **kw)
+        return _RefFit(res), (res.cs, res.alphas, np.asarray(res.pip_all), np.asarray(res.pip_cs))
     cs_kw = {k: kw.pop(k) for k in list(kw) if k in ("threshold", "purity", "purity_method", "max_select", "seed")}
     fit = ibss.fit_individual(Xs, ys, covar, **kw)
     cs_args = dict(threshold=0.95, purity=0.5, purity_method="weighted", max_select=250, seed=12345)
@@ -143,6 +184,9 @@ def fit_and_cs_ind(Xs, ys, covar, **kw):
 
 
 def fit_and_cs_ss(lds, ns, zs, **kw):
+    if not USE_ORACLE:
+        res = reference().infer_ss.infer_sushie_ss(np.array(lds, dtype=float), np.array(ns), np.array(zs, dtype=float), **kw)
+        return _RefFit(res), (res.cs, res.alphas, np.asarray(res.pip_all), np.asarray(res.pip_cs))
     fit = ibss.fit_summary(lds, ns, zs, **kw)
     cs_out = credible_sets.make_cs(
         fit.posteriors.alpha, fit.posteriors.log_bf, fit.sample_size, lds=fit.lds,
@@ -270,11 +314,109 @@ def golden_synthetic():
     np.savez_compressed(os.path.join(HERE, "synthetic_small.npz"), **out)
 
 
+# ---- BASELINE.json configs 3, 5, 4 at their real shapes ------------------------------------------------
+
+
+def _headline_job(args):
+    import warnings
+
+    warnings.filterwarnings("ignore")
+    g, tol = args
+    import bench
+
+    Xs, ys = bench.make_gene(g)
+    fit, cs_out = fit_and_cs_ind([x.astype(float) for x in Xs], ys, None, L=bench.L_EFF, min_tol=tol)
+    out = {}
+    pack_fit(f"g{g}_{'tol4' if tol == 1e-4 else 'tol3'}", fit, cs_out, out, slim=True)
+    return g, tol, fit.n_iter, out
+
+
+def golden_headline(genes=(0, 1, 2, 3)):
+    import multiprocessing as mp
+
+    jobs = [(g, tol) for g in genes for tol in (1e-4, 1e-3)]
+    out = {"genes": np.asarray(genes)}
+    with mp.get_context("fork").Pool(min(len(jobs), os.cpu_count() or 1)) as pool:
+        for g, tol, n_iter, part in pool.imap_unordered(_headline_job, jobs):
+            out.update(part)
+            print(f"headline gene {g} min_tol={tol}: n_iter={n_iter}", flush=True)
+    np.savez_compressed(os.path.join(HERE, "headline_genes.npz"), **out)
+
+
+def golden_config5(gene=7, cv_num=5, seed=12345):
+    import types
+
+    import bench
+    import bench_cv
+
+    ref = reference()
+    p = bench_cv.gene_width(gene, 500, 4000)
+    Xs, ys = bench.make_gene(gene, bench.N_IND, p)
+    out = {"gene": gene, "p": p, "cv_num": cv_num, "seed": seed}
+    # the row shuffles themselves: run the reference's splitter on row-index "genotypes"
+    idx_folds = ref.cli._prepare_cv([np.arange(x.shape[0])[:, None] for x in Xs], [np.asarray(y, float) for y in ys], cv_num, seed)
+    folds = ref.cli._prepare_cv([x.astype(float) for x in Xs], [np.asarray(y, float) for y in ys], cv_num, seed)
+    for j in range(cv_num):
+        for a in range(len(Xs)):
+            out[f"fold{j}_train_rows{a}"] = np.asarray(idx_folds[j].train_geno[a])[:, 0].astype(np.int64)
+            out[f"fold{j}_valid_rows{a}"] = np.asarray(idx_folds[j].valid_geno[a])[:, 0].astype(np.int64)
+            # copies: infer_sushie standardises its inputs in place (infer.py:326-333)
+            out[f"fold{j}_train_pheno{a}"] = np.array(folds[j].train_pheno[a], dtype=float)
+            out[f"fold{j}_valid_pheno{a}"] = np.array(folds[j].valid_pheno[a], dtype=float)
+    fit, cs_out = fit_and_cs_ind([x.astype(float) for x in Xs], ys, None, L=bench.L_EFF, min_tol=1e-4)
+    pack_fit("full", fit, cs_out, out, slim=True)
+    print(f"config5 gene {gene} p={p}: full fit n_iter={fit.n_iter}", flush=True)
+    # cli._run_cv with its infer_sushie calls recorded (cli.py:378-419)
+    captured = []
+    real = ref.infer.infer_sushie
+
+    def recording(*a, **k):
+        res = real(*a, **k)
+        captured.append(res)
+        return res
+
+    args = types.SimpleNamespace(cv_num=cv_num, L=bench.L_EFF, no_scale=False, no_regress=False, no_update=False,
+                                 resid_var=None, effect_var=None, rho=None, max_iter=500, min_tol=1e-4, threshold=0.95,
+                                 purity=0.5, max_select=250, seed=seed)
+    ref.infer.infer_sushie = recording
+    try:
+        cv_res = ref.cli._run_cv(args, folds, None)
+    finally:
+        ref.infer.infer_sushie = real
+    out["cv_res"] = np.asarray(cv_res, dtype=float)  # [ancestry][adj_r2, p_value]
+    for j, res in enumerate(captured):
+        pack_fit(f"fold{j}", _RefFit(res), (res.cs, res.alphas, np.asarray(res.pip_all), np.asarray(res.pip_cs)), out, slim=True)
+        print(f"config5 fold {j}: n_iter={len(res.elbo) - 1}", flush=True)
+    print("config5 cv_res", out["cv_res"].tolist())
+    np.savez_compressed(os.path.join(HERE, "config5_gene.npz"), **out)
+
+
+def golden_config4(p=10000, iters=3):
+    import bench_ss
+
+    lds, ns, zs, causal = bench_ss.make_locus(p, np.float32)  # the fp32 LD the device stores, widened exactly
+    fit, cs_out = fit_and_cs_ss(np.stack([ld.astype(np.float64) for ld in lds]), ns, np.stack(zs), L=10, max_iter=iters,
+                                min_tol=0.0)
+    out = {"p": p, "iters": iters, "causal": causal}
+    pack_fit("c4", fit, cs_out, out, slim=True)
+    print(f"config4 p={p}: n_iter={fit.n_iter} elbo={fit.elbo[1:]}", flush=True)
+    np.savez_compressed(os.path.join(HERE, "config4_summary.npz"), **out)
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["ind", "ss", "syn"]
+    import warnings
+
+    warnings.filterwarnings("ignore")
+    which = [a for a in sys.argv[1:] if not a.startswith("--")] or ["ind", "ss", "syn", "headline", "config5", "config4"]
     if "ind" in which:
         golden_example_ind()
     if "ss" in which:
         golden_example_ss()
     if "syn" in which:
         golden_synthetic()
+    if "headline" in which:
+        golden_headline()
+    if "config5" in which:
+        golden_config5()
+    if "config4" in which:
+        golden_config4()

@@ -213,3 +213,18 @@ def test_finemap_batch_worker_processes_plumbing(tmp_path):
     for g in range(5):
         assert f"GENE{g}" in text
     assert "arguments could not be parsed" in text
+
+
+def test_vcf_genotype_classes_follow_cyvcf2_gts012(tmp_path):
+    """``read_vcf`` codes ``2 - gt_types`` with cyvcf2's ``gts012`` classes (reference ``io.py:243-255``): a
+    half-missing call and a two-ALT heterozygote are HET, ``2/2`` is HOM_ALT, haploid calls are 0 or 2 copies."""
+    calls = ["0/0", "0|1", "1/1", "./.", "0/.", "./1", "1/2", "2/2", "0", "1", ".", "2", "1|0:35"]
+    path = tmp_path / "t.vcf"
+    with open(path, "w") as fh:
+        fh.write("##fileformat=VCFv4.2\n")
+        fh.write("#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\tFORMAT\t" + "\t".join(f"s{i}" for i in range(len(calls))) + "\n")
+        fh.write("1\t100\trs1\tA\tC,G\t.\tPASS\t.\tGT:DP\t" + "\t".join(c if ":" in c else c + ":9" for c in calls) + "\n")
+    bim, fam, bed = io.read_vcf(str(path))
+    want = [2, 1, 0, np.nan, 1, 1, 1, 0, 2, 0, np.nan, np.nan, 1]
+    np.testing.assert_array_equal(bed[:, 0], np.asarray(want, dtype=float))
+    assert bim.a0[0] == "C" and bim.a1[0] == "A" and list(fam.iid) == [f"s{i}" for i in range(len(calls))]

@@ -1,5 +1,6 @@
-"""GPU parity tests: the CUDA path through the Python API / C ABI vs the committed oracle
-goldens (tests/golden/*.npz, produced by tests/golden/make_golden.py)."""
+"""GPU parity tests: the CUDA path through the Python API / C ABI vs the committed goldens
+(tests/golden/*.npz: outputs of the reference's own source run through tests/refshim, produced by
+tests/golden/make_golden.py)."""
 import numpy as np
 import pytest
 
@@ -359,3 +360,70 @@ def test_purity_of_a_whole_chunk_in_one_launch(engine_lib, storage):
             want = [np.min(np.abs(x[:, idx].T @ x[:, idx] / x.shape[0])) for x in xs]
             np.testing.assert_allclose(row, want, rtol=1e-10, atol=1e-12)
     np.testing.assert_array_equal(one, got[1])
+
+
+# ---- BASELINE.json configurations at their real shapes ------------------------------------------------
+
+
+@pytest.mark.parametrize("tol_tag,tol", [("tol4", 1e-4), ("tol3", 1e-3)])
+@pytest.mark.parametrize("gene", [0, 1, 2, 3])
+def test_headline_genes_to_convergence(engine_lib, golden_headline, gene, tol_tag, tol, geno_storage):
+    """Config 3: genes 0..3 of the bench generator (k=3, n=500, p=2000, L=10; null gene, 1, 2, 3 causal SNPs) fitted
+    TO CONVERGENCE at the API (1e-4) and CLI (1e-3) tolerances, both genotype storages, against the reference's
+    own source: same iteration count, ELBO trace, PIPs, credible sets, prior covariances."""
+    import bench
+    import sushie_b200
+
+    Xs, ys = bench.make_gene(gene)
+    res = sushie_b200.infer_sushie([x.astype(np.float64) for x in Xs], ys, L=bench.L_EFF, min_tol=tol)
+    assert_fit_matches(res, golden_headline, f"g{gene}_{tol_tag}")
+
+
+def test_config5_gene_full_and_fold_fits(engine_lib, golden_config5, geno_storage):
+    """Config 5: one ragged-width gene, the fit on all samples plus the 5 cross-validation training folds as ONE
+    device batch; every fit and the out-of-fold scores against the reference's ``_prepare_cv`` / ``_run_cv``."""
+    import bench
+    import bench_cv
+    import sushie_b200
+    from sushie_b200 import cli
+
+    g = golden_config5
+    gene, cv_num, seed = int(g["gene"]), int(g["cv_num"]), int(g["seed"])
+    p = bench_cv.gene_width(gene, 500, 4000)
+    assert p == int(g["p"]) and p % 32 != 0
+    Xs, ys = bench.make_gene(gene, bench.N_IND, p)
+    folds = cli._prepare_cv(list(Xs), list(ys), cv_num, seed)
+    for j, fold in enumerate(folds):
+        for a in range(len(Xs)):
+            np.testing.assert_array_equal(fold.train_geno[a], Xs[a][g[f"fold{j}_train_rows{a}"]])
+            np.testing.assert_allclose(fold.train_pheno[a], g[f"fold{j}_train_pheno{a}"], rtol=0, atol=1e-12)
+            np.testing.assert_allclose(fold.valid_pheno[a], g[f"fold{j}_valid_pheno{a}"], rtol=0, atol=1e-12)
+    specs = [dict(Xs=Xs, ys=ys)] + [dict(Xs=f.train_geno, ys=f.train_pheno) for f in folds]
+    fits = sushie_b200.infer_sushie_batch(specs, L=bench.L_EFF, min_tol=1e-4)
+    assert_fit_matches(fits[0], g, "full")
+    for j in range(cv_num):
+        assert_fit_matches(fits[1 + j], g, f"fold{j}")
+    scores = np.asarray(cli._cv_scores(folds, fits[1:]))
+    np.testing.assert_allclose(scores[:, 0], g["cv_res"][:, 0], atol=1e-8)             # adjusted r-squared
+    np.testing.assert_allclose(scores[:, 1], g["cv_res"][:, 1], rtol=1e-6, atol=1e-300)  # p-value
+
+
+@pytest.mark.slow
+def test_config4_full_size_fp32_storage(engine_lib, golden_config4):
+    """Config 4 at its full size: k=3, p=10 000 LD stored fp32 (1.2 GB, fp64 arithmetic), L=10, EM on, 3 fixed
+    iterations, co-operative team over the whole device, against the reference's source on the same
+    fp32-rounded LD in fp64."""
+    import bench_ss
+    import sushie_b200
+    from sushie_b200 import config
+
+    g = golden_config4
+    lds, ns, zs, causal = bench_ss.make_locus(int(g["p"]), np.float32)
+    assert np.array_equal(causal, g["causal"])
+    old = config.precision
+    config.precision = 32
+    try:
+        res = sushie_b200.infer_sushie_ss(lds, ns, zs, L=10, max_iter=int(g["iters"]), min_tol=0.0)
+    finally:
+        config.precision = old
+    assert_fit_matches(res, g, "c4")

@@ -125,3 +125,35 @@ def test_oracle_make_cs_schema(golden_syn):
     want += ["pip_all", "pip_cs"]
     assert list(alphas.columns) == want
     assert sorted(set(cs.SNPIndex.astype(int))) == sorted(set(g["k2_cs_snp"].tolist()))
+
+
+@pytest.mark.parametrize("seed,k,n,p,kw", [
+    (1, 1, (150,), 120, dict(L=3)),
+    (2, 2, (120, 100), 140, dict(L=4)),
+    (3, 3, (90, 80, 100), 130, dict(L=3, min_tol=1e-3)),
+    (4, 4, (60, 70, 80, 50), 110, dict(L=2)),
+    (5, 2, (120, 100), 140, dict(L=3, no_update=True)),
+])
+def test_fast_form_equals_literal_form(seed, k, n, p, kw):
+    """oracle/ibss_fast.py (the timed CPU arm of bench.py: cached X b_l, ERSS without a pass over X, closed-form
+    per-SNP posterior) computes what the literal restatement oracle/ibss.py computes."""
+    from oracle import ibss_fast
+
+    rng = np.random.default_rng(seed)
+    Xs = [rng.binomial(2, rng.uniform(0.1, 0.5, size=p), size=(ni, p)).astype(float) for ni in n]
+    for X in Xs:
+        X[0, X.std(axis=0) == 0] = 1.0
+    beta = np.zeros(p)
+    beta[[7, 60]] = [0.8, -0.6]
+    ys = [((X - X.mean(0)) / X.std(0)) @ beta + rng.standard_normal(X.shape[0]) for X in Xs]
+    fast = ibss_fast.fit_individual(Xs, ys, **kw)
+    lit = ibss.fit_individual(Xs, ys, no_reorder=True, **kw)
+    assert fast.n_iter == lit.n_iter and fast.elbo_increase == lit.elbo_increase
+    np.testing.assert_allclose(fast.elbo[1:], lit.elbo[1:], rtol=1e-9)
+    np.testing.assert_allclose(fast.alpha, lit.posteriors.alpha, atol=1e-9)
+    np.testing.assert_allclose(fast.post_mean, lit.posteriors.post_mean, atol=1e-9)
+    np.testing.assert_allclose(fast.weighted_sum_covar, lit.posteriors.weighted_sum_covar, rtol=1e-7, atol=1e-14)
+    np.testing.assert_allclose(fast.kl, lit.posteriors.kl, rtol=1e-7, atol=1e-9)
+    np.testing.assert_allclose(fast.log_bf, lit.posteriors.log_bf, rtol=1e-8, atol=1e-9)
+    np.testing.assert_allclose(fast.effect_covar, lit.priors.effect_covar, rtol=1e-7, atol=1e-14)
+    np.testing.assert_allclose(fast.resid_var, np.ravel(lit.priors.resid_var), rtol=1e-10)
