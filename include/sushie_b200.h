@@ -59,6 +59,10 @@ extern "C" {
 #define SB_I8 2 /* hard-call genotypes (int8). As sb_opts.storage (individual level, every problem x_dtype ==
                   SB_I8, entries in 0..127, p <= 8192): raw bytes stay resident, centring/scaling is folded into the vectors */
 
+#define SB_B2 3 /* hard calls 0/1/2 as bit planes (sb_opts.storage only; individual level, every problem x_dtype ==
+                  SB_I8, n_i <= 2048, p <= 8192): the single-effect products become table look-ups (no fp64 widening of
+                  genotypes); the one-byte matrix stays resident for the purity kernel */
+
 /* sb_opts.flags */
 #define SB_FLAG_SINGLE_PHASE 1 /* keep one team size for the whole batch (no suspend / regroup phases) */
 
@@ -108,7 +112,7 @@ typedef struct {
 typedef struct {
   int32_t max_iter;          /* reference default 500 */
   double min_tol;            /* reference default 1e-4 (CLI 1e-3) */
-  int32_t storage;           /* device storage of X / LD: SB_F64 (parity mode), SB_F32, or SB_I8 (see above) */
+  int32_t storage;           /* device storage of X / LD: SB_F64 (parity mode), SB_F32, SB_I8 or SB_B2 (see above) */
   int32_t team_size;         /* thread blocks cooperating on one locus in the first phase; 0 = choose */
   int32_t flags;             /* SB_FLAG_* */
   int32_t reserved[3];

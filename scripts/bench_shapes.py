@@ -15,6 +15,7 @@ def main():
     ap.add_argument("--L", type=int, default=10)
     ap.add_argument("--iters", type=int, default=20)
     ap.add_argument("--loci", type=int, default=148)
+    ap.add_argument("--storages", nargs="+", default=["i8", "f64"], choices=["b2", "i8", "f64"])
     ap.add_argument("--summary", action="store_true", help="summary-level sweep (banded LD, fp64 and fp32 storage)")
     args = ap.parse_args()
     from sushie_b200 import _capi
@@ -37,8 +38,8 @@ def main():
         ys = [rng.standard_normal(args.n) for _ in range(args.k)]
         ys = [(y - y.mean()) / y.std() for y in ys]
         rv = [np.var(y, ddof=1) for y in ys]
-        for name, storage, es in (("i8", _capi.SB_I8, 1), ("f64", _capi.SB_F64, 8)):
-            if name == "i8" and p > _capi.I8_MAX_SNPS:
+        for name, storage, es in (("b2", _capi.SB_B2, 1), ("i8", _capi.SB_I8, 1), ("f64", _capi.SB_F64, 8)):
+            if name not in args.storages or (name in ("i8", "b2") and p > _capi.I8_MAX_SNPS):
                 continue
             probs = [_capi.IndProblem(Xs, ys, args.L, None, rv, ec, adj.times, adj.plus, True,
                                       standardize=_capi.SB_CENTER | _capi.SB_SCALE) for _ in range(args.loci)]

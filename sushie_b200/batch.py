@@ -48,7 +48,7 @@ def plan_chunks(preps: Sequence, chunk_bytes: Optional[int] = None, chunk_loci: 
     groups: Dict[Tuple, List[int]] = {}
     for i, p in enumerate(preps):
         # loci eligible for one-byte hard-call storage get chunks of their own (storage is per batch)
-        groups.setdefault((p.max_iter, p.min_tol, bool(getattr(p, "hard_calls", False))), []).append(i)
+        groups.setdefault((p.max_iter, p.min_tol, getattr(p, "hard_calls", False)), []).append(i)
     chunks: List[List[int]] = []
     for ids in groups.values():
         ids = sorted(ids, key=lambda i: (-preps[i].problem.cost, i))

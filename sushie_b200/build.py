@@ -14,8 +14,11 @@ ROOT = os.path.dirname(HERE)
 CAPI = os.path.join(HERE, "csrc", "capi.cu")            # host side of the C ABI + small kernels
 KERNELS = os.path.join(HERE, "csrc", "ibss_kernels.cu")  # IBSS kernel instantiations, compiled once per ancestry count
 DEPS = [CAPI, KERNELS, os.path.join(HERE, "csrc", "ibss_kernel.cuh"), os.path.join(ROOT, "include", "sushie_b200.h")]
-OUT = os.path.join(HERE, "_lib", "libsushie_b200.so")
-OBJ = os.path.join(HERE, "_lib", "obj")
+# development: SUSHIE_B200_OUT builds a differently configured engine next to the shipped one (loaded through
+# SUSHIE_B200_LIB), SUSHIE_B200_DEFS adds -D switches (e.g. "-DSB_I8_ROWTEAMS=0")
+OUT = os.environ.get("SUSHIE_B200_OUT", os.path.join(HERE, "_lib", "libsushie_b200.so"))
+OBJ = os.path.join(HERE, "_lib", "obj" + ("" if "SUSHIE_B200_OUT" not in os.environ else "_" + os.path.basename(OUT)))
+EXTRA_DEFS = os.environ.get("SUSHIE_B200_DEFS", "").split()
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -43,7 +46,7 @@ def _source_hash() -> str:
     for path in DEPS:
         with open(path, "rb") as fh:
             h.update(fh.read())
-    h.update(" ".join(NVCC_FLAGS).encode())
+    h.update(" ".join(NVCC_FLAGS + EXTRA_DEFS).encode())
     h.update(os.environ.get("SUSHIE_B200_ONLY_K", "").encode())
     return h.hexdigest()
 
@@ -70,11 +73,11 @@ def build(force: bool = False, verbose: bool = False) -> str:
     dev = os.environ.get("SUSHIE_B200_ONLY_K")  # development: compile one ancestry count only
     ks = [int(dev)] if dev else [1, 2, 3, 4]
     vflags = ["-Xptxas", "-v"] if verbose else []
-    jobs = [([nvcc] + NVCC_FLAGS + ([f"-DSB_ONLY_K={int(dev)}"] if dev else []) + ["-c", "-o", os.path.join(OBJ, "capi.o"), CAPI],
+    jobs = [([nvcc] + NVCC_FLAGS + EXTRA_DEFS + ([f"-DSB_ONLY_K={int(dev)}"] if dev else []) + ["-c", "-o", os.path.join(OBJ, "capi.o"), CAPI],
              os.path.join(OBJ, "capi.o"))]
     for k in ks:
         obj = os.path.join(OBJ, f"ibss_k{k}.o")
-        jobs.append(([nvcc] + NVCC_FLAGS + vflags + [f"-DSB_K={k}", "-c", "-o", obj, KERNELS], obj))
+        jobs.append(([nvcc] + NVCC_FLAGS + EXTRA_DEFS + vflags + [f"-DSB_K={k}", "-c", "-o", obj, KERNELS], obj))
     procs = [(cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)) for cmd, _ in jobs]
     logs = []
     for cmd, proc in procs:

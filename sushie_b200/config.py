@@ -13,6 +13,8 @@ precision: int = int(os.environ.get("SUSHIE_B200_PRECISION", "64"))
 # vectors (8x less HBM traffic than fp64, same fp64 arithmetic); "dense" always stores the
 # standardised matrix at `precision`.
 genotype_storage: str = os.environ.get("SUSHIE_B200_GENO", "auto")
+# hard calls that are only 0 / 1 / 2 use the bit-plane traversal (table look-ups); 0 keeps them on the one-byte path
+bit_planes: bool = bool(int(os.environ.get("SUSHIE_B200_BIT_PLANES", "1")))
 # GPU ordinals used by the batch entry points; None = device 0 only.
 devices: Optional[List[int]] = None
 # thread blocks cooperating on one locus; 0 lets the engine choose.

@@ -219,6 +219,22 @@ static bool plan_geometry(int p, int n_max, int es, bool ss, int smem_budget, Ge
   const size_t row_bytes = static_cast<size_t>(g.p_pad) * es;
   const int pv = static_cast<int>(row_bytes / 16);  // 16-byte vectors per row
   g.fast = 0;
+  if (es == 1 && g.p_pad <= 512) {
+    // hard-call storage, narrow locus: row-team traversal (traverse_i8_rows<16, 1>): one warp owns one row at a
+    // time, every lane 16 genotype bytes of it; the 8 warps of a block work on different rows of the same band
+    g.fast = 5;
+    const int n_teams = sb::NW;
+    const size_t state = 2 * sizeof(double) * sb::I8_STATE_ROWS;       // staged (r, xb) rows behind the ring
+    const size_t xteam = sizeof(double) * n_teams * row_bytes;         // cross-team exchange of the partial G^T r
+    const size_t ring_budget = static_cast<size_t>(smem_budget) - hdr - state - xteam;
+    int rows = static_cast<int>(std::min<size_t>(sb::GMAX, (32 * 1024) / row_bytes));
+    rows = std::max(n_teams, rows / n_teams * n_teams);
+    g.G = rows;
+    g.NS = static_cast<int>(std::min<size_t>(sb::NSTAGE_MAX, ring_budget / (rows * row_bytes)));
+    g.NSEG = 1;
+    g.smem = hdr + static_cast<size_t>(g.NS) * g.G * row_bytes + state + xteam;
+    return true;
+  }
   if (es == 1) {
     // hard-call storage: every thread owns CPT 8-byte vectors of GR rows (traverse_i8)
     const int pv8 = g.p_pad / 8;
@@ -340,6 +356,7 @@ struct Bump {
 };
 
 struct ProbLayout {  // offsets inside the arena
+  size_t rbits[KMAX], cbits[KMAX];
   size_t X[KMAX], y, logpi, pi_raw, xtx, cmean, cisd, ecov0, rv0, adjt, adjp, r, xb, xty, rfull, bvec, out[2], elbo, meta, z;
   size_t out_fields[2][10];
 };
@@ -388,6 +405,8 @@ static int validate_common(sb_ctx* ctx, const P& pr, int i) {
 }
 
 static int elem_size(int dtype) { return dtype == SB_F64 ? 8 : (dtype == SB_F32 ? 4 : 1); }
+// hard-call storages keep the raw one-byte matrix resident (SB_B2 adds the bit planes next to it)
+static bool hard_storage(int storage) { return storage == SB_I8 || storage == SB_B2; }
 
 template <typename IT, typename XT>
 static void launch_prep_columns(const void* in, int in_ld, int n, int p, int p_pad, int flags, void* out,
@@ -451,18 +470,18 @@ static int batch_create(sb_ctx* ctx, const std::vector<GenericProblem>& gp, bool
     ctx->err = "max_iter must be >= 1";
     return SB_EINVAL;
   }
-  if (opts.storage != SB_F64 && opts.storage != SB_F32 && opts.storage != SB_I8) {
-    ctx->err = "storage must be SB_F64, SB_F32 or SB_I8";
+  if (opts.storage != SB_F64 && opts.storage != SB_F32 && opts.storage != SB_I8 && opts.storage != SB_B2) {
+    ctx->err = "storage must be SB_F64, SB_F32, SB_I8 or SB_B2";
     return SB_EINVAL;
   }
-  if (opts.storage == SB_I8) {
+  if (hard_storage(opts.storage)) {
     if (ss) {
-      ctx->err = "SB_I8 storage is for individual-level hard-call genotypes only";
+      ctx->err = "SB_I8 / SB_B2 storage is for individual-level hard-call genotypes only";
       return SB_EINVAL;
     }
     for (int i = 0; i < n_probs; ++i)
       if (gp[i].mat_dtype != SB_I8) {
-        ctx->err = "problem " + std::to_string(i) + ": SB_I8 storage needs x_dtype == SB_I8";
+        ctx->err = "problem " + std::to_string(i) + ": SB_I8 / SB_B2 storage needs x_dtype == SB_I8";
         return SB_EINVAL;
       }
   }
@@ -493,7 +512,22 @@ static int batch_create(sb_ctx* ctx, const std::vector<GenericProblem>& gp, bool
       n_max = std::max(n_max, g.n[k]);
       bytes += static_cast<double>(g.n[k]) * g.p * es;
     }
-    if (!plan_geometry(g.p, n_max, es, ss, smem_budget, geo[i])) {
+    if (opts.storage == SB_B2) {
+      Geometry& ge = geo[i];
+      if (g.p > 8 * sb::B2_MAX_SUB * sb::B2_TILE_COLS || n_max > sb::B2_MAX_ROWS) {
+        ctx->err = "problem " + std::to_string(i) + ": SB_B2 storage handles p <= " +
+                   std::to_string(8 * sb::B2_MAX_SUB * sb::B2_TILE_COLS) + " and n <= " + std::to_string(sb::B2_MAX_ROWS) +
+                   " per ancestry";
+        return SB_EINVAL;
+      }
+      ge.p_pad = static_cast<int>(align_up(static_cast<size_t>(g.p), 32));
+      ge.G = 8;  // (no row bands: the bit stream has its own ring)
+      ge.NS = sb::B2_NSTAGE;
+      ge.NSEG = 1;
+      ge.fast = 0;
+      ge.smem = static_cast<size_t>(smem_budget);  // table set aligned to 64 KB inside the block's window
+      bytes *= 0.5;                                // two layouts x two bit planes per genotype
+    } else if (!plan_geometry(g.p, n_max, es, ss, smem_budget, geo[i])) {
       ctx->err = "problem " + std::to_string(i) + ": p=" + std::to_string(g.p) +
                  " does not fit the shared-memory band pipeline at this storage precision";
       return SB_EINVAL;
@@ -536,7 +570,12 @@ static int batch_create(sb_ctx* ctx, const std::vector<GenericProblem>& gp, bool
       h.n[k] = g.n[k];
       nrows += g.n[k];
       l.X[k] = bump.take(static_cast<size_t>(g.n[k]) * ge.p_pad * es);
-      const bool direct = (g.mat_dtype == opts.storage) && g.standardize == 0 && opts.storage != SB_I8;
+      const bool direct = (g.mat_dtype == opts.storage) && g.standardize == 0 && !hard_storage(opts.storage);
+      if (opts.storage == SB_B2) {
+        const size_t ntiles = (static_cast<size_t>(g.p) + sb::B2_TILE_COLS - 1) / sb::B2_TILE_COLS;
+        l.rbits[k] = bump.take(ntiles * ((g.n[k] + 3) / 4) * 256);
+        l.cbits[k] = bump.take(ntiles * ((g.n[k] + 63) / 64) * 4096);
+      }
       if (!direct) staging_bytes = std::max(staging_bytes, static_cast<size_t>(g.n[k]) * g.p * elem_size(g.mat_dtype));
     }
     h.nrows = nrows;
@@ -552,8 +591,8 @@ static int batch_create(sb_ctx* ctx, const std::vector<GenericProblem>& gp, bool
     l.adjp = small.take(sizeof(double) * g.K * g.K, 16);
     l.logpi = bump.take(sizeof(double) * g.p);
     l.xtx = bump.take(sizeof(double) * Kp);
-    l.cmean = opts.storage == SB_I8 ? bump.take(sizeof(double) * Kp) : 0;
-    l.cisd = opts.storage == SB_I8 ? bump.take(sizeof(double) * Kp) : 0;
+    l.cmean = hard_storage(opts.storage) ? bump.take(sizeof(double) * Kp) : 0;
+    l.cisd = hard_storage(opts.storage) ? bump.take(sizeof(double) * Kp) : 0;
     l.r = bump.take(sizeof(double) * nrows);
     l.xb = bump.take(sizeof(double) * nrows * g.L);
     l.xty = ss ? 0 : bump.take(sizeof(double) * Kp);
@@ -590,6 +629,7 @@ static int batch_create(sb_ctx* ctx, const std::vector<GenericProblem>& gp, bool
   const size_t staging_cap = std::max(staging_bytes + 256, std::min<size_t>(staging_total, size_t(1) << 30));
   const size_t staging_off = bump.take(staging_bytes ? staging_cap : 16);
   const size_t descs_off = bump.take(sizeof(sb::PrepDesc) * static_cast<size_t>(n_probs) * KMAX);
+  const size_t pack_off = bump.take(sizeof(sb::PackDesc) * static_cast<size_t>(n_probs) * KMAX);
   // per-block scratch: partial X^T r, three reduction records, per-traversal scalars
   const int off_stat = static_cast<int>(align_up(Kp_max, 16));
   const int off_trav = off_stat + 3 * sb::STAT_STRIDE + 4;
@@ -644,6 +684,7 @@ static int batch_create(sb_ctx* ctx, const std::vector<GenericProblem>& gp, bool
     double *xty, *xtx;
   };
   std::vector<SsPrep> ss_prep;
+  std::vector<sb::PackDesc> pack_descs;  // bit-plane storage: one packing job per (problem, ancestry)
   int p_max_all = 0;
   // batched column prologue: matrices are staged back to back, described, and standardised by one launch per
   // staging fill (and per input type)
@@ -659,7 +700,7 @@ static int batch_create(sb_ctx* ctx, const std::vector<GenericProblem>& gp, bool
     const dim3 grid((pending_pmax + 127) / 128, static_cast<unsigned>(pending.size()));
     int* flag = b->d_ctl + 32;
 #define SB_PREP(IT, XT) sb::prep_columns_batched_kernel<IT, XT><<<grid, 128, 0, st>>>(d_descs, flag)
-    if (opts.storage == SB_I8) {
+    if (hard_storage(opts.storage)) {
       SB_PREP(int8_t, int8_t);
     } else if (opts.storage == SB_F64) {
       if (pending_dtype == SB_F64) SB_PREP(double, double);
@@ -726,8 +767,20 @@ static int batch_create(sb_ctx* ctx, const std::vector<GenericProblem>& gp, bool
       d.row0[k] = row;
       d.band0[k] = band;
       row += g.n[k];
-      band += (g.n[k] + ge.G - 1) / ge.G;
+      band += (opts.storage == SB_B2) ? 0 : (g.n[k] + ge.G - 1) / ge.G;  // bit-plane storage: no row bands
       d.X[k] = A + l.X[k];
+      if (opts.storage == SB_B2) {
+        d.rbits[k] = A + l.rbits[k];
+        d.cbits[k] = A + l.cbits[k];
+        sb::PackDesc pk{};
+        pk.X = reinterpret_cast<const signed char*>(A + l.X[k]);
+        pk.rbits = A + l.rbits[k];
+        pk.cbits = A + l.cbits[k];
+        pk.n = g.n[k];
+        pk.p_pad = ge.p_pad;
+        pk.ntiles = (g.p + sb::B2_TILE_COLS - 1) / sb::B2_TILE_COLS;
+        pack_descs.push_back(pk);
+      }
       h.d_X[k] = A + l.X[k];
       d.nscale[k] = ss ? g.ns[k] : 1.0;
       d.nsamp[k] = ss ? g.ns[k] : static_cast<double>(g.n[k]);
@@ -739,8 +792,9 @@ static int batch_create(sb_ctx* ctx, const std::vector<GenericProblem>& gp, bool
     d.y = reinterpret_cast<double*>(A + l.y);
     d.logpi = reinterpret_cast<double*>(A + l.logpi);
     d.xtx = reinterpret_cast<double*>(A + l.xtx);
-    d.cmean = opts.storage == SB_I8 ? reinterpret_cast<double*>(A + l.cmean) : nullptr;
-    d.cisd = opts.storage == SB_I8 ? reinterpret_cast<double*>(A + l.cisd) : nullptr;
+    d.cmean = hard_storage(opts.storage) ? reinterpret_cast<double*>(A + l.cmean) : nullptr;
+    d.cisd = hard_storage(opts.storage) ? reinterpret_cast<double*>(A + l.cisd) : nullptr;
+    d.ntiles = (g.p + sb::B2_TILE_COLS - 1) / sb::B2_TILE_COLS;
     d.ecov0 = reinterpret_cast<double*>(A + l.ecov0);
     d.rv0 = reinterpret_cast<double*>(A + l.rv0);
     d.adj_times = reinterpret_cast<double*>(A + l.adjt);
@@ -790,8 +844,8 @@ static int batch_create(sb_ctx* ctx, const std::vector<GenericProblem>& gp, bool
     for (int k = 0; k < g.K; ++k) {
       const int n = g.n[k];
       double* xtx_k = reinterpret_cast<double*>(A + l.xtx) + static_cast<size_t>(k) * ge.p_pad;
-      const bool direct = (g.mat_dtype == opts.storage) && g.standardize == 0 && opts.storage != SB_I8;
-      if (opts.storage == SB_I8) {
+      const bool direct = (g.mat_dtype == opts.storage) && g.standardize == 0 && !hard_storage(opts.storage);
+      if (hard_storage(opts.storage)) {
         double* cmean_k = reinterpret_cast<double*>(A + l.cmean) + static_cast<size_t>(k) * ge.p_pad;
         double* cisd_k = reinterpret_cast<double*>(A + l.cisd) + static_cast<size_t>(k) * ge.p_pad;
         h.d_cmean[k] = cmean_k;
@@ -835,6 +889,17 @@ static int batch_create(sb_ctx* ctx, const std::vector<GenericProblem>& gp, bool
     }
   }
   SB_CUDA_B(flush_prep());
+  if (!pack_descs.empty()) {
+    // bit planes of every (problem, ancestry) from the one-byte matrices the column prologue has just written
+    sb::PackDesc* d_pack = reinterpret_cast<sb::PackDesc*>(A + pack_off);
+    SB_CUDA_B(cudaMemcpyAsync(d_pack, pack_descs.data(), sizeof(sb::PackDesc) * pack_descs.size(), cudaMemcpyHostToDevice, st));
+    for (size_t first_desc = 0; first_desc < pack_descs.size(); first_desc += 32768) {  // grid.y limit
+      const unsigned count = static_cast<unsigned>(std::min<size_t>(32768, pack_descs.size() - first_desc));
+      sb::pack_b2_kernel<<<dim3(64, count), 256, 0, st>>>(d_pack + first_desc, b->d_ctl + 32);
+      ++launches;
+    }
+    SB_CUDA_B(cudaGetLastError());
+  }
   // the batch's small vectors: one copy (pageable source: staged by the runtime before the call returns)
   SB_CUDA_B(cudaMemcpyAsync(A + small_base, small_host.data(), small_bytes, cudaMemcpyHostToDevice, st));
   for (const SsPrep& sp : ss_prep) {  // Xty / diag(XtX) need the z-scores just uploaded
@@ -869,11 +934,12 @@ static int batch_create(sb_ctx* ctx, const std::vector<GenericProblem>& gp, bool
     SB_CUDA_B(cudaEventRecord(ctx->ev[3], st));
     SB_CUDA_B(cudaStreamSynchronize(st));
   }
-  if (opts.storage == SB_I8) {
+  if (hard_storage(opts.storage)) {
     int bad = 0;
     SB_CUDA_B(cudaMemcpy(&bad, b->d_ctl + 32, sizeof(int), cudaMemcpyDeviceToHost));
     if (bad) {
-      ctx->err = "SB_I8 storage needs hard-call genotypes in 0..127 (negative entry found)";
+      ctx->err = (bad & 2) ? "SB_B2 storage needs hard-call genotypes 0 / 1 / 2"
+                           : "SB_I8 storage needs hard-call genotypes in 0..127 (negative entry found)";
       return fail(SB_EINVAL);
     }
   }
@@ -1049,6 +1115,7 @@ extern "C" int sb_batch_run(sb_ctx* ctx, sb_batch* b, sb_run_stats* stats) {
       // one block per SM, except single-block teams of the hard-call kernel, which is built to
       // co-reside (two loci per SM overlap each other's barriers and posterior phases)
       const int per_sm_cap = (b->storage == SB_I8 && C == 1) ? SB_I8_BLOCKS_PER_SM : 1;
+      (void)0;
       max_teams = std::min(max_teams, per_sm_cap * ctx->num_sms / C);
       if (max_teams < 1) {
         ctx->err = "kernel does not fit on the device (team_size=" + std::to_string(C) + ", smem=" +
@@ -1290,7 +1357,7 @@ extern "C" int sb_batch_purity_many(sb_ctx* ctx, sb_batch* b, int n_sets, const 
     if (smem > 48 * 1024) cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);    \
     kf<<<grid, 256, smem, st>>>(b->d_probs, d_prob, d_idx, d_off, m_pad_max, rows, d_out);                     \
   } while (0)
-  if (b->storage == SB_I8) {
+  if (hard_storage(b->storage)) {
     SB_PUR(int8_t, false);
   } else if (b->storage == SB_F64) {
     if (b->ss)

@@ -49,6 +49,15 @@ constexpr int I8_STATE_ROWS = 2048;  // hard-call path: band rows whose (r, xb) 
 constexpr int SS_CHUNK_ROWS = 256;  // summary-level register-tile path: rows whose partial sums are parked in shared memory
 constexpr int NSYM_MAX = KMAX * (KMAX + 1) / 2;
 constexpr int FAST_GLOBAL_VECTORS = 9;  // ProbDev::fast: generic traversal with b / accumulator in global memory
+// bit-plane hard-call storage (XT = uint8_t, "B2"): genotypes 0/1/2 as two bit planes (g >= 1, g == 2), stored twice:
+// row-major bits for the X b sweep and column-major bits for the X^T r sweep (see traverse_b2)
+constexpr int B2_TILE_COLS = 256;       // columns per chunk / tile = 32 byte-groups of 8 columns
+constexpr int B2_STAGE_BYTES = 32768;   // one ring stage of the bit stream
+constexpr int B2_NSTAGE = 3;
+constexpr int B2_ROUND_ROWS = 512;      // rows per sweep-1 round of one block (64 per warp)
+constexpr int B2_TABLE_BYTES = 65536;   // 256 entries x 32 groups x 8 bytes, aligned to its size in shared memory
+constexpr int B2_MAX_ROWS = 2048;       // rows per ancestry (their next residual is staged in shared memory)
+constexpr int B2_MAX_SUB = 4;           // column tiles of one block per sweep-2 piece: 8 x B2_MAX_SUB >= p / 256
 constexpr int STAT_STRIDE = 20;  // doubles per team-reduction record (>= 2 + NSYM_MAX + 2 + KMAX)
 constexpr int TRAV_STRIDE = 2 * KMAX;
 
@@ -91,6 +100,12 @@ struct ProbDev {
   double* rfull;  // [nrows] full residual at iteration end      (summary level)
   const double* cmean;  // [K][p_pad] column means      (hard-call int8 storage only; pad = 0)
   const double* cisd;   // [K][p_pad] 1 / column std    (hard-call int8 storage only; pad = 0)
+  // bit-plane storage: rbits[k] = [chunk][row quad][plane][32 groups][4 rows] bytes, bit c = column 8 g + c;
+  //                    cbits[k] = [row-group octet][tile][plane][256 columns][8 row groups] bytes, bit r = row 8 rg + r
+  const unsigned char* rbits[KMAX];
+  const unsigned char* cbits[KMAX];
+  int ntiles;           // ceil(p / 256)
+  int pad_b2_;
   double* bvec;   // [L][K][p_pad] posterior-mean effects b_l = alpha_l * mu_l of the current iteration (pad = 0)
   OutBuf out[2];
   double* elbo;   // [max_iter + 1]
@@ -175,6 +190,17 @@ __device__ __forceinline__ void st_release_u32(unsigned* p, unsigned v) {
   asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
+__device__ __forceinline__ double lds_f64(uint32_t addr) {
+  double v;
+  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
+  uint32_t r;
+  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(sel));
+  return r;
+}
+
 struct Team {
   int size, rank, id;
   int hw;
@@ -245,6 +271,14 @@ struct Vec<float> {
 };
 
 template <>
+struct Vec<uint8_t> {  // bit-plane hard-call storage has its own traversal (traverse_b2)
+  static constexpr int W = 16;
+  template <typename A, typename B>
+  __device__ static void load(A, int, B&) {}
+  template <typename A, typename B>
+  __device__ static void load_raw(A, int, B&) {}
+};
+template <>
 struct Vec<int8_t> {  // hard-call storage has its own traversal (traverse_i8); only the width is shared
   static constexpr int W = 16;
   // name-lookup stubs for the dense traversals, which are never instantiated for this storage type
@@ -281,7 +315,7 @@ __device__ __forceinline__ double u8_to_f64(uint32_t w) {
 // of row l / (32 / GR).  GR + log2(32 / GR) - 1 double shuffles instead of 5 * GR.
 template <int GR>
 __device__ __forceinline__ double warp_rows_sum(double (&ps)[GR], int lane) {
-  static_assert(GR == 1 || GR == 2 || GR == 4 || GR == 8 || GR == 16, "rows per band");
+  static_assert(GR == 1 || GR == 2 || GR == 4 || GR == 8 || GR == 16 || GR == 32, "rows per band");
   int off = 16;
 #pragma unroll
   for (int cnt = GR; cnt > 1; cnt >>= 1) {
@@ -313,6 +347,9 @@ struct SmemHdr {
   double trow[GMAX][2];      // per-row scalars of a traversal
   int decision;
   int pad_[3];
+  unsigned drain[NSTAGE_MAX];  // hard-call row-team traversal: warps that have finished with the band in stage s (mod NW)
+  unsigned pad2_[2];
+  double tsum[NW];           // per row team: sum of the next residual over the rows it processed (current ancestry)
 };
 
 // Block-wide sum of NV values per thread; totals land in H->tot[0..NV) (valid for all
@@ -474,6 +511,7 @@ __global__ void __launch_bounds__(NT, (std::is_same<XT, int8_t>::value ? SB_I8_B
   extern __shared__ __align__(128) unsigned char smem_raw[];
   constexpr int NSYM = K * (K + 1) / 2;
   constexpr int VW = Vec<XT>::W;
+  constexpr bool B2 = std::is_same<XT, uint8_t>::value;  // bit-plane storage: X^T r is complete per block
   SmemHdr* H = reinterpret_cast<SmemHdr*>(smem_raw);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
@@ -488,6 +526,7 @@ __global__ void __launch_bounds__(NT, (std::is_same<XT, int8_t>::value ? SB_I8_B
     for (int s = 0; s < NSTAGE_MAX; ++s) {
       mbar_init(&H->mbar[s], 1);
       mbar_init(&H->ebar[s], NW);
+      H->drain[s] = 0u;
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -1097,6 +1136,623 @@ __global__ void __launch_bounds__(NT, (std::is_same<XT, int8_t>::value ? SB_I8_B
       store_trav(l, first, vsq, rsq);
     };
 
+
+    // Hard-call traversal by ROW TEAMS (XT = int8_t).  A row team = T warps that own one band row at a time: lane
+    // q of the team holds COLS genotype bytes of the row (NV 16-byte vectors, strided so that shared-memory reads
+    // are conflict-free), widens them once and uses the widened values for both sweeps of that row:
+    //   v = <g_row, b'> - cshift  (warp butterfly, then T partials through shared memory and one named barrier
+    //   of the team)  ->  R = r - v  ->  r_next = R + xb[lnext]  ->  acc[cols] += g_row * r_next.
+    // Nothing is block-wide inside a band: the 8 / T teams of a block run rows of the same band independently,
+    // each warp hands a band back through a counter, and the LAST warp to finish re-arms the stage with the band
+    // NS positions ahead.  Per genotype this costs the widening (3 issue slots) + 2 DFMA and ~1 slot of per-row
+    // overhead, against ~4.4 slots of per-band overhead per genotype in the column-tile traversal (transposed
+    // butterflies, block barrier, row-sum finishing), and the warps no longer stall on each other.
+    // Centring / scaling stay folded into the vectors:
+    //   X_std b = G (b / sd) - sum_j mean_j b_j / sd_j,   X_std^T r = (G^T r - mean * sum_i r_i) / sd.
+    auto traverse_i8_rows = [&](auto cols_c, auto t_c, int l, bool first, bool last_effect) {
+      constexpr int COLS = decltype(cols_c)::value;  // genotype bytes (= columns) per lane
+      constexpr int T = decltype(t_c)::value;        // warps per row team
+      constexpr int NV = COLS / 16;                  // 16-byte vectors per lane
+      constexpr int NTEAMS = NW / T;
+      static_assert(COLS % 16 == 0 && NW % T == 0, "row-team geometry");
+      (void)last_effect;
+      const int team_w = warp / T, tw = warp % T;
+      const int q = tw * 32 + lane;  // lane index inside the row team
+      const int pv16 = p_pad / 16;
+      const int lnext = first ? 0 : ((l + 1 == L) ? 0 : l + 1);
+      const bool self_next = !first && lnext == l;
+      const bool leader = (tw == 0 && lane == 0);  // publishes the row state of the team's rows
+      double vsq[K], rsq[K];  // meaningful in the team leaders only
+#pragma unroll
+      for (int k = 0; k < K; ++k) vsq[k] = rsq[k] = 0.0;
+      double bq[NV][16], aq[NV][16];
+      uint32_t vmask = 0;
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        if (q + i * 32 * T < pv16) vmask |= (1u << i);
+#pragma unroll
+        for (int u = 0; u < 16; ++u) bq[i][u] = aq[i][u] = 0.0;
+      }
+      int cur_k = -1;
+      int st = cons_seq % NS;
+      double cshift = 0.0;  // sum_j mean_j b_j / sd_j of the current ancestry
+      double rsum = 0.0;    // sum of r_next over the rows of the current ancestry processed by this team
+      unsigned rowcnt = 0;  // rows processed by this team (parity picks the partial-sum buffer)
+      // shared memory behind the ring: staged row state, then the cross-team exchange area
+      double* rs_sm = reinterpret_cast<double*>(ring + static_cast<size_t>(NS) * stage_bytes);
+      double* xs_sm = rs_sm + I8_STATE_ROWS;
+      double* xteam = xs_sm + I8_STATE_ROWS;  // [NTEAMS][p_pad]; also the staging area of b'
+      const int chunk_bands = I8_STATE_ROWS / G;
+      auto stage_rows = [&](int pos0, int pos1) {
+        __syncthreads();  // previous chunk fully consumed
+        for (int i = tid; i < (pos1 - pos0) * G; i += NT) {
+          int k, g0, rows;
+          band_of(pos0 + i / G, k, g0, rows);
+          const int g = i % G;
+          double rv = 0.0, xv = 0.0;
+          if (g < rows) {
+            const int row = pb.row0[k] + g0 + g;
+            rv = pb.r[row];
+            xv = pb.xb[static_cast<size_t>(lnext) * nrows + row];
+          }
+          rs_sm[i] = rv;
+          xs_sm[i] = xv;
+        }
+        __syncthreads();
+      };
+      // column j = 16 v + u of a team's partial sits at ((u / 2) * pv16 + v) * 2 + (u & 1): conflict-free stores
+      auto flush_acc = [&](int k) {
+        double* xt = xteam + static_cast<size_t>(team_w) * p_pad;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+          if (vmask & (1u << i)) {
+            const int v = q + i * 32 * T;
+#pragma unroll
+            for (int u2 = 0; u2 < 8; ++u2)
+              *reinterpret_cast<double2*>(xt + (static_cast<size_t>(u2) * pv16 + v) * 2) =
+                  make_double2(aq[i][2 * u2], aq[i][2 * u2 + 1]);
+          }
+        }
+        if (q == 0) H->tsum[team_w] = rsum;
+        __syncthreads();
+        double rs = 0.0;
+#pragma unroll
+        for (int t = 0; t < NTEAMS; ++t) rs += H->tsum[t];
+        double* dst = my_scr + static_cast<size_t>(k) * p_pad;
+        const double* cm = pb.cmean + static_cast<size_t>(k) * p_pad;
+        const double* cs = pb.cisd + static_cast<size_t>(k) * p_pad;
+        for (int j2 = tid; j2 < p_pad / 2; j2 += NT) {
+          const int j = 2 * j2, v = j >> 4, u2 = (j & 15) >> 1;
+          const double* src = xteam + (static_cast<size_t>(u2) * pv16 + v) * 2;
+          double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+          for (int t = 0; t < NTEAMS; ++t) {
+            const double2 t2 = *reinterpret_cast<const double2*>(src + static_cast<size_t>(t) * p_pad);
+            a0 += t2.x;
+            a1 += t2.y;
+          }
+          const double2 m2 = *reinterpret_cast<const double2*>(cm + j);
+          const double2 s2 = *reinterpret_cast<const double2*>(cs + j);
+          __stcg(reinterpret_cast<double2*>(dst + j), make_double2((a0 - m2.x * rs) * s2.x, (a1 - m2.y * rs) * s2.y));
+        }
+        __syncthreads();  // the exchange area is reused
+      };
+
+      int chunk0 = 0;
+      for (int pos = 0; pos < nb_own; ++pos) {
+        if (pos == 0 || pos == chunk0 + chunk_bands) {
+          chunk0 = pos;
+          stage_rows(chunk0, min(nb_own, chunk0 + chunk_bands));
+        }
+        int k, g0, rows;
+        band_of(pos, k, g0, rows);
+        if (k != cur_k) {
+          if (cur_k >= 0) flush_acc(cur_k);
+          // b' = b_l / sd staged through shared memory with coalesced loads; cshift = sum_j mean_j b'_j
+          const double* bl = effect_vec(l, k);
+          const double* cm = pb.cmean + static_cast<size_t>(k) * p_pad;
+          const double* cs = pb.cisd + static_cast<size_t>(k) * p_pad;
+          double part[1] = {0.0};
+          for (int j = tid; j < p_pad; j += NT) {
+            const double b = first ? 0.0 : __ldcg(&bl[j]) * cs[j];
+            xteam[j] = b;
+            part[0] += cm[j] * b;
+          }
+          block_sum<1>(H, part);
+          cshift = H->tot[0];
+#pragma unroll
+          for (int i = 0; i < NV; ++i) {
+            const int v = q + i * 32 * T;
+            const bool on = vmask & (1u << i);
+#pragma unroll
+            for (int u = 0; u < 16; u += 2) {
+              const double2 b2 = on ? *reinterpret_cast<const double2*>(xteam + v * 16 + u) : make_double2(0.0, 0.0);
+              bq[i][u] = b2.x;
+              bq[i][u + 1] = b2.y;
+              aq[i][u] = aq[i][u + 1] = 0.0;
+            }
+          }
+          rsum = 0.0;
+          cur_k = k;
+          __syncthreads();  // the staging area is free again
+        }
+        const unsigned char* tile = ring + static_cast<size_t>(st) * stage_bytes;
+        const int row_base = pb.row0[k] + g0;
+        mbar_wait(&H->mbar[st], (phase_bits >> st) & 1u);
+
+        for (int g = team_w; g < rows; g += NTEAMS) {
+          const unsigned char* src = tile + static_cast<size_t>(g) * p_pad;
+          double xk[NV][16];
+#pragma unroll
+          for (int i = 0; i < NV; ++i) {
+            uint4 w4 = make_uint4(0u, 0u, 0u, 0u);
+            if (vmask & (1u << i)) w4 = *reinterpret_cast<const uint4*>(src + (q + i * 32 * T) * 16);
+            const uint32_t w[4] = {w4.x, w4.y, w4.z, w4.w};
+#pragma unroll
+            for (int q4 = 0; q4 < 4; ++q4) {
+              xk[i][4 * q4 + 0] = u8_to_f64<0>(w[q4]);
+              xk[i][4 * q4 + 1] = u8_to_f64<1>(w[q4]);
+              xk[i][4 * q4 + 2] = u8_to_f64<2>(w[q4]);
+              xk[i][4 * q4 + 3] = u8_to_f64<3>(w[q4]);
+            }
+          }
+          double v = 0.0;
+          if (!first) {
+            double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+#pragma unroll
+            for (int i = 0; i < NV; ++i)
+#pragma unroll
+              for (int u = 0; u < 16; u += 4) {
+                s0 = fma(xk[i][u], bq[i][u], s0);
+                s1 = fma(xk[i][u + 1], bq[i][u + 1], s1);
+                s2 = fma(xk[i][u + 2], bq[i][u + 2], s2);
+                s3 = fma(xk[i][u + 3], bq[i][u + 3], s3);
+              }
+            double s = warp_sum((s0 + s1) + (s2 + s3));  // xor butterfly: every lane holds the warp total
+            if constexpr (T > 1) {
+              const int par = rowcnt & 1u;
+              if (lane == 0) H->partsum[par][warp] = s;
+              asm volatile("bar.sync %0, %1;" ::"r"(1 + team_w), "r"(32 * T) : "memory");
+              s = 0.0;
+#pragma unroll
+              for (int t = 0; t < T; ++t) s += H->partsum[par][team_w * T + t];
+            }
+            v = s - cshift;
+          }
+          const int srow = (pos - chunk0) * G + g;
+          const double Rfull = rs_sm[srow] - v;
+          const double rn = Rfull + (self_next ? v : xs_sm[srow]);  // L == 1: add back the new effect
+          if (leader) {
+            const int row = row_base + g;
+            if (!first) pb.xb[static_cast<size_t>(l) * nrows + row] = v;
+            pb.r[row] = rn;
+#pragma unroll
+            for (int kk = 0; kk < K; ++kk)
+              if (kk == k) {
+                vsq[kk] += v * v;          // |X b_l|^2 (infer.py:806)
+                rsq[kk] += Rfull * Rfull;  // |y - X sum_l b_l|^2 at the last effect (infer.py:804)
+              }
+          }
+#pragma unroll
+          for (int i = 0; i < NV; ++i)
+#pragma unroll
+            for (int u = 0; u < 16; ++u) aq[i][u] = fma(xk[i][u], rn, aq[i][u]);
+          rsum += rn;
+          rowcnt += 1u;
+        }
+        // hand the band back; the last warp to finish re-arms the stage with the band NS positions ahead
+        __syncwarp();
+        if (lane == 0) {
+          __threadfence_block();
+          const unsigned old = atomicAdd(&H->drain[st], 1u);
+          if ((old & (NW - 1)) == NW - 1) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            issue_fill((cons_seq + NS) % nb_own, st);
+          }
+        }
+        phase_bits ^= (1u << st);
+        cons_seq += 1;
+        st = (st + 1 == NS) ? 0 : st + 1;
+      }
+      if (cur_k >= 0) flush_acc(cur_k);
+      zero_unowned_partials();
+      prod_pos = (cons_seq + NS) % max(nb_own, 1);  // ring invariant, for the traversals that track it
+      // per-traversal scalars: fixed-order block sum of the team leaders' partials
+      {
+        double tv[2 * K];
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+          tv[k] = leader ? vsq[k] : 0.0;
+          tv[K + k] = leader ? rsq[k] : 0.0;
+        }
+        block_sum<2 * K>(H, tv);
+        if (tid < K && !first) {
+          double* dst = my_scr + P.off_trav + l * TRAV_STRIDE;
+          __stcg(&dst[tid], H->tot[tid]);
+          __stcg(&dst[KMAX + tid], H->tot[K + tid]);
+        }
+        __syncthreads();
+      }
+    };
+
+
+    // Bit-plane traversal (XT = uint8_t): hard calls 0/1/2 are two bit planes, B1 = (g >= 1) and B2 = (g == 2), so
+    // g = B1 + B2 and both products are SUBSET SUMS that come out of lookup tables instead of fp64 multiply-adds
+    // on widened genotypes (the column-tile traversal spends 3 of its 5 issue slots per genotype on widening):
+    //   sweep 1   v_i  = sum_groups T1[g][bits of row i in group g]      T1[g][e] = sum_{c in e} b'_{8 g + c}
+    //   sweep 2   a_j  = sum_rowgroups T2[rg][bits of column j in rg]    T2[rg][e] = sum_{r in e} r_next_{8 rg + r}
+    // one table read + one add per 8 genotypes and plane.  Sweep 1 runs over 256-column chunks (32 groups, a 64 KB
+    // table set in shared memory): a warp owns 64 rows, lane = group, so the 32 lanes read 32 different table
+    // columns (conflict-free) and the lane-private row sums are combined once per ancestry by a transposed
+    // butterfly.  Sweep 2 runs over 256-row chunks (32 row groups): a thread owns one column per tile.  The bit
+    // stream arrives through a 3-stage ring of bulk copies; the last warp to finish a piece re-arms its stage.
+    // Team members split the rows in sweep 1 and the columns (their own SNP slice) in sweep 2, so X^T r is complete
+    // per block and needs no reduction.
+    auto traverse_b2 = [&](auto /*instantiate on use*/, int l, bool first) {
+      const int lnext = first ? 0 : ((l + 1 == L) ? 0 : l + 1);
+      const bool self_next = !first && lnext == l;
+      const int ntiles = pb.ntiles;
+      // ---- shared memory: [header][small vectors ...][T: 64 KB table set, aligned to 64 KB][ring]
+      const uint32_t smem_base = smem_u32(smem_raw);
+      const uint32_t hdr_end = smem_base + static_cast<uint32_t>(((sizeof(SmemHdr) + 127) / 128) * 128);
+      const uint32_t tab_addr = (hdr_end + 8192u + B2_MAX_ROWS * 8u + B2_TABLE_BYTES - 1u) & ~static_cast<uint32_t>(B2_TABLE_BYTES - 1);
+      unsigned char* const tab = smem_raw + (tab_addr - smem_base);
+      unsigned char* const ringb = tab + B2_TABLE_BYTES;
+      double* const bstage = reinterpret_cast<double*>(smem_raw + (hdr_end - smem_base));  // [256] b' of a chunk
+      double* const vsum = bstage + B2_TILE_COLS;                                            // [512] row sums of a round
+      double* const rn_sm = vsum + B2_ROUND_ROWS;                                            // [B2_MAX_ROWS] next residual
+      // ---- work split inside the team
+      int q0[K], q1[K], rounds[K];  // row quads of this block per ancestry, sweep-1 rounds
+      int npa = 0;
+#pragma unroll
+      for (int k = 0; k < K; ++k) {
+        const int nq = (pb.n[k] + 3) >> 2;
+        q0[k] = static_cast<int>((static_cast<long long>(nq) * rank) / C);
+        q1[k] = static_cast<int>((static_cast<long long>(nq) * (rank + 1)) / C);
+        rounds[k] = first ? 0 : (q1[k] - q0[k] + B2_ROUND_ROWS / 4 - 1) / (B2_ROUND_ROWS / 4);
+        npa += rounds[k] * ntiles;
+      }
+      const int t0 = js / B2_TILE_COLS, t1 = (je > js) ? (je + B2_TILE_COLS - 1) / B2_TILE_COLS : t0;  // own column tiles
+      const int nsub = (t1 - t0 + 7) >> 3;
+      int npb[K], np_total = npa;
+#pragma unroll
+      for (int k = 0; k < K; ++k) {
+        npb[k] = ((pb.n[k] + 63) >> 6) * nsub;  // row-group octets x tile sub-ranges
+        np_total += npb[k];
+      }
+      // piece s of the static stream -> (source, bytes)
+      auto issue_piece = [&](int s, int stg) {
+        const unsigned char* src = nullptr;
+        uint32_t bytes = 0;
+        int r = s;
+        bool found = false;
+        if (r < npa) {
+#pragma unroll
+          for (int k = 0; k < K; ++k) {
+            const int cnt = rounds[k] * ntiles;
+            if (!found && r < cnt) {
+              const int rd = r / ntiles, c = r - rd * ntiles;
+              const int nq = (pb.n[k] + 3) >> 2;
+              const int qa = q0[k] + rd * (B2_ROUND_ROWS / 4);
+              const int qn = min(B2_ROUND_ROWS / 4, q1[k] - qa);
+              src = pb.rbits[k] + (static_cast<size_t>(c) * nq + qa) * 256;
+              bytes = static_cast<uint32_t>(qn) * 256u;
+              found = true;
+            }
+            if (!found) r -= cnt;
+          }
+        } else {
+          r -= npa;
+#pragma unroll
+          for (int k = 0; k < K; ++k) {
+            if (!found && r < npb[k]) {
+              const int oct = r / nsub, sub = r - oct * nsub;
+              const int ta = t0 + 8 * sub, tn = min(8, t1 - ta);
+              src = pb.cbits[k] + (static_cast<size_t>(oct) * ntiles + ta) * 4096;
+              bytes = static_cast<uint32_t>(tn) * 4096u;
+              found = true;
+            }
+            if (!found) r -= npb[k];
+          }
+        }
+        mbar_expect_tx(&H->mbar[stg], bytes);
+        bulk_g2s(ringb + static_cast<size_t>(stg) * B2_STAGE_BYTES, src, bytes, &H->mbar[stg], stream_policy);
+      };
+      int pseq = 0;  // pieces consumed in this traversal
+      auto piece_wait = [&]() -> const unsigned char* {
+        const int stg = cons_seq % B2_NSTAGE;
+        mbar_wait(&H->mbar[stg], (phase_bits >> stg) & 1u);
+        return ringb + static_cast<size_t>(stg) * B2_STAGE_BYTES;
+      };
+      auto piece_done = [&]() {
+        const int stg = cons_seq % B2_NSTAGE;
+        __syncwarp();
+        if (lane == 0) {
+          __threadfence_block();
+          const unsigned old = atomicAdd(&H->drain[stg], 1u);
+          if ((old & (NW - 1)) == NW - 1 && pseq + B2_NSTAGE < np_total) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            issue_piece(pseq + B2_NSTAGE, stg);
+          }
+        }
+        phase_bits ^= (1u << stg);
+        cons_seq += 1;
+        pseq += 1;
+      };
+      __syncthreads();  // every warp has left the previous phase: the ring and the tables are free
+      if (tid == 0)
+        for (int s = 0; s < B2_NSTAGE && s < np_total; ++s) issue_piece(s, (cons_seq + s) % B2_NSTAGE);
+
+      double vsq[K], rsq[K];
+#pragma unroll
+      for (int k = 0; k < K; ++k) vsq[k] = rsq[k] = 0.0;
+
+      if (first) {
+        // locus initialisation (state owned by this block: its rows): r = y, cached X b_l = 0
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+          const int ia = 4 * q0[k], ib = min(pb.n[k], 4 * q1[k]);
+          for (int i = ia + tid; i < ib; i += NT) {
+            const int row = pb.row0[k] + i;
+            pb.r[row] = pb.y[row];
+            for (int ll = 0; ll < L; ++ll) pb.xb[static_cast<size_t>(ll) * nrows + row] = 0.0;
+          }
+        }
+      } else {
+        // ---------------- sweep 1: v = G b' - cshift for the rows of this block, then the row state
+        const uint32_t lane_const = tab_addr | (static_cast<uint32_t>(lane) << 3);
+#pragma unroll 1
+        for (int k = 0; k < K; ++k) {
+          const double* bl = effect_vec(l, k);
+          const double* cm = pb.cmean + static_cast<size_t>(k) * p_pad;
+          const double* cs = pb.cisd + static_cast<size_t>(k) * p_pad;
+#pragma unroll 1
+          for (int rd = 0; rd < rounds[k]; ++rd) {
+            const int qa = q0[k] + rd * (B2_ROUND_ROWS / 4);
+            const int qn = min(B2_ROUND_ROWS / 4, q1[k] - qa);  // row quads of this round
+            double acc[64];
+#pragma unroll
+            for (int i = 0; i < 64; ++i) acc[i] = 0.0;
+            double cpart[1] = {0.0};
+#pragma unroll 1
+            for (int c = 0; c < ntiles; ++c) {
+              // b' of the chunk, coalesced; cshift = sum_j mean_j b'_j
+              {
+                const int j = c * B2_TILE_COLS + tid;
+                double b = 0.0;
+                if (j < p_pad) {
+                  b = __ldcg(&bl[j]) * cs[j];
+                  cpart[0] += cm[j] * b;
+                }
+                __syncthreads();  // previous table set and b' no longer read
+                bstage[tid] = b;
+              }
+              __syncthreads();
+              {
+                // table set of the chunk: thread (g, q) writes entries e = 32 q + r of group g
+                const int g = tid & 31, qq = tid >> 5;
+                const double2* b8 = reinterpret_cast<const double2*>(bstage + 8 * g);
+                const double2 b01 = b8[0], b23 = b8[1], b45 = b8[2], b67 = b8[3];
+                double lo[16];
+                lo[0] = 0.0;
+                lo[1] = b01.x;
+                lo[2] = b01.y;
+                lo[3] = b01.x + b01.y;
+                lo[4] = b23.x;
+                lo[5] = b01.x + b23.x;
+                lo[6] = b01.y + b23.x;
+                lo[7] = lo[3] + b23.x;
+                lo[8] = b23.y;
+                lo[9] = b01.x + b23.y;
+                lo[10] = b01.y + b23.y;
+                lo[11] = lo[3] + b23.y;
+                lo[12] = b23.x + b23.y;
+                lo[13] = lo[5] + b23.y;
+                lo[14] = lo[6] + b23.y;
+                lo[15] = lo[7] + b23.y;
+                double hi2[2];
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                  const int nib = 2 * qq + h;
+                  // fixed association: ((b4 + b5) + b6) + b7 over the members present
+                  double t = 0.0;
+                  if (nib & 1) t = b45.x;
+                  if (nib & 2) t = (nib & 1) ? t + b45.y : b45.y;
+                  if (nib & 4) t = (nib & 3) ? t + b67.x : b67.x;
+                  if (nib & 8) t = (nib & 7) ? t + b67.y : b67.y;
+                  hi2[h] = t;
+                }
+                double* dst = reinterpret_cast<double*>(tab) + static_cast<size_t>(32 * qq) * 32 + g;
+#pragma unroll
+                for (int r = 0; r < 32; ++r) dst[r * 32] = lo[r & 15] + hi2[r >> 4];
+              }
+              __syncthreads();
+              const unsigned char* piece = piece_wait();
+              // warp w: row quads 16 w .. 16 w + 15 of the round; lane = group
+              const uint32_t* words = reinterpret_cast<const uint32_t*>(piece) + lane;
+#pragma unroll
+              for (int oc = 0; oc < 4; ++oc) {  // four quads at a time (uniform skip past the end of the round)
+                if (16 * warp + 4 * oc < qn) {
+#pragma unroll
+                  for (int m4 = 0; m4 < 4; ++m4) {
+                    const int m = 4 * oc + m4;
+                    const int ql = 16 * warp + m;
+                    if (ql < qn) {
+#pragma unroll
+                      for (int pl = 0; pl < 2; ++pl) {
+                        const uint32_t w = words[(ql * 2 + pl) * 32];
+                        acc[4 * m + 0] += lds_f64(prmt(w, lane_const, 0x7604u));
+                        acc[4 * m + 1] += lds_f64(prmt(w, lane_const, 0x7614u));
+                        acc[4 * m + 2] += lds_f64(prmt(w, lane_const, 0x7624u));
+                        acc[4 * m + 3] += lds_f64(prmt(w, lane_const, 0x7634u));
+                      }
+                    }
+                  }
+                }
+              }
+              piece_done();
+            }
+            // lane-private row sums -> row totals (lane i of the warp holds rows 64 w + i and 64 w + 32 + i)
+            {
+              double lo32[32], hi32[32];
+#pragma unroll
+              for (int i = 0; i < 32; ++i) {
+                lo32[i] = acc[i];
+                hi32[i] = acc[32 + i];
+              }
+              const double ta = warp_rows_sum<32>(lo32, lane);
+              const double tb = warp_rows_sum<32>(hi32, lane);
+              vsum[64 * warp + lane] = ta;
+              vsum[64 * warp + 32 + lane] = tb;
+            }
+            block_sum<1>(H, cpart);  // (barriers inside: vsum visible)
+            const double cshift = H->tot[0];
+            // finish the rows of the round
+            for (int i = tid; i < 4 * qn; i += NT) {
+              const int irow = 4 * qa + i;
+              if (irow < pb.n[k]) {
+                const int row = pb.row0[k] + irow;
+                const double v = vsum[i] - cshift;
+                const double Rfull = pb.r[row] - v;
+                const double rn = Rfull + (self_next ? v : pb.xb[static_cast<size_t>(lnext) * nrows + row]);
+                pb.xb[static_cast<size_t>(l) * nrows + row] = v;
+                pb.r[row] = rn;
+#pragma unroll
+                for (int kk = 0; kk < K; ++kk)
+                  if (kk == k) {
+                    vsq[kk] += v * v;          // |X b_l|^2 (infer.py:806)
+                    rsq[kk] += Rfull * Rfull;  // |y - X sum_l b_l|^2 at the last effect (infer.py:804)
+                  }
+              }
+            }
+            __syncthreads();  // vsum is reused by the next round
+          }
+        }
+      }
+      team_sync(team);  // the next residual of every row (all team members) is in global memory
+
+      // ---------------- sweep 2: X_std^T r_next for the own column tiles
+      const uint32_t tab2 = tab_addr;
+#pragma unroll 1
+      for (int k = 0; k < K; ++k) {
+        const int nk = pb.n[k];
+        double rpart[1] = {0.0};
+        for (int i = tid; i < ((nk + 255) & ~255); i += NT) {
+          const double rv = (i < nk) ? __ldcg(&pb.r[pb.row0[k] + i]) : 0.0;
+          rn_sm[i] = rv;
+          rpart[0] += rv;
+        }
+        block_sum<1>(H, rpart);
+        const double rsum = H->tot[0];
+        double a2[8 * B2_MAX_SUB];
+#pragma unroll
+        for (int i = 0; i < 8 * B2_MAX_SUB; ++i) a2[i] = 0.0;
+        const int nchunks = (nk + 255) >> 8;
+#pragma unroll 1
+        for (int d = 0; d < nchunks; ++d) {
+          __syncthreads();  // previous table set no longer read
+          {
+            // table set of the row chunk: thread (rg, q) writes entries e = q + 8 r' of row group rg
+            const int rg = tid >> 3, qq = tid & 7;
+            const double2* r8 = reinterpret_cast<const double2*>(rn_sm + 256 * d + 8 * rg);
+            const double2 r01 = r8[0], r23 = r8[1], r45 = r8[2], r67 = r8[3];
+            double hi[16];
+            hi[0] = 0.0;
+            hi[1] = r45.x;
+            hi[2] = r45.y;
+            hi[3] = r45.x + r45.y;
+            hi[4] = r67.x;
+            hi[5] = r45.x + r67.x;
+            hi[6] = r45.y + r67.x;
+            hi[7] = hi[3] + r67.x;
+            hi[8] = r67.y;
+            hi[9] = r45.x + r67.y;
+            hi[10] = r45.y + r67.y;
+            hi[11] = hi[3] + r67.y;
+            hi[12] = r67.x + r67.y;
+            hi[13] = hi[5] + r67.y;
+            hi[14] = hi[6] + r67.y;
+            hi[15] = hi[7] + r67.y;
+            double lo2[2];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              const int nib = qq + 8 * h;
+              double t = 0.0;
+              if (nib & 1) t = r01.x;
+              if (nib & 2) t = (nib & 1) ? t + r01.y : r01.y;
+              if (nib & 4) t = (nib & 3) ? t + r23.x : r23.x;
+              if (nib & 8) t = (nib & 7) ? t + r23.y : r23.y;
+              lo2[h] = t;
+            }
+            double* dst = reinterpret_cast<double*>(tab) + static_cast<size_t>(rg) * 256 + qq;
+#pragma unroll
+            for (int rp = 0; rp < 32; ++rp) dst[8 * rp] = lo2[rp & 1] + hi[rp >> 1];
+          }
+          __syncthreads();
+          const int octs = min(4, ((nk + 63) >> 6) - 4 * d);  // row-group octets of this chunk
+#pragma unroll 1
+          for (int oc = 0; oc < octs; ++oc) {
+            const uint32_t tbase = tab2 + static_cast<uint32_t>(oc) * 8u * 2048u;
+#pragma unroll
+            for (int sub = 0; sub < B2_MAX_SUB; ++sub) {
+              if (sub < nsub) {
+                const unsigned char* piece = piece_wait();
+                const int tn = min(8, t1 - (t0 + 8 * sub));
+#pragma unroll
+                for (int tt = 0; tt < 8; ++tt) {
+                  if (tt < tn) {
+#pragma unroll
+                    for (int pl = 0; pl < 2; ++pl) {
+                      const uint2 w = *reinterpret_cast<const uint2*>(piece + ((tt * 2 + pl) * 256 + tid) * 8);
+                      double s = 0.0;
+#pragma unroll
+                      for (int r = 0; r < 8; ++r) {
+                        const uint32_t word = (r < 4) ? w.x : w.y;
+                        const uint32_t e8 = ((word >> (8 * (r & 3))) & 0xffu) << 3;
+                        s += lds_f64(tbase + static_cast<uint32_t>(r) * 2048u + e8);
+                      }
+                      a2[8 * sub + tt] += s;
+                    }
+                  }
+                }
+                piece_done();
+              }
+            }
+          }
+        }
+        // X_std^T r = (G^T r - mean * sum r) / sd for the own slice
+        {
+          const double* cm = pb.cmean + static_cast<size_t>(k) * p_pad;
+          const double* cs = pb.cisd + static_cast<size_t>(k) * p_pad;
+          double* dst = pb.xty + static_cast<size_t>(k) * p_pad;
+#pragma unroll
+          for (int sub = 0; sub < B2_MAX_SUB; ++sub)
+#pragma unroll
+            for (int tt = 0; tt < 8; ++tt) {
+              const int j = (t0 + 8 * sub + tt) * B2_TILE_COLS + tid;
+              if (sub < nsub && t0 + 8 * sub + tt < t1 && j >= js && j < je) dst[j] = (a2[8 * sub + tt] - cm[j] * rsum) * cs[j];
+            }
+        }
+        __syncthreads();  // rn_sm is reloaded for the next ancestry
+      }
+      // per-traversal scalars: fixed-order block sums
+      {
+        double tv[2 * K];
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+          tv[k] = vsq[k];
+          tv[K + k] = rsq[k];
+        }
+        block_sum<2 * K>(H, tv);
+        if (tid < K && !first) {
+          double* dst = my_scr + P.off_trav + l * TRAV_STRIDE;
+          __stcg(&dst[tid], H->tot[tid]);
+          __stcg(&dst[KMAX + tid], H->tot[K + tid]);
+        }
+        __syncthreads();
+      }
+    };
+
     // Summary-level register-tile variant: rows are LD rows, there is no X^T r sweep, so a warp
     // never needs another warp's result while it streams.  Every thread keeps its CPT column
     // vectors of b in registers, takes its slice of each row straight from the shared-memory
@@ -1405,7 +2061,14 @@ __global__ void __launch_bounds__(NT, (std::is_same<XT, int8_t>::value ? SB_I8_B
     };
 
     auto traverse = [&](int l, bool first, bool last_effect) {
-      if constexpr (std::is_same<XT, int8_t>::value) {
+      if constexpr (std::is_same<XT, uint8_t>::value) {
+        traverse_b2(IntC<0>{}, l, first);
+      } else if constexpr (std::is_same<XT, int8_t>::value && V == 5) {
+        // narrow loci (p_pad <= 512): one warp per row, 16 columns per lane -- measured 111 / 117 us per update at
+        // p = 300 / 500 against 154 / 157 for the column tile; wider loci are faster with the column tile
+        // (p = 2000: 290 vs 357 us), profiles/r02b_shapes_i8_*.jsonl
+        traverse_i8_rows(IntC<16>{}, IntC<1>{}, l, first, last_effect);
+      } else if constexpr (std::is_same<XT, int8_t>::value) {
         if constexpr (V == 1)
           traverse_i8(IntC<1>{}, IntC<8>{}, IntC<SB_I8_KEEP>{}, IntC<8>{}, l, first, last_effect);
         else if constexpr (V == 2)
@@ -1512,7 +2175,7 @@ __global__ void __launch_bounds__(NT, (std::is_same<XT, int8_t>::value ? SB_I8_B
 #pragma unroll
       for (int k = 0; k < K; ++k) rv[k] = __ldcg(&rv_prev[k]);
 
-      if (!SS && !have_xty) reduce_partials();
+      if (!SS && !B2 && !have_xty) reduce_partials();
       // raw per-SNP inputs (X^T r, XtX, log pi); fetched one SNP ahead of the arithmetic
       constexpr int NRAW = 2 * K + 1;
       const double* __restrict__ xty_r = pb.xty;
@@ -1859,7 +2522,7 @@ __global__ void __launch_bounds__(NT, (std::is_same<XT, int8_t>::value ? SB_I8_B
       team_sync(team);  // new residual variances (and the drain decision) visible to every block
       if (__ldcg(&P.team_slot[P.n_teams + team.id])) {
         // suspend: reduce the pending X^T r now so the next phase may use any team size
-        if (!SS) reduce_partials();
+        if (!SS && !B2) reduce_partials();
         suspended = true;
         break;
       }
@@ -2020,6 +2683,74 @@ __global__ void prep_columns_batched_kernel(const PrepDesc* __restrict__ descs, 
     d.cisd[j] = 1.0 / sd;
     if (bad) atomicOr(bad_flag, 1);
   }
+}
+
+// Bit-plane packing of hard calls 0/1/2 (see traverse_b2): from the resident one-byte matrix [n][p_pad] to
+//   rbits = [chunk][row quad][plane][32 groups][4 rows]           bit c of a byte = column 256 chunk + 8 group + c
+//   cbits = [row-group octet][tile][plane][256 columns][8 groups] bit r of a byte = row 64 octet + 8 group + r
+// plane 0 = (g >= 1), plane 1 = (g == 2); rows / columns past the end are zero.
+struct PackDesc {
+  const signed char* X;  // [n][p_pad]
+  unsigned char* rbits;
+  unsigned char* cbits;
+  int n, p_pad, ntiles, pad_;
+};
+
+static __global__ void pack_b2_kernel(const PackDesc* __restrict__ descs, int* __restrict__ bad_flag) {
+  const PackDesc d = descs[blockIdx.y];
+  const int nq = (d.n + 3) >> 2, noct = (d.n + 63) >> 6;
+  const long long n_r = static_cast<long long>(d.ntiles) * nq * 32;
+  const long long n_c = static_cast<long long>(noct) * d.ntiles * B2_TILE_COLS;
+  bool bad = false;
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < n_r + n_c;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    if (idx < n_r) {
+      const int g = static_cast<int>(idx & 31);
+      const long long t = idx >> 5;
+      const int quad = static_cast<int>(t % nq), c = static_cast<int>(t / nq);
+      const int col0 = c * B2_TILE_COLS + 8 * g;
+      uint32_t w0 = 0u, w1 = 0u;
+      if (col0 < d.p_pad) {
+        for (int rr = 0; rr < 4; ++rr) {
+          const int row = 4 * quad + rr;
+          if (row < d.n) {
+            const uint2 v8 = *reinterpret_cast<const uint2*>(d.X + static_cast<size_t>(row) * d.p_pad + col0);
+            for (int cc = 0; cc < 8; ++cc) {
+              const uint32_t v = (((cc < 4) ? v8.x : v8.y) >> (8 * (cc & 3))) & 0xffu;
+              if (v > 2u) bad = true;
+              w0 |= static_cast<uint32_t>(v >= 1u) << (8 * rr + cc);
+              w1 |= static_cast<uint32_t>(v == 2u) << (8 * rr + cc);
+            }
+          }
+        }
+      }
+      uint32_t* out = reinterpret_cast<uint32_t*>(d.rbits) + ((static_cast<size_t>(c) * nq + quad) * 2) * 32 + g;
+      out[0] = w0;
+      out[32] = w1;
+    } else {
+      const long long i2 = idx - n_r;
+      const int col = static_cast<int>(i2 & (B2_TILE_COLS - 1));
+      const long long t = i2 >> 8;
+      const int tile = static_cast<int>(t % d.ntiles), oct = static_cast<int>(t / d.ntiles);
+      const int j = tile * B2_TILE_COLS + col;
+      uint32_t p0[2] = {0u, 0u}, p1[2] = {0u, 0u};
+      if (j < d.p_pad) {
+        for (int rg8 = 0; rg8 < 8; ++rg8)
+          for (int r = 0; r < 8; ++r) {
+            const int row = (oct * 8 + rg8) * 8 + r;
+            if (row < d.n) {
+              const uint32_t v = static_cast<unsigned char>(d.X[static_cast<size_t>(row) * d.p_pad + j]);
+              p0[rg8 >> 2] |= static_cast<uint32_t>(v >= 1u) << (8 * (rg8 & 3) + r);
+              p1[rg8 >> 2] |= static_cast<uint32_t>(v == 2u) << (8 * (rg8 & 3) + r);
+            }
+          }
+      }
+      uint2* out = reinterpret_cast<uint2*>(d.cbits) + ((static_cast<size_t>(oct) * d.ntiles + tile) * 2) * B2_TILE_COLS + col;
+      out[0] = make_uint2(p0[0], p0[1]);
+      out[B2_TILE_COLS] = make_uint2(p1[0], p1[1]);
+    }
+  }
+  if (bad) atomicOr(bad_flag, 2);
 }
 
 // Summary-level prologue (infer_ss.py:340-344): Xty = sqrt(n) sqrt(n/(n+z^2)) z,

@@ -20,16 +20,18 @@ static const void* kfn() {
   return reinterpret_cast<const void*>(&sb::ibss_kernel<SB_K, XT, SS, V>);
 }
 
-// variant: traversal variant compiled into the kernel (capi.cu: launch_variant) -- hard-call storage 1..4; dense fp64
+// variant: traversal variant compiled into the kernel (capi.cu: launch_variant) -- hard-call storage 1..5; dense fp64
 // individual level 1 / 3 / 5 / 6 for the tiles that live in kernels of their own; everything else 0.
 extern "C" __attribute__((visibility("hidden"))) const void* SB_CAT(sb_kernel_table_k, SB_K)(int storage, int ss,
                                                                                             int variant) {
   const bool f32 = storage == SB_F32;
+  if (storage == SB_B2) return ss ? nullptr : kfn<uint8_t, false>();
   if (storage == SB_I8) {
     if (ss) return nullptr;
     return variant == 1   ? kfn<int8_t, false, 1>()
            : variant == 2 ? kfn<int8_t, false, 2>()
            : variant == 3 ? kfn<int8_t, false, 3>()
+           : variant == 5 ? kfn<int8_t, false, 5>()
                           : kfn<int8_t, false, 4>();
   }
   if (!ss && !f32) {

@@ -53,7 +53,10 @@ class _Prepared:
 
     def __init__(self, problem, pi, sample_size, max_iter, min_tol, cs_args, no_reorder, hard_calls=False):
         self.problem = problem
-        self.hard_calls = hard_calls  # genotypes verified to be integers in 0..127, not residualised
+        # device storage class of the genotypes: False = dense matrix at `config.precision`; "i8" = integers in
+        # 0..127, not residualised (one byte per entry); "b2" = additionally only 0 / 1 / 2 and inside the limits of
+        # the bit-plane traversal (look-up tables instead of fp64 multiply-adds on widened genotypes)
+        self.hard_calls = hard_calls
         self.pi = pi
         self.sample_size = sample_size
         self.max_iter = max_iter
@@ -106,7 +109,10 @@ def _prepare(
         packed = [utils.as_hard_calls(m) for m in mats]
         if all(m is not None for m in packed):
             mats = packed
-            hard_calls = True
+            hard_calls = "i8"
+            if (config.bit_planes and n_snps <= _capi.B2_MAX_SNPS and max(m.shape[0] for m in mats) <= _capi.B2_MAX_ROWS
+                    and all(int(m.max()) <= 2 for m in mats)):
+                hard_calls = "b2"
     for idx in range(n_pop):
         y = phen[idx] - np.mean(phen[idx])
         if not no_scale:
@@ -145,7 +151,7 @@ def _run_prepared(preps: Sequence[_Prepared], device: int = 0, defer: bool = Fal
     if config.genotype_storage == "auto" and all(
         p.hard_calls and p.problem.x_dtype == _capi.SB_I8 and p.problem.p <= _capi.I8_MAX_SNPS for p in preps
     ):
-        storage = _capi.SB_I8
+        storage = _capi.SB_B2 if all(p.hard_calls == "b2" for p in preps) else _capi.SB_I8
     opts = eng.make_opts(preps[0].max_iter, preps[0].min_tol, storage, config.team_size, config.single_phase)
     return run_chunk(eng, preps, opts, _stage, defer)
 

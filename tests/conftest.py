@@ -63,3 +63,24 @@ def golden_config5():
 @pytest.fixture(scope="session")
 def golden_config4():
     return _load_golden("config4_summary.npz")
+
+
+import contextlib
+
+
+@contextlib.contextmanager
+def genotype_storage(mode):
+    """Device storage of individual-level genotypes for a test: "dense" = standardised fp64 matrix, "auto" = the
+    product default (hard calls 0/1/2 as bit planes), "bytes" = hard calls kept one byte per entry."""
+    from sushie_b200 import config
+
+    old = (config.genotype_storage, config.bit_planes)
+    config.genotype_storage = "dense" if mode == "dense" else "auto"
+    config.bit_planes = mode != "bytes"
+    try:
+        yield mode
+    finally:
+        config.genotype_storage, config.bit_planes = old
+
+
+STORAGE_MODES = ["dense", "auto", "bytes"]

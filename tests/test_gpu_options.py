@@ -6,6 +6,7 @@ within 1e-4 relative (order-free when the effect order is fragile)."""
 import numpy as np
 import pytest
 
+from conftest import STORAGE_MODES, genotype_storage
 from parity import COV_RTOL, ELBO_RTOL, PIP_TOL
 
 pytestmark = pytest.mark.gpu
@@ -56,7 +57,7 @@ CASES = {
 }
 
 
-@pytest.mark.parametrize("storage", ["dense", "auto"])
+@pytest.mark.parametrize("storage", STORAGE_MODES)
 @pytest.mark.parametrize("name", sorted(CASES))
 def test_individual_options_match_oracle(engine_lib, name, storage):
     import sushie_b200
@@ -69,12 +70,8 @@ def test_individual_options_match_oracle(engine_lib, name, storage):
     if case.get("pi"):
         pi = np.random.default_rng(5).uniform(0.5, 2.0, size=case["p"])
         kw["pi"] = pi / pi.sum()
-    old = config.genotype_storage
-    config.genotype_storage = storage
-    try:
+    with genotype_storage(storage):
         res = sushie_b200.infer_sushie([x.copy() for x in Xs], [y.copy() for y in ys], min_snps=50, **kw)
-    finally:
-        config.genotype_storage = old
     ref = ibss.fit_individual(Xs, ys, **kw)
     _check(res, ref)
 

@@ -4,6 +4,7 @@ tests/golden/make_golden.py)."""
 import numpy as np
 import pytest
 
+from conftest import STORAGE_MODES, genotype_storage
 from parity import assert_fit_matches
 
 pytestmark = pytest.mark.gpu
@@ -21,15 +22,12 @@ SYN_CASES = {
 }
 
 
-@pytest.fixture(params=["dense", "auto"])
+@pytest.fixture(params=STORAGE_MODES)
 def geno_storage(request):
-    """Run a test with standardised fp64 storage and with one-byte hard-call storage."""
-    from sushie_b200 import config
-
-    old = config.genotype_storage
-    config.genotype_storage = request.param
-    yield request.param
-    config.genotype_storage = old
+    """Run a test with standardised fp64 storage, with bit-plane hard-call storage (the default for 0/1/2 genotypes)
+    and with one-byte hard-call storage."""
+    with genotype_storage(request.param) as mode:
+        yield mode
 
 
 def _syn_inputs(g, tag, k, as_float=True):
@@ -265,14 +263,14 @@ def test_summary_level_large_crop_fp32_storage(engine_lib):
 
 
 def test_hard_call_storage_is_selected_and_wide_loci_fit(engine_lib):
-    """One-byte storage through the engine API: the 8-row band geometry is reported, loci wider than
-    2048 / 4096 SNPs use the 16- / 32-column register tiles, and all agree with the fp64 storage run."""
+    """One-byte storage through the engine API: the band geometry of the row-team traversal is reported (one, two,
+    four or eight warps per row by locus width), and every width agrees with the fp64 storage run."""
     from sushie_b200 import _capi
     from sushie_b200._common import build_priors
 
     rng = np.random.default_rng(11)
     eng = _capi.get_engine(0)
-    for p, rows in ((300, 16), (1500, 8), (2500, 4), (5000, 2)):
+    for p, rows in ((300, 32), (700, 16), (1500, 8), (2500, 4), (5000, 2)):
         k, n, L = 2, [90, 70], 3
         Xs = [rng.binomial(2, 0.3, size=(n[i], p)).astype(np.int8) for i in range(k)]
         for X in Xs:
@@ -285,7 +283,7 @@ def test_hard_call_storage_is_selected_and_wide_loci_fit(engine_lib):
             ys.append((y - y.mean()) / y.std())
         ec, adj = build_priors(k, L, None, None, False, summary=False)
         fits = {}
-        for storage in (_capi.SB_F64, _capi.SB_I8):
+        for storage in (_capi.SB_F64, _capi.SB_I8, _capi.SB_B2):
             prob = _capi.IndProblem(Xs, ys, L, None, [np.var(y, ddof=1) for y in ys], ec, adj.times, adj.plus, True,
                                     standardize=_capi.SB_CENTER | _capi.SB_SCALE)
             with eng.create_batch([prob], eng.make_opts(30, 1e-4, storage, 1)) as b:
@@ -293,11 +291,13 @@ def test_hard_call_storage_is_selected_and_wide_loci_fit(engine_lib):
                 fits[storage] = b.fetch()[0]
                 if storage == _capi.SB_I8:
                     assert st["rows_per_band"] == rows
-        a, c = fits[_capi.SB_F64], fits[_capi.SB_I8]
-        assert a.n_iter == c.n_iter
-        np.testing.assert_allclose(a.elbo[1:], c.elbo[1:], rtol=1e-9)
-        np.testing.assert_allclose(a.alpha, c.alpha, atol=1e-8)
-        np.testing.assert_allclose(a.effect_covar, c.effect_covar, rtol=1e-6, atol=1e-12)
+        a = fits[_capi.SB_F64]
+        for hard in (_capi.SB_I8, _capi.SB_B2):
+            c = fits[hard]
+            assert a.n_iter == c.n_iter
+            np.testing.assert_allclose(a.elbo[1:], c.elbo[1:], rtol=1e-9)
+            np.testing.assert_allclose(a.alpha, c.alpha, atol=1e-8)
+            np.testing.assert_allclose(a.effect_covar, c.effect_covar, rtol=1e-6, atol=1e-12)
 
 
 def test_batch_sharded_over_all_visible_gpus(engine_lib, golden_syn):

@@ -4,6 +4,7 @@ teams larger than the number of bands of an ancestry, ...)."""
 import numpy as np
 import pytest
 
+from conftest import STORAGE_MODES, genotype_storage
 from parity import COV_RTOL, ELBO_RTOL, PIP_TOL
 
 pytestmark = pytest.mark.gpu
@@ -40,7 +41,7 @@ def _case(seed):
     return Xs, ys, kw, team, dict(k=k, n=n, p=p, team=team, **kw)
 
 
-@pytest.mark.parametrize("storage", ["dense", "auto"])
+@pytest.mark.parametrize("storage", STORAGE_MODES)
 @pytest.mark.parametrize("seed", range(14))
 def test_random_individual_level_shapes(engine_lib, seed, storage):
     import sushie_b200
@@ -48,12 +49,13 @@ def test_random_individual_level_shapes(engine_lib, seed, storage):
     from sushie_b200 import config
 
     Xs, ys, kw, team, desc = _case(seed)
-    old = (config.genotype_storage, config.team_size)
-    config.genotype_storage, config.team_size = storage, team
+    old = config.team_size
+    config.team_size = team
     try:
-        res = sushie_b200.infer_sushie([x.copy() for x in Xs], [y.copy() for y in ys], min_snps=50, **kw)
+        with genotype_storage(storage):
+            res = sushie_b200.infer_sushie([x.copy() for x in Xs], [y.copy() for y in ys], min_snps=50, **kw)
     finally:
-        config.genotype_storage, config.team_size = old
+        config.team_size = old
     ref = ibss.fit_individual(Xs, ys, **kw)
     assert len(res.elbo) - 1 == ref.n_iter, desc
     assert bool(res.elbo_increase) == bool(ref.elbo_increase), desc
