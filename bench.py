@@ -343,9 +343,10 @@ def main():
     ap.add_argument("--genes", type=int, default=1000, help="loci per GPU per step")
     ap.add_argument("--max-iter", type=int, default=500)
     ap.add_argument("--min-tol", type=float, default=1e-4)
-    ap.add_argument("--storage", default="i8", choices=["i8", "f64", "f32"],
-                    help="device storage of the genotypes: i8 = raw hard calls (1 B/entry, centring/scaling folded "
-                         "into the vectors), f64 / f32 = standardised dense matrix; arithmetic is fp64 in every case")
+    ap.add_argument("--storage", default="b2", choices=["b2", "i8", "f64", "f32"],
+                    help="device storage of the genotypes: b2 = hard calls 0/1/2 as bit planes (products by table "
+                         "look-up), i8 = raw hard calls (1 B/entry), both with centring/scaling folded into the "
+                         "vectors; f64 / f32 = standardised dense matrix; arithmetic is fp64 in every case")
     ap.add_argument("--team", type=int, default=0)
     ap.add_argument("--single-phase", action="store_true")
     ap.add_argument("--ref-loci", type=int, default=0)
@@ -420,8 +421,8 @@ def main():
                 em_update=True, standardize=_capi.SB_CENTER | _capi.SB_SCALE))
         return probs
 
-    storage = {"i8": _capi.SB_I8, "f64": _capi.SB_F64, "f32": _capi.SB_F32}[args.storage]
-    elem_bytes = {"i8": 1, "f64": 8, "f32": 4}[args.storage]
+    storage = {"b2": _capi.SB_B2, "i8": _capi.SB_I8, "f64": _capi.SB_F64, "f32": _capi.SB_F32}[args.storage]
+    elem_bytes = {"b2": 0.5, "i8": 1, "f64": 8, "f32": 4}[args.storage]
     opts = eng.make_opts(args.max_iter, args.min_tol, storage, args.team, args.single_phase)
 
     def barrier():
@@ -621,14 +622,14 @@ def main():
             # DRAM view: ncu read+write bytes per update x updates / time -- what the memory system actually moves
             "achieved_dram": (traffic_per_ser * ser_per_gpu_s / 1e9) if traffic_per_ser else None,
             "frac_dram": (traffic_per_ser * ser_per_gpu_s / 1e9 / peak) if traffic_per_ser else None,
-            "limiter": ("fp64 issue" if args.storage == "i8" else "hbm"),
+            "limiter": {"b2": "shared-memory table look-ups / issue", "i8": "fp64 issue"}.get(args.storage, "hbm"),
             "note": ("achieved = #single-effect updates x k*n*p*%d B (one traversal of the genotype tensor at the "
                      "precision under test) / CUDA-event time, per GPU" % alg_elem)
-                    + ("; genotypes are stored as 1-byte hard calls (compressed), so `frac` counts fp64-equivalent "
+                    + ("; genotypes are stored as hard calls (bit planes or bytes: compressed), so `frac` counts fp64-equivalent "
                        "bytes and is NOT a fraction of HBM bandwidth: the memory system moves `achieved_dram` "
                        "(`frac_dram` of peak) and the kernel is bound by fp64 / issue slots (`limiter`); the "
                        "HBM-roofline claims are roofline_dense_fp64 and roofline_ss_f32, where DRAM traffic equals "
-                       "the algorithmic bytes" if args.storage == "i8" else ""),
+                       "the algorithmic bytes" if args.storage in ("i8", "b2") else ""),
         }
         line = {
             "metric": "loci_per_sec",
@@ -649,7 +650,8 @@ def main():
             "mean_iters_per_locus": n_iter / (total_loci * args.steps),
             "wall_ms_per_step": wall_ms / args.steps,
             "gpu_launches": launches,
-            "kernel": dict(geom, name="sb::ibss_kernel<3,%s>" % {"i8": "int8_t,false,1", "f64": "double,false,1", "f32": "float,false,0"}[args.storage],
+            "kernel": dict(geom, name="sb::ibss_kernel<3,%s>" % {"b2": "uint8_t,false,0", "i8": "int8_t,false,1", "f64": "double,false,1",
+                                                         "f32": "float,false,0"}[args.storage],
                            launches_per_step=launches / args.steps, genotype_storage=args.storage,
                            stored_mb_per_locus=K_ANC * N_IND * P_SNP * elem_bytes / 1e6),
             "roofline": roofline,

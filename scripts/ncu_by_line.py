@@ -8,10 +8,15 @@ rep, lib, kname = sys.argv[1:4]
 topn = int(sys.argv[4]) if len(sys.argv) > 4 else 40
 tmp = tempfile.mkdtemp()
 subprocess.run(["cuobjdump", "-xelf", "all", os.path.abspath(lib)], cwd=tmp, check=True, stdout=subprocess.DEVNULL)
-cubin = [f for f in os.listdir(tmp) if f.endswith(".cubin")][0]
-sass = subprocess.run(["nvdisasm", "-g", "-c", os.path.join(tmp, cubin)], capture_output=True, text=True).stdout.splitlines()
-# locate function
-start = next(i for i, l in enumerate(sass) if l.startswith(".text.") and kname in l)
+# the library holds one cubin per translation unit: take the one that defines the kernel
+start = None
+for cubin in sorted(f for f in os.listdir(tmp) if f.endswith(".cubin")):
+    sass = subprocess.run(["nvdisasm", "-g", "-c", os.path.join(tmp, cubin)], capture_output=True, text=True).stdout.splitlines()
+    start = next((i for i, l in enumerate(sass) if l.startswith(".text.") and kname in l), None)
+    if start is not None:
+        break
+if start is None:
+    sys.exit(f"kernel {kname} not found in {lib}")
 lines = []  # source line per instruction in order
 cur = None
 for l in sass[start + 1:]:

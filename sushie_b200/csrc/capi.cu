@@ -574,7 +574,7 @@ static int batch_create(sb_ctx* ctx, const std::vector<GenericProblem>& gp, bool
       if (opts.storage == SB_B2) {
         const size_t ntiles = (static_cast<size_t>(g.p) + sb::B2_TILE_COLS - 1) / sb::B2_TILE_COLS;
         l.rbits[k] = bump.take(ntiles * ((g.n[k] + 3) / 4) * 256);
-        l.cbits[k] = bump.take(ntiles * ((g.n[k] + 63) / 64) * 4096);
+        l.cbits[k] = bump.take(((g.n[k] + 255) / 256) * (64 * ntiles) * 256);
       }
       if (!direct) staging_bytes = std::max(staging_bytes, static_cast<size_t>(g.n[k]) * g.p * elem_size(g.mat_dtype));
     }

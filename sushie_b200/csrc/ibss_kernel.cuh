@@ -101,7 +101,7 @@ struct ProbDev {
   const double* cmean;  // [K][p_pad] column means      (hard-call int8 storage only; pad = 0)
   const double* cisd;   // [K][p_pad] 1 / column std    (hard-call int8 storage only; pad = 0)
   // bit-plane storage: rbits[k] = [chunk][row quad][plane][32 groups][4 rows] bytes, bit c = column 8 g + c;
-  //                    cbits[k] = [row-group octet][tile][plane][256 columns][8 row groups] bytes, bit r = row 8 rg + r
+  //                    cbits[k] = [row chunk][column quad][plane][32 row groups][4 columns] bytes, bit r = row 8 rg + r
   const unsigned char* rbits[KMAX];
   const unsigned char* cbits[KMAX];
   int ntiles;           // ceil(p / 256)
@@ -1379,46 +1379,51 @@ __global__ void __launch_bounds__(NT, (std::is_same<XT, int8_t>::value ? SB_I8_B
     // Bit-plane traversal (XT = uint8_t): hard calls 0/1/2 are two bit planes, B1 = (g >= 1) and B2 = (g == 2), so
     // g = B1 + B2 and both products are SUBSET SUMS that come out of lookup tables instead of fp64 multiply-adds
     // on widened genotypes (the column-tile traversal spends 3 of its 5 issue slots per genotype on widening):
-    //   sweep 1   v_i  = sum_groups T1[g][bits of row i in group g]      T1[g][e] = sum_{c in e} b'_{8 g + c}
-    //   sweep 2   a_j  = sum_rowgroups T2[rg][bits of column j in rg]    T2[rg][e] = sum_{r in e} r_next_{8 rg + r}
-    // one table read + one add per 8 genotypes and plane.  Sweep 1 runs over 256-column chunks (32 groups, a 64 KB
-    // table set in shared memory): a warp owns 64 rows, lane = group, so the 32 lanes read 32 different table
-    // columns (conflict-free) and the lane-private row sums are combined once per ancestry by a transposed
-    // butterfly.  Sweep 2 runs over 256-row chunks (32 row groups): a thread owns one column per tile.  The bit
-    // stream arrives through a 3-stage ring of bulk copies; the last warp to finish a piece re-arms its stage.
-    // Team members split the rows in sweep 1 and the columns (their own SNP slice) in sweep 2, so X^T r is complete
-    // per block and needs no reduction.
+    //   sweep 1   v_i  = sum_groups T[g][bits of row i in column group g]     T[g][e]  = sum_{c in e} b'_{8 g + c}
+    //   sweep 2   a_j  = sum_groups T[rg][bits of column j in row group rg]   T[rg][e] = sum_{r in e} r_next_{8 rg + r}
+    // i.e. one table read + one add per 8 genotypes and plane.  The two sweeps are the same code on the two bit
+    // layouts (row-major / column-major).  A pass handles 256 "inner" indices (32 groups of 8: one 64 KB table set
+    // in shared memory, entry-major so that the 32 lanes of a warp -- lane = group -- always read 32 different
+    // banks) against up to 512 "outer" indices (a warp owns 64 of them, 64 lane-private sums in registers); after
+    // the last pass of a round a transposed butterfly turns the lane-private sums into totals.  The look-up address
+    // is built by ONE prmt: the table set is aligned to 64 KB, so (base | bits << 8 | lane << 3) is a byte splice.
+    // The bit stream arrives through a 3-stage ring of bulk copies; the last warp to finish a piece re-arms its
+    // stage.  Team members split the rows in sweep 1 and the columns (their own SNP slice) in sweep 2, so X^T r is
+    // complete per block and needs no reduction.
     auto traverse_b2 = [&](auto /*instantiate on use*/, int l, bool first) {
       const int lnext = first ? 0 : ((l + 1 == L) ? 0 : l + 1);
       const bool self_next = !first && lnext == l;
       const int ntiles = pb.ntiles;
-      // ---- shared memory: [header][small vectors ...][T: 64 KB table set, aligned to 64 KB][ring]
+      constexpr int RQ = B2_ROUND_ROWS / 4;  // outer quads per round
+      // ---- shared memory: [header][small vectors ...][64 KB table set, aligned to 64 KB][ring]
       const uint32_t smem_base = smem_u32(smem_raw);
       const uint32_t hdr_end = smem_base + static_cast<uint32_t>(((sizeof(SmemHdr) + 127) / 128) * 128);
       const uint32_t tab_addr = (hdr_end + 8192u + B2_MAX_ROWS * 8u + B2_TABLE_BYTES - 1u) & ~static_cast<uint32_t>(B2_TABLE_BYTES - 1);
-      unsigned char* const tab = smem_raw + (tab_addr - smem_base);
-      unsigned char* const ringb = tab + B2_TABLE_BYTES;
-      double* const bstage = reinterpret_cast<double*>(smem_raw + (hdr_end - smem_base));  // [256] b' of a chunk
-      double* const vsum = bstage + B2_TILE_COLS;                                            // [512] row sums of a round
+      double* const tab = reinterpret_cast<double*>(smem_raw + (tab_addr - smem_base));
+      unsigned char* const ringb = reinterpret_cast<unsigned char*>(tab) + B2_TABLE_BYTES;
+      double* const bstage = reinterpret_cast<double*>(smem_raw + (hdr_end - smem_base));  // [2][256] b' of a chunk
+      double* const vsum = bstage + 2 * B2_TILE_COLS;                                        // [512] row sums of a round
       double* const rn_sm = vsum + B2_ROUND_ROWS;                                            // [B2_MAX_ROWS] next residual
+      const uint32_t lane_const = tab_addr | (static_cast<uint32_t>(lane) << 3);
       // ---- work split inside the team
-      int q0[K], q1[K], rounds[K];  // row quads of this block per ancestry, sweep-1 rounds
-      int npa = 0;
+      int q0[K], q1[K], rounds1[K], rounds2[K], nch2[K];
+      int npa = 0, np_total;
 #pragma unroll
       for (int k = 0; k < K; ++k) {
-        const int nq = (pb.n[k] + 3) >> 2;
+        const int nq = (pb.n[k] + 3) >> 2;  // row quads, split over the team
         q0[k] = static_cast<int>((static_cast<long long>(nq) * rank) / C);
         q1[k] = static_cast<int>((static_cast<long long>(nq) * (rank + 1)) / C);
-        rounds[k] = first ? 0 : (q1[k] - q0[k] + B2_ROUND_ROWS / 4 - 1) / (B2_ROUND_ROWS / 4);
-        npa += rounds[k] * ntiles;
+        rounds1[k] = first ? 0 : (q1[k] - q0[k] + RQ - 1) / RQ;
+        npa += rounds1[k] * ntiles;
       }
       const int t0 = js / B2_TILE_COLS, t1 = (je > js) ? (je + B2_TILE_COLS - 1) / B2_TILE_COLS : t0;  // own column tiles
-      const int nsub = (t1 - t0 + 7) >> 3;
-      int npb[K], np_total = npa;
+      const int cq0 = 64 * t0, cq1 = 64 * t1;  // own column quads
+      np_total = npa;
 #pragma unroll
       for (int k = 0; k < K; ++k) {
-        npb[k] = ((pb.n[k] + 63) >> 6) * nsub;  // row-group octets x tile sub-ranges
-        np_total += npb[k];
+        nch2[k] = (pb.n[k] + 255) >> 8;  // 256-row chunks
+        rounds2[k] = (cq1 - cq0 + RQ - 1) / RQ;
+        np_total += rounds2[k] * nch2[k];
       }
       // piece s of the static stream -> (source, bytes)
       auto issue_piece = [&](int s, int stg) {
@@ -1429,14 +1434,13 @@ __global__ void __launch_bounds__(NT, (std::is_same<XT, int8_t>::value ? SB_I8_B
         if (r < npa) {
 #pragma unroll
           for (int k = 0; k < K; ++k) {
-            const int cnt = rounds[k] * ntiles;
+            const int cnt = rounds1[k] * ntiles;
             if (!found && r < cnt) {
               const int rd = r / ntiles, c = r - rd * ntiles;
               const int nq = (pb.n[k] + 3) >> 2;
-              const int qa = q0[k] + rd * (B2_ROUND_ROWS / 4);
-              const int qn = min(B2_ROUND_ROWS / 4, q1[k] - qa);
+              const int qa = q0[k] + rd * RQ;
               src = pb.rbits[k] + (static_cast<size_t>(c) * nq + qa) * 256;
-              bytes = static_cast<uint32_t>(qn) * 256u;
+              bytes = static_cast<uint32_t>(min(RQ, q1[k] - qa)) * 256u;
               found = true;
             }
             if (!found) r -= cnt;
@@ -1445,14 +1449,15 @@ __global__ void __launch_bounds__(NT, (std::is_same<XT, int8_t>::value ? SB_I8_B
           r -= npa;
 #pragma unroll
           for (int k = 0; k < K; ++k) {
-            if (!found && r < npb[k]) {
-              const int oct = r / nsub, sub = r - oct * nsub;
-              const int ta = t0 + 8 * sub, tn = min(8, t1 - ta);
-              src = pb.cbits[k] + (static_cast<size_t>(oct) * ntiles + ta) * 4096;
-              bytes = static_cast<uint32_t>(tn) * 4096u;
+            const int cnt = rounds2[k] * nch2[k];
+            if (!found && r < cnt) {
+              const int rd = r / nch2[k], d = r - rd * nch2[k];
+              const int qa = cq0 + rd * RQ;
+              src = pb.cbits[k] + (static_cast<size_t>(d) * (64 * ntiles) + qa) * 256;
+              bytes = static_cast<uint32_t>(min(RQ, cq1 - qa)) * 256u;
               found = true;
             }
-            if (!found) r -= npb[k];
+            if (!found) r -= cnt;
           }
         }
         mbar_expect_tx(&H->mbar[stg], bytes);
@@ -1479,6 +1484,67 @@ __global__ void __launch_bounds__(NT, (std::is_same<XT, int8_t>::value ? SB_I8_B
         cons_seq += 1;
         pseq += 1;
       };
+      // table set of 32 groups from 256 weights: thread (g, q) writes entries e = 32 q + r of group g
+      // (fixed association: low nibble sum + high nibble sum)
+      auto build_tables = [&](const double* w256) {
+        const int g = tid & 31, qq = tid >> 5;
+        const double2* b8 = reinterpret_cast<const double2*>(w256 + 8 * g);
+        const double2 b01 = b8[0], b23 = b8[1], b45 = b8[2], b67 = b8[3];
+        double lo[16];
+        lo[0] = 0.0;
+        lo[1] = b01.x;
+        lo[2] = b01.y;
+        lo[3] = b01.x + b01.y;
+        lo[4] = b23.x;
+        lo[5] = b01.x + b23.x;
+        lo[6] = b01.y + b23.x;
+        lo[7] = lo[3] + b23.x;
+        lo[8] = b23.y;
+        lo[9] = b01.x + b23.y;
+        lo[10] = b01.y + b23.y;
+        lo[11] = lo[3] + b23.y;
+        lo[12] = b23.x + b23.y;
+        lo[13] = lo[5] + b23.y;
+        lo[14] = lo[6] + b23.y;
+        lo[15] = lo[7] + b23.y;
+        double hi2[2];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int nib = 2 * qq + h;
+          double t = 0.0;
+          if (nib & 1) t = b45.x;
+          if (nib & 2) t = (nib & 1) ? t + b45.y : b45.y;
+          if (nib & 4) t = (nib & 3) ? t + b67.x : b67.x;
+          if (nib & 8) t = (nib & 7) ? t + b67.y : b67.y;
+          hi2[h] = t;
+        }
+        double* dst = tab + static_cast<size_t>(32 * qq) * 32 + g;
+#pragma unroll
+        for (int r = 0; r < 32; ++r) dst[r * 32] = lo[r & 15] + hi2[r >> 4];
+      };
+      // one pass: the warp's 16 outer quads (64 outer indices) of the piece against the resident table set
+      auto lookup_pass = [&](const unsigned char* piece, int qn, double (&acc)[64]) {
+        const uint32_t* words = reinterpret_cast<const uint32_t*>(piece) + (16 * warp) * 64 + lane;
+#pragma unroll
+        for (int oc = 0; oc < 4; ++oc) {  // four quads at a time (uniform skip past the end of the round)
+          if (16 * warp + 4 * oc < qn) {
+#pragma unroll
+            for (int m4 = 0; m4 < 4; ++m4) {
+              const int m = 4 * oc + m4;
+              if (16 * warp + m < qn) {
+#pragma unroll
+                for (int pl = 0; pl < 2; ++pl) {
+                  const uint32_t w = words[(m * 2 + pl) * 32];
+                  acc[4 * m + 0] += lds_f64(prmt(w, lane_const, 0x7604u));
+                  acc[4 * m + 1] += lds_f64(prmt(w, lane_const, 0x7614u));
+                  acc[4 * m + 2] += lds_f64(prmt(w, lane_const, 0x7624u));
+                  acc[4 * m + 3] += lds_f64(prmt(w, lane_const, 0x7634u));
+                }
+              }
+            }
+          }
+        }
+      };
       __syncthreads();  // every warp has left the previous phase: the ring and the tables are free
       if (tid == 0)
         for (int s = 0; s < B2_NSTAGE && s < np_total; ++s) issue_piece(s, (cons_seq + s) % B2_NSTAGE);
@@ -1500,96 +1566,41 @@ __global__ void __launch_bounds__(NT, (std::is_same<XT, int8_t>::value ? SB_I8_B
         }
       } else {
         // ---------------- sweep 1: v = G b' - cshift for the rows of this block, then the row state
-        const uint32_t lane_const = tab_addr | (static_cast<uint32_t>(lane) << 3);
 #pragma unroll 1
         for (int k = 0; k < K; ++k) {
           const double* bl = effect_vec(l, k);
           const double* cm = pb.cmean + static_cast<size_t>(k) * p_pad;
           const double* cs = pb.cisd + static_cast<size_t>(k) * p_pad;
+          auto load_b = [&](int c, double& b, double& mb) {  // b' of column 256 c + tid and its mean
+            const int j = c * B2_TILE_COLS + tid;
+            b = 0.0;
+            mb = 0.0;
+            if (c < ntiles && j < p_pad) {
+              b = __ldcg(&bl[j]) * cs[j];
+              mb = cm[j];
+            }
+          };
 #pragma unroll 1
-          for (int rd = 0; rd < rounds[k]; ++rd) {
-            const int qa = q0[k] + rd * (B2_ROUND_ROWS / 4);
-            const int qn = min(B2_ROUND_ROWS / 4, q1[k] - qa);  // row quads of this round
+          for (int rd = 0; rd < rounds1[k]; ++rd) {
+            const int qa = q0[k] + rd * RQ;
+            const int qn = min(RQ, q1[k] - qa);  // row quads of this round
             double acc[64];
 #pragma unroll
             for (int i = 0; i < 64; ++i) acc[i] = 0.0;
             double cpart[1] = {0.0};
+            double b_cur, m_cur;
+            load_b(0, b_cur, m_cur);
 #pragma unroll 1
             for (int c = 0; c < ntiles; ++c) {
-              // b' of the chunk, coalesced; cshift = sum_j mean_j b'_j
-              {
-                const int j = c * B2_TILE_COLS + tid;
-                double b = 0.0;
-                if (j < p_pad) {
-                  b = __ldcg(&bl[j]) * cs[j];
-                  cpart[0] += cm[j] * b;
-                }
-                __syncthreads();  // previous table set and b' no longer read
-                bstage[tid] = b;
-              }
-              __syncthreads();
-              {
-                // table set of the chunk: thread (g, q) writes entries e = 32 q + r of group g
-                const int g = tid & 31, qq = tid >> 5;
-                const double2* b8 = reinterpret_cast<const double2*>(bstage + 8 * g);
-                const double2 b01 = b8[0], b23 = b8[1], b45 = b8[2], b67 = b8[3];
-                double lo[16];
-                lo[0] = 0.0;
-                lo[1] = b01.x;
-                lo[2] = b01.y;
-                lo[3] = b01.x + b01.y;
-                lo[4] = b23.x;
-                lo[5] = b01.x + b23.x;
-                lo[6] = b01.y + b23.x;
-                lo[7] = lo[3] + b23.x;
-                lo[8] = b23.y;
-                lo[9] = b01.x + b23.y;
-                lo[10] = b01.y + b23.y;
-                lo[11] = lo[3] + b23.y;
-                lo[12] = b23.x + b23.y;
-                lo[13] = lo[5] + b23.y;
-                lo[14] = lo[6] + b23.y;
-                lo[15] = lo[7] + b23.y;
-                double hi2[2];
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                  const int nib = 2 * qq + h;
-                  // fixed association: ((b4 + b5) + b6) + b7 over the members present
-                  double t = 0.0;
-                  if (nib & 1) t = b45.x;
-                  if (nib & 2) t = (nib & 1) ? t + b45.y : b45.y;
-                  if (nib & 4) t = (nib & 3) ? t + b67.x : b67.x;
-                  if (nib & 8) t = (nib & 7) ? t + b67.y : b67.y;
-                  hi2[h] = t;
-                }
-                double* dst = reinterpret_cast<double*>(tab) + static_cast<size_t>(32 * qq) * 32 + g;
-#pragma unroll
-                for (int r = 0; r < 32; ++r) dst[r * 32] = lo[r & 15] + hi2[r >> 4];
-              }
+              double* bs = bstage + (c & 1) * B2_TILE_COLS;
+              bs[tid] = b_cur;  // (the other half may still be read by a slow builder of the previous chunk)
+              cpart[0] += m_cur * b_cur;
+              load_b(c + 1, b_cur, m_cur);  // in flight during this chunk's look-ups
+              __syncthreads();  // b' complete; the previous table set is no longer read
+              build_tables(bs);
               __syncthreads();
               const unsigned char* piece = piece_wait();
-              // warp w: row quads 16 w .. 16 w + 15 of the round; lane = group
-              const uint32_t* words = reinterpret_cast<const uint32_t*>(piece) + lane;
-#pragma unroll
-              for (int oc = 0; oc < 4; ++oc) {  // four quads at a time (uniform skip past the end of the round)
-                if (16 * warp + 4 * oc < qn) {
-#pragma unroll
-                  for (int m4 = 0; m4 < 4; ++m4) {
-                    const int m = 4 * oc + m4;
-                    const int ql = 16 * warp + m;
-                    if (ql < qn) {
-#pragma unroll
-                      for (int pl = 0; pl < 2; ++pl) {
-                        const uint32_t w = words[(ql * 2 + pl) * 32];
-                        acc[4 * m + 0] += lds_f64(prmt(w, lane_const, 0x7604u));
-                        acc[4 * m + 1] += lds_f64(prmt(w, lane_const, 0x7614u));
-                        acc[4 * m + 2] += lds_f64(prmt(w, lane_const, 0x7624u));
-                        acc[4 * m + 3] += lds_f64(prmt(w, lane_const, 0x7634u));
-                      }
-                    }
-                  }
-                }
-              }
+              lookup_pass(piece, qn, acc);
               piece_done();
             }
             // lane-private row sums -> row totals (lane i of the warp holds rows 64 w + i and 64 w + 32 + i)
@@ -1625,113 +1636,55 @@ __global__ void __launch_bounds__(NT, (std::is_same<XT, int8_t>::value ? SB_I8_B
                   }
               }
             }
-            __syncthreads();  // vsum is reused by the next round
+            __syncthreads();  // vsum / bstage are reused by the next round
           }
         }
       }
       team_sync(team);  // the next residual of every row (all team members) is in global memory
 
-      // ---------------- sweep 2: X_std^T r_next for the own column tiles
-      const uint32_t tab2 = tab_addr;
+      // ---------------- sweep 2: X_std^T r_next for the own column tiles (same passes on the column-major bits)
 #pragma unroll 1
       for (int k = 0; k < K; ++k) {
         const int nk = pb.n[k];
         double rpart[1] = {0.0};
-        for (int i = tid; i < ((nk + 255) & ~255); i += NT) {
+        for (int i = tid; i < (nch2[k] << 8); i += NT) {
           const double rv = (i < nk) ? __ldcg(&pb.r[pb.row0[k] + i]) : 0.0;
           rn_sm[i] = rv;
           rpart[0] += rv;
         }
-        block_sum<1>(H, rpart);
+        block_sum<1>(H, rpart);  // (barriers inside: rn_sm visible)
         const double rsum = H->tot[0];
-        double a2[8 * B2_MAX_SUB];
-#pragma unroll
-        for (int i = 0; i < 8 * B2_MAX_SUB; ++i) a2[i] = 0.0;
-        const int nchunks = (nk + 255) >> 8;
+        const double* cm = pb.cmean + static_cast<size_t>(k) * p_pad;
+        const double* cs = pb.cisd + static_cast<size_t>(k) * p_pad;
+        double* dst = pb.xty + static_cast<size_t>(k) * p_pad;
 #pragma unroll 1
-        for (int d = 0; d < nchunks; ++d) {
-          __syncthreads();  // previous table set no longer read
-          {
-            // table set of the row chunk: thread (rg, q) writes entries e = q + 8 r' of row group rg
-            const int rg = tid >> 3, qq = tid & 7;
-            const double2* r8 = reinterpret_cast<const double2*>(rn_sm + 256 * d + 8 * rg);
-            const double2 r01 = r8[0], r23 = r8[1], r45 = r8[2], r67 = r8[3];
-            double hi[16];
-            hi[0] = 0.0;
-            hi[1] = r45.x;
-            hi[2] = r45.y;
-            hi[3] = r45.x + r45.y;
-            hi[4] = r67.x;
-            hi[5] = r45.x + r67.x;
-            hi[6] = r45.y + r67.x;
-            hi[7] = hi[3] + r67.x;
-            hi[8] = r67.y;
-            hi[9] = r45.x + r67.y;
-            hi[10] = r45.y + r67.y;
-            hi[11] = hi[3] + r67.y;
-            hi[12] = r67.x + r67.y;
-            hi[13] = hi[5] + r67.y;
-            hi[14] = hi[6] + r67.y;
-            hi[15] = hi[7] + r67.y;
-            double lo2[2];
+        for (int rd = 0; rd < rounds2[k]; ++rd) {
+          const int qa = cq0 + rd * RQ;
+          const int qn = min(RQ, cq1 - qa);  // column quads of this round
+          double acc[64];
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-              const int nib = qq + 8 * h;
-              double t = 0.0;
-              if (nib & 1) t = r01.x;
-              if (nib & 2) t = (nib & 1) ? t + r01.y : r01.y;
-              if (nib & 4) t = (nib & 3) ? t + r23.x : r23.x;
-              if (nib & 8) t = (nib & 7) ? t + r23.y : r23.y;
-              lo2[h] = t;
-            }
-            double* dst = reinterpret_cast<double*>(tab) + static_cast<size_t>(rg) * 256 + qq;
-#pragma unroll
-            for (int rp = 0; rp < 32; ++rp) dst[8 * rp] = lo2[rp & 1] + hi[rp >> 1];
-          }
-          __syncthreads();
-          const int octs = min(4, ((nk + 63) >> 6) - 4 * d);  // row-group octets of this chunk
+          for (int i = 0; i < 64; ++i) acc[i] = 0.0;
 #pragma unroll 1
-          for (int oc = 0; oc < octs; ++oc) {
-            const uint32_t tbase = tab2 + static_cast<uint32_t>(oc) * 8u * 2048u;
-#pragma unroll
-            for (int sub = 0; sub < B2_MAX_SUB; ++sub) {
-              if (sub < nsub) {
-                const unsigned char* piece = piece_wait();
-                const int tn = min(8, t1 - (t0 + 8 * sub));
-#pragma unroll
-                for (int tt = 0; tt < 8; ++tt) {
-                  if (tt < tn) {
-#pragma unroll
-                    for (int pl = 0; pl < 2; ++pl) {
-                      const uint2 w = *reinterpret_cast<const uint2*>(piece + ((tt * 2 + pl) * 256 + tid) * 8);
-                      double s = 0.0;
-#pragma unroll
-                      for (int r = 0; r < 8; ++r) {
-                        const uint32_t word = (r < 4) ? w.x : w.y;
-                        const uint32_t e8 = ((word >> (8 * (r & 3))) & 0xffu) << 3;
-                        s += lds_f64(tbase + static_cast<uint32_t>(r) * 2048u + e8);
-                      }
-                      a2[8 * sub + tt] += s;
-                    }
-                  }
-                }
-                piece_done();
-              }
-            }
+          for (int d = 0; d < nch2[k]; ++d) {
+            __syncthreads();  // the previous table set is no longer read
+            build_tables(rn_sm + 256 * d);
+            __syncthreads();
+            const unsigned char* piece = piece_wait();
+            lookup_pass(piece, qn, acc);
+            piece_done();
           }
-        }
-        // X_std^T r = (G^T r - mean * sum r) / sd for the own slice
-        {
-          const double* cm = pb.cmean + static_cast<size_t>(k) * p_pad;
-          const double* cs = pb.cisd + static_cast<size_t>(k) * p_pad;
-          double* dst = pb.xty + static_cast<size_t>(k) * p_pad;
+          // lane-private column sums -> totals; X_std^T r = (G^T r - mean * sum r) / sd for the own slice
+          double lo32[32], hi32[32];
 #pragma unroll
-          for (int sub = 0; sub < B2_MAX_SUB; ++sub)
-#pragma unroll
-            for (int tt = 0; tt < 8; ++tt) {
-              const int j = (t0 + 8 * sub + tt) * B2_TILE_COLS + tid;
-              if (sub < nsub && t0 + 8 * sub + tt < t1 && j >= js && j < je) dst[j] = (a2[8 * sub + tt] - cm[j] * rsum) * cs[j];
-            }
+          for (int i = 0; i < 32; ++i) {
+            lo32[i] = acc[i];
+            hi32[i] = acc[32 + i];
+          }
+          const double ta = warp_rows_sum<32>(lo32, lane);
+          const double tb = warp_rows_sum<32>(hi32, lane);
+          const int ja = 4 * qa + 64 * warp + lane, jb = ja + 32;
+          if (ja >= js && ja < je) dst[ja] = (ta - cm[ja] * rsum) * cs[ja];
+          if (jb >= js && jb < je) dst[jb] = (tb - cm[jb] * rsum) * cs[jb];
         }
         __syncthreads();  // rn_sm is reloaded for the next ancestry
       }
@@ -2687,7 +2640,7 @@ __global__ void prep_columns_batched_kernel(const PrepDesc* __restrict__ descs, 
 
 // Bit-plane packing of hard calls 0/1/2 (see traverse_b2): from the resident one-byte matrix [n][p_pad] to
 //   rbits = [chunk][row quad][plane][32 groups][4 rows]           bit c of a byte = column 256 chunk + 8 group + c
-//   cbits = [row-group octet][tile][plane][256 columns][8 groups] bit r of a byte = row 64 octet + 8 group + r
+//   cbits = [row chunk][column quad][plane][32 groups][4 columns]   bit r of a byte = row 256 chunk + 8 group + r
 // plane 0 = (g >= 1), plane 1 = (g == 2); rows / columns past the end are zero.
 struct PackDesc {
   const signed char* X;  // [n][p_pad]
@@ -2698,9 +2651,9 @@ struct PackDesc {
 
 static __global__ void pack_b2_kernel(const PackDesc* __restrict__ descs, int* __restrict__ bad_flag) {
   const PackDesc d = descs[blockIdx.y];
-  const int nq = (d.n + 3) >> 2, noct = (d.n + 63) >> 6;
+  const int nq = (d.n + 3) >> 2, nch = (d.n + 255) >> 8, ncq = 64 * d.ntiles;
   const long long n_r = static_cast<long long>(d.ntiles) * nq * 32;
-  const long long n_c = static_cast<long long>(noct) * d.ntiles * B2_TILE_COLS;
+  const long long n_c = static_cast<long long>(nch) * ncq * 32;
   bool bad = false;
   for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < n_r + n_c;
        idx += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -2728,26 +2681,29 @@ static __global__ void pack_b2_kernel(const PackDesc* __restrict__ descs, int* _
       out[0] = w0;
       out[32] = w1;
     } else {
+      // thread = (row chunk, column quad, row group): 8 rows x 4 columns -> one word per plane
       const long long i2 = idx - n_r;
-      const int col = static_cast<int>(i2 & (B2_TILE_COLS - 1));
-      const long long t = i2 >> 8;
-      const int tile = static_cast<int>(t % d.ntiles), oct = static_cast<int>(t / d.ntiles);
-      const int j = tile * B2_TILE_COLS + col;
-      uint32_t p0[2] = {0u, 0u}, p1[2] = {0u, 0u};
-      if (j < d.p_pad) {
-        for (int rg8 = 0; rg8 < 8; ++rg8)
-          for (int r = 0; r < 8; ++r) {
-            const int row = (oct * 8 + rg8) * 8 + r;
-            if (row < d.n) {
-              const uint32_t v = static_cast<unsigned char>(d.X[static_cast<size_t>(row) * d.p_pad + j]);
-              p0[rg8 >> 2] |= static_cast<uint32_t>(v >= 1u) << (8 * (rg8 & 3) + r);
-              p1[rg8 >> 2] |= static_cast<uint32_t>(v == 2u) << (8 * (rg8 & 3) + r);
+      const int rg = static_cast<int>(i2 & 31);
+      const long long t = i2 >> 5;
+      const int cq = static_cast<int>(t % ncq), ch = static_cast<int>(t / ncq);
+      const int j0 = 4 * cq, row0 = 256 * ch + 8 * rg;
+      uint32_t w0 = 0u, w1 = 0u;
+      if (j0 < d.p_pad) {
+        for (int r = 0; r < 8; ++r) {
+          const int row = row0 + r;
+          if (row < d.n) {
+            const uint32_t v4 = *reinterpret_cast<const uint32_t*>(d.X + static_cast<size_t>(row) * d.p_pad + j0);
+            for (int cc = 0; cc < 4; ++cc) {
+              const uint32_t v = (v4 >> (8 * cc)) & 0xffu;
+              w0 |= static_cast<uint32_t>(v >= 1u) << (8 * cc + r);
+              w1 |= static_cast<uint32_t>(v == 2u) << (8 * cc + r);
             }
           }
+        }
       }
-      uint2* out = reinterpret_cast<uint2*>(d.cbits) + ((static_cast<size_t>(oct) * d.ntiles + tile) * 2) * B2_TILE_COLS + col;
-      out[0] = make_uint2(p0[0], p0[1]);
-      out[B2_TILE_COLS] = make_uint2(p1[0], p1[1]);
+      uint32_t* out = reinterpret_cast<uint32_t*>(d.cbits) + ((static_cast<size_t>(ch) * ncq + cq) * 2) * 32 + rg;
+      out[0] = w0;
+      out[32] = w1;
     }
   }
   if (bad) atomicOr(bad_flag, 2);
