@@ -60,7 +60,7 @@ extern "C" {
                   SB_I8, entries in 0..127, p <= 8192): raw bytes stay resident, centring/scaling is folded into the vectors */
 
 #define SB_B2 3 /* hard calls 0/1/2 as bit planes (sb_opts.storage only; individual level, every problem x_dtype ==
-                  SB_I8, n_i <= 2048, p <= 8192): the single-effect products become table look-ups (no fp64 widening of
+                  SB_I8, n_i <= 1024, p <= 8192): the single-effect products become table look-ups (no fp64 widening of
                   genotypes); the one-byte matrix stays resident for the purity kernel */
 
 /* sb_opts.flags */

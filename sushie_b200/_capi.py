@@ -18,7 +18,7 @@ SB_F64, SB_F32, SB_I8, SB_B2 = 0, 1, 2, 3
 SB_CENTER, SB_SCALE = 1, 2
 SB_FLAG_SINGLE_PHASE = 1
 I8_MAX_SNPS = 8192  # widest locus the hard-call (one byte per entry) traversal handles
-B2_MAX_SNPS, B2_MAX_ROWS = 8192, 2048  # limits of the bit-plane (0 / 1 / 2 hard calls) traversal
+B2_MAX_SNPS, B2_MAX_ROWS = 8192, 1024  # limits of the bit-plane (0 / 1 / 2 hard calls) traversal
 
 _LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_lib", "libsushie_b200.so")
 # development: A/B a differently built engine without touching the tree

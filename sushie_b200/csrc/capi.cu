@@ -1082,7 +1082,8 @@ extern "C" int sb_batch_run(sb_ctx* ctx, sb_batch* b, sb_run_stats* stats) {
       // (re)upload the id list of this phase: a previous run leaves the last phase's list behind
       SB_CUDA(cudaMemcpyAsync(b->d_ids + g0, ids.data(), sizeof(int) * ids.size(), cudaMemcpyHostToDevice, st));
       cudaLaunchConfig_t cfg{};
-      cfg.blockDim = dim3(sb::NT);
+      const int block_threads = (b->storage == SB_B2) ? sb::NT_B2 : sb::NT;
+      cfg.blockDim = dim3(block_threads);
       cfg.dynamicSmemBytes = b->smem_bytes;
       cfg.stream = st;
       cudaLaunchAttribute attrs[2];
@@ -1090,7 +1091,7 @@ extern "C" int sb_batch_run(sb_ctx* ctx, sb_batch* b, sb_run_stats* stats) {
       int max_teams;
       if (C == 1) {
         int per_sm = 0;
-        SB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, sb::NT, b->smem_bytes));
+        SB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, block_threads, b->smem_bytes));
         max_teams = per_sm * ctx->num_sms;
       } else if (hw) {
         attrs[na].id = cudaLaunchAttributeClusterDimension;
@@ -1106,7 +1107,7 @@ extern "C" int sb_batch_run(sb_ctx* ctx, sb_batch* b, sb_run_stats* stats) {
         max_teams = ncl;
       } else {
         int per_sm = 0;
-        SB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, sb::NT, b->smem_bytes));
+        SB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, block_threads, b->smem_bytes));
         max_teams = (per_sm * ctx->num_sms) / C;
         attrs[na].id = cudaLaunchAttributeCooperative;
         attrs[na].val.cooperative = 1;

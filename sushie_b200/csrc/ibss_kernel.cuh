@@ -43,6 +43,8 @@ namespace sb {
 constexpr int KMAX = 4;
 constexpr int NT = 256;  // threads per block
 constexpr int NW = NT / 32;
+constexpr int NT_B2 = 256;  // threads of the bit-plane kernel (512 measured slower: 230 vs 204 us per update at p = 2000)
+constexpr int NW_MAX = NT_B2 / 32;
 constexpr int GMAX = 32;  // max rows per band
 constexpr int NSTAGE_MAX = 6;
 constexpr int I8_STATE_ROWS = 2048;  // hard-call path: band rows whose (r, xb) state is staged in shared memory at a time
@@ -53,10 +55,10 @@ constexpr int FAST_GLOBAL_VECTORS = 9;  // ProbDev::fast: generic traversal with
 // row-major bits for the X b sweep and column-major bits for the X^T r sweep (see traverse_b2)
 constexpr int B2_TILE_COLS = 256;       // columns per chunk / tile = 32 byte-groups of 8 columns
 constexpr int B2_STAGE_BYTES = 32768;   // one ring stage of the bit stream
-constexpr int B2_NSTAGE = 3;
+constexpr int B2_NSTAGE = 2;             // one stage below the table sets, one above (shared-memory alignment)
 constexpr int B2_ROUND_ROWS = 512;      // rows per sweep-1 round of one block (64 per warp)
-constexpr int B2_TABLE_BYTES = 65536;   // 256 entries x 32 groups x 8 bytes, aligned to its size in shared memory
-constexpr int B2_MAX_ROWS = 2048;       // rows per ancestry (their next residual is staged in shared memory)
+constexpr int B2_TABLE_BYTES = 65536;   // 256 entries x 32 groups x 8 bytes; two sets, aligned to 64 KB in shared memory
+constexpr int B2_MAX_ROWS = 1024;       // rows per ancestry (their next residual is staged in shared memory)
 constexpr int B2_MAX_SUB = 4;           // column tiles of one block per sweep-2 piece: 8 x B2_MAX_SUB >= p / 256
 constexpr int STAT_STRIDE = 20;  // doubles per team-reduction record (>= 2 + NSYM_MAX + 2 + KMAX)
 constexpr int TRAV_STRIDE = 2 * KMAX;
@@ -341,7 +343,7 @@ struct SmemHdr {
   ProbDev pb;                // the locus being processed
   alignas(16) double partsum[2][4 * GMAX];  // sweep-1 partial dot products [band parity][g * nseg + seg]
   double rn[GMAX];           // next residual of the band's rows
-  double red[NW][STAT_STRIDE];
+  double red[NW_MAX][STAT_STRIDE];
   double tot[STAT_STRIDE];   // block / team totals
   double cst[2 * KMAX * KMAX + 8];  // Cinv, misc per-pass constants
   double trow[GMAX][2];      // per-row scalars of a traversal
@@ -349,12 +351,12 @@ struct SmemHdr {
   int pad_[3];
   unsigned drain[NSTAGE_MAX];  // hard-call row-team traversal: warps that have finished with the band in stage s (mod NW)
   unsigned pad2_[2];
-  double tsum[NW];           // per row team: sum of the next residual over the rows it processed (current ancestry)
+  double tsum[NW_MAX];       // per row team: sum of the next residual over the rows it processed (current ancestry)
 };
 
 // Block-wide sum of NV values per thread; totals land in H->tot[0..NV) (valid for all
 // threads after return).  Fixed order => deterministic.
-template <int NV>
+template <int NV, int NWARPS = NW>
 __device__ __forceinline__ void block_sum(SmemHdr* H, double (&v)[NV]) {
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
 #pragma unroll
@@ -368,12 +370,13 @@ __device__ __forceinline__ void block_sum(SmemHdr* H, double (&v)[NV]) {
   if (threadIdx.x < NV) {
     double s = 0.0;
 #pragma unroll
-    for (int ww = 0; ww < NW; ++ww) s += H->red[ww][threadIdx.x];
+    for (int ww = 0; ww < NWARPS; ++ww) s += H->red[ww][threadIdx.x];
     H->tot[threadIdx.x] = s;
   }
   __syncthreads();
 }
 
+template <int NWARPS = NW>
 __device__ __forceinline__ double block_max(SmemHdr* H, double v) {
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   v = warp_max(v);
@@ -382,7 +385,7 @@ __device__ __forceinline__ double block_max(SmemHdr* H, double v) {
   __syncthreads();
   double m = H->red[0][0];
 #pragma unroll
-  for (int ww = 1; ww < NW; ++ww) m = fmax(m, H->red[ww][0]);
+  for (int ww = 1; ww < NWARPS; ++ww) m = fmax(m, H->red[ww][0]);
   return m;  // red is protected by the leading barrier of the next block_* call
 }
 
@@ -507,7 +510,11 @@ using IntC = std::integral_constant<int, N>;
 // 3 = 32 x 2, 4 = 4 x 8 for narrow loci, so each variant gets its own register allocation); 0 = chosen per
 // locus at run time.
 template <int K, typename XT, bool SS, int V = 0>
-__global__ void __launch_bounds__(NT, (std::is_same<XT, int8_t>::value ? SB_I8_BLOCKS_PER_SM : 1)) ibss_kernel(const LaunchParams P) {
+__global__ void __launch_bounds__((std::is_same<XT, uint8_t>::value ? NT_B2 : NT),
+                                  (std::is_same<XT, int8_t>::value ? SB_I8_BLOCKS_PER_SM : 1)) ibss_kernel(const LaunchParams P) {
+  // threads / warps per block of THIS instantiation (shadow the namespace constants inside the kernel body)
+  constexpr int NT = std::is_same<XT, uint8_t>::value ? sb::NT_B2 : sb::NT;
+  constexpr int NW = NT / 32;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   constexpr int NSYM = K * (K + 1) / 2;
   constexpr int VW = Vec<XT>::W;
@@ -844,7 +851,7 @@ __global__ void __launch_bounds__(NT, (std::is_same<XT, int8_t>::value ? SB_I8_B
           double v = 0.0;
           if (!first) {
             const double2* ps2 = reinterpret_cast<const double2*>(&H->partsum[pbuf][g * NW]);
-            static_assert(NW == 8, "pairwise tree below assumes 8 warps");
+            static_assert(NW == 8 || B2, "pairwise tree below assumes 8 warps");
             const double2 q0 = ps2[0], q1 = ps2[1], q2 = ps2[2], q3 = ps2[3];
             v = (((q0.x + q0.y) + (q1.x + q1.y)) + ((q2.x + q2.y) + (q3.x + q3.y))) * nsc;
           }
@@ -1000,7 +1007,7 @@ __global__ void __launch_bounds__(NT, (std::is_same<XT, int8_t>::value ? SB_I8_B
               bq[c][u + 1] = b2.y;
             }
           }
-          block_sum<1>(H, part);
+          block_sum<1, NW>(H, part);
           cshift = H->tot[0];
           rsum = 0.0;
           cur_k = k;
@@ -1258,7 +1265,7 @@ __global__ void __launch_bounds__(NT, (std::is_same<XT, int8_t>::value ? SB_I8_B
             xteam[j] = b;
             part[0] += cm[j] * b;
           }
-          block_sum<1>(H, part);
+          block_sum<1, NW>(H, part);
           cshift = H->tot[0];
 #pragma unroll
           for (int i = 0; i < NV; ++i) {
@@ -1365,7 +1372,7 @@ __global__ void __launch_bounds__(NT, (std::is_same<XT, int8_t>::value ? SB_I8_B
           tv[k] = leader ? vsq[k] : 0.0;
           tv[K + k] = leader ? rsq[k] : 0.0;
         }
-        block_sum<2 * K>(H, tv);
+        block_sum<2 * K, NW>(H, tv);
         if (tid < K && !first) {
           double* dst = my_scr + P.off_trav + l * TRAV_STRIDE;
           __stcg(&dst[tid], H->tot[tid]);
@@ -1395,16 +1402,21 @@ __global__ void __launch_bounds__(NT, (std::is_same<XT, int8_t>::value ? SB_I8_B
       const bool self_next = !first && lnext == l;
       const int ntiles = pb.ntiles;
       constexpr int RQ = B2_ROUND_ROWS / 4;  // outer quads per round
-      // ---- shared memory: [header][small vectors ...][64 KB table set, aligned to 64 KB][ring]
+      // ---- shared memory: [header][small vectors][ring stage 0] | 64 KB boundary | [table set 0][table set 1][ring stage 1]
       const uint32_t smem_base = smem_u32(smem_raw);
       const uint32_t hdr_end = smem_base + static_cast<uint32_t>(((sizeof(SmemHdr) + 127) / 128) * 128);
-      const uint32_t tab_addr = (hdr_end + 8192u + B2_MAX_ROWS * 8u + B2_TABLE_BYTES - 1u) & ~static_cast<uint32_t>(B2_TABLE_BYTES - 1);
-      double* const tab = reinterpret_cast<double*>(smem_raw + (tab_addr - smem_base));
-      unsigned char* const ringb = reinterpret_cast<unsigned char*>(tab) + B2_TABLE_BYTES;
+      const uint32_t low_end = hdr_end + 8192u + B2_MAX_ROWS * 8u + B2_STAGE_BYTES;
+      const uint32_t tab_addr = (low_end + B2_TABLE_BYTES - 1u) & ~static_cast<uint32_t>(B2_TABLE_BYTES - 1);
+      double* const tab0 = reinterpret_cast<double*>(smem_raw + (tab_addr - smem_base));
       double* const bstage = reinterpret_cast<double*>(smem_raw + (hdr_end - smem_base));  // [2][256] b' of a chunk
       double* const vsum = bstage + 2 * B2_TILE_COLS;                                        // [512] row sums of a round
       double* const rn_sm = vsum + B2_ROUND_ROWS;                                            // [B2_MAX_ROWS] next residual
-      const uint32_t lane_const = tab_addr | (static_cast<uint32_t>(lane) << 3);
+      unsigned char* const stage_lo = reinterpret_cast<unsigned char*>(rn_sm + B2_MAX_ROWS);
+      unsigned char* const stage_hi = reinterpret_cast<unsigned char*>(tab0) + 2 * B2_TABLE_BYTES;
+      auto stage_ptr = [&](int stg) { return stg == 0 ? stage_lo : stage_hi; };
+      auto table_ptr = [&](int t) { return tab0 + static_cast<size_t>(t) * (B2_TABLE_BYTES / 8); };
+      const uint32_t lane_const0 = tab_addr | (static_cast<uint32_t>(lane) << 3);
+      auto lane_const_of = [&](int t) { return lane_const0 + static_cast<uint32_t>(t) * B2_TABLE_BYTES; };
       // ---- work split inside the team
       int q0[K], q1[K], rounds1[K], rounds2[K], nch2[K];
       int npa = 0, np_total;
@@ -1461,13 +1473,13 @@ __global__ void __launch_bounds__(NT, (std::is_same<XT, int8_t>::value ? SB_I8_B
           }
         }
         mbar_expect_tx(&H->mbar[stg], bytes);
-        bulk_g2s(ringb + static_cast<size_t>(stg) * B2_STAGE_BYTES, src, bytes, &H->mbar[stg], stream_policy);
+        bulk_g2s(stage_ptr(stg), src, bytes, &H->mbar[stg], stream_policy);
       };
       int pseq = 0;  // pieces consumed in this traversal
       auto piece_wait = [&]() -> const unsigned char* {
         const int stg = cons_seq % B2_NSTAGE;
         mbar_wait(&H->mbar[stg], (phase_bits >> stg) & 1u);
-        return ringb + static_cast<size_t>(stg) * B2_STAGE_BYTES;
+        return stage_ptr(stg);
       };
       auto piece_done = [&]() {
         const int stg = cons_seq % B2_NSTAGE;
@@ -1484,9 +1496,9 @@ __global__ void __launch_bounds__(NT, (std::is_same<XT, int8_t>::value ? SB_I8_B
         cons_seq += 1;
         pseq += 1;
       };
-      // table set of 32 groups from 256 weights: thread (g, q) writes entries e = 32 q + r of group g
+      // table set of 32 groups from 256 weights: thread (g, q) writes entries e = (256 / NW) q + r of group g
       // (fixed association: low nibble sum + high nibble sum)
-      auto build_tables = [&](const double* w256) {
+      auto build_tables = [&](double* tab, const double* w256) {
         const int g = tid & 31, qq = tid >> 5;
         const double2* b8 = reinterpret_cast<const double2*>(w256 + 8 * g);
         const double2 b01 = b8[0], b23 = b8[1], b45 = b8[2], b67 = b8[3];
@@ -1507,10 +1519,11 @@ __global__ void __launch_bounds__(NT, (std::is_same<XT, int8_t>::value ? SB_I8_B
         lo[13] = lo[5] + b23.y;
         lo[14] = lo[6] + b23.y;
         lo[15] = lo[7] + b23.y;
-        double hi2[2];
+        constexpr int EPT = 256 / NW;  // entries per thread: 32 q .. or 16 q .. of group g
+        double hi2[EPT / 16];
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const int nib = 2 * qq + h;
+        for (int h = 0; h < EPT / 16; ++h) {
+          const int nib = (EPT / 16) * qq + h;
           double t = 0.0;
           if (nib & 1) t = b45.x;
           if (nib & 2) t = (nib & 1) ? t + b45.y : b45.y;
@@ -1518,20 +1531,21 @@ __global__ void __launch_bounds__(NT, (std::is_same<XT, int8_t>::value ? SB_I8_B
           if (nib & 8) t = (nib & 7) ? t + b67.y : b67.y;
           hi2[h] = t;
         }
-        double* dst = tab + static_cast<size_t>(32 * qq) * 32 + g;
+        double* dst = tab + static_cast<size_t>(EPT * qq) * 32 + g;
 #pragma unroll
-        for (int r = 0; r < 32; ++r) dst[r * 32] = lo[r & 15] + hi2[r >> 4];
+        for (int r = 0; r < EPT; ++r) dst[r * 32] = lo[r & 15] + hi2[r >> 4];
       };
-      // one pass: the warp's 16 outer quads (64 outer indices) of the piece against the resident table set
-      auto lookup_pass = [&](const unsigned char* piece, int qn, double (&acc)[64]) {
-        const uint32_t* words = reinterpret_cast<const uint32_t*>(piece) + (16 * warp) * 64 + lane;
+      // one pass: the warp's OQ outer quads (OW outer indices) of the piece against the resident table set
+      constexpr int OW = B2_ROUND_ROWS / NW, OQ = OW / 4;
+      auto lookup_pass = [&](const unsigned char* piece, int qn, uint32_t lane_const, double (&acc)[OW]) {
+        const uint32_t* words = reinterpret_cast<const uint32_t*>(piece) + (OQ * warp) * 64 + lane;
 #pragma unroll
-        for (int oc = 0; oc < 4; ++oc) {  // four quads at a time (uniform skip past the end of the round)
-          if (16 * warp + 4 * oc < qn) {
+        for (int oc = 0; oc < OQ / 4; ++oc) {  // four quads at a time (uniform skip past the end of the round)
+          if (OQ * warp + 4 * oc < qn) {
 #pragma unroll
             for (int m4 = 0; m4 < 4; ++m4) {
               const int m = 4 * oc + m4;
-              if (16 * warp + m < qn) {
+              if (OQ * warp + m < qn) {
 #pragma unroll
                 for (int pl = 0; pl < 2; ++pl) {
                   const uint32_t w = words[(m * 2 + pl) * 32];
@@ -1543,6 +1557,16 @@ __global__ void __launch_bounds__(NT, (std::is_same<XT, int8_t>::value ? SB_I8_B
               }
             }
           }
+        }
+      };
+      // lane-private sums -> totals: lane i of the warp gets outer indices OW w + 32 s + i (s < OW / 32)
+      auto totals = [&](double (&acc)[OW], double (&tot)[OW / 32]) {
+#pragma unroll
+        for (int sset = 0; sset < OW / 32; ++sset) {
+          double part[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) part[i] = acc[32 * sset + i];
+          tot[sset] = warp_rows_sum<32>(part, lane);
         }
       };
       __syncthreads();  // every warp has left the previous phase: the ring and the tables are free
@@ -1575,7 +1599,7 @@ __global__ void __launch_bounds__(NT, (std::is_same<XT, int8_t>::value ? SB_I8_B
             const int j = c * B2_TILE_COLS + tid;
             b = 0.0;
             mb = 0.0;
-            if (c < ntiles && j < p_pad) {
+            if (tid < B2_TILE_COLS && c < ntiles && j < p_pad) {
               b = __ldcg(&bl[j]) * cs[j];
               mb = cm[j];
             }
@@ -1584,39 +1608,40 @@ __global__ void __launch_bounds__(NT, (std::is_same<XT, int8_t>::value ? SB_I8_B
           for (int rd = 0; rd < rounds1[k]; ++rd) {
             const int qa = q0[k] + rd * RQ;
             const int qn = min(RQ, q1[k] - qa);  // row quads of this round
-            double acc[64];
+            double acc[OW];
 #pragma unroll
-            for (int i = 0; i < 64; ++i) acc[i] = 0.0;
+            for (int i = 0; i < OW; ++i) acc[i] = 0.0;
             double cpart[1] = {0.0};
-            double b_cur, m_cur;
-            load_b(0, b_cur, m_cur);
+            // chunk pipeline: b' of chunk c + 2 is loaded and staged, the table set of chunk c + 1 is built and the
+            // look-ups of chunk c run between two block barriers (two table sets, two staging halves)
+            double b_reg, m_reg;
+            load_b(0, b_reg, m_reg);
+            auto stage_b = [&](int c) {  // stage b' of chunk c (held in b_reg), start loading chunk c + 1
+              if (tid < B2_TILE_COLS) bstage[(c & 1) * B2_TILE_COLS + tid] = b_reg;
+              cpart[0] += m_reg * b_reg;
+              load_b(c + 1, b_reg, m_reg);
+            };
+            stage_b(0);
+            __syncthreads();
+            build_tables(table_ptr(0), bstage);
+            if (ntiles > 1) stage_b(1);
+            __syncthreads();
 #pragma unroll 1
             for (int c = 0; c < ntiles; ++c) {
-              double* bs = bstage + (c & 1) * B2_TILE_COLS;
-              bs[tid] = b_cur;  // (the other half may still be read by a slow builder of the previous chunk)
-              cpart[0] += m_cur * b_cur;
-              load_b(c + 1, b_cur, m_cur);  // in flight during this chunk's look-ups
-              __syncthreads();  // b' complete; the previous table set is no longer read
-              build_tables(bs);
-              __syncthreads();
               const unsigned char* piece = piece_wait();
-              lookup_pass(piece, qn, acc);
+              lookup_pass(piece, qn, lane_const_of(c & 1), acc);
               piece_done();
+              if (c + 1 < ntiles) build_tables(table_ptr((c + 1) & 1), bstage + ((c + 1) & 1) * B2_TILE_COLS);
+              if (c + 2 < ntiles) stage_b(c + 2);
+              __syncthreads();
             }
-            // lane-private row sums -> row totals (lane i of the warp holds rows 64 w + i and 64 w + 32 + i)
             {
-              double lo32[32], hi32[32];
+              double tot[OW / 32];
+              totals(acc, tot);
 #pragma unroll
-              for (int i = 0; i < 32; ++i) {
-                lo32[i] = acc[i];
-                hi32[i] = acc[32 + i];
-              }
-              const double ta = warp_rows_sum<32>(lo32, lane);
-              const double tb = warp_rows_sum<32>(hi32, lane);
-              vsum[64 * warp + lane] = ta;
-              vsum[64 * warp + 32 + lane] = tb;
+              for (int sset = 0; sset < OW / 32; ++sset) vsum[OW * warp + 32 * sset + lane] = tot[sset];
             }
-            block_sum<1>(H, cpart);  // (barriers inside: vsum visible)
+            block_sum<1, NW>(H, cpart);  // (barriers inside: vsum visible)
             const double cshift = H->tot[0];
             // finish the rows of the round
             for (int i = tid; i < 4 * qn; i += NT) {
@@ -1652,39 +1677,44 @@ __global__ void __launch_bounds__(NT, (std::is_same<XT, int8_t>::value ? SB_I8_B
           rn_sm[i] = rv;
           rpart[0] += rv;
         }
-        block_sum<1>(H, rpart);  // (barriers inside: rn_sm visible)
+        block_sum<1, NW>(H, rpart);  // (barriers inside: rn_sm visible)
         const double rsum = H->tot[0];
         const double* cm = pb.cmean + static_cast<size_t>(k) * p_pad;
         const double* cs = pb.cisd + static_cast<size_t>(k) * p_pad;
         double* dst = pb.xty + static_cast<size_t>(k) * p_pad;
+        // up to two 256-row chunks: both table sets stay resident for every round of the ancestry (no block barrier
+        // inside the rounds); more rows: one table set is rebuilt per pass
+        const bool resident = nch2[k] <= 2;
+        if (resident) {
+          for (int d = 0; d < nch2[k]; ++d) build_tables(table_ptr(d), rn_sm + 256 * d);
+          __syncthreads();
+        }
 #pragma unroll 1
         for (int rd = 0; rd < rounds2[k]; ++rd) {
           const int qa = cq0 + rd * RQ;
           const int qn = min(RQ, cq1 - qa);  // column quads of this round
-          double acc[64];
+          double acc[OW];
 #pragma unroll
-          for (int i = 0; i < 64; ++i) acc[i] = 0.0;
+          for (int i = 0; i < OW; ++i) acc[i] = 0.0;
 #pragma unroll 1
           for (int d = 0; d < nch2[k]; ++d) {
-            __syncthreads();  // the previous table set is no longer read
-            build_tables(rn_sm + 256 * d);
-            __syncthreads();
+            if (!resident) {
+              __syncthreads();  // the previous table set is no longer read
+              build_tables(table_ptr(0), rn_sm + 256 * d);
+              __syncthreads();
+            }
             const unsigned char* piece = piece_wait();
-            lookup_pass(piece, qn, acc);
+            lookup_pass(piece, qn, lane_const_of(resident ? d : 0), acc);
             piece_done();
           }
           // lane-private column sums -> totals; X_std^T r = (G^T r - mean * sum r) / sd for the own slice
-          double lo32[32], hi32[32];
+          double tot[OW / 32];
+          totals(acc, tot);
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            lo32[i] = acc[i];
-            hi32[i] = acc[32 + i];
+          for (int sset = 0; sset < OW / 32; ++sset) {
+            const int j = 4 * qa + OW * warp + 32 * sset + lane;
+            if (j >= js && j < je) dst[j] = (tot[sset] - cm[j] * rsum) * cs[j];
           }
-          const double ta = warp_rows_sum<32>(lo32, lane);
-          const double tb = warp_rows_sum<32>(hi32, lane);
-          const int ja = 4 * qa + 64 * warp + lane, jb = ja + 32;
-          if (ja >= js && ja < je) dst[ja] = (ta - cm[ja] * rsum) * cs[ja];
-          if (jb >= js && jb < je) dst[jb] = (tb - cm[jb] * rsum) * cs[jb];
         }
         __syncthreads();  // rn_sm is reloaded for the next ancestry
       }
@@ -1696,7 +1726,7 @@ __global__ void __launch_bounds__(NT, (std::is_same<XT, int8_t>::value ? SB_I8_B
           tv[k] = vsq[k];
           tv[K + k] = rsq[k];
         }
-        block_sum<2 * K>(H, tv);
+        block_sum<2 * K, NW>(H, tv);
         if (tid < K && !first) {
           double* dst = my_scr + P.off_trav + l * TRAV_STRIDE;
           __stcg(&dst[tid], H->tot[tid]);
@@ -1834,7 +1864,7 @@ __global__ void __launch_bounds__(NT, (std::is_same<XT, int8_t>::value ? SB_I8_B
             if (g < rows) {
               const int row = pb.row0[k] + g0 + g;
               const double2* ps2 = reinterpret_cast<const double2*>(&psum[tid * NW]);
-              static_assert(NW == 8, "pairwise tree below assumes 8 warps");
+              static_assert(NW == 8 || B2, "pairwise tree below assumes 8 warps");
               const double2 q0 = ps2[0], q1 = ps2[1], q2 = ps2[2], q3 = ps2[3];
               const double v = (((q0.x + q0.y) + (q1.x + q1.y)) + ((q2.x + q2.y) + (q3.x + q3.y))) * pb.nscale[k];
               const double Rfull = pb.r[row] - v;
@@ -1853,7 +1883,7 @@ __global__ void __launch_bounds__(NT, (std::is_same<XT, int8_t>::value ? SB_I8_B
         }
         __syncthreads();  // the parking area is reused by the next chunk
       }
-      block_sum<2 * K>(H, tv);
+      block_sum<2 * K, NW>(H, tv);
       if (tid < K) {
         double* dst = my_scr + P.off_trav + l * TRAV_STRIDE;
         __stcg(&dst[tid], H->tot[tid]);
@@ -2083,14 +2113,14 @@ __global__ void __launch_bounds__(NT, (std::is_same<XT, int8_t>::value ? SB_I8_B
 #pragma unroll
         for (int i = 0; i < NV; ++i) v[i] = __ldcg(rec + 1 + i);
       }
-      const double m = block_max(H, mc);
+      const double m = block_max<NW>(H, mc);
       if (tid < C) {
         // NaN anywhere must poison the result like the reference's softmax would
         const double sc = (mc == -CUDART_INF) ? 0.0 : exp(mc - m);
 #pragma unroll
         for (int i = 0; i < NV; ++i) v[i] = (mc != mc) ? mc : v[i] * sc;
       }
-      block_sum<NV>(H, v);
+      block_sum<NV, NW>(H, v);
       if (tid == 0) {
         for (int i = NV - 1; i >= 0; --i) H->tot[i + 1] = H->tot[i];
         H->tot[0] = m;
@@ -2209,11 +2239,11 @@ __global__ void __launch_bounds__(NT, (std::is_same<XT, int8_t>::value ? SB_I8_B
 #pragma unroll
             for (int b = a; b < K; ++b) sv[t++] += e * (S[a][b] + mu[a] * mu[b]);
         }
-        const double mb = block_max(H, m);
+        const double mb = block_max<NW>(H, m);
         const double sc = (m == -CUDART_INF) ? 0.0 : exp(m - mb);
 #pragma unroll
         for (int i = 0; i < 1 + NSYM; ++i) sv[i] *= sc;
-        block_sum<1 + NSYM>(H, sv);
+        block_sum<1 + NSYM, NW>(H, sv);
         if (tid == 0) {
           for (int i = NSYM; i >= 0; --i) H->tot[i + 1] = H->tot[i];
           H->tot[0] = mb;
@@ -2304,11 +2334,11 @@ __global__ void __launch_bounds__(NT, (std::is_same<XT, int8_t>::value ? SB_I8_B
 #pragma unroll
           for (int k = 0; k < K; ++k) sv[t++] += e * raw[K + k] * (S[k][k] + mu[k] * mu[k]);
         }
-        const double mb = block_max(H, m);
+        const double mb = block_max<NW>(H, m);
         const double sc = (m == -CUDART_INF) ? 0.0 : exp(m - mb);
 #pragma unroll
         for (int i = 0; i < NVB; ++i) sv[i] *= sc;
-        block_sum<NVB>(H, sv);
+        block_sum<NVB, NW>(H, sv);
         if (tid == 0) {
           for (int i = NVB - 1; i >= 0; --i) H->tot[i + 1] = H->tot[i];
           H->tot[0] = mb;
@@ -2394,14 +2424,14 @@ __global__ void __launch_bounds__(NT, (std::is_same<XT, int8_t>::value ? SB_I8_B
             tv[K + k] += eb * (xty - __ldcg(&pb.rfull[pb.row0[k] + j]));  // E[b]^T XtX E[b]
           }
         }
-        block_sum<2 * K>(H, tv);
+        block_sum<2 * K, NW>(H, tv);
         if (C > 1) {
           const int so = P.off_stat + 2 * STAT_STRIDE;
           if (tid < 2 * K) __stcg(&my_scr[so + tid], H->tot[tid]);
           team_sync(team);
 #pragma unroll
           for (int i = 0; i < 2 * K; ++i) tv[i] = (tid < C) ? __ldcg(&scr(tid)[so + i]) : 0.0;
-          block_sum<2 * K>(H, tv);
+          block_sum<2 * K, NW>(H, tv);
         }
       }
       double ssv[2 * K];  // summary level: E[b]^T Xty, E[b]^T XtX E[b] per ancestry
@@ -2421,7 +2451,7 @@ __global__ void __launch_bounds__(NT, (std::is_same<XT, int8_t>::value ? SB_I8_B
 #pragma unroll
           for (int k = 0; k < K; ++k) tr[K + k] = __ldcg(&rec[(L - 1) * TRAV_STRIDE + KMAX + k]);
         }
-        block_sum<2 * K>(H, tr);
+        block_sum<2 * K, NW>(H, tr);
       }
       if (tid < K) {
         const int k = tid;
