@@ -181,6 +181,128 @@ def parity_record(gpu_fits, cpu_records):
 
 
 # ----------------------------------------------------------------------------------------
+# config 5 (BASELINE.json): genes x (1 full + 5 cross-validation fold) fits through the host work queue
+
+SEED_P = 20263000
+CV_NUM = 5
+
+
+def gene_width(g: int, lo: int = 500, hi: int = 4000) -> int:
+    return int(np.random.default_rng(SEED_P + g).integers(lo, hi + 1))
+
+
+def _gen_to_dir(args):
+    g, path = args
+    Xs, ys = make_gene(g, N_IND, gene_width(g))
+    np.save(os.path.join(path, f"g{g}_X.npy"), np.stack(Xs))
+    np.save(os.path.join(path, f"g{g}_y.npy"), np.stack(ys))
+    return g
+
+
+def config5_dir(world: int) -> str:
+    tag = os.environ.get("MASTER_PORT", str(os.getpid())) if world > 1 else str(os.getpid())
+    base = "/dev/shm" if os.path.isdir("/dev/shm") else tempfile.gettempdir()
+    return os.path.join(base, f"sushie_b200_c5_{tag}")
+
+
+def config5_generate(n_genes: int, rank: int, world: int, workers: int) -> str:
+    """This rank's share of the genes (g = rank mod world) into a directory every rank of the box can read: any
+    rank may pull any gene from the queue.  Host work, before CUDA exists in this process (fork pool)."""
+    import multiprocessing as mp
+
+    path = config5_dir(world)
+    os.makedirs(path, exist_ok=True)
+    mine = [(g, path) for g in range(n_genes) if g % world == rank]
+    with mp.get_context("fork").Pool(max(1, workers)) as pool:
+        pool.map(_gen_to_dir, mine, chunksize=4)
+    return path
+
+
+def config5_run(args, path, rank, local_rank, world, dist):
+    """Strong scaling: a FIXED total of genes, one process per GPU, ONE global cost-sorted chunk list pulled through
+    an atomic counter in the torch.distributed store; every gene = the public-API work of `finemap --cv` (fold split,
+    6 fits, credible sets, tables, out-of-fold r2).  NCCL only gathers the per-gene result records."""
+    import shutil
+
+    import torch
+
+    import sushie_b200
+    from sushie_b200 import batch, cli
+
+    n_genes = args.config5_genes
+    widths = [gene_width(g) for g in range(n_genes)]
+    kw = dict(L=L_EFF, max_iter=args.max_iter, min_tol=args.min_tol, devices=[local_rank])
+
+    def process(ids):
+        specs, folds_of = [], []
+        for g in ids:
+            X = np.load(os.path.join(path, f"g{g}_X.npy"), mmap_mode="r")
+            y = np.load(os.path.join(path, f"g{g}_y.npy"))
+            Xs, ys = [X[a] for a in range(K_ANC)], [y[a] for a in range(K_ANC)]
+            folds = cli._prepare_cv(list(Xs), list(ys), CV_NUM, 12345)
+            folds_of.append(folds)
+            specs.append(dict(Xs=Xs, ys=ys))
+            specs.extend(dict(Xs=f.train_geno, ys=f.train_pheno) for f in folds)
+        fits = sushie_b200.infer_sushie_batch(specs, **kw)
+        out = []
+        for i, g in enumerate(ids):
+            base = i * (1 + CV_NUM)
+            full = fits[base]
+            r2 = cli._cv_scores(folds_of[i], fits[base + 1: base + 1 + CV_NUM])
+            out.append((len(full.elbo) - 1, int(len(set(full.cs.CSIndex.values.tolist()))), float(np.sum(full.pip_all)),
+                        [float(r[0]) for r in r2]))
+        return out
+
+    store = dist.distributed_c10d._get_default_store() if world > 1 else None
+    if world > 1:
+        dist.barrier()  # every rank's genes are on disk
+    # warm-up: a few genes per rank outside the queue (imports, kernels, shuffle cache)
+    process([g for g in range(n_genes) if g % world == rank][:4])
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    records, trace = batch.run_distributed(
+        [float(w) for w in widths], process, store=store, rank=rank, world=world, workers_per_rank=2,
+        key=f"sushie_b200/config5/{os.environ.get('MASTER_PORT', '0')}")
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([wall], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)  # (also the closing barrier of the timed region)
+        wall = float(t[0])
+        gathered = [None] * world
+        dist.all_gather_object(gathered, (records, trace))  # result records only; inputs never move
+    else:
+        gathered = [(records, trace)]
+    out = None
+    if rank == 0:
+        recs = dict(pair for part, _ in gathered for pair in part)
+        assert sorted(recs) == list(range(n_genes)), "every gene exactly once"
+        per_rank = [sum(n for _, _, n in tr) for _, tr in gathered]
+        out = {
+            "workload": f"config 5: {n_genes} genes x (1 full + {CV_NUM} cross-validation fold fits), p ~ U{{500..4000}}, "
+                        f"n = {N_IND} (folds {N_IND - N_IND // CV_NUM}) per ancestry, k = {K_ANC}, L = {L_EFF}, to convergence",
+            "genes": n_genes, "fits": n_genes * (1 + CV_NUM), "scaling": "strong (fixed total)", "n_gpus": world,
+            "wall_s": wall, "genes_per_sec": n_genes / wall, "fits_per_sec": n_genes * (1 + CV_NUM) / wall,
+            "path": "per gene: load from the shared host directory, threefry fold split, infer_sushie_batch (host prologue, "
+                    "upload, IBSS, download, credible sets + purity, tables), out-of-fold r2 -- one process per GPU, two "
+                    "worker threads each, chunks pulled from one global cost-sorted list (sushie_b200.batch.StoreQueue)",
+            "collective": "none on the data path; NCCL all_gather of the per-gene result records at the end",
+            "chunks": sum(len(tr) for _, tr in gathered), "genes_per_rank": per_rank,
+            "mean_iters_full_fit": float(np.mean([r[0] for r in recs.values()])),
+            "credible_sets": int(sum(r[1] for r in recs.values())),
+            "mean_cv_adj_r2": [float(np.mean([r[3][a] for r in recs.values()])) for a in range(K_ANC)],
+            "data": "synthetic genes generated before the timed region into a host directory shared by the ranks",
+        }
+    if world > 1:
+        dist.barrier()
+    if rank == 0:
+        shutil.rmtree(path, ignore_errors=True)
+    return out
+
+
+# ----------------------------------------------------------------------------------------
 # helpers
 
 
@@ -359,6 +481,8 @@ def main():
     ap.add_argument("--no-ss-arm", action="store_true", help="skip the summary-level (config 4) roofline run (N=1 only)")
     ap.add_argument("--ss-p", type=int, default=10000)
     ap.add_argument("--ss-iters", type=int, default=20)
+    ap.add_argument("--config5-genes", type=int, default=1184,
+                    help="genes of the config-5 arm (fixed total for every N: strong scaling; 0 = skip)")
     ap.add_argument("--no-api-arm", action="store_true", help="skip the public-API end-to-end run")
     ap.add_argument("--api-genes", type=int, default=0, help="loci of the public-API end-to-end run (0 = --genes)")
     args = ap.parse_args()
@@ -377,6 +501,7 @@ def main():
     gen_workers = max(1, cores // max(1, world))
     t0 = time.time()
     genes = generate_genes(rank * B, B, gen_workers)
+    c5_path = config5_generate(args.config5_genes, rank, world, gen_workers) if args.config5_genes > 0 else None
     t_gen = time.time() - t0
 
     cpu_baseline, cpu_records = None, None
@@ -577,6 +702,9 @@ def main():
                "n_cs": int(sum(len(set(r.cs.CSIndex.values.tolist())) for r in results))}
         del results
 
+    # ---- config 5 arm: the multi-GPU design itself (work queue, ragged genes, CV folds, public API)
+    config5 = config5_run(args, c5_path, rank, local_rank, world, dist) if c5_path else None
+
     # ---- reduce over ranks (max time), gather a small result record with NCCL
     if world > 1:
         t = torch.tensor([dev_ms, wall_ms, e2e["ms"] if e2e else 0.0, api["ms"] if api else 0.0], device="cuda",
@@ -682,6 +810,8 @@ def main():
             ss_arm["peak"] = peak
             ss_arm["frac"] = ss_arm["achieved"] / peak
             line["roofline_ss_f32"] = ss_arm
+        if config5:
+            line["config5"] = config5
         if parity:
             line["parity"] = parity
         line["nonfinite_loci_rank0"] = n_nonfinite

@@ -203,5 +203,63 @@ def run_sharded(preps: Sequence, runner: Callable, devices: Optional[Sequence[in
     return results
 
 
+def plan_items(costs: Sequence[float], n_workers: int, min_items: int = 8, max_items: int = 64) -> List[List[int]]:
+    """Cut work items (genes) into chunks for dynamic pulling: items sorted by descending cost, chunk sizes that
+    shrink as the queue drains (guided self-scheduling: about 1 / (2 n_workers) of what is left, between
+    ``min_items`` and ``max_items``), so the GPUs finish together however uneven the fits are.  Every rank computes
+    the same list from the same costs."""
+    order = sorted(range(len(costs)), key=lambda i: (-float(costs[i]), i))
+    chunks: List[List[int]] = []
+    pos = 0
+    while pos < len(order):
+        left = len(order) - pos
+        size = max(min_items, min(max_items, -(-left // (2 * max(1, n_workers)))))
+        chunks.append(order[pos: pos + size])
+        pos += size
+    return chunks
+
+
+def run_distributed(costs: Sequence[float], process_chunk: Callable[[List[int]], list], *, store=None, rank: int = 0,
+                    world: int = 1, workers_per_rank: int = 2, key: str = "sushie_b200/items", min_items: int = 8,
+                    max_items: int = 64):
+    """One process per GPU (``torchrun``): every rank plans the same global chunk list and pulls chunk indices from
+    an atomic counter in the ``torch.distributed`` store (``StoreQueue``) -- a host work queue, no collective on the
+    data path.  ``process_chunk(item_ids)`` does everything for those items on this rank's GPU (loading, fits,
+    epilogue) and returns one small record per item.  ``workers_per_rank`` threads pull concurrently so that the host
+    half of one chunk (set selection, tables, scores) overlaps the device half of the next.
+
+    Returns ``(records, trace)``: this rank's ``(item, record)`` pairs and the chunks it pulled."""
+    chunks = plan_items(costs, world, min_items, max_items)
+    q = StoreQueue(store, len(chunks), key) if store is not None else ChunkQueue(len(chunks))
+    records: list = []
+    trace: list = []
+    errors: list = []
+    lock = threading.Lock()
+
+    def work():
+        try:
+            while True:
+                c = q.next()
+                if c is None:
+                    break
+                out = process_chunk(chunks[c])
+                with lock:
+                    records.extend(zip(chunks[c], out))
+                    trace.append((rank, c, len(chunks[c])))
+        except BaseException as exc:  # surfaced after join
+            errors.append(exc)
+        finally:
+            _capi.release_thread_engines()
+
+    threads = [threading.Thread(target=work, daemon=True) for _ in range(max(1, workers_per_rank))]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    if errors:
+        raise errors[0]
+    return records, trace
+
+
 def device_count() -> int:
     return _capi.device_count()
