@@ -39,6 +39,7 @@ extern "C" {
 
 #define SB_VERSION 100 /* 0.1.0 */
 #define SB_MAX_ANCESTRIES 4
+#define SB_MAX_COVAR_BASIS 8 /* intercept + 7 covariates */
 
 /* return codes */
 #define SB_OK 0
@@ -90,6 +91,12 @@ typedef struct {
   const double *adj_times;   /* [k][k] _PriorAdjustor.times (used when em_update == 0) */
   const double *adj_plus;    /* [k][k] _PriorAdjustor.plus  (used when em_update == 0) */
   int32_t em_update;         /* 1: _EMOptFunc (infer.py:128-140); 0: _NoopOptFunc (143-159) */
+  /* Genotypes residualised on covariates (utils.regress_covar, infer.py:319-335) WITHOUT leaving hard-call storage
+   * (sb_opts.storage == SB_B2 only): covar_q[i] = orthonormal basis of [1, covariates_i], row-major
+   * [n_i][covar_q_cols[i]] (the Q of the reduced QR the reference's `ols` computes), at most SB_MAX_COVAR_BASIS
+   * columns; the engine applies (I - Q Q^T) as a low-rank correction and centring is implied.  NULL: no covariates. */
+  const double *const *covar_q;
+  const int32_t *covar_q_cols;
 } sb_ind_problem;
 
 /* One summary-level problem = the arguments of _update_effects_ss (infer_ss.py:437-446);

@@ -18,7 +18,7 @@ SB_F64, SB_F32, SB_I8, SB_B2 = 0, 1, 2, 3
 SB_CENTER, SB_SCALE = 1, 2
 SB_FLAG_SINGLE_PHASE = 1
 I8_MAX_SNPS = 8192  # widest locus the hard-call (one byte per entry) traversal handles
-B2_MAX_SNPS, B2_MAX_ROWS = 8192, 1024  # limits of the bit-plane (0 / 1 / 2 hard calls) traversal
+B2_MAX_SNPS, B2_MAX_ROWS, B2_MAX_COVAR_BASIS = 8192, 1024, 8  # limits of the bit-plane (0 / 1 / 2 hard calls) traversal
 
 _LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_lib", "libsushie_b200.so")
 # development: A/B a differently built engine without touching the tree
@@ -62,6 +62,8 @@ class SbIndProblem(C.Structure):
         ("adj_times", _pd),
         ("adj_plus", _pd),
         ("em_update", C.c_int32),
+        ("covar_q", C.POINTER(_pd)),
+        ("covar_q_cols", C.POINTER(C.c_int32)),
     ]
 
 
@@ -207,8 +209,13 @@ class EngineError(RuntimeError):
 class IndProblem:
     """Host-side description of one individual-level problem (keeps the arrays alive)."""
 
-    def __init__(self, Xs, ys, L, pi, resid_var, effect_covar, adj_times, adj_plus, em_update, standardize=0):
+    def __init__(self, Xs, ys, L, pi, resid_var, effect_covar, adj_times, adj_plus, em_update, standardize=0, covar_q=None):
         self.k = len(Xs)
+        # orthonormal bases of [1, covariates] per ancestry: genotypes are residualised on device (SB_B2 storage)
+        self.covar_q = None if covar_q is None else [_f64(q) for q in covar_q]
+        if self.covar_q is not None:
+            self._qptr = (_pd * self.k)(*[_dptr(q) for q in self.covar_q])
+            self._qcols = np.asarray([q.shape[1] for q in self.covar_q], dtype=np.int32)
         mats = [_matrix_and_dtype(x, allow_i8=True) for x in Xs]
         dts = {d for _, d in mats}
         if len(dts) > 1:  # mixed input types: promote everything to fp64
@@ -246,6 +253,12 @@ class IndProblem:
         s.adj_times = _dptr(self.adj_times)
         s.adj_plus = _dptr(self.adj_plus)
         s.em_update = self.em_update
+        if self.covar_q is not None:
+            s.covar_q = C.cast(self._qptr, C.POINTER(_pd))
+            s.covar_q_cols = self._qcols.ctypes.data_as(C.POINTER(C.c_int32))
+        else:
+            s.covar_q = None
+            s.covar_q_cols = None
 
 
 class SsProblem:

@@ -175,12 +175,14 @@ def run_sharded(preps: Sequence, runner: Callable, devices: Optional[Sequence[in
     if devices is None:
         devices = config.devices or [0]
     devices = list(devices)
-    chunks = plan_chunks(preps, n_workers=len(devices))
+    # several worker threads per GPU: the host half of one chunk overlaps the device half of the next
+    workers = [d for d in devices for _ in range(max(1, config.workers_per_device))]
+    chunks = plan_chunks(preps, n_workers=len(workers))
     q = ChunkQueue(len(chunks))
     results: list = [None] * len(preps)
     trace: list = []
     defer = len(chunks) > 1  # a single chunk has nothing to overlap with
-    if len(devices) == 1:
+    if len(workers) == 1 or len(chunks) == 1:
         drain(q, chunks, preps, runner, devices[0], results, trace, defer)
         return results
     errors: list = []
@@ -193,7 +195,7 @@ def run_sharded(preps: Sequence, runner: Callable, devices: Optional[Sequence[in
         finally:
             _capi.release_thread_engines()  # this thread ends here: do not leak its sb_ctx
 
-    threads = [threading.Thread(target=work, args=(d,), daemon=True) for d in devices]
+    threads = [threading.Thread(target=work, args=(d,), daemon=True) for d in workers[: len(chunks)]]
     for t in threads:
         t.start()
     for t in threads:

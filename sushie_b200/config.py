@@ -27,6 +27,9 @@ chunk_loci: int = int(os.environ.get("SUSHIE_B200_CHUNK", "0"))
 # `chunks_per_worker` per worker while a chunk keeps `min_chunk_loci` loci (two per SM)
 chunks_per_worker: int = int(os.environ.get("SUSHIE_B200_CHUNKS_PER_WORKER", "3"))
 min_chunk_loci: int = int(os.environ.get("SUSHIE_B200_MIN_CHUNK", "296"))
+# worker threads (each with its own sb_ctx and resident batch) per GPU in the batch entry points: while one sits in
+# the engine call of its chunk, the other does the host half (set selection, tables) of the previous one
+workers_per_device: int = int(os.environ.get("SUSHIE_B200_WORKERS_PER_DEVICE", "2"))
 # print the wall time of the host-side phases of every chunk (upload, run, download, purity, tables) to stderr
 trace_host: bool = bool(int(os.environ.get("SUSHIE_B200_TRACE_HOST", "0")))
 # device memory budget per chunk, bytes

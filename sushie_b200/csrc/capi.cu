@@ -356,7 +356,7 @@ struct Bump {
 };
 
 struct ProbLayout {  // offsets inside the arena
-  size_t rbits[KMAX], cbits[KMAX];
+  size_t rbits[KMAX], cbits[KMAX], Qb[KMAX], Mq[KMAX];
   size_t X[KMAX], y, logpi, pi_raw, xtx, cmean, cisd, ecov0, rv0, adjt, adjp, r, xb, xty, rfull, bvec, out[2], elbo, meta, z;
   size_t out_fields[2][10];
 };
@@ -449,6 +449,8 @@ struct GenericProblem {
   const double* vec[KMAX];  // y (individual) or z (summary)
   double ns[KMAX];
   const double *pi, *resid_var, *effect_covar, *adj_times, *adj_plus;
+  const double* Q[KMAX] = {nullptr, nullptr, nullptr, nullptr};  // covariate basis per ancestry (SB_B2 only)
+  int qc[KMAX] = {0, 0, 0, 0};
 };
 
 static int batch_create(sb_ctx* ctx, const std::vector<GenericProblem>& gp, bool ss, const sb_opts* opts_in,
@@ -571,6 +573,11 @@ static int batch_create(sb_ctx* ctx, const std::vector<GenericProblem>& gp, bool
       nrows += g.n[k];
       l.X[k] = bump.take(static_cast<size_t>(g.n[k]) * ge.p_pad * es);
       const bool direct = (g.mat_dtype == opts.storage) && g.standardize == 0 && !hard_storage(opts.storage);
+      l.Qb[k] = l.Mq[k] = 0;
+      if (g.qc[k] > 0) {
+        l.Qb[k] = bump.take(sizeof(double) * g.n[k] * g.qc[k]);  // (uploaded before the column prologue that reads it)
+        l.Mq[k] = bump.take(sizeof(double) * g.qc[k] * ge.p_pad);
+      }
       if (opts.storage == SB_B2) {
         const size_t ntiles = (static_cast<size_t>(g.p) + sb::B2_TILE_COLS - 1) / sb::B2_TILE_COLS;
         l.rbits[k] = bump.take(ntiles * ((g.n[k] + 3) / 4) * 256);
@@ -720,7 +727,8 @@ static int batch_create(sb_ctx* ctx, const std::vector<GenericProblem>& gp, bool
     return cudaGetLastError();
   };
   auto enqueue_prep = [&](const void* host_mat, int dtype, int n, int p, int p_pad, int flags, void* out, double* xtx,
-                          double* cmean, double* cisd) -> cudaError_t {
+                          double* cmean, double* cisd, const double* d_Q = nullptr, double* d_M = nullptr,
+                          int qc = 0) -> cudaError_t {
     const size_t bytes = static_cast<size_t>(n) * p * elem_size(dtype);
     if (!pending.empty() && (dtype != pending_dtype || staged + bytes > staging_cap)) {
       cudaError_t e = flush_prep();
@@ -739,6 +747,9 @@ static int batch_create(sb_ctx* ctx, const std::vector<GenericProblem>& gp, bool
     pd.p = p;
     pd.p_pad = p_pad;
     pd.flags = flags;
+    pd.qc = qc;
+    pd.Q = d_Q;
+    pd.M = d_M;
     pending.push_back(pd);
     pending_dtype = dtype;
     pending_pmax = std::max(pending_pmax, p_pad);
@@ -850,7 +861,18 @@ static int batch_create(sb_ctx* ctx, const std::vector<GenericProblem>& gp, bool
         double* cisd_k = reinterpret_cast<double*>(A + l.cisd) + static_cast<size_t>(k) * ge.p_pad;
         h.d_cmean[k] = cmean_k;
         h.d_cisd[k] = cisd_k;
-        SB_CUDA_B(enqueue_prep(g.mat[k], SB_I8, n, g.p, ge.p_pad, g.standardize, A + l.X[k], xtx_k, cmean_k, cisd_k));
+        const double* d_Q = nullptr;
+        double* d_M = nullptr;
+        if (g.qc[k] > 0) {
+          d_Q = reinterpret_cast<const double*>(A + l.Qb[k]);
+          d_M = reinterpret_cast<double*>(A + l.Mq[k]);
+          SB_CUDA_B(cudaMemcpyAsync(A + l.Qb[k], g.Q[k], sizeof(double) * n * g.qc[k], cudaMemcpyHostToDevice, st));
+        }
+        d.Qb[k] = d_Q;
+        d.Mq[k] = d_M;
+        d.qc[k] = g.qc[k];
+        SB_CUDA_B(enqueue_prep(g.mat[k], SB_I8, n, g.p, ge.p_pad, g.standardize, A + l.X[k], xtx_k, cmean_k, cisd_k, d_Q,
+                               d_M, g.qc[k]));
       } else if (direct) {
         SB_CUDA_B(cudaMemcpy2DAsync(A + l.X[k], static_cast<size_t>(ge.p_pad) * es, g.mat[k],
                                     static_cast<size_t>(g.p) * es, static_cast<size_t>(g.p) * es, n,
@@ -993,6 +1015,20 @@ extern "C" int sb_batch_create_ind(sb_ctx* ctx, const sb_ind_problem* probs, int
     g.effect_covar = pr.effect_covar;
     g.adj_times = pr.adj_times;
     g.adj_plus = pr.adj_plus;
+    if (pr.covar_q) {
+      if (!pr.covar_q_cols || !opts || opts->storage != SB_B2) {
+        ctx->err = "problem " + std::to_string(i) + ": covar_q needs covar_q_cols and SB_B2 storage";
+        return SB_EINVAL;
+      }
+      for (int k = 0; k < pr.k; ++k) {
+        if (!pr.covar_q[k] || pr.covar_q_cols[k] < 1 || pr.covar_q_cols[k] > SB_MAX_COVAR_BASIS) {
+          ctx->err = "problem " + std::to_string(i) + ": covar_q_cols must be 1.." + std::to_string(SB_MAX_COVAR_BASIS);
+          return SB_EINVAL;
+        }
+        g.Q[k] = pr.covar_q[k];
+        g.qc[k] = pr.covar_q_cols[k];
+      }
+    }
   }
   return batch_create(ctx, gp, false, opts, out);
 }

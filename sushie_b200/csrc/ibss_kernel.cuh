@@ -60,6 +60,7 @@ constexpr int B2_ROUND_ROWS = 512;      // rows per sweep-1 round of one block (
 constexpr int B2_TABLE_BYTES = 65536;   // 256 entries x 32 groups x 8 bytes; two sets, aligned to 64 KB in shared memory
 constexpr int B2_MAX_ROWS = 1024;       // rows per ancestry (their next residual is staged in shared memory)
 constexpr int B2_MAX_SUB = 4;           // column tiles of one block per sweep-2 piece: 8 x B2_MAX_SUB >= p / 256
+constexpr int B2_QMAX = 8;              // columns of the covariate basis Q (intercept included) the bit-plane path handles
 constexpr int STAT_STRIDE = 20;  // doubles per team-reduction record (>= 2 + NSYM_MAX + 2 + KMAX)
 constexpr int TRAV_STRIDE = 2 * KMAX;
 
@@ -108,6 +109,13 @@ struct ProbDev {
   const unsigned char* cbits[KMAX];
   int ntiles;           // ceil(p / 256)
   int pad_b2_;
+  // genotypes residualised on covariates (infer.py:319-335) without leaving hard-call storage: with Q the
+  // orthonormal basis of [1, covariates] and M = G^T Q,  X_std b = (I - Q Q^T) G b'  and
+  // X_std^T r = (G^T r - M Q^T r) / sd  -- rank-(c+1) corrections on the n- and p-vectors.  qc = 0: no covariates
+  // (centring through cmean).
+  const double* Qb[KMAX];  // [n_k][qc]
+  const double* Mq[KMAX];  // [qc][p_pad]
+  int qc[KMAX];
   double* bvec;   // [L][K][p_pad] posterior-mean effects b_l = alpha_l * mu_l of the current iteration (pad = 0)
   OutBuf out[2];
   double* elbo;   // [max_iter + 1]
@@ -1595,13 +1603,24 @@ __global__ void __launch_bounds__((std::is_same<XT, uint8_t>::value ? NT_B2 : NT
           const double* bl = effect_vec(l, k);
           const double* cm = pb.cmean + static_cast<size_t>(k) * p_pad;
           const double* cs = pb.cisd + static_cast<size_t>(k) * p_pad;
-          auto load_b = [&](int c, double& b, double& mb) {  // b' of column 256 c + tid and its mean
+          // centring weights of column j: its mean, or -- genotypes residualised on covariates -- row j of M = G^T Q
+          const int qc = pb.qc[k];
+          const double* Mq = pb.Mq[k];
+          const double* Qb = pb.Qb[k];
+          auto load_b = [&](int c, double& b, double (&wq)[B2_QMAX]) {  // b' of column 256 c + tid and its weights
             const int j = c * B2_TILE_COLS + tid;
             b = 0.0;
-            mb = 0.0;
+#pragma unroll
+            for (int t = 0; t < B2_QMAX; ++t) wq[t] = 0.0;
             if (tid < B2_TILE_COLS && c < ntiles && j < p_pad) {
               b = __ldcg(&bl[j]) * cs[j];
-              mb = cm[j];
+              if (qc == 0) {
+                wq[0] = cm[j];
+              } else {
+#pragma unroll
+                for (int t = 0; t < B2_QMAX; ++t)
+                  if (t < qc) wq[t] = Mq[static_cast<size_t>(t) * p_pad + j];
+              }
             }
           };
 #pragma unroll 1
@@ -1611,15 +1630,18 @@ __global__ void __launch_bounds__((std::is_same<XT, uint8_t>::value ? NT_B2 : NT
             double acc[OW];
 #pragma unroll
             for (int i = 0; i < OW; ++i) acc[i] = 0.0;
-            double cpart[1] = {0.0};
+            double cpart[B2_QMAX];
+#pragma unroll
+            for (int t = 0; t < B2_QMAX; ++t) cpart[t] = 0.0;
             // chunk pipeline: b' of chunk c + 2 is loaded and staged, the table set of chunk c + 1 is built and the
             // look-ups of chunk c run between two block barriers (two table sets, two staging halves)
-            double b_reg, m_reg;
-            load_b(0, b_reg, m_reg);
+            double b_reg, w_reg[B2_QMAX];
+            load_b(0, b_reg, w_reg);
             auto stage_b = [&](int c) {  // stage b' of chunk c (held in b_reg), start loading chunk c + 1
               if (tid < B2_TILE_COLS) bstage[(c & 1) * B2_TILE_COLS + tid] = b_reg;
-              cpart[0] += m_reg * b_reg;
-              load_b(c + 1, b_reg, m_reg);
+#pragma unroll
+              for (int t = 0; t < B2_QMAX; ++t) cpart[t] += w_reg[t] * b_reg;
+              load_b(c + 1, b_reg, w_reg);
             };
             stage_b(0);
             __syncthreads();
@@ -1641,14 +1663,23 @@ __global__ void __launch_bounds__((std::is_same<XT, uint8_t>::value ? NT_B2 : NT
 #pragma unroll
               for (int sset = 0; sset < OW / 32; ++sset) vsum[OW * warp + 32 * sset + lane] = tot[sset];
             }
-            block_sum<1, NW>(H, cpart);  // (barriers inside: vsum visible)
-            const double cshift = H->tot[0];
+            block_sum<B2_QMAX, NW>(H, cpart);  // (barriers inside: vsum visible)
+            double tq[B2_QMAX];  // sum_j mean_j b'_j, or Q^T G b'
+#pragma unroll
+            for (int t = 0; t < B2_QMAX; ++t) tq[t] = H->tot[t];
             // finish the rows of the round
             for (int i = tid; i < 4 * qn; i += NT) {
               const int irow = 4 * qa + i;
               if (irow < pb.n[k]) {
                 const int row = pb.row0[k] + irow;
-                const double v = vsum[i] - cshift;
+                double shift = tq[0];
+                if (qc > 0) {
+                  shift = 0.0;
+#pragma unroll
+                  for (int t = 0; t < B2_QMAX; ++t)
+                    if (t < qc) shift += Qb[static_cast<size_t>(irow) * qc + t] * tq[t];
+                }
+                const double v = vsum[i] - shift;
                 const double Rfull = pb.r[row] - v;
                 const double rn = Rfull + (self_next ? v : pb.xb[static_cast<size_t>(lnext) * nrows + row]);
                 pb.xb[static_cast<size_t>(l) * nrows + row] = v;
@@ -1671,14 +1702,27 @@ __global__ void __launch_bounds__((std::is_same<XT, uint8_t>::value ? NT_B2 : NT
 #pragma unroll 1
       for (int k = 0; k < K; ++k) {
         const int nk = pb.n[k];
-        double rpart[1] = {0.0};
+        const int qc = pb.qc[k];
+        const double* Mq = pb.Mq[k];
+        const double* Qb = pb.Qb[k];
+        double rpart[B2_QMAX];  // sum_i r_i, or Q^T r
+#pragma unroll
+        for (int t = 0; t < B2_QMAX; ++t) rpart[t] = 0.0;
         for (int i = tid; i < (nch2[k] << 8); i += NT) {
           const double rv = (i < nk) ? __ldcg(&pb.r[pb.row0[k] + i]) : 0.0;
           rn_sm[i] = rv;
-          rpart[0] += rv;
+          if (qc == 0) {
+            rpart[0] += rv;
+          } else if (i < nk) {
+#pragma unroll
+            for (int t = 0; t < B2_QMAX; ++t)
+              if (t < qc) rpart[t] += Qb[static_cast<size_t>(i) * qc + t] * rv;
+          }
         }
-        block_sum<1, NW>(H, rpart);  // (barriers inside: rn_sm visible)
-        const double rsum = H->tot[0];
+        block_sum<B2_QMAX, NW>(H, rpart);  // (barriers inside: rn_sm visible)
+        double sq[B2_QMAX];
+#pragma unroll
+        for (int t = 0; t < B2_QMAX; ++t) sq[t] = H->tot[t];
         const double* cm = pb.cmean + static_cast<size_t>(k) * p_pad;
         const double* cs = pb.cisd + static_cast<size_t>(k) * p_pad;
         double* dst = pb.xty + static_cast<size_t>(k) * p_pad;
@@ -1713,7 +1757,16 @@ __global__ void __launch_bounds__((std::is_same<XT, uint8_t>::value ? NT_B2 : NT
 #pragma unroll
           for (int sset = 0; sset < OW / 32; ++sset) {
             const int j = 4 * qa + OW * warp + 32 * sset + lane;
-            if (j >= js && j < je) dst[j] = (tot[sset] - cm[j] * rsum) * cs[j];
+            if (j >= js && j < je) {
+              double corr = cm[j] * sq[0];
+              if (qc > 0) {
+                corr = 0.0;
+#pragma unroll
+                for (int t = 0; t < B2_QMAX; ++t)
+                  if (t < qc) corr += Mq[static_cast<size_t>(t) * p_pad + j] * sq[t];
+              }
+              dst[j] = (tot[sset] - corr) * cs[j];
+            }
           }
         }
         __syncthreads();  // rn_sm is reloaded for the next ancestry
@@ -2604,7 +2657,9 @@ struct PrepDesc {
   double* xtx;      // [p_pad]
   double* cmean;    // [p_pad] (hard-call storage only)
   double* cisd;     // [p_pad] (hard-call storage only)
-  int in_ld, n, p, p_pad, flags, pad_;
+  int in_ld, n, p, p_pad, flags, qc;
+  const double* Q;  // [n][qc] covariate basis (hard-call storage, qc > 0) or nullptr
+  double* M;        // [qc][p_pad] out: G^T Q
 };
 
 template <typename IT, typename XT>
@@ -2622,7 +2677,54 @@ __global__ void prep_columns_batched_kernel(const PrepDesc* __restrict__ descs, 
     if (HARD) {
       d.cmean[j] = 0.0;
       d.cisd[j] = 0.0;
+      for (int t = 0; t < d.qc; ++t) d.M[static_cast<size_t>(t) * p_pad + j] = 0.0;
     }
+    return;
+  }
+  if (HARD && d.qc > 0) {
+    // covariate-residualised column (utils.py:114-136 then infer.py:326-333): x = g - Q (Q^T g); the intercept is a
+    // column of Q, so x is centred; sd = numpy.std(x), XtX = sum (x / sd)^2
+    const int qc = d.qc;
+    double m[B2_QMAX];
+    for (int t = 0; t < B2_QMAX; ++t) m[t] = 0.0;
+    bool bad = false;
+    for (int i = 0; i < n; ++i) {
+      const IT g = in[static_cast<size_t>(i) * in_ld + j];
+      out[static_cast<size_t>(i) * p_pad + j] = static_cast<XT>(g);
+      if (g < IT(0)) bad = true;
+      const double gd = static_cast<double>(g);
+      for (int t = 0; t < qc; ++t) m[t] += gd * d.Q[static_cast<size_t>(i) * qc + t];
+    }
+    for (int t = 0; t < qc; ++t) d.M[static_cast<size_t>(t) * p_pad + j] = m[t];
+    double s1 = 0.0;
+    for (int i = 0; i < n; ++i) {
+      double x = static_cast<double>(in[static_cast<size_t>(i) * in_ld + j]);
+      for (int t = 0; t < qc; ++t) x -= d.Q[static_cast<size_t>(i) * qc + t] * m[t];
+      s1 += x;
+    }
+    const double mu = s1 / n;  // rounding-level mean the reference subtracts again (infer.py:327)
+    double sd = 1.0;
+    if (d.flags & 2) {
+      double s2 = 0.0;
+      for (int i = 0; i < n; ++i) {
+        double x = static_cast<double>(in[static_cast<size_t>(i) * in_ld + j]);
+        for (int t = 0; t < qc; ++t) x -= d.Q[static_cast<size_t>(i) * qc + t] * m[t];
+        const double c = x - mu;
+        s2 += c * c;
+      }
+      sd = sqrt(s2 / n);
+    }
+    double ss = 0.0;
+    for (int i = 0; i < n; ++i) {
+      double x = static_cast<double>(in[static_cast<size_t>(i) * in_ld + j]);
+      for (int t = 0; t < qc; ++t) x -= d.Q[static_cast<size_t>(i) * qc + t] * m[t];
+      const double v = (x - mu) / sd;
+      ss += v * v;
+    }
+    d.xtx[j] = ss;
+    d.cmean[j] = 0.0;
+    d.cisd[j] = 1.0 / sd;
+    if (bad) atomicOr(bad_flag, 1);
     return;
   }
   double mean = 0.0, sd = 1.0;
@@ -2790,7 +2892,7 @@ __device__ __forceinline__ double nan_min(double a, double b) { return (a != a |
 
 __host__ __device__ inline size_t purity_smem_bytes(int m, int rows) {
   const size_t m_pad = static_cast<size_t>((m + 3) / 4) * 4;
-  return m_pad * (sizeof(double) * (rows + 2) + sizeof(int));
+  return m_pad * (sizeof(double) * (rows + 2 + B2_QMAX) + sizeof(int));
 }
 
 template <typename XT, bool SS>
@@ -2818,10 +2920,14 @@ __global__ void __launch_bounds__(256) purity_kernel(const ProbDev* __restrict__
     double* tile = reinterpret_cast<double*>(pur_smem);           // [rows][m_pad]
     double* c_mean = tile + static_cast<size_t>(rows) * m_pad_max;  // [m_pad]
     double* c_isd = c_mean + m_pad_max;                            // [m_pad]
-    int* c_sel = reinterpret_cast<int*>(c_isd + m_pad_max);        // [m_pad]
+    double* c_mq = c_isd + m_pad_max;                              // [B2_QMAX][m_pad] rows of M = G^T Q (covariates)
+    int* c_sel = reinterpret_cast<int*>(c_mq + static_cast<size_t>(B2_QMAX) * m_pad_max);  // [m_pad]
+    const int qc = I8 ? P.qc[k] : 0;
+    const double* Qb = I8 ? P.Qb[k] : nullptr;
     for (int c = threadIdx.x; c < m_pad; c += blockDim.x) {
       const int j = c < m ? sel[c] : 0;
       c_sel[c] = j;
+      for (int t = 0; t < qc; ++t) c_mq[static_cast<size_t>(t) * m_pad_max + c] = (c < m) ? P.Mq[k][static_cast<size_t>(t) * p_pad + j] : 0.0;
       c_mean[c] = (I8 && c < m) ? P.cmean[static_cast<size_t>(k) * p_pad + j] : 0.0;
       c_isd[c] = (I8 && c < m) ? P.cisd[static_cast<size_t>(k) * p_pad + j] : (c < m ? 1.0 : 0.0);
     }
@@ -2848,7 +2954,10 @@ __global__ void __launch_bounds__(256) purity_kernel(const ProbDev* __restrict__
         for (int e = threadIdx.x; e < rc * m_pad; e += blockDim.x) {
           const int rr = e / m_pad, c = e - rr * m_pad;
           double val = static_cast<double>(X[static_cast<size_t>(r0 + rr) * p_pad + c_sel[c]]);
-          if (I8) val = (val - c_mean[c]) * c_isd[c];  // hard-call storage: standardise on the fly
+          if (I8 && qc > 0) {  // hard calls residualised on covariates: x = g - Q (Q^T g)
+            for (int t = 0; t < qc; ++t) val -= Qb[static_cast<size_t>(r0 + rr) * qc + t] * c_mq[static_cast<size_t>(t) * m_pad_max + c];
+            val *= c_isd[c];
+          } else if (I8) val = (val - c_mean[c]) * c_isd[c];  // hard-call storage: standardise on the fly
           else val *= c_isd[c];                        // zero for the padding columns
           tile[rr * m_pad + c] = val;
         }

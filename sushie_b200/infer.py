@@ -95,24 +95,40 @@ def _prepare(
     n_snps = Xs[0].shape[1]
     pi = resolve_pi(pi, n_snps, summary=False)
 
-    # covariates: QR residualisation on the host, as the reference does before its jitted loop
+    # covariates: QR residualisation on the host, as the reference does before its jitted loop -- except that hard
+    # calls 0 / 1 / 2 stay hard calls: their residualisation (I - Q Q^T) G is applied on the device as a low-rank
+    # correction of the bit-plane products (SB_B2 storage), so `--covar` runs do not fall back to the dense matrix
     mats: List[np.ndarray] = list(Xs)
     phen: List[np.ndarray] = [np.asarray(y, dtype=float) for y in ys]
-    if covar is not None:
+    hard_calls = False
+    covar_q = None
+
+    def bit_plane_ok(packed):
+        return (config.bit_planes and n_snps <= _capi.B2_MAX_SNPS and max(m.shape[0] for m in packed) <= _capi.B2_MAX_ROWS
+                and all(int(m.max()) <= 2 for m in packed))
+
+    auto = config.genotype_storage == "auto"
+    if covar is not None and not no_regress and auto:
+        packed = [utils.as_hard_calls(m) for m in mats]
+        cov = [np.asarray(c, dtype=float) for c in covar]
+        n_basis = max(1 + (c.reshape(c.shape[0], -1).shape[1]) for c in cov)
+        if all(m is not None for m in packed) and bit_plane_ok(packed) and n_basis <= _capi.B2_MAX_COVAR_BASIS:
+            covar_q = [utils.covar_basis(c) for c in cov]
+            for idx in range(n_pop):
+                _, phen[idx] = utils.regress_covar(None, phen[idx], cov[idx], True)  # phenotype only
+            mats = packed
+            hard_calls = "b2"
+    if covar is not None and covar_q is None:
         for idx in range(n_pop):
             mats[idx], phen[idx] = utils.regress_covar(
                 np.asarray(mats[idx], dtype=float), phen[idx], np.asarray(covar[idx], dtype=float), no_regress
             )
-    # hard calls that were not residualised stay one byte per entry on the device
-    hard_calls = False
-    if config.genotype_storage == "auto" and (covar is None or no_regress):
+    # hard calls that were not residualised stay one byte per entry (or bit planes) on the device
+    if auto and covar_q is None and (covar is None or no_regress):
         packed = [utils.as_hard_calls(m) for m in mats]
         if all(m is not None for m in packed):
             mats = packed
-            hard_calls = "i8"
-            if (config.bit_planes and n_snps <= _capi.B2_MAX_SNPS and max(m.shape[0] for m in mats) <= _capi.B2_MAX_ROWS
-                    and all(int(m.max()) <= 2 for m in mats)):
-                hard_calls = "b2"
+            hard_calls = "b2" if bit_plane_ok(packed) else "i8"
     for idx in range(n_pop):
         y = phen[idx] - np.mean(phen[idx])
         if not no_scale:
@@ -128,7 +144,7 @@ def _prepare(
     standardize = _capi.SB_CENTER | (0 if no_scale else _capi.SB_SCALE)
     problem = _capi.IndProblem(
         mats, phen, L, pi, given_resid, effect_covar, adj.times, adj.plus, em_update=not no_update,
-        standardize=standardize,
+        standardize=standardize, covar_q=covar_q,
     )
     sample_size = np.asarray([m.shape[0] for m in mats])[:, np.newaxis]
     cs_args = dict(threshold=threshold, purity=purity, purity_method=purity_method, max_select=max_select, seed=seed)

@@ -61,6 +61,14 @@ def ols(X: np.ndarray, y: np.ndarray) -> Tuple[np.ndarray, np.ndarray, np.ndarra
     return residual, adj_r, p_value
 
 
+def covar_basis(covar: np.ndarray) -> np.ndarray:
+    """Orthonormal basis Q of ``[1, covar]`` -- the reduced-QR factor ``ols`` residualises with: ``y - Q Q^T y``."""
+    covar = np.asarray(covar, dtype=float)
+    design = np.column_stack([np.ones(covar.shape[0]), covar.reshape(covar.shape[0], -1)])
+    q, _ = np.linalg.qr(design, mode="reduced")
+    return np.ascontiguousarray(q)
+
+
 def regress_covar(X: np.ndarray, y: np.ndarray, covar: np.ndarray, no_regress: bool) -> Tuple[np.ndarray, np.ndarray]:
     """Residualise the phenotype (and, unless ``no_regress``, the genotypes) on covariates."""
     y, _, _ = ols(covar, y)

@@ -76,18 +76,29 @@ def test_individual_options_match_oracle(engine_lib, name, storage):
     _check(res, ref)
 
 
-def test_covariates_with_and_without_genotype_regression(engine_lib):
+@pytest.mark.parametrize("storage", STORAGE_MODES)
+def test_covariates_with_and_without_genotype_regression(engine_lib, storage):
+    """Covariates (reference `utils.regress_covar`, infer.py:319-335).  With the default storage the hard calls stay
+    bit planes and (I - Q Q^T) is applied on the device as a low-rank correction; "dense" / "bytes" residualise on the
+    host and store the dense matrix."""
     import sushie_b200
     from oracle import ibss
+    from sushie_b200 import infer
 
     Xs, ys = _locus(11, 2, (100, 120), 110)
     rng = np.random.default_rng(2)
-    covar = [np.column_stack([rng.standard_normal(x.shape[0]), rng.integers(0, 2, x.shape[0])]).astype(float) for x in Xs]
+    covar = [np.column_stack([rng.standard_normal(x.shape[0]), rng.integers(0, 2, x.shape[0]),
+                              rng.standard_normal(x.shape[0])]).astype(float) for x in Xs]
     for no_regress in (False, True):
-        res = sushie_b200.infer_sushie([x.copy() for x in Xs], [y.copy() for y in ys], covar, L=3,
-                                       no_regress=no_regress, min_tol=1e-4)
-        ref = ibss.fit_individual(Xs, ys, covar=covar, L=3, no_regress=no_regress, min_tol=1e-4)
-        _check(res, ref)
+        for kw in (dict(L=3), dict(L=2, no_scale=True)):
+            with genotype_storage(storage):
+                prep = infer._prepare_kw([x.copy() for x in Xs], [y.copy() for y in ys], covar, no_regress=no_regress,
+                                         min_tol=1e-4, **kw)
+                assert (prep.problem.covar_q is not None) == (storage == "auto" and not no_regress)
+                res = sushie_b200.infer_sushie([x.copy() for x in Xs], [y.copy() for y in ys], covar,
+                                               no_regress=no_regress, min_tol=1e-4, **kw)
+            ref = ibss.fit_individual(Xs, ys, covar=covar, no_regress=no_regress, min_tol=1e-4, **kw)
+            _check(res, ref)
 
 
 @pytest.mark.parametrize("kw", [dict(L=3), dict(L=2, no_update=True, effect_var=[0.02, 0.01]), dict(L=1),

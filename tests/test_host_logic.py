@@ -261,7 +261,7 @@ def test_c_abi_exports_every_declared_symbol(engine_lib):
     assert ctypes.sizeof(_capi.SbOpts) == 40
     assert ctypes.sizeof(_capi.SbResult) == 9 * 8 + 16
     assert ctypes.sizeof(_capi.SbRunStats) == 72  # 5 x 8 + 7 x int32, padded to 8
-    assert ctypes.sizeof(_capi.SbIndProblem) == 96
+    assert ctypes.sizeof(_capi.SbIndProblem) == 112  # + covar_q, covar_q_cols
     assert ctypes.sizeof(_capi.SbSsProblem) == 96
 
 
