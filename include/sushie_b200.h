@@ -38,7 +38,7 @@ extern "C" {
 #endif
 
 #define SB_VERSION 100 /* 0.1.0 */
-#define SB_MAX_ANCESTRIES 4
+#define SB_MAX_ANCESTRIES 6
 #define SB_MAX_COVAR_BASIS 8 /* intercept + 7 covariates */
 
 /* return codes */

@@ -13,7 +13,7 @@ from typing import List, Optional, Sequence
 
 import numpy as np
 
-SB_MAX_ANCESTRIES = 4
+SB_MAX_ANCESTRIES = 6
 SB_F64, SB_F32, SB_I8, SB_B2 = 0, 1, 2, 3
 SB_CENTER, SB_SCALE = 1, 2
 SB_FLAG_SINGLE_PHASE = 1

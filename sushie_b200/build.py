@@ -65,13 +65,13 @@ def up_to_date() -> bool:
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
-    """Compile capi.cu and the four per-ancestry-count kernel units in parallel, then link the shared library."""
+    """Compile capi.cu and the six per-ancestry-count kernel units in parallel, then link the shared library."""
     if not force and up_to_date():
         return OUT
     os.makedirs(OBJ, exist_ok=True)
     nvcc = find_nvcc()
     dev = os.environ.get("SUSHIE_B200_ONLY_K")  # development: compile one ancestry count only
-    ks = [int(dev)] if dev else [1, 2, 3, 4]
+    ks = [int(dev)] if dev else [1, 2, 3, 4, 5, 6]
     vflags = ["-Xptxas", "-v"] if verbose else []
     jobs = [([nvcc] + NVCC_FLAGS + EXTRA_DEFS + ([f"-DSB_ONLY_K={int(dev)}"] if dev else []) + ["-c", "-o", os.path.join(OBJ, "capi.o"), CAPI],
              os.path.join(OBJ, "capi.o"))]

@@ -41,14 +41,14 @@ struct sb_ctx {
 
 struct HostProb {
   int K = 0, p = 0, L = 0, p_pad = 0, nrows = 0;
-  int n[KMAX] = {0, 0, 0, 0};
+  int n[KMAX] = {};
   size_t out_off[2] = {0, 0};  // offsets of the two output blocks inside the arena
   size_t elbo_off = 0, meta_off = 0;
   double bytes_per_ser = 0.0;  // algorithmic: one traversal of X / LD at storage precision
   std::vector<double> ecov0, rv0;
-  void* d_X[KMAX] = {nullptr, nullptr, nullptr, nullptr};
-  const double* d_cmean[KMAX] = {nullptr, nullptr, nullptr, nullptr};  // hard-call storage: column means, 1/std
-  const double* d_cisd[KMAX] = {nullptr, nullptr, nullptr, nullptr};
+  void* d_X[KMAX] = {};
+  const double* d_cmean[KMAX] = {};  // hard-call storage: column means, 1/std
+  const double* d_cisd[KMAX] = {};
 };
 
 struct sb_batch {
@@ -105,6 +105,9 @@ extern "C" const void* sb_kernel_table_k1(int storage, int ss, int variant);
 extern "C" const void* sb_kernel_table_k2(int storage, int ss, int variant);
 extern "C" const void* sb_kernel_table_k3(int storage, int ss, int variant);
 extern "C" const void* sb_kernel_table_k4(int storage, int ss, int variant);
+extern "C" const void* sb_kernel_table_k5(int storage, int ss, int variant);
+extern "C" const void* sb_kernel_table_k6(int storage, int ss, int variant);
+static_assert(KMAX == 6 && SB_MAX_ANCESTRIES == KMAX, "one kernel translation unit per ancestry count");
 
 // variant: traversal variant compiled into the kernel -- hard-call storage: Geometry::fast (1..4); dense fp64
 // individual level: 3 for the wide 12 x 1 tile; everything else 0 (variant chosen per locus at run time)
@@ -125,6 +128,8 @@ static const void* pick_kernel(int K, int storage, bool ss, int variant) {
     case 2: return sb_kernel_table_k2(storage, ss ? 1 : 0, variant);
     case 3: return sb_kernel_table_k3(storage, ss ? 1 : 0, variant);
     case 4: return sb_kernel_table_k4(storage, ss ? 1 : 0, variant);
+    case 5: return sb_kernel_table_k5(storage, ss ? 1 : 0, variant);
+    case 6: return sb_kernel_table_k6(storage, ss ? 1 : 0, variant);
   }
   return nullptr;
 #endif
@@ -449,8 +454,8 @@ struct GenericProblem {
   const double* vec[KMAX];  // y (individual) or z (summary)
   double ns[KMAX];
   const double *pi, *resid_var, *effect_covar, *adj_times, *adj_plus;
-  const double* Q[KMAX] = {nullptr, nullptr, nullptr, nullptr};  // covariate basis per ancestry (SB_B2 only)
-  int qc[KMAX] = {0, 0, 0, 0};
+  const double* Q[KMAX] = {};  // covariate basis per ancestry (SB_B2 only)
+  int qc[KMAX] = {};
 };
 
 static int batch_create(sb_ctx* ctx, const std::vector<GenericProblem>& gp, bool ss, const sb_opts* opts_in,

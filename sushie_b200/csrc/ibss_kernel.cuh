@@ -40,7 +40,7 @@
 
 namespace sb {
 
-constexpr int KMAX = 4;
+constexpr int KMAX = 6;  // ancestries per fit (the kernels are instantiated per count, 1..KMAX)
 constexpr int NT = 256;  // threads per block
 constexpr int NW = NT / 32;
 constexpr int NT_B2 = 256;  // threads of the bit-plane kernel (512 measured slower: 230 vs 204 us per update at p = 2000)
@@ -61,7 +61,7 @@ constexpr int B2_TABLE_BYTES = 65536;   // 256 entries x 32 groups x 8 bytes; tw
 constexpr int B2_MAX_ROWS = 1024;       // rows per ancestry (their next residual is staged in shared memory)
 constexpr int B2_MAX_SUB = 4;           // column tiles of one block per sweep-2 piece: 8 x B2_MAX_SUB >= p / 256
 constexpr int B2_QMAX = 8;              // columns of the covariate basis Q (intercept included) the bit-plane path handles
-constexpr int STAT_STRIDE = 20;  // doubles per team-reduction record (>= 2 + NSYM_MAX + 2 + KMAX)
+constexpr int STAT_STRIDE = 32;  // doubles per team-reduction record (>= 2 + NSYM_MAX + 2 + KMAX)
 constexpr int TRAV_STRIDE = 2 * KMAX;
 
 struct OutBuf {

@@ -1,4 +1,4 @@
-// ibss_kernels.cu -- the instantiations of the persistent IBSS kernel for ONE ancestry count (SB_K = 1..4).
+// ibss_kernels.cu -- the instantiations of the persistent IBSS kernel for ONE ancestry count (SB_K = 1..6).
 //
 // Compiled once per ancestry count (nvcc -DSB_K=k), in parallel, and linked with capi.cu into the one shared
 // library: every (storage type, summary / individual level, traversal variant) combination is a kernel of its
@@ -9,7 +9,7 @@
 #include "ibss_kernel.cuh"
 
 #ifndef SB_K
-#error "compile with -DSB_K=<ancestries>, 1..4"
+#error "compile with -DSB_K=<ancestries>, 1..6"
 #endif
 
 #define SB_CAT2(a, b) a##b

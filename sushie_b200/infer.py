@@ -10,7 +10,7 @@ stopping rule, and the purity Gram matrices run in the CUDA engine behind the C 
 Deliberate differences from the reference:
   * the caller's ``Xs`` / ``ys`` lists are not mutated;
   * arrays in the result are numpy, not ``jax.Array``;
-  * at most ``SB_MAX_ANCESTRIES`` (4) ancestries.
+  * at most ``SB_MAX_ANCESTRIES`` (6) ancestries (one kernel instantiation per count).
 """
 from __future__ import annotations
 

@@ -54,6 +54,8 @@ CASES = {
     "wide_dense": dict(k=2, n=(60, 50), p=2300, kw=dict(L=2)),
     "very_wide": dict(k=2, n=(60, 50), p=5000, kw=dict(L=2, max_iter=6)),   # 12 x 1 fp64 tile / 32 x 2 int8 tile
     "narrow": dict(k=3, n=(120, 90, 70), p=700, kw=dict(L=3)),              # 4-byte int8 vectors
+    "k5": dict(k=5, n=(60, 70, 50, 80, 65), p=140, kw=dict(L=3)),           # more than four ancestries (infer.py:241-246
+    "k6": dict(k=6, n=(50, 60, 45, 70, 55, 40), p=130, kw=dict(L=2)),       #  has no limit): kernels per count up to 6
 }
 
 
@@ -187,3 +189,28 @@ def test_loci_too_wide_for_shared_memory_vectors(engine_lib):
         assert np.max(np.abs(res.pip_all - ibss.make_pip(ref.posteriors.alpha))) <= PIP_TOL
     finally:
         config.team_size = old
+
+
+def test_summary_level_six_ancestries(engine_lib):
+    import sushie_b200
+    from oracle import ibss
+
+    k = 6
+    Xs, ys = _locus(31, k, (150, 170, 140, 160, 130, 180), 120)
+    lds, zs = [], []
+    for X, y in zip(Xs, ys):
+        Xstd = (X - X.mean(0)) / X.std(0)
+        lds.append(Xstd.T @ Xstd / X.shape[0])
+        zs.append(Xstd.T @ ((y - y.mean()) / y.std()) / np.sqrt(X.shape[0]))
+    ns = np.array([[x.shape[0]] for x in Xs])
+    res = sushie_b200.infer_sushie_ss(lds, ns, zs, L=3, min_tol=1e-4)
+    ref = ibss.fit_summary(lds, ns, zs, L=3, min_tol=1e-4)
+    _check(res, ref)
+
+
+def test_more_ancestries_than_kernels_is_an_error(engine_lib):
+    import sushie_b200
+
+    Xs, ys = _locus(32, 7, (40,) * 7, 110)
+    with pytest.raises(ValueError, match="at most 6 ancestries"):
+        sushie_b200.infer_sushie(Xs, ys, L=2)
