@@ -4,15 +4,18 @@ This module is the *oracle* the CUDA path is checked against.  It is never impor
 the product package ``sushie_b200`` (only ``tests/``, ``__graft_entry__.smoke()`` and
 the ``cpu_baseline`` / ``--impl reference`` legs of ``bench.py`` may use it).
 
-PARITY UNPINNED: the reference (``/root/reference/sushie``) is pure Python on top of
-``jax==0.4.33`` / ``equinox==0.10.2`` (``setup.cfg:35-40``), neither of which is
-installed or installable in this environment, and the reference's own tests pin no
-numbers (``tests/test_infer.py:57,93`` only assert ``res is not None``).  The only
-external anchors are (i) the documented causal SNPs of the bundled example,
-rs1886340 and rs10914958 (``docs/manual.rst:88``), which this oracle recovers with
-PIP = 1, and (ii) independent scipy/numpy identities checked in
-``tests/test_oracle_math.py``.  Everything below follows the reference operation by
-operation ("literal form"); each function cites the lines it restates.
+PARITY: the reference (``/root/reference/sushie``) is pure Python on top of ``jax==0.4.33`` /
+``equinox==0.10.2`` (``setup.cfg:35-40``), neither of which is installed or installable in this
+environment, and the reference's own tests pin no numbers (``tests/test_infer.py:57,93`` only assert
+``res is not None``).  The oracle is therefore pinned against the REFERENCE'S OWN SOURCE executed through
+``tests/refshim`` (numpy-backed stand-ins for the jax / equinox primitives; ``tests/test_reference_shim.py``
+compares it with this module on 20+ option mixes: identical iteration counts, effect order and credible sets,
+ELBO to 1e-10 relative) and the committed goldens under ``tests/golden/`` are outputs of that run
+(``tests/golden/make_golden.py``).  What stays unpinned is the third-party arithmetic underneath (XLA's LU /
+Cholesky / reductions versus LAPACK / numpy) -- rounding-level differences.  Further anchors: the documented
+causal SNPs of the bundled example, rs1886340 and rs10914958 (``docs/manual.rst:88``), which come out with
+PIP = 1, and independent scipy identities (``tests/test_oracle.py``).  Everything below follows the reference
+operation by operation ("literal form"); each function cites the lines it restates.
 
 Primitive mapping (third-party, restated from their published definitions):
   jnp.linalg.inv            -> numpy.linalg.inv (LU)

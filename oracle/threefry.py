@@ -21,8 +21,8 @@ its *published* algorithm:
 
 Pinned by: the Random123 known-answer vectors for threefry2x32 and the
 ``split(PRNGKey(0))`` values printed in the JAX documentation
-(``tests/test_oracle_threefry.py``).  Parity with the real ``jax.random.choice`` is
-otherwise unpinned (JAX cannot be imported in this environment).
+(``tests/test_oracle.py``).  Parity with the real ``jax.random.choice`` is otherwise unpinned (JAX cannot be
+imported in this environment); ``tests/refshim`` uses this module where the reference's source calls ``jax.random``.
 """
 from __future__ import annotations
 

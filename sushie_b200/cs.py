@@ -101,20 +101,21 @@ def select_sets(alpha: np.ndarray, threshold: float, max_select: int, seed: int)
     """Per effect: descending order, cumulative alpha, number of SNPs in the set and the
     (possibly sub-sampled) SNP indices used for purity."""
     n_l, p = alpha.shape
+    # pandas ``sort_values(ascending=False)``: argsort of the reversed column, reversed -- all effects in one call
+    rev = np.argsort(alpha[:, ::-1], axis=1, kind="quicksort")
+    order_all = (p - 1 - rev)[:, ::-1]
+    csum_all = np.cumsum(np.take_along_axis(alpha, order_all, axis=1), axis=1)
+    n_rows = np.count_nonzero(csum_all < threshold, axis=1)
     orders, csums, sizes, purity_idx = [], [], [], []
-    base = np.arange(p)
     for ldx in range(n_l):
-        a = alpha[ldx]
-        # pandas ``sort_values(ascending=False)``: argsort of the reversed column, reversed
-        order = base[::-1][np.argsort(a[::-1], kind="quicksort")][::-1]
-        csum = np.cumsum(a[order])
-        n_row = int(np.count_nonzero(csum < threshold))
+        n_row = int(n_rows[ldx])
         size = n_row if n_row == p else n_row + 1
+        order = order_all[ldx]
         idx = order[:size].astype(np.int64)
         if idx.size > max_select:
             idx = jax_choice_no_replace(seed, idx, max_select)
         orders.append(order)
-        csums.append(csum)
+        csums.append(csum_all[ldx])
         sizes.append(size)
         purity_idx.append(idx)
     return orders, csums, sizes, purity_idx

@@ -359,6 +359,7 @@ struct SmemHdr {
   int pad_[3];
   unsigned drain[NSTAGE_MAX];  // hard-call row-team traversal: warps that have finished with the band in stage s (mod NW)
   unsigned pad2_[2];
+  double qv[2 * 8];          // bit-plane traversal: centring terms of the current ancestry (Q^T G b' | Q^T r_next)
   double tsum[NW_MAX];       // per row team: sum of the next residual over the rows it processed (current ancestry)
 };
 
@@ -1607,22 +1608,35 @@ __global__ void __launch_bounds__((std::is_same<XT, uint8_t>::value ? NT_B2 : NT
           const int qc = pb.qc[k];
           const double* Mq = pb.Mq[k];
           const double* Qb = pb.Qb[k];
-          auto load_b = [&](int c, double& b, double (&wq)[B2_QMAX]) {  // b' of column 256 c + tid and its weights
+          auto load_b = [&](int c) -> double {  // b' of column 256 c + tid
             const int j = c * B2_TILE_COLS + tid;
-            b = 0.0;
+            return (tid < B2_TILE_COLS && c < ntiles && j < p_pad) ? __ldcg(&bl[j]) * cs[j] : 0.0;
+          };
+          // centring terms of the ancestry, once, outside the chunk pipeline (its registers are the look-up sums):
+          // sum_j mean_j b'_j, or Q^T G b' = M^T b' with covariates; parked in shared memory until the rows finish
+          {
+            double part[B2_QMAX];
 #pragma unroll
-            for (int t = 0; t < B2_QMAX; ++t) wq[t] = 0.0;
-            if (tid < B2_TILE_COLS && c < ntiles && j < p_pad) {
-              b = __ldcg(&bl[j]) * cs[j];
+            for (int t = 0; t < B2_QMAX; ++t) part[t] = 0.0;
+            for (int j = tid; j < p_pad; j += NT) {
+              const double b = __ldcg(&bl[j]) * cs[j];
               if (qc == 0) {
-                wq[0] = cm[j];
+                part[0] += cm[j] * b;
               } else {
 #pragma unroll
                 for (int t = 0; t < B2_QMAX; ++t)
-                  if (t < qc) wq[t] = Mq[static_cast<size_t>(t) * p_pad + j];
+                  if (t < qc) part[t] += Mq[static_cast<size_t>(t) * p_pad + j] * b;
               }
             }
-          };
+            if (qc == 0) {  // (block-uniform) one value to reduce instead of B2_QMAX
+              double one[1] = {part[0]};
+              block_sum<1, NW>(H, one);
+            } else {
+              block_sum<B2_QMAX, NW>(H, part);
+            }
+            if (tid < B2_QMAX) H->qv[tid] = H->tot[tid];
+            __syncthreads();
+          }
 #pragma unroll 1
           for (int rd = 0; rd < rounds1[k]; ++rd) {
             const int qa = q0[k] + rd * RQ;
@@ -1630,18 +1644,12 @@ __global__ void __launch_bounds__((std::is_same<XT, uint8_t>::value ? NT_B2 : NT
             double acc[OW];
 #pragma unroll
             for (int i = 0; i < OW; ++i) acc[i] = 0.0;
-            double cpart[B2_QMAX];
-#pragma unroll
-            for (int t = 0; t < B2_QMAX; ++t) cpart[t] = 0.0;
             // chunk pipeline: b' of chunk c + 2 is loaded and staged, the table set of chunk c + 1 is built and the
             // look-ups of chunk c run between two block barriers (two table sets, two staging halves)
-            double b_reg, w_reg[B2_QMAX];
-            load_b(0, b_reg, w_reg);
+            double b_reg = load_b(0);
             auto stage_b = [&](int c) {  // stage b' of chunk c (held in b_reg), start loading chunk c + 1
               if (tid < B2_TILE_COLS) bstage[(c & 1) * B2_TILE_COLS + tid] = b_reg;
-#pragma unroll
-              for (int t = 0; t < B2_QMAX; ++t) cpart[t] += w_reg[t] * b_reg;
-              load_b(c + 1, b_reg, w_reg);
+              b_reg = load_b(c + 1);
             };
             stage_b(0);
             __syncthreads();
@@ -1663,10 +1671,10 @@ __global__ void __launch_bounds__((std::is_same<XT, uint8_t>::value ? NT_B2 : NT
 #pragma unroll
               for (int sset = 0; sset < OW / 32; ++sset) vsum[OW * warp + 32 * sset + lane] = tot[sset];
             }
-            block_sum<B2_QMAX, NW>(H, cpart);  // (barriers inside: vsum visible)
+            __syncthreads();  // vsum visible
             double tq[B2_QMAX];  // sum_j mean_j b'_j, or Q^T G b'
 #pragma unroll
-            for (int t = 0; t < B2_QMAX; ++t) tq[t] = H->tot[t];
+            for (int t = 0; t < B2_QMAX; ++t) tq[t] = H->qv[t];
             // finish the rows of the round
             for (int i = tid; i < 4 * qn; i += NT) {
               const int irow = 4 * qa + i;
@@ -1719,10 +1727,14 @@ __global__ void __launch_bounds__((std::is_same<XT, uint8_t>::value ? NT_B2 : NT
               if (t < qc) rpart[t] += Qb[static_cast<size_t>(i) * qc + t] * rv;
           }
         }
-        block_sum<B2_QMAX, NW>(H, rpart);  // (barriers inside: rn_sm visible)
-        double sq[B2_QMAX];
-#pragma unroll
-        for (int t = 0; t < B2_QMAX; ++t) sq[t] = H->tot[t];
+        if (qc == 0) {  // (block-uniform) one value to reduce instead of B2_QMAX
+          double one[1] = {rpart[0]};
+          block_sum<1, NW>(H, one);  // (barriers inside: rn_sm visible)
+        } else {
+          block_sum<B2_QMAX, NW>(H, rpart);
+        }
+        if (tid < B2_QMAX) H->qv[B2_QMAX + tid] = H->tot[tid];  // parked: the rounds' registers are the look-up sums
+        __syncthreads();
         const double* cm = pb.cmean + static_cast<size_t>(k) * p_pad;
         const double* cs = pb.cisd + static_cast<size_t>(k) * p_pad;
         double* dst = pb.xty + static_cast<size_t>(k) * p_pad;
@@ -1758,12 +1770,10 @@ __global__ void __launch_bounds__((std::is_same<XT, uint8_t>::value ? NT_B2 : NT
           for (int sset = 0; sset < OW / 32; ++sset) {
             const int j = 4 * qa + OW * warp + 32 * sset + lane;
             if (j >= js && j < je) {
-              double corr = cm[j] * sq[0];
+              double corr = cm[j] * H->qv[B2_QMAX];
               if (qc > 0) {
                 corr = 0.0;
-#pragma unroll
-                for (int t = 0; t < B2_QMAX; ++t)
-                  if (t < qc) corr += Mq[static_cast<size_t>(t) * p_pad + j] * sq[t];
+                for (int t = 0; t < qc; ++t) corr += Mq[static_cast<size_t>(t) * p_pad + j] * H->qv[B2_QMAX + t];
               }
               dst[j] = (tot[sset] - corr) * cs[j];
             }
