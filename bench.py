@@ -253,6 +253,9 @@ def config5_run(args, path, rank, local_rank, world, dist):
                         [float(r[0]) for r in r2]))
         return out
 
+    from sushie_b200 import config as sb_config
+
+    inner_workers, sb_config.workers_per_device = sb_config.workers_per_device, 1  # the queue's two workers overlap already
     store = dist.distributed_c10d._get_default_store() if world > 1 else None
     if world > 1:
         dist.barrier()  # every rank's genes are on disk
@@ -264,9 +267,10 @@ def config5_run(args, path, rank, local_rank, world, dist):
     t0 = time.perf_counter()
     records, trace = batch.run_distributed(
         [float(w) for w in widths], process, store=store, rank=rank, world=world, workers_per_rank=2,
-        key=f"sushie_b200/config5/{os.environ.get('MASTER_PORT', '0')}")
+        key=f"sushie_b200/config5/{os.environ.get('MASTER_PORT', '0')}", min_items=16, max_items=64)
     torch.cuda.synchronize()
     wall = time.perf_counter() - t0
+    sb_config.workers_per_device = inner_workers
     if world > 1:
         t = torch.tensor([wall], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)  # (also the closing barrier of the timed region)
@@ -517,6 +521,18 @@ def main():
 
     import torch
     import torch.distributed as dist
+
+    # one process per GPU: keep the BLAS / OpenMP pools of the ranks inside their share of the host cores (8 ranks x
+    # 32 spinning BLAS threads on a 32-core box halved the per-rank throughput of the config-5 arm)
+    blas_limit = None
+    if world > 1:
+        try:
+            from threadpoolctl import threadpool_limits
+
+            blas_limit = threadpool_limits(limits=max(1, cores // world))
+        except Exception:
+            pass
+        torch.set_num_threads(max(1, cores // world))
 
     torch.cuda.set_device(local_rank)
     if world > 1:

@@ -1051,7 +1051,7 @@ def _run_window(parser, lines: List[Tuple[int, str]], devices) -> Tuple[int, int
     return n_ok, n_bad
 
 
-def _batch_worker(device: int, work_q, done_q, log_q, precision: int, level: int) -> None:
+def _batch_worker(device: int, work_q, done_q, log_q, precision: int, level: int, n_workers: int = 1) -> None:
     """Body of one `finemap-batch` worker process: owns one GPU, pulls windows of manifest lines until the
     queue is drained, reads / fits / writes its genes itself (no data goes through the parent) and sends its log
     records to the parent's log."""
@@ -1063,6 +1063,14 @@ def _batch_worker(device: int, work_q, done_q, log_q, precision: int, level: int
         log.logger.removeHandler(handler)
     log.logger.addHandler(logging.handlers.QueueHandler(log_q))
     config.precision = precision
+    # several worker processes share the host: keep each one's BLAS / OpenMP pool inside its share of the cores
+    # (N processes x all-core spinning BLAS pools halve the per-process throughput)
+    try:
+        from threadpoolctl import threadpool_limits
+
+        _blas_limit = threadpool_limits(limits=max(1, (os.cpu_count() or 1) // max(1, n_workers)))  # noqa: F841
+    except Exception:
+        pass
     parser = _finemap_line_parser()
     while True:
         lines = work_q.get()
@@ -1093,7 +1101,7 @@ def _run_windows_in_processes(lines, devices: List[int], window: int, precision:
         work_q.put(None)
     listener = logging.handlers.QueueListener(log_q, *log.logger.handlers, respect_handler_level=True)
     listener.start()
-    procs = [ctx.Process(target=_batch_worker, args=(d, work_q, done_q, log_q, precision, log.logger.level), daemon=True)
+    procs = [ctx.Process(target=_batch_worker, args=(d, work_q, done_q, log_q, precision, log.logger.level, len(devices)), daemon=True)
              for d in devices]
     for p in procs:
         p.start()

@@ -36,6 +36,7 @@ struct sb_ctx {
   int cluster_ok = 0;
   int coop_ok = 0;
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t ev_block = nullptr;  // blocking-sync event: host waits sleep instead of spinning on a core
   std::string err;
   // pinned staging for result downloads: device -> pinned at full PCIe rate, then host memcpy into the caller's
   // (pageable) buffers; pageable destinations alone ran at ~1 GB/s for the ~8 small fields of each fit
@@ -192,6 +193,7 @@ extern "C" int sb_init(int device, sb_ctx** out) {
     return SB_ECUDA;
   }
   for (auto& ev : ctx->ev) cudaEventCreate(&ev);
+  cudaEventCreateWithFlags(&ctx->ev_block, cudaEventBlockingSync | cudaEventDisableTiming);
   *out = ctx;
   return SB_OK;
 }
@@ -202,6 +204,7 @@ extern "C" int sb_destroy(sb_ctx* ctx) {
   for (auto& ev : ctx->ev)
     if (ev) cudaEventDestroy(ev);
   if (ctx->pinned) cudaFreeHost(ctx->pinned);
+  if (ctx->ev_block) cudaEventDestroy(ctx->ev_block);
   if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
   return SB_OK;
@@ -213,6 +216,16 @@ extern "C" int sb_set_stream(sb_ctx* ctx, void* cuda_stream) {
   ctx->stream = static_cast<cudaStream_t>(cuda_stream);
   ctx->own_stream = false;
   return SB_OK;
+}
+
+// Wait for the context's stream WITHOUT spinning: several worker threads (and, under torchrun, several processes)
+// wait on their GPUs at the same time, and a spinning cudaStreamSynchronize per waiter takes the host cores away
+// from the threads doing the host half of other chunks (8 ranks on a 32-core box: config-5 throughput halved).
+static cudaError_t sync_stream(sb_ctx* ctx) {
+  if (!ctx->ev_block) return cudaStreamSynchronize(ctx->stream);
+  cudaError_t e = cudaEventRecord(ctx->ev_block, ctx->stream);
+  if (e != cudaSuccess) return e;
+  return cudaEventSynchronize(ctx->ev_block);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -675,7 +688,7 @@ static int batch_create(sb_ctx* ctx, const std::vector<GenericProblem>& gp, bool
   b->off_trav = off_trav;
   cudaStream_t st = ctx->stream;
   auto fail = [&](int code) {
-    cudaStreamSynchronize(st);
+    sync_stream(ctx);
     cudaFree(b->arena);
     b->arena = nullptr;
     return code;
@@ -964,7 +977,7 @@ static int batch_create(sb_ctx* ctx, const std::vector<GenericProblem>& gp, bool
     ++launches;
     SB_CUDA_B(cudaGetLastError());
     SB_CUDA_B(cudaEventRecord(ctx->ev[3], st));
-    SB_CUDA_B(cudaStreamSynchronize(st));
+    SB_CUDA_B(sync_stream(ctx));
   }
   if (hard_storage(opts.storage)) {
     int bad = 0;
@@ -1202,7 +1215,7 @@ extern "C" int sb_batch_run(sb_ctx* ctx, sb_batch* b, sb_run_stats* stats) {
       void* args[] = {&lp};
       static const bool trace = std::getenv("SUSHIE_B200_TRACE_PHASES") != nullptr;
       if (trace) {  // development aid: wall time of the previous phase ends where this line is printed
-        cudaStreamSynchronize(st);
+        sync_stream(ctx);
         std::fprintf(stderr, "[sushie_b200] phase %d: team_size=%d hw=%d teams=%d loci=%d\n", phases, C, hw, n_teams, n_ids);
       }
       SB_CUDA(cudaLaunchKernelExC(&cfg, fn, args));
@@ -1210,7 +1223,7 @@ extern "C" int sb_batch_run(sb_ctx* ctx, sb_batch* b, sb_run_stats* stats) {
         cudaEvent_t e0 = ctx->ev[2];
         (void)e0;
         auto t0 = std::chrono::steady_clock::now();
-        cudaStreamSynchronize(st);
+        sync_stream(ctx);
         const double ms_phase = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
         std::fprintf(stderr, "[sushie_b200] phase %d took %.1f ms\n", phases, ms_phase);
       }
@@ -1220,7 +1233,7 @@ extern "C" int sb_batch_run(sb_ctx* ctx, sb_batch* b, sb_run_stats* stats) {
       // which loci were suspended?
       SB_CUDA(cudaMemcpyAsync(meta.data(), b->arena + b->metas_off, sizeof(int) * 8 * b->n_probs,
                               cudaMemcpyDeviceToHost, st));
-      SB_CUDA(cudaStreamSynchronize(st));
+      SB_CUDA(sync_stream(ctx));
       std::vector<int> rest;
       for (int id : ids)
         if (meta[static_cast<size_t>(id) * 8 + 4] != 2) rest.push_back(id);
@@ -1234,7 +1247,7 @@ extern "C" int sb_batch_run(sb_ctx* ctx, sb_batch* b, sb_run_stats* stats) {
     }
   }
   SB_CUDA(cudaEventRecord(ctx->ev[1], st));
-  SB_CUDA(cudaStreamSynchronize(st));
+  SB_CUDA(sync_stream(ctx));
   SB_CUDA(cudaGetLastError());
   b->ran = true;
   b->phases = phases;
@@ -1253,7 +1266,7 @@ extern "C" int sb_batch_run(sb_ctx* ctx, sb_batch* b, sb_run_stats* stats) {
     stats->n_run_launches = launches;
     SB_CUDA(cudaMemcpyAsync(meta.data(), b->arena + b->metas_off, sizeof(int) * 8 * b->n_probs,
                             cudaMemcpyDeviceToHost, st));
-    SB_CUDA(cudaStreamSynchronize(st));
+    SB_CUDA(sync_stream(ctx));
     for (int i = 0; i < b->n_probs; ++i) {
       stats->n_iter += meta[i * 8 + 0];
       stats->n_ser += meta[i * 8 + 3];
@@ -1274,7 +1287,7 @@ extern "C" int sb_batch_fetch(sb_ctx* ctx, sb_batch* b, sb_result* results) {
   std::vector<int> meta(static_cast<size_t>(b->n_probs) * 8);
   SB_CUDA(cudaMemcpyAsync(meta.data(), b->arena + b->metas_off, sizeof(int) * 8 * b->n_probs, cudaMemcpyDeviceToHost,
                           st));
-  SB_CUDA(cudaStreamSynchronize(st));
+  SB_CUDA(sync_stream(ctx));
   // pinned staging (grown on demand, kept by the context)
   const size_t want = size_t(256) << 20;
   if (ctx->pinned_bytes < want) {
@@ -1293,7 +1306,7 @@ extern "C" int sb_batch_fetch(sb_ctx* ctx, sb_batch* b, sb_result* results) {
   std::vector<Piece> pieces;
   size_t staged = 0;
   auto flush = [&]() -> cudaError_t {
-    cudaError_t e = cudaStreamSynchronize(st);
+    cudaError_t e = sync_stream(ctx);
     if (e != cudaSuccess) return e;
     for (const Piece& pc : pieces) std::memcpy(pc.dst, ctx->pinned + pc.stage_off, pc.bytes);
     pieces.clear();
@@ -1425,7 +1438,7 @@ extern "C" int sb_batch_purity_many(sb_ctx* ctx, sb_batch* b, int n_sets, const 
   double* d_out = reinterpret_cast<double*>(d_buf + idx_b + off_b + prob_b);
   auto bail = [&](cudaError_t e, const char* what) {
     ctx->err = std::string(what) + ": " + cudaGetErrorString(e);
-    cudaStreamSynchronize(st);
+    sync_stream(ctx);
     cudaFree(d_buf);
     return SB_ECUDA;
   };
@@ -1462,7 +1475,7 @@ extern "C" int sb_batch_purity_many(sb_ctx* ctx, sb_batch* b, int n_sets, const 
   if ((e = cudaGetLastError()) != cudaSuccess) return bail(e, "purity launch");
   if ((e = cudaMemcpyAsync(out_min_abs, d_out, sizeof(double) * out_n, cudaMemcpyDeviceToHost, st)) != cudaSuccess)
     return bail(e, "purity D2H");
-  if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return bail(e, "purity sync");
+  if ((e = sync_stream(ctx)) != cudaSuccess) return bail(e, "purity sync");
   cudaFree(d_buf);
   return SB_OK;
 }
