@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define SB_VERSION 100 /* 0.1.0 */
+#define SB_VERSION 110 /* 0.1.1 */
 #define SB_MAX_ANCESTRIES 6
 #define SB_MAX_COVAR_BASIS 8 /* intercept + 7 covariates */
 
@@ -97,6 +97,12 @@ typedef struct {
    * columns; the engine applies (I - Q Q^T) as a low-rank correction and centring is implied.  NULL: no covariates. */
   const double *const *covar_q;
   const int32_t *covar_q_cols;
+  /* Row views (cross-validation folds, cli.py:323-375: every fold is a row subset of one shuffled matrix): when
+   * x_rows is not NULL, X[i] points at a SOURCE matrix of x_src_rows[i] rows and this problem's genotypes are its rows
+   * x_rows[i][0 .. n[i]) in that order.  Problems of one batch that pass the same X[i] pointer (a gene's full fit and
+   * its folds) share ONE upload of the source; the rows are gathered on the device.  NULL: X[i] has n[i] rows. */
+  const int32_t *const *x_rows;
+  const int32_t *x_src_rows;
 } sb_ind_problem;
 
 /* One summary-level problem = the arguments of _update_effects_ss (infer_ss.py:437-446);
@@ -140,7 +146,20 @@ typedef struct {
   int32_t elbo_increase;     /* 0 => ELBO decreased, previous iteration returned */
   int32_t status;            /* SB_STATUS_* */
   int32_t reserved;
+  /* in: NULL, or a permutation of 0..L-1: effect l of every array above is the engine's effect effect_order[l]
+   * (the reference's _reorder_l, infer.py:811-832, applied while the download is copied out) */
+  const int32_t *effect_order;
 } sb_result;
+
+/* Credible-set selection of one problem (reference make_cs, infer.py:899-935), computed on the device per effect l
+ * (engine order, before any re-ordering): SNPs by descending alpha (ties: ascending SNP index), the running sum of
+ * the sorted alphas accumulated left to right as pandas' cumsum does, and the number of SNPs of the set
+ * (first position whose running sum reaches the threshold, inclusive).  Caller-allocated; any pointer may be NULL. */
+typedef struct {
+  int32_t *order;            /* [L][p] SNP indices, descending alpha */
+  double *csum;              /* [L][p] running sum of alpha in that order */
+  int32_t *sizes;            /* [L] SNPs in the credible set */
+} sb_selection;
 
 typedef struct {
   double device_ms;          /* CUDA-event time of the IBSS kernel(s) on the ctx stream */
@@ -190,6 +209,10 @@ int sb_batch_storage(sb_batch *batch, int prob, int ancestry, void **d_ptr, int6
  * LD sub-matrix. */
 int sb_batch_purity(sb_ctx *ctx, sb_batch *batch, int prob, const int32_t *idx,
                     const int32_t *offsets, int n_sets, double *out_min_abs);
+/* Device-side credible-set selection for every problem of a batch that has run: one block per (problem, effect)
+ * sorts alpha in shared memory and scans it; thresholds[n_probs] (make_cs's `threshold` of every problem),
+ * out[n_probs]. */
+int sb_batch_select(sb_ctx *ctx, sb_batch *batch, const double *thresholds, sb_selection *out);
 /* The same for the sets of many problems of the batch in one launch (one call per chunk of loci instead of
  * one per locus): set s belongs to problem set_prob[s] and lists idx[offsets[s] .. offsets[s+1]);
  * out[n_sets][SB_MAX_ANCESTRIES], entries of ancestries a problem does not have are 0. */

@@ -13,6 +13,8 @@ from typing import List, Optional, Sequence
 
 import numpy as np
 
+from .utils import RowView
+
 SB_MAX_ANCESTRIES = 6
 SB_F64, SB_F32, SB_I8, SB_B2 = 0, 1, 2, 3
 SB_CENTER, SB_SCALE = 1, 2
@@ -41,6 +43,7 @@ EXPORTED_SYMBOLS = (
     "sb_batch_storage",
     "sb_batch_purity",
     "sb_batch_purity_many",
+    "sb_batch_select",
 )
 
 _pd = C.POINTER(C.c_double)
@@ -64,6 +67,8 @@ class SbIndProblem(C.Structure):
         ("em_update", C.c_int32),
         ("covar_q", C.POINTER(_pd)),
         ("covar_q_cols", C.POINTER(C.c_int32)),
+        ("x_rows", C.POINTER(C.POINTER(C.c_int32))),
+        ("x_src_rows", C.POINTER(C.c_int32)),
     ]
 
 
@@ -111,6 +116,15 @@ class SbResult(C.Structure):
         ("elbo_increase", C.c_int32),
         ("status", C.c_int32),
         ("reserved", C.c_int32),
+        ("effect_order", C.POINTER(C.c_int32)),
+    ]
+
+
+class SbSelection(C.Structure):
+    _fields_ = [
+        ("order", C.POINTER(C.c_int32)),
+        ("csum", _pd),
+        ("sizes", C.POINTER(C.c_int32)),
     ]
 
 
@@ -173,6 +187,7 @@ def load_library():
         lib.sb_batch_purity.argtypes = [vp, vp, C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_int, _pd]
         lib.sb_batch_purity_many.argtypes = [vp, vp, C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_int32),
                                              C.POINTER(C.c_int32), _pd]
+        lib.sb_batch_select.argtypes = [vp, vp, _pd, C.POINTER(SbSelection)]
         for name in EXPORTED_SYMBOLS:
             fn = getattr(lib, name)
             if name not in ("sb_last_error",):
@@ -216,14 +231,23 @@ class IndProblem:
         if self.covar_q is not None:
             self._qptr = (_pd * self.k)(*[_dptr(q) for q in self.covar_q])
             self._qcols = np.asarray([q.shape[1] for q in self.covar_q], dtype=np.int32)
-        mats = [_matrix_and_dtype(x, allow_i8=True) for x in Xs]
+        # row views (utils.RowView: cross-validation folds): the base matrix is what the engine reads, the row list
+        # says which of its rows this problem is made of (gathered on the device)
+        views = [x if isinstance(x, RowView) else None for x in Xs]
+        mats = [_matrix_and_dtype(x.base if v is not None else x, allow_i8=True) for x, v in zip(Xs, views)]
         dts = {d for _, d in mats}
         if len(dts) > 1:  # mixed input types: promote everything to fp64
             mats = [(np.ascontiguousarray(m, dtype=np.float64), SB_F64) for m, _ in mats]
         self.Xs = [m for m, _ in mats]
         self.x_dtype = mats[0][1]
         self.ys = [_f64(y).reshape(-1) for y in ys]
-        self.n = np.asarray([x.shape[0] for x in self.Xs], dtype=np.int32)
+        self.n = np.asarray([m.shape[0] if v is None else len(v) for m, v in zip(self.Xs, views)], dtype=np.int32)
+        self.rows = None
+        if any(v is not None for v in views):
+            self.rows = [None if v is None else v.rows for v in views]
+            i32p = C.POINTER(C.c_int32)
+            self._rowsptr = (i32p * self.k)(*[None if r is None else r.ctypes.data_as(i32p) for r in self.rows])
+            self._src_rows = np.asarray([m.shape[0] for m in self.Xs], dtype=np.int32)
         self.p = int(self.Xs[0].shape[1])
         self.L = int(L)
         self.pi = None if pi is None else _f64(pi).reshape(-1)
@@ -259,6 +283,12 @@ class IndProblem:
         else:
             s.covar_q = None
             s.covar_q_cols = None
+        if self.rows is not None:
+            s.x_rows = C.cast(self._rowsptr, C.POINTER(C.POINTER(C.c_int32)))
+            s.x_src_rows = self._src_rows.ctypes.data_as(C.POINTER(C.c_int32))
+        else:
+            s.x_rows = None
+            s.x_src_rows = None
 
 
 class SsProblem:
@@ -307,24 +337,36 @@ class SsProblem:
 class RawFit:
     """Numpy view of one ``sb_result``."""
 
-    def __init__(self, k, p, L, max_iter):
-        self.alpha = np.empty((L, p))
-        self.post_mean = np.empty((L, p, k))
-        self.post_mean_sq = np.empty((L, p, k, k))
-        self.weighted_sum_covar = np.empty((L, k, k))
-        self.kl = np.empty(L)
-        self.log_bf = np.empty((L, p))
-        self.effect_covar = np.empty((L, k, k))
-        self.resid_var = np.empty(k)
-        self._elbo = np.full(max_iter + 1, np.nan)
+    FIELDS = ("alpha", "post_mean", "post_mean_sq", "weighted_sum_covar", "kl", "log_bf", "effect_covar", "resid_var")
+
+    def __init__(self, k, p, L, max_iter, small_only: bool = False):
+        shapes = {"alpha": (L, p), "post_mean": (L, p, k), "post_mean_sq": (L, p, k, k), "weighted_sum_covar": (L, k, k),
+                  "kl": (L,), "log_bf": (L, p), "effect_covar": (L, k, k), "resid_var": (k,)}
+        if small_only:  # what the effect order and the convergence log need
+            shapes = {name: shapes[name] for name in ("weighted_sum_covar",)}
+        sizes = {name: int(np.prod(shape)) for name, shape in shapes.items()}
+        buf = np.empty(sum(sizes.values()) + max_iter + 1)  # one allocation per fit, the fields are views
+        pos = 0
+        for name in self.FIELDS:
+            if name in shapes:
+                setattr(self, name, buf[pos: pos + sizes[name]].reshape(shapes[name]))
+                pos += sizes[name]
+            else:
+                setattr(self, name, None)
+        self._elbo = buf[pos:]
+        self._elbo.fill(np.nan)
         self.n_iter = 0
         self.elbo_increase = True
         self.status = 0  # SB_STATUS_*: 1 = the run stopped on a NaN ELBO
+        self.l_order = None  # effect order applied by the download (None: engine order)
 
-    def fill(self, s: SbResult):
-        for name in ("alpha", "post_mean", "post_mean_sq", "weighted_sum_covar", "kl", "log_bf", "effect_covar", "resid_var"):
+    def fill(self, s: SbResult, effect_order: Optional[np.ndarray] = None):
+        for name in self.FIELDS:
             setattr(s, name, _dptr(getattr(self, name)))
         s.elbo = _dptr(self._elbo)
+        if effect_order is not None:
+            self.l_order = np.ascontiguousarray(effect_order, dtype=np.int32)
+            s.effect_order = self.l_order.ctypes.data_as(C.POINTER(C.c_int32))
 
     def finish(self, s: SbResult):
         self.n_iter = int(s.n_iter)
@@ -417,18 +459,41 @@ class Batch:
         self.engine._check(self.engine.lib.sb_batch_run(self.engine._ctx, self._h, C.byref(stats)), "sb_batch_run")
         return stats.as_dict()
 
-    def fetch(self) -> List[RawFit]:
+    def fetch(self, effect_orders: Optional[Sequence] = None, small_only: bool = False) -> List[RawFit]:
+        """Download the fits.  ``effect_orders[i]`` (a permutation of 0..L-1 or None) re-orders the effects of
+        problem i while the download is copied out (``_reorder_l``); ``small_only`` fetches just the ELBO trace,
+        the iteration counts and ``weighted_sum_covar`` -- what decides the effect order."""
         n = len(self.problems)
         res = (SbResult * n)()
         fits = []
         for i, pr in enumerate(self.problems):
-            f = RawFit(pr.k, pr.p, pr.L, self.opts.max_iter)
-            f.fill(res[i])
+            f = RawFit(pr.k, pr.p, pr.L, self.opts.max_iter, small_only)
+            f.fill(res[i], None if effect_orders is None else effect_orders[i])
             fits.append(f)
         self.engine._check(self.engine.lib.sb_batch_fetch(self.engine._ctx, self._h, res), "sb_batch_fetch")
         for f, r in zip(fits, res):
             f.finish(r)
         return fits
+
+    def select(self, thresholds: Sequence[float]):
+        """Credible-set selection on the device (``sb_batch_select``): per problem the SNP order by descending
+        alpha ``[L, p]`` int32, the running sum in that order ``[L, p]`` and the set sizes ``[L]`` -- effects in
+        ENGINE order."""
+        n = len(self.problems)
+        thr = np.ascontiguousarray(thresholds, dtype=np.float64)
+        if thr.shape != (n,):
+            raise ValueError("one threshold per problem")
+        sel = (SbSelection * n)()
+        out = []
+        i32p = C.POINTER(C.c_int32)
+        for i, pr in enumerate(self.problems):
+            order = np.empty((pr.L, pr.p), dtype=np.int32)
+            csum = np.empty((pr.L, pr.p))
+            sizes = np.empty(pr.L, dtype=np.int32)
+            sel[i].order, sel[i].csum, sel[i].sizes = order.ctypes.data_as(i32p), _dptr(csum), sizes.ctypes.data_as(i32p)
+            out.append((order, csum, sizes))
+        self.engine._check(self.engine.lib.sb_batch_select(self.engine._ctx, self._h, _dptr(thr), sel), "sb_batch_select")
+        return out
 
     def purity(self, prob: int, index_sets: Sequence[np.ndarray]) -> np.ndarray:
         """min |corr| per (set, ancestry) on the device-resident genotypes / LD."""

@@ -40,19 +40,69 @@ class Posterior(NamedTuple):
     log_bf: np.ndarray
 
 
-class SushieResult(NamedTuple):
-    """Inference result; field names, order and shapes follow the reference."""
+class SushieResult:
+    """Inference result; field names, order and shapes follow the reference's ``SushieResult`` named tuple
+    (``infer.py:67-101``): attribute access, positional construction, unpacking, indexing, ``_fields``,
+    ``_asdict`` and ``_replace`` behave as there.
 
-    priors: Prior
-    posteriors: Posterior
-    pip_all: np.ndarray
-    pip_cs: np.ndarray
-    cs: pd.DataFrame
-    alphas: pd.DataFrame
-    sample_size: np.ndarray
-    elbo: np.ndarray
-    elbo_increase: bool
-    l_order: np.ndarray
+    One difference: the two pandas tables (``cs``, ``alphas``) may be handed over as a zero-argument ``tables``
+    callable and are then built on first access.  Everything they are made of (set selection, purity, PIPs) is
+    computed up front; only the ``DataFrame`` assembly -- about as expensive as the fit itself at batch
+    throughput, and never looked at for e.g. cross-validation folds -- is deferred."""
+
+    _fields = ("priors", "posteriors", "pip_all", "pip_cs", "cs", "alphas", "sample_size", "elbo", "elbo_increase",
+               "l_order")
+    __slots__ = ("priors", "posteriors", "pip_all", "pip_cs", "_cs", "_alphas", "sample_size", "elbo",
+                 "elbo_increase", "l_order", "_tables")
+
+    def __init__(self, priors, posteriors, pip_all, pip_cs, cs=None, alphas=None, sample_size=None, elbo=None,
+                 elbo_increase=True, l_order=None, *, tables=None):
+        if tables is None and (cs is None or alphas is None):
+            raise TypeError("SushieResult needs `cs` and `alphas`, or a `tables` callable that builds them")
+        self.priors, self.posteriors, self.pip_all, self.pip_cs = priors, posteriors, pip_all, pip_cs
+        self._cs, self._alphas, self._tables = cs, alphas, tables
+        self.sample_size, self.elbo, self.elbo_increase, self.l_order = sample_size, elbo, elbo_increase, l_order
+
+    def _build(self) -> None:
+        if self._tables is not None:
+            self._cs, self._alphas = self._tables()
+            self._tables = None
+
+    @property
+    def cs(self) -> pd.DataFrame:
+        self._build()
+        return self._cs
+
+    @property
+    def alphas(self) -> pd.DataFrame:
+        self._build()
+        return self._alphas
+
+    def __iter__(self):
+        return (getattr(self, name) for name in self._fields)
+
+    def __len__(self):
+        return len(self._fields)
+
+    def __getitem__(self, item):
+        return tuple(self)[item]
+
+    def _asdict(self) -> dict:
+        return {name: getattr(self, name) for name in self._fields}
+
+    def _replace(self, **changes) -> "SushieResult":
+        fields = self._asdict()
+        unknown = set(changes) - set(fields)
+        if unknown:
+            raise ValueError(f"Got unexpected field names: {sorted(unknown)}")
+        fields.update(changes)
+        return SushieResult(**fields)
+
+    def __reduce__(self):
+        return (SushieResult, tuple(self))
+
+    def __repr__(self) -> str:
+        return "SushieResult(" + ", ".join(f"{name}={getattr(self, name)!r}" for name in self._fields) + ")"
 
 
 class _PriorAdjustor(NamedTuple):
@@ -234,6 +284,36 @@ def log_convergence(n_iter: int, max_iter: int, min_tol: float, elbo: np.ndarray
         )
 
 
+def effect_orders(fits, no_reorder: List[bool]) -> List[Optional[np.ndarray]]:
+    """``_reorder_l``'s effect order of every fit of a chunk from its ``weighted_sum_covar`` (None where
+    ``no_reorder``): the same SVD and stable argsort as :func:`_reorder_l`, but one LAPACK-batched call per
+    (L, k) shape instead of one numpy call per fit.  The big posterior arrays are then downloaded straight into
+    this order (``sb_result.effect_order``)."""
+    out: List[Optional[np.ndarray]] = [None] * len(fits)
+    groups = {}
+    for i, (fit, skip) in enumerate(zip(fits, no_reorder)):
+        if not skip:
+            groups.setdefault(fit.weighted_sum_covar.shape, []).append(i)
+    for shape, ids in groups.items():
+        stack = np.concatenate([fits[i].weighted_sum_covar for i in ids])
+        with np.errstate(all="ignore"):
+            try:
+                norms = np.linalg.svd(stack, compute_uv=False).sum(axis=1).reshape(len(ids), shape[0])
+            except np.linalg.LinAlgError:  # some fit of the group is not finite: decide one by one
+                norms = None
+        for row, i in enumerate(ids):
+            if norms is not None:
+                norm = norms[row]
+            else:
+                with np.errstate(all="ignore"):
+                    try:
+                        norm = np.linalg.svd(fits[i].weighted_sum_covar, compute_uv=False).sum(axis=1)
+                    except np.linalg.LinAlgError:
+                        norm = np.full(shape[0], np.nan)
+            out[i] = np.argsort(-norm, kind="stable").astype(np.int32)
+    return out
+
+
 def _reordered(fit, pi, no_reorder):
     k = fit.resid_var.shape[0]
     L, p = fit.alpha.shape
@@ -249,7 +329,11 @@ def _reordered(fit, pi, no_reorder):
         log_bf=fit.log_bf,
     )
     l_order = np.arange(L)
-    if not no_reorder:
+    done = getattr(fit, "l_order", None)  # the download has put the effects in this order already
+    if done is not None:
+        log.logger.debug("Reordering effects based on Frobenius norm of effect size covariance prior.")
+        l_order = np.asarray(done, dtype=np.int64)
+    elif not no_reorder:
         log.logger.debug("Reordering effects based on Frobenius norm of effect size covariance prior.")
         priors, posteriors, l_order = _reorder_l(priors, posteriors)
     return priors, posteriors, l_order
@@ -267,13 +351,15 @@ def assemble_result(fit, pi, sample_size, no_reorder, cs_builder) -> SushieResul
 
 
 class StagedResult:
-    """Epilogue of one fit in two halves.  Construction does the effect re-ordering and the credible-set
-    selection; ``purity_sets`` is what the device has to look at (one index list per effect).  ``finisher``
-    takes the min |corr| per (effect, ancestry) and returns the host-only rest (output tables) as a
-    zero-argument callable, so a batch entry point can ask for the purity of a whole chunk of loci in one
-    launch, release the device batch and start the next chunk before the tables are assembled."""
+    """Epilogue of one fit in two halves.  Construction does the effect re-ordering (unless the download did it)
+    and the credible-set selection -- from the device's sort / running sum when ``selection`` is given, else on
+    the host; ``purity_sets`` is what the purity kernel has to look at (one index list per effect).  ``finisher``
+    takes the min |corr| per (effect, ancestry) and returns the rest as a zero-argument callable, so a batch
+    entry point can ask for the purity of a whole chunk of loci in one launch, release the device batch and
+    start the next chunk before results are assembled."""
 
-    def __init__(self, fit, pi, sample_size, no_reorder, threshold, purity, purity_method, max_select, seed):
+    def __init__(self, fit, pi, sample_size, no_reorder, threshold, purity, purity_method, max_select, seed,
+                 selection=None):
         from . import cs as _cs
 
         if purity_method not in ("weighted", "max", "min"):
@@ -282,7 +368,10 @@ class StagedResult:
         self._purity, self._purity_method = purity, purity_method
         self._priors, self._posteriors, self._l_order = _reordered(fit, pi, no_reorder)
         log.logger.debug("Computing credible sets.")
-        self._selection = _cs.select_sets(self._posteriors.alpha, threshold, max_select, seed)
+        if selection is not None:
+            self._selection = _cs.selection_from_device(*selection, self._l_order, max_select, seed)
+        else:
+            self._selection = _cs.select_sets(self._posteriors.alpha, threshold, max_select, seed)
         self.purity_sets = self._selection[3]
 
     def finisher(self, min_abs):
@@ -291,14 +380,20 @@ class StagedResult:
         min_abs = np.asarray(min_abs, dtype=float)
 
         def finish() -> SushieResult:
-            cs, full_alphas, pip_all, pip_cs = _cs.finish_tables(
-                self._posteriors.alpha, self._posteriors.log_bf, self._sample_size, self._selection, min_abs,
-                self._purity, self._purity_method,
-            )
+            # purity, kept sets and PIPs now (cheap, and the reference's log line needs them); the two pandas
+            # tables on first access
+            alpha, log_bf = self._posteriors.alpha, self._posteriors.log_bf
+            selection = self._selection
+            purities, kept, pip_all, pip_cs = _cs.summarise_sets(
+                alpha, self._sample_size, min_abs, self._purity, self._purity_method, selection)
+
+            def tables():
+                return _cs.frames(alpha, log_bf, selection, purities, kept, pip_all, pip_cs)
+
             log.logger.debug("Inference and credible set computation complete. Beginning to write results.")
             return SushieResult(
-                self._priors, self._posteriors, pip_all, pip_cs, cs, full_alphas, self._sample_size, self._fit.elbo,
-                self._fit.elbo_increase, self._l_order,
+                self._priors, self._posteriors, pip_all, pip_cs, None, None, self._sample_size, self._fit.elbo,
+                self._fit.elbo_increase, self._l_order, tables=tables,
             )
 
         return finish

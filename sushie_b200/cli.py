@@ -204,20 +204,23 @@ def _prepare_cv(geno: List[np.ndarray], pheno: List[np.ndarray], cv_num: int, se
     training and validation phenotypes separately."""
     key = _cs.prng_key(seed)
     n_pop = len(geno)
-    g_parts, y_parts = [], []
+    bases, r_parts, y_parts = [], [], []
     for idx in range(n_pop):
         n = geno[idx].shape[0]
         key, sub = _cs.split_key(key)
         order = _cs.shuffle_with_key(sub, np.arange(n))
-        g_parts.append(np.array_split(np.asarray(geno[idx])[order], cv_num))
+        bases.append(np.asarray(geno[idx]))
+        r_parts.append(np.array_split(order, cv_num))  # the folds as row lists of the un-shuffled matrix
         y_parts.append(np.array_split(np.asarray(pheno[idx])[order], cv_num))
     folds = []
     for cv in range(cv_num):
         rest = [j for j in range(cv_num) if j != cv]
         folds.append(io.CVData(
-            train_geno=[np.concatenate([g_parts[i][j] for j in rest]) for i in range(n_pop)],
+            # training genotypes stay row VIEWS of the gene's matrix: the engine uploads that matrix once and gathers
+            # every fold's rows on the device (np.asarray(view) is the matrix the reference builds)
+            train_geno=[utils.RowView(bases[i], np.concatenate([r_parts[i][j] for j in rest])) for i in range(n_pop)],
             train_pheno=[utils.rint(np.concatenate([y_parts[i][j] for j in rest])) for i in range(n_pop)],
-            valid_geno=[g_parts[i][cv] for i in range(n_pop)],
+            valid_geno=[bases[i][r_parts[i][cv]] for i in range(n_pop)],
             valid_pheno=[utils.rint(y_parts[i][cv]) for i in range(n_pop)],
         ))
     return folds

@@ -1,11 +1,12 @@
 """Credible sets, purity and the output tables (reference ``make_cs``, ``infer.py:835-1008``).
 
-The selection logic (sort by alpha, cumulative cut at ``threshold``, optional
-``max_select`` sub-sample) runs on the host in numpy; the purity Gram matrices -- the only
-heavy part -- are computed on the GPU from the device-resident, standardised genotypes
-(or LD) through ``sb_batch_purity``.  The sub-sample reproduces
-``jax.random.choice(PRNGKey(seed), idx, (max_select,), replace=False)`` (threefry2x32,
-same un-split key for every effect, ``infer.py:894,940-943``).
+On the inference path the selection (sort by alpha, running sum, cut at ``threshold``) is computed on the device
+(``sb_batch_select``) and arrives here as ``selection_from_device``; the stand-alone ``make_cs`` entry point, which
+starts from host arrays, selects in numpy (``select_sets``).  The purity Gram matrices are computed on the GPU from
+the device-resident genotypes (or LD) through ``sb_batch_purity_many``.  The ``max_select`` sub-sample reproduces
+``jax.random.choice(PRNGKey(seed), idx, (max_select,), replace=False)`` (threefry2x32, same un-split key for every
+effect, ``infer.py:894,940-943``).  The two pandas tables are assembled by ``frames`` -- lazily, on first access of
+``SushieResult.cs`` / ``.alphas``.
 """
 from __future__ import annotations
 
@@ -156,40 +157,93 @@ def build_tables(
     return finish_tables(alpha, log_bf, ns, selection, min_abs, purity, purity_method)
 
 
-def finish_tables(alpha, log_bf, ns, selection, min_abs, purity: float, purity_method: str):
-    """Host-only second half of :func:`build_tables`: from the selected sets (``select_sets``) and their
-    min |corr| per ancestry to the output tables.  The batch entry points run this half on a finisher
-    thread while the GPU works on the next chunk of loci."""
-    alpha = np.asarray(alpha, dtype=float)
-    log_bf = np.asarray(log_bf, dtype=float)
-    if purity_method not in ("weighted", "max", "min"):
-        raise ValueError(f"Invalid purity method {purity_method}. Choose from 'weighted', 'max', or 'min'.")
-    n_l, p = alpha.shape
-    orders, csums, sizes, _ = selection
+def selection_from_device(order: np.ndarray, csum: np.ndarray, sizes: np.ndarray, l_order, max_select: int, seed: int):
+    """The tuple :func:`select_sets` returns, from the device's selection (``sb_batch_select``: SNP order by
+    descending alpha, running sum, set size per effect in ENGINE effect order), put into the result's effect
+    order ``l_order``; the ``max_select`` sub-sample of large sets is drawn here (cached threefry orders)."""
+    l_order = np.asarray(l_order)
+    if not np.array_equal(l_order, np.arange(l_order.size)):
+        order, csum, sizes = order[l_order], csum[l_order], sizes[l_order]
+    sizes = [int(v) for v in sizes]
+    purity_idx = []
+    for ldx, size in enumerate(sizes):
+        idx = order[ldx, :size]
+        if size > max_select:
+            idx = jax_choice_no_replace(seed, idx, max_select)
+        purity_idx.append(idx)
+    return order, csum, sizes, purity_idx
+
+
+def summarise_sets(alpha, ns, min_abs, purity: float, purity_method: str, selection=None):
+    """Purity per effect, which sets are kept, and the two PIP vectors (``infer.py:952-985``) -- everything of
+    ``make_cs`` except the two tables.  With ``selection`` the reference's log lines are emitted here."""
+    n_l = alpha.shape[0]
     purities = combine_purity(np.asarray(min_abs, dtype=float).reshape(n_l, -1), ns, purity_method)
     kept = purities > purity
-
     pip_all = make_pip(alpha)
     pip_cs = make_pip(alpha[np.nonzero(kept)[0]])
+    if selection is not None:
+        orders, _, sizes, _ = selection
+        members = [np.asarray(orders[ldx][: sizes[ldx]]) for ldx in range(n_l) if kept[ldx]]
+        if members:
+            snp_in_cs = np.concatenate(members)
+            if len(snp_in_cs) != len(np.unique(snp_in_cs)):
+                log.logger.warning(
+                    "Same SNPs appear in different credible set, which is very unusual."
+                    + " You may want to check this gene in details."
+                )
+        log.logger.info(
+            f"{len(members)} out of {n_l} credible sets remain after pruning based on purity ({purity})."
+            + " For detailed results, specify --alphas."
+        )
+    return purities, kept, pip_all, pip_cs
 
-    columns = {"SNPIndex": np.arange(p)}
+
+def _frame_from_blocks(columns: List[str], float_cols: dict, int_cols: dict, n_rows: int) -> pd.DataFrame:
+    """A frame of float64 and int64 columns in the given column order, assembled as two ready-made blocks
+    (``pandas.api.internals.create_dataframe_from_blocks``) -- the dict constructor spends ~1 ms per fit
+    sanitising and consolidating 53 columns.  Older pandas: the dict constructor."""
+    make = getattr(getattr(pd.api, "internals", None), "create_dataframe_from_blocks", None)
+    if make is None:
+        merged = {**float_cols, **int_cols}
+        return pd.DataFrame({name: merged[name] for name in columns})
+    position = {name: i for i, name in enumerate(columns)}
+    blocks = []
+    for cols, dtype in ((float_cols, np.float64), (int_cols, np.int64)):
+        if not cols:
+            continue
+        block = np.empty((len(cols), n_rows), dtype=dtype)
+        for r, values in enumerate(cols.values()):
+            block[r] = values
+        blocks.append((block, np.asarray([position[name] for name in cols], dtype=np.intp)))
+    return make(blocks, index=pd.RangeIndex(n_rows), columns=pd.Index(columns))
+
+
+def frames(alpha, log_bf, selection, purities, kept, pip_all, pip_cs):
+    """The ``cs`` and ``alphas`` tables in the reference's schema (``infer.py:897-1008``) from the selected sets."""
+    n_l, p = alpha.shape
+    orders, csums, sizes, _ = selection
+    columns = ["SNPIndex"]
+    float_cols, int_cols = {}, {"SNPIndex": np.arange(p)}
     cs_parts = []
     for ldx in range(n_l):
         order, csum, size = orders[ldx], csums[ldx], sizes[ldx]
         in_cs = np.zeros(p, dtype=np.int64)
         in_cs[order[:size]] = 1
         tag = f"l{ldx + 1}"
-        columns[f"alpha_{tag}"] = alpha[ldx]
-        columns[f"in_cs_{tag}"] = in_cs
-        columns[f"purity_{tag}"] = np.full(p, purities[ldx])
-        columns[f"kept_{tag}"] = np.full(p, int(kept[ldx]), dtype=np.int64)
-        columns[f"log_bf_{tag}"] = log_bf[ldx]
+        columns += [f"alpha_{tag}", f"in_cs_{tag}", f"purity_{tag}", f"kept_{tag}", f"log_bf_{tag}"]
+        float_cols[f"alpha_{tag}"] = alpha[ldx]
+        int_cols[f"in_cs_{tag}"] = in_cs
+        float_cols[f"purity_{tag}"] = purities[ldx]
+        int_cols[f"kept_{tag}"] = int(kept[ldx])
+        float_cols[f"log_bf_{tag}"] = log_bf[ldx]
         if kept[ldx]:
-            sel = order[:size]
+            sel = np.asarray(order[:size])
             cs_parts.append((np.full(size, ldx + 1, dtype=np.int64), sel.astype(np.int64), alpha[ldx][sel], csum[:size]))
-    columns["pip_all"] = pip_all
-    columns["pip_cs"] = pip_cs
-    full_alphas = pd.DataFrame(columns)
+    columns += ["pip_all", "pip_cs"]
+    float_cols["pip_all"] = pip_all
+    float_cols["pip_cs"] = pip_cs
+    full_alphas = _frame_from_blocks(columns, float_cols, int_cols, p)
 
     # one frame for all kept sets, built in one go (a frame per effect, or adding columns afterwards, costs
     # more than the fit at batch throughput)
@@ -201,24 +255,21 @@ def finish_tables(alpha, log_bf, ns, selection, min_abs, purity: float, purity_m
     else:
         cs_index = snp_in_cs = np.zeros(0, dtype=np.int64)
         cs_alpha = cs_c_alpha = np.zeros(0)
-    if len(snp_in_cs) != len(np.unique(snp_in_cs)):
-        log.logger.warning(
-            "Same SNPs appear in different credible set, which is very unusual."
-            + " You may want to check this gene in details."
-        )
-    cs = pd.DataFrame(
-        {
-            "CSIndex": cs_index,
-            "SNPIndex": snp_in_cs,
-            "alpha": cs_alpha,
-            "c_alpha": cs_c_alpha,
-            "pip_all": pip_all[snp_in_cs],
-            "pip_cs": pip_cs[snp_in_cs],
-        }
+    cs = _frame_from_blocks(
+        ["CSIndex", "SNPIndex", "alpha", "c_alpha", "pip_all", "pip_cs"],
+        {"alpha": cs_alpha, "c_alpha": cs_c_alpha, "pip_all": pip_all[snp_in_cs], "pip_cs": pip_cs[snp_in_cs]},
+        {"CSIndex": cs_index, "SNPIndex": snp_in_cs}, len(snp_in_cs),
     )
+    return cs, full_alphas
 
-    log.logger.info(
-        f"{len(cs_parts)} out of {n_l} credible sets remain after pruning based on purity ({purity})."
-        + " For detailed results, specify --alphas."
-    )
+
+def finish_tables(alpha, log_bf, ns, selection, min_abs, purity: float, purity_method: str):
+    """Host-only second half of :func:`build_tables`: from the selected sets (``select_sets`` or the device's
+    selection) and their min |corr| per ancestry to the output tables and PIPs."""
+    alpha = np.asarray(alpha, dtype=float)
+    log_bf = np.asarray(log_bf, dtype=float)
+    if purity_method not in ("weighted", "max", "min"):
+        raise ValueError(f"Invalid purity method {purity_method}. Choose from 'weighted', 'max', or 'min'.")
+    purities, kept, pip_all, pip_cs = summarise_sets(alpha, ns, min_abs, purity, purity_method, selection)
+    cs, full_alphas = frames(alpha, log_bf, selection, purities, kept, pip_all, pip_cs)
     return cs, full_alphas, pip_all, pip_cs

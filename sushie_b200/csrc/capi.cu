@@ -13,6 +13,7 @@
 #include <cstdio>
 #include <cstring>
 #include <limits>
+#include <map>
 #include <memory>
 #include <string>
 #include <vector>
@@ -35,6 +36,7 @@ struct sb_ctx {
   int smem_optin = 0;
   int cluster_ok = 0;
   int coop_ok = 0;
+  int pool_ok = 0;  // stream-ordered allocator available (cudaMallocAsync)
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t ev_block = nullptr;  // blocking-sync event: host waits sleep instead of spinning on a core
   std::string err;
@@ -194,6 +196,16 @@ extern "C" int sb_init(int device, sb_ctx** out) {
   }
   for (auto& ev : ctx->ev) cudaEventCreate(&ev);
   cudaEventCreateWithFlags(&ctx->ev_block, cudaEventBlockingSync | cudaEventDisableTiming);
+  cudaDeviceGetAttribute(&v, cudaDevAttrMemoryPoolsSupported, device);
+  if (v && std::getenv("SUSHIE_B200_NO_POOL") == nullptr) {
+    cudaMemPool_t pool = nullptr;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+      unsigned long long keep = ~0ull;  // never hand memory back between chunks
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+      ctx->pool_ok = 1;
+    }
+    cudaGetLastError();
+  }
   *out = ctx;
   return SB_OK;
 }
@@ -226,6 +238,19 @@ static cudaError_t sync_stream(sb_ctx* ctx) {
   cudaError_t e = cudaEventRecord(ctx->ev_block, ctx->stream);
   if (e != cudaSuccess) return e;
   return cudaEventSynchronize(ctx->ev_block);
+}
+
+// Device memory comes from the device's stream-ordered pool: cudaFree (and often cudaMalloc) synchronise the WHOLE
+// device, so with two worker threads per GPU the one releasing its finished batch used to wait for the other's IBSS
+// kernel.  Allocation and release are ordered on the context's stream instead; the pool keeps what it has been
+// given (release threshold raised in sb_init), so steady-state chunks allocate without a driver call.
+static cudaError_t dev_alloc(sb_ctx* ctx, void** ptr, size_t bytes) {
+  return ctx->pool_ok ? cudaMallocAsync(ptr, bytes, ctx->stream) : cudaMalloc(ptr, bytes);
+}
+static void dev_free(sb_ctx* ctx, void* ptr) {
+  if (!ptr) return;
+  if (ctx && ctx->pool_ok) cudaFreeAsync(ptr, ctx->stream);
+  else cudaFree(ptr);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -474,6 +499,14 @@ struct GenericProblem {
   const double *pi, *resid_var, *effect_covar, *adj_times, *adj_plus;
   const double* Q[KMAX] = {};  // covariate basis per ancestry (SB_B2 only)
   int qc[KMAX] = {};
+  const int32_t* rows[KMAX] = {};  // row view: this problem's rows inside the source matrix mat[k] (nullptr: all rows)
+  int src_rows[KMAX] = {};         // rows of the source matrix when rows[k] is given
+  // bytes of staging one (problem, ancestry) needs: the source matrix plus, for a row view, its row list
+  size_t stage_need(int k) const {
+    const size_t es_in = mat_dtype == SB_F64 ? 8 : (mat_dtype == SB_F32 ? 4 : 1);
+    const size_t src = static_cast<size_t>(rows[k] ? src_rows[k] : n[k]) * p * es_in;
+    return (src + 255) / 256 * 256 + (rows[k] ? (sizeof(int32_t) * n[k] + 255) / 256 * 256 : 0);
+  }
 };
 
 static int batch_create(sb_ctx* ctx, const std::vector<GenericProblem>& gp, bool ss, const sb_opts* opts_in,
@@ -595,7 +628,7 @@ static int batch_create(sb_ctx* ctx, const std::vector<GenericProblem>& gp, bool
       h.n[k] = g.n[k];
       nrows += g.n[k];
       l.X[k] = bump.take(static_cast<size_t>(g.n[k]) * ge.p_pad * es);
-      const bool direct = (g.mat_dtype == opts.storage) && g.standardize == 0 && !hard_storage(opts.storage);
+      const bool direct = (g.mat_dtype == opts.storage) && g.standardize == 0 && !hard_storage(opts.storage) && !g.rows[k];
       l.Qb[k] = l.Mq[k] = 0;
       if (g.qc[k] > 0) {
         l.Qb[k] = bump.take(sizeof(double) * g.n[k] * g.qc[k]);  // (uploaded before the column prologue that reads it)
@@ -606,7 +639,7 @@ static int batch_create(sb_ctx* ctx, const std::vector<GenericProblem>& gp, bool
         l.rbits[k] = bump.take(ntiles * ((g.n[k] + 3) / 4) * 256);
         l.cbits[k] = bump.take(((g.n[k] + 255) / 256) * (64 * ntiles) * 256);
       }
-      if (!direct) staging_bytes = std::max(staging_bytes, static_cast<size_t>(g.n[k]) * g.p * elem_size(g.mat_dtype));
+      if (!direct) staging_bytes = std::max(staging_bytes, g.stage_need(k));
     }
     h.nrows = nrows;
     const size_t Kp = static_cast<size_t>(g.K) * ge.p_pad;
@@ -655,8 +688,8 @@ static int batch_create(sb_ctx* ctx, const std::vector<GenericProblem>& gp, bool
   size_t staging_total = 0;
   for (int i = 0; i < n_probs; ++i)
     for (int k = 0; k < gp[i].K; ++k)
-      staging_total += align_up(static_cast<size_t>(gp[i].n[k]) * gp[i].p * elem_size(gp[i].mat_dtype), 256);
-  const size_t staging_cap = std::max(staging_bytes + 256, std::min<size_t>(staging_total, size_t(1) << 30));
+      staging_total += gp[i].stage_need(k);
+  const size_t staging_cap = std::max(staging_bytes + 512, std::min<size_t>(staging_total + 512, size_t(1) << 30));
   const size_t staging_off = bump.take(staging_bytes ? staging_cap : 16);
   const size_t descs_off = bump.take(sizeof(sb::PrepDesc) * static_cast<size_t>(n_probs) * KMAX);
   const size_t pack_off = bump.take(sizeof(sb::PackDesc) * static_cast<size_t>(n_probs) * KMAX);
@@ -667,9 +700,10 @@ static int batch_create(sb_ctx* ctx, const std::vector<GenericProblem>& gp, bool
   const size_t scratch_off = bump.take(sizeof(double) * scratch_stride * (2 * ctx->num_sms + 8));
   b->arena_bytes = align_up(bump.off, 256);
   {
-    cudaError_t e = cudaMalloc(&b->arena, b->arena_bytes);
+    cudaError_t e = dev_alloc(ctx, reinterpret_cast<void**>(&b->arena), b->arena_bytes);
     if (e != cudaSuccess) {
-      ctx->err = "cudaMalloc(" + std::to_string(b->arena_bytes) + " bytes): " + cudaGetErrorString(e);
+      cudaGetLastError();
+      ctx->err = "device allocation (" + std::to_string(b->arena_bytes) + " bytes): " + cudaGetErrorString(e);
       b->arena = nullptr;
       return SB_ENOMEM;
     }
@@ -689,7 +723,7 @@ static int batch_create(sb_ctx* ctx, const std::vector<GenericProblem>& gp, bool
   cudaStream_t st = ctx->stream;
   auto fail = [&](int code) {
     sync_stream(ctx);
-    cudaFree(b->arena);
+    dev_free(ctx, b->arena);
     b->arena = nullptr;
     return code;
   };
@@ -719,6 +753,8 @@ static int batch_create(sb_ctx* ctx, const std::vector<GenericProblem>& gp, bool
   // batched column prologue: matrices are staged back to back, described, and standardised by one launch per
   // staging fill (and per input type)
   std::vector<sb::PrepDesc> pending;
+  std::map<const void*, std::pair<size_t, size_t>> staged_src;  // host matrix -> (staging offset, bytes):
+  // source matrices in the current staging fill (row views share them)
   size_t staged = 0, descs_used = 0;
   int pending_dtype = -1, pending_pmax = 0;
   auto flush_prep = [&]() -> cudaError_t {
@@ -745,22 +781,50 @@ static int batch_create(sb_ctx* ctx, const std::vector<GenericProblem>& gp, bool
     ++launches;
     descs_used += pending.size();
     pending.clear();
+    staged_src.clear();
     staged = 0;
     pending_pmax = 0;
     return cudaGetLastError();
   };
   auto enqueue_prep = [&](const void* host_mat, int dtype, int n, int p, int p_pad, int flags, void* out, double* xtx,
                           double* cmean, double* cisd, const double* d_Q = nullptr, double* d_M = nullptr,
-                          int qc = 0) -> cudaError_t {
-    const size_t bytes = static_cast<size_t>(n) * p * elem_size(dtype);
-    if (!pending.empty() && (dtype != pending_dtype || staged + bytes > staging_cap)) {
+                          int qc = 0, const int32_t* rows_host = nullptr, int src_rows = 0) -> cudaError_t {
+    // the source matrix: `n` rows, or -- for a row view -- `src_rows` rows of which the problem uses rows_host[0..n)
+    const size_t bytes = static_cast<size_t>(rows_host ? src_rows : n) * p * elem_size(dtype);
+    const size_t rows_bytes = rows_host ? align_up(sizeof(int32_t) * n, 256) : 0;
+    if (!pending.empty() && dtype != pending_dtype) {
       cudaError_t e = flush_prep();
       if (e != cudaSuccess) return e;
     }
-    cudaError_t e = cudaMemcpyAsync(A + staging_off + staged, host_mat, bytes, cudaMemcpyHostToDevice, st);
-    if (e != cudaSuccess) return e;
+    auto hit = staged_src.find(host_mat);
+    if (hit != staged_src.end() && hit->second.second != bytes) hit = staged_src.end();  // same pointer, other extent
+    if (hit == staged_src.end() ? staged + align_up(bytes, 256) + rows_bytes > staging_cap
+                                : staged + rows_bytes > staging_cap) {
+      cudaError_t e = flush_prep();  // (also forgets the staged sources)
+      if (e != cudaSuccess) return e;
+      hit = staged_src.end();
+    }
+    cudaError_t e;
+    size_t src_off;
+    if (hit != staged_src.end()) {
+      src_off = hit->second.first;  // a problem of this staging fill has uploaded the same matrix already
+    } else {
+      src_off = staged;
+      e = cudaMemcpyAsync(A + staging_off + staged, host_mat, bytes, cudaMemcpyHostToDevice, st);
+      if (e != cudaSuccess) return e;
+      staged_src[host_mat] = std::make_pair(src_off, bytes);
+      staged += align_up(bytes, 256);
+    }
+    const int* d_rows = nullptr;
+    if (rows_host) {
+      e = cudaMemcpyAsync(A + staging_off + staged, rows_host, sizeof(int32_t) * n, cudaMemcpyHostToDevice, st);
+      if (e != cudaSuccess) return e;
+      d_rows = reinterpret_cast<const int*>(A + staging_off + staged);
+      staged += rows_bytes;
+    }
     sb::PrepDesc pd{};
-    pd.in = A + staging_off + staged;
+    pd.in = A + staging_off + src_off;
+    pd.rows = d_rows;
     pd.out = out;
     pd.xtx = xtx;
     pd.cmean = cmean;
@@ -776,7 +840,6 @@ static int batch_create(sb_ctx* ctx, const std::vector<GenericProblem>& gp, bool
     pending.push_back(pd);
     pending_dtype = dtype;
     pending_pmax = std::max(pending_pmax, p_pad);
-    staged += align_up(bytes, 256);
     return cudaSuccess;
   };
   for (int i = 0; i < n_probs; ++i) {
@@ -878,7 +941,7 @@ static int batch_create(sb_ctx* ctx, const std::vector<GenericProblem>& gp, bool
     for (int k = 0; k < g.K; ++k) {
       const int n = g.n[k];
       double* xtx_k = reinterpret_cast<double*>(A + l.xtx) + static_cast<size_t>(k) * ge.p_pad;
-      const bool direct = (g.mat_dtype == opts.storage) && g.standardize == 0 && !hard_storage(opts.storage);
+      const bool direct = (g.mat_dtype == opts.storage) && g.standardize == 0 && !hard_storage(opts.storage) && !g.rows[k];
       if (hard_storage(opts.storage)) {
         double* cmean_k = reinterpret_cast<double*>(A + l.cmean) + static_cast<size_t>(k) * ge.p_pad;
         double* cisd_k = reinterpret_cast<double*>(A + l.cisd) + static_cast<size_t>(k) * ge.p_pad;
@@ -895,7 +958,7 @@ static int batch_create(sb_ctx* ctx, const std::vector<GenericProblem>& gp, bool
         d.Mq[k] = d_M;
         d.qc[k] = g.qc[k];
         SB_CUDA_B(enqueue_prep(g.mat[k], SB_I8, n, g.p, ge.p_pad, g.standardize, A + l.X[k], xtx_k, cmean_k, cisd_k, d_Q,
-                               d_M, g.qc[k]));
+                               d_M, g.qc[k], g.rows[k], g.src_rows[k]));
       } else if (direct) {
         SB_CUDA_B(cudaMemcpy2DAsync(A + l.X[k], static_cast<size_t>(ge.p_pad) * es, g.mat[k],
                                     static_cast<size_t>(g.p) * es, static_cast<size_t>(g.p) * es, n,
@@ -910,7 +973,7 @@ static int batch_create(sb_ctx* ctx, const std::vector<GenericProblem>& gp, bool
       } else {
         if (!ss) {
           SB_CUDA_B(enqueue_prep(g.mat[k], g.mat_dtype, n, g.p, ge.p_pad, g.standardize, A + l.X[k], xtx_k, nullptr,
-                                 nullptr));
+                                 nullptr, nullptr, nullptr, 0, g.rows[k], g.src_rows[k]));
         } else {
           SB_CUDA_B(cudaMemcpyAsync(A + staging_off, g.mat[k], static_cast<size_t>(n) * g.p * elem_size(g.mat_dtype),
                                     cudaMemcpyHostToDevice, st));
@@ -1023,6 +1086,10 @@ extern "C" int sb_batch_create_ind(sb_ctx* ctx, const sb_ind_problem* probs, int
     g.em = pr.em_update ? 1 : 0;
     g.mat_dtype = pr.x_dtype;
     g.standardize = pr.standardize & 3;
+    if (pr.x_rows && !pr.x_src_rows) {
+      ctx->err = "problem " + std::to_string(i) + ": x_rows needs x_src_rows";
+      return SB_EINVAL;
+    }
     for (int k = 0; k < pr.k; ++k) {
       g.n[k] = pr.n[k];
       g.mat[k] = pr.X[k];
@@ -1031,6 +1098,15 @@ extern "C" int sb_batch_create_ind(sb_ctx* ctx, const sb_ind_problem* probs, int
       if (!pr.X[k] || !pr.y[k]) {
         ctx->err = "problem " + std::to_string(i) + ": null X / y pointer";
         return SB_EINVAL;
+      }
+      if (pr.x_rows && pr.x_rows[k]) {
+        g.rows[k] = pr.x_rows[k];
+        g.src_rows[k] = pr.x_src_rows[k];
+        for (int r = 0; r < pr.n[k]; ++r)
+          if (pr.x_rows[k][r] < 0 || pr.x_rows[k][r] >= pr.x_src_rows[k]) {
+            ctx->err = "problem " + std::to_string(i) + ": x_rows entry outside the source matrix";
+            return SB_EINVAL;
+          }
       }
     }
     g.pi = pr.pi;
@@ -1276,6 +1352,19 @@ extern "C" int sb_batch_run(sb_ctx* ctx, sb_batch* b, sb_run_stats* stats) {
   return SB_OK;
 }
 
+// pinned staging for downloads (allocated on first use, kept by the context)
+static void ensure_pinned(sb_ctx* ctx) {
+  const size_t want = size_t(256) << 20;
+  if (ctx->pinned_bytes >= want) return;
+  if (ctx->pinned) cudaFreeHost(ctx->pinned);
+  ctx->pinned = nullptr;
+  ctx->pinned_bytes = 0;
+  if (cudaHostAlloc(reinterpret_cast<void**>(&ctx->pinned), want, cudaHostAllocDefault) == cudaSuccess)
+    ctx->pinned_bytes = want;
+  else
+    cudaGetLastError();  // callers fall back to direct copies
+}
+
 extern "C" int sb_batch_fetch(sb_ctx* ctx, sb_batch* b, sb_result* results) {
   if (!ctx || !b || !results || !b->arena) return SB_EINVAL;
   if (!b->ran) {
@@ -1288,17 +1377,7 @@ extern "C" int sb_batch_fetch(sb_ctx* ctx, sb_batch* b, sb_result* results) {
   SB_CUDA(cudaMemcpyAsync(meta.data(), b->arena + b->metas_off, sizeof(int) * 8 * b->n_probs, cudaMemcpyDeviceToHost,
                           st));
   SB_CUDA(sync_stream(ctx));
-  // pinned staging (grown on demand, kept by the context)
-  const size_t want = size_t(256) << 20;
-  if (ctx->pinned_bytes < want) {
-    if (ctx->pinned) cudaFreeHost(ctx->pinned);
-    ctx->pinned = nullptr;
-    ctx->pinned_bytes = 0;
-    if (cudaHostAlloc(reinterpret_cast<void**>(&ctx->pinned), want, cudaHostAllocDefault) == cudaSuccess)
-      ctx->pinned_bytes = want;
-    else
-      cudaGetLastError();  // fall back to direct copies below
-  }
+  ensure_pinned(ctx);
   struct Piece {
     unsigned char* dst;
     size_t stage_off, bytes;
@@ -1314,17 +1393,35 @@ extern "C" int sb_batch_fetch(sb_ctx* ctx, sb_batch* b, sb_result* results) {
     return cudaSuccess;
   };
   bool direct = false;  // the caller's buffers of the current problem are page-locked already: copy straight into them
-  auto get = [&](double* dst, size_t off, size_t count) -> cudaError_t {
+  // per-effect arrays: `stride` doubles per effect, written to dst in the caller's effect order (sb_result.effect_order)
+  const int32_t* order = nullptr;
+  int order_L = 0;
+  auto get = [&](double* dst, size_t off, size_t count, size_t stride = 0) -> cudaError_t {
     if (!dst || count == 0) return cudaSuccess;
     const size_t bytes = sizeof(double) * count;
-    if (direct || !ctx->pinned || bytes > ctx->pinned_bytes)
-      return cudaMemcpyAsync(dst, b->arena + off, bytes, cudaMemcpyDeviceToHost, st);
+    const bool permute = order && stride;  // effect l of the output = the engine's effect order[l]
+    if (direct || !ctx->pinned || bytes > ctx->pinned_bytes) {
+      if (!permute) return cudaMemcpyAsync(dst, b->arena + off, bytes, cudaMemcpyDeviceToHost, st);
+      cudaError_t e = cudaSuccess;
+      for (int l = 0; l < order_L && e == cudaSuccess; ++l)
+        e = cudaMemcpyAsync(dst + static_cast<size_t>(l) * stride,
+                            b->arena + off + sizeof(double) * stride * static_cast<size_t>(order[l]),
+                            sizeof(double) * stride, cudaMemcpyDeviceToHost, st);
+      return e;
+    }
     if (staged + bytes > ctx->pinned_bytes) {
       cudaError_t e = flush();
       if (e != cudaSuccess) return e;
     }
+    // one contiguous device -> pinned copy; the permutation costs nothing extra in the pinned -> caller memcpy
     cudaError_t e = cudaMemcpyAsync(ctx->pinned + staged, b->arena + off, bytes, cudaMemcpyDeviceToHost, st);
-    pieces.push_back({reinterpret_cast<unsigned char*>(dst), staged, bytes});
+    if (!permute) {
+      pieces.push_back({reinterpret_cast<unsigned char*>(dst), staged, bytes});
+    } else {
+      for (int l = 0; l < order_L; ++l)
+        pieces.push_back({reinterpret_cast<unsigned char*>(dst + static_cast<size_t>(l) * stride),
+                          staged + sizeof(double) * stride * static_cast<size_t>(order[l]), sizeof(double) * stride});
+    }
     staged += align_up(bytes, 64);
     return e;
   };
@@ -1343,6 +1440,20 @@ extern "C" int sb_batch_fetch(sb_ctx* ctx, sb_batch* b, sb_result* results) {
       direct = probe && cudaPointerGetAttributes(&attr, probe) == cudaSuccess && attr.type == cudaMemoryTypeHost;
       cudaGetLastError();
     }
+    order = nullptr;
+    order_L = h.L;
+    if (r.effect_order) {
+      std::vector<char> seen(h.L, 0);
+      for (int l = 0; l < h.L; ++l) {
+        const int e = r.effect_order[l];
+        if (e < 0 || e >= h.L || seen[e]) {
+          ctx->err = "problem " + std::to_string(i) + ": effect_order is not a permutation of 0..L-1";
+          return SB_EINVAL;
+        }
+        seen[e] = 1;
+      }
+      order = r.effect_order;
+    }
     SB_CUDA(get(r.elbo, h.elbo_off, static_cast<size_t>(n_iter + 1)));
     if (fb < 0) {
       // ELBO failed to improve in the very first iteration: the reference returns the
@@ -1353,19 +1464,24 @@ extern "C" int sb_batch_fetch(sb_ctx* ctx, sb_batch* b, sb_result* results) {
       if (r.log_bf) std::memset(r.log_bf, 0, sizeof(double) * Lp);
       if (r.weighted_sum_covar) std::memset(r.weighted_sum_covar, 0, sizeof(double) * h.L * KK);
       if (r.kl) std::memset(r.kl, 0, sizeof(double) * h.L);
-      if (r.effect_covar) std::memcpy(r.effect_covar, h.ecov0.data(), sizeof(double) * h.L * KK);
+      if (r.effect_covar) {
+        for (int l = 0; l < h.L; ++l)
+          std::memcpy(r.effect_covar + static_cast<size_t>(l) * KK,
+                      h.ecov0.data() + static_cast<size_t>(order ? order[l] : l) * KK, sizeof(double) * KK);
+      }
       if (r.resid_var) std::memcpy(r.resid_var, h.rv0.data(), sizeof(double) * K);
       continue;
     }
     size_t f[10];
     out_block_fields(h.L, h.p, K, h.out_off[fb], f);
-    SB_CUDA(get(r.alpha, f[0], Lp));
-    SB_CUDA(get(r.post_mean, f[1], Lp * K));
-    SB_CUDA(get(r.post_mean_sq, f[2], Lp * KK));
-    SB_CUDA(get(r.log_bf, f[3], Lp));
-    SB_CUDA(get(r.weighted_sum_covar, f[4], static_cast<size_t>(h.L) * KK));
-    SB_CUDA(get(r.kl, f[5], h.L));
-    SB_CUDA(get(r.effect_covar, f[6], static_cast<size_t>(h.L) * KK));
+    const size_t pp = static_cast<size_t>(h.p);
+    SB_CUDA(get(r.alpha, f[0], Lp, pp));
+    SB_CUDA(get(r.post_mean, f[1], Lp * K, pp * K));
+    SB_CUDA(get(r.post_mean_sq, f[2], Lp * KK, pp * KK));
+    SB_CUDA(get(r.log_bf, f[3], Lp, pp));
+    SB_CUDA(get(r.weighted_sum_covar, f[4], static_cast<size_t>(h.L) * KK, KK));
+    SB_CUDA(get(r.kl, f[5], h.L, 1));
+    SB_CUDA(get(r.effect_covar, f[6], static_cast<size_t>(h.L) * KK, KK));
     SB_CUDA(get(r.resid_var, f[7], K));
   }
   SB_CUDA(flush());
@@ -1375,7 +1491,7 @@ extern "C" int sb_batch_fetch(sb_ctx* ctx, sb_batch* b, sb_result* results) {
 extern "C" int sb_batch_destroy(sb_ctx* ctx, sb_batch* b) {
   if (!b) return SB_OK;
   if (ctx) cudaSetDevice(ctx->device);
-  if (b->arena) cudaFree(b->arena);
+  if (b->arena) dev_free(ctx, b->arena);
   delete b;
   return SB_OK;
 }
@@ -1384,6 +1500,127 @@ extern "C" int sb_batch_storage(sb_batch* b, int prob, int ancestry, void** d_pt
   if (!b || prob < 0 || prob >= b->n_probs || ancestry < 0 || ancestry >= b->hp[prob].K) return SB_EINVAL;
   if (d_ptr) *d_ptr = b->hp[prob].d_X[ancestry];
   if (ld_elems) *ld_elems = b->hp[prob].p_pad;
+  return SB_OK;
+}
+
+// Credible-set selection on the device (make_cs, infer.py:899-915): sort, running sum and cut of every effect of
+// every problem in one pass of launches (one per power-of-two width class), then one staged download.
+extern "C" int sb_batch_select(sb_ctx* ctx, sb_batch* b, const double* thresholds, sb_selection* out) {
+  if (!ctx || !b || !out || !thresholds || !b->arena) return SB_EINVAL;
+  if (!b->ran) {
+    ctx->err = "sb_batch_select before sb_batch_run";
+    return SB_EINVAL;
+  }
+  cudaSetDevice(ctx->device);
+  cudaStream_t st = ctx->stream;
+  const int n = b->n_probs;
+  // device layout: descriptors | per problem: csum [L][p] | order [L][p] | sizes [L]
+  std::vector<sb::SelectDesc> descs(n);
+  std::vector<size_t> off_csum(n), off_order(n), off_sizes(n);
+  Bump bump;
+  const size_t descs_off = bump.take(sizeof(sb::SelectDesc) * n);
+  const size_t ids_off = bump.take(sizeof(int) * n);
+  const size_t thr_off = bump.take(sizeof(double) * n);
+  for (int i = 0; i < n; ++i) {
+    const size_t Lp = static_cast<size_t>(b->hp[i].L) * b->hp[i].p;
+    off_csum[i] = bump.take(sizeof(double) * Lp);
+    off_order[i] = bump.take(sizeof(int) * Lp);
+    off_sizes[i] = bump.take(sizeof(int) * b->hp[i].L);
+  }
+  // width classes: problems sorted by the power of two their p pads to (shared memory is sized per launch)
+  auto pow2 = [](int p) {
+    int N = 1;
+    while (N < p) N <<= 1;
+    return N;
+  };
+  std::vector<int> ids(n);
+  for (int i = 0; i < n; ++i) ids[i] = i;
+  std::stable_sort(ids.begin(), ids.end(), [&](int a, int c) { return pow2(b->hp[a].p) < pow2(b->hp[c].p); });
+  const size_t smem_cap = static_cast<size_t>(ctx->smem_optin) - 1024;
+  size_t scratch_bytes = 0;
+  for (int i = 0; i < n; ++i) {
+    const size_t need = static_cast<size_t>(pow2(b->hp[i].p)) * 12;
+    if (need > smem_cap) scratch_bytes = std::max(scratch_bytes, align_up(need, 256) * b->hp[i].L);
+  }
+  const size_t scratch_off = bump.take(scratch_bytes ? scratch_bytes : 16);
+  unsigned char* d_buf = nullptr;
+  SB_CUDA(dev_alloc(ctx, reinterpret_cast<void**>(&d_buf), align_up(bump.off, 256)));
+  auto bail = [&](cudaError_t e, const char* what) {
+    ctx->err = std::string(what) + ": " + cudaGetErrorString(e);
+    sync_stream(ctx);
+    dev_free(ctx, d_buf);
+    return SB_ECUDA;
+  };
+  for (int i = 0; i < n; ++i) {
+    descs[i].csum = out[i].csum ? reinterpret_cast<double*>(d_buf + off_csum[i]) : nullptr;
+    descs[i].order = out[i].order ? reinterpret_cast<int*>(d_buf + off_order[i]) : nullptr;
+    descs[i].sizes = out[i].sizes ? reinterpret_cast<int*>(d_buf + off_sizes[i]) : nullptr;
+  }
+  cudaError_t e;
+  if ((e = cudaMemcpyAsync(d_buf + descs_off, descs.data(), sizeof(sb::SelectDesc) * n, cudaMemcpyHostToDevice, st)) != cudaSuccess)
+    return bail(e, "select H2D descriptors");
+  if ((e = cudaMemcpyAsync(d_buf + ids_off, ids.data(), sizeof(int) * n, cudaMemcpyHostToDevice, st)) != cudaSuccess)
+    return bail(e, "select H2D ids");
+  if ((e = cudaMemcpyAsync(d_buf + thr_off, thresholds, sizeof(double) * n, cudaMemcpyHostToDevice, st)) != cudaSuccess)
+    return bail(e, "select H2D thresholds");
+  const double* d_thr = reinterpret_cast<const double*>(d_buf + thr_off);
+  const sb::SelectDesc* d_descs = reinterpret_cast<const sb::SelectDesc*>(d_buf + descs_off);
+  const int* d_ids = reinterpret_cast<const int*>(d_buf + ids_off);
+  for (int first = 0; first < n;) {
+    const int N = pow2(b->hp[ids[first]].p);
+    int last = first, L_max = 1;
+    while (last < n && pow2(b->hp[ids[last]].p) == N && last - first < 32768) L_max = std::max(L_max, b->hp[ids[last++]].L);
+    const size_t smem = static_cast<size_t>(N) * 12;
+    if (smem <= smem_cap) {
+      // (static + dynamic shared memory above 48 KB needs the opt-in: N = 4096 is 48 KB of keys + the two counters)
+      cudaFuncSetAttribute(sb::select_sets_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+      sb::select_sets_kernel<<<dim3(L_max, last - first), sb::SEL_THREADS, smem, st>>>(b->d_probs, d_descs, d_ids + first,
+                                                                                   d_thr, nullptr, 0);
+    } else {
+      // too wide for shared memory: one problem per launch, keys and indices in global scratch (one slot per effect)
+      for (int t = first; t < last; ++t)
+        sb::select_sets_kernel<<<dim3(b->hp[ids[t]].L, 1), sb::SEL_THREADS, 0, st>>>(
+            b->d_probs, d_descs, d_ids + t, d_thr, d_buf + scratch_off, static_cast<long long>(align_up(smem, 256)));
+    }
+    if ((e = cudaGetLastError()) != cudaSuccess) return bail(e, "select launch");
+    first = last;
+  }
+  // download through the pinned staging buffer
+  ensure_pinned(ctx);
+  struct Piece {
+    void* dst;
+    size_t stage_off, bytes;
+  };
+  std::vector<Piece> pieces;
+  size_t staged = 0;
+  auto flush = [&]() -> cudaError_t {
+    cudaError_t fe = sync_stream(ctx);
+    if (fe != cudaSuccess) return fe;
+    for (const Piece& pc : pieces) std::memcpy(pc.dst, ctx->pinned + pc.stage_off, pc.bytes);
+    pieces.clear();
+    staged = 0;
+    return cudaSuccess;
+  };
+  auto get = [&](void* dst, size_t off, size_t bytes) -> cudaError_t {
+    if (!dst || bytes == 0) return cudaSuccess;
+    if (!ctx->pinned || bytes > ctx->pinned_bytes) return cudaMemcpyAsync(dst, d_buf + off, bytes, cudaMemcpyDeviceToHost, st);
+    if (staged + bytes > ctx->pinned_bytes) {
+      cudaError_t fe = flush();
+      if (fe != cudaSuccess) return fe;
+    }
+    cudaError_t ge = cudaMemcpyAsync(ctx->pinned + staged, d_buf + off, bytes, cudaMemcpyDeviceToHost, st);
+    pieces.push_back({dst, staged, bytes});
+    staged += align_up(bytes, 64);
+    return ge;
+  };
+  for (int i = 0; i < n; ++i) {
+    const size_t Lp = static_cast<size_t>(b->hp[i].L) * b->hp[i].p;
+    if ((e = get(out[i].csum, off_csum[i], sizeof(double) * Lp)) != cudaSuccess) return bail(e, "select D2H csum");
+    if ((e = get(out[i].order, off_order[i], sizeof(int) * Lp)) != cudaSuccess) return bail(e, "select D2H order");
+    if ((e = get(out[i].sizes, off_sizes[i], sizeof(int) * b->hp[i].L)) != cudaSuccess) return bail(e, "select D2H sizes");
+  }
+  if ((e = flush()) != cudaSuccess) return bail(e, "select sync");
+  dev_free(ctx, d_buf);
   return SB_OK;
 }
 
@@ -1431,7 +1668,7 @@ extern "C" int sb_batch_purity_many(sb_ctx* ctx, sb_batch* b, int n_sets, const 
   const size_t idx_b = align_up(sizeof(int) * total, 256), off_b = align_up(sizeof(int) * (n_sets + 1), 256);
   const size_t prob_b = align_up(sizeof(int) * n_sets, 256);
   const size_t out_n = static_cast<size_t>(n_sets) * sb::KMAX;
-  SB_CUDA(cudaMalloc(&d_buf, idx_b + off_b + prob_b + align_up(sizeof(double) * out_n, 256)));
+  SB_CUDA(dev_alloc(ctx, reinterpret_cast<void**>(&d_buf), idx_b + off_b + prob_b + align_up(sizeof(double) * out_n, 256)));
   int* d_idx = reinterpret_cast<int*>(d_buf);
   int* d_off = reinterpret_cast<int*>(d_buf + idx_b);
   int* d_prob = reinterpret_cast<int*>(d_buf + idx_b + off_b);
@@ -1439,7 +1676,7 @@ extern "C" int sb_batch_purity_many(sb_ctx* ctx, sb_batch* b, int n_sets, const 
   auto bail = [&](cudaError_t e, const char* what) {
     ctx->err = std::string(what) + ": " + cudaGetErrorString(e);
     sync_stream(ctx);
-    cudaFree(d_buf);
+    dev_free(ctx, d_buf);
     return SB_ECUDA;
   };
   cudaError_t e;
@@ -1458,7 +1695,20 @@ extern "C" int sb_batch_purity_many(sb_ctx* ctx, sb_batch* b, int n_sets, const 
     if (smem > 48 * 1024) cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);    \
     kf<<<grid, 256, smem, st>>>(b->d_probs, d_prob, d_idx, d_off, m_pad_max, rows, d_out);                     \
   } while (0)
-  if (hard_storage(b->storage)) {
+  int n_max_rows = 1;
+  if (hard_storage(b->storage))
+    for (int s2 = 0; s2 < n_sets; ++s2) {
+      const HostProb& h = b->hp[set_prob[s2]];
+      for (int k = 0; k < h.K; ++k) n_max_rows = std::max(n_max_rows, h.n[k]);
+    }
+  const int nq_max = (n_max_rows + 3) / 4;
+  const size_t smem_i8 = sb::purity_i8_smem_bytes(m_pad_max, nq_max);
+  static const bool no_dp4a = std::getenv("SUSHIE_B200_PURITY_FP64") != nullptr;  // development: the fp64 kernel
+  if (hard_storage(b->storage) && smem_i8 <= smem_cap && !no_dp4a) {
+    // exact integer Gram matrices from columns gathered once (dp4a)
+    cudaFuncSetAttribute(sb::purity_i8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_i8));
+    sb::purity_i8_kernel<<<grid, 256, smem_i8, st>>>(b->d_probs, d_prob, d_idx, d_off, m_pad_max, nq_max, d_out);
+  } else if (hard_storage(b->storage)) {
     SB_PUR(int8_t, false);
   } else if (b->storage == SB_F64) {
     if (b->ss)
@@ -1476,7 +1726,7 @@ extern "C" int sb_batch_purity_many(sb_ctx* ctx, sb_batch* b, int n_sets, const 
   if ((e = cudaMemcpyAsync(out_min_abs, d_out, sizeof(double) * out_n, cudaMemcpyDeviceToHost, st)) != cudaSuccess)
     return bail(e, "purity D2H");
   if ((e = sync_stream(ctx)) != cudaSuccess) return bail(e, "purity sync");
-  cudaFree(d_buf);
+  dev_free(ctx, d_buf);
   return SB_OK;
 }
 

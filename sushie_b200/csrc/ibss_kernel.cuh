@@ -2670,6 +2670,8 @@ struct PrepDesc {
   int in_ld, n, p, p_pad, flags, qc;
   const double* Q;  // [n][qc] covariate basis (hard-call storage, qc > 0) or nullptr
   double* M;        // [qc][p_pad] out: G^T Q
+  const int* rows;  // row view: row i of this matrix is row rows[i] of `in` (cross-validation folds share the
+                    // staged copy of their gene's matrix); nullptr = rows 0..n-1
 };
 
 template <typename IT, typename XT>
@@ -2681,6 +2683,8 @@ __global__ void prep_columns_batched_kernel(const PrepDesc* __restrict__ descs, 
   const IT* in = static_cast<const IT*>(d.in);
   XT* out = static_cast<XT*>(d.out);
   const int n = d.n, in_ld = d.in_ld, p_pad = d.p_pad;
+  const int* __restrict__ rows = d.rows;
+  auto src = [&](int i) -> IT { return in[static_cast<size_t>(rows ? rows[i] : i) * in_ld + j]; };
   if (j >= d.p) {
     for (int i = 0; i < n; ++i) out[static_cast<size_t>(i) * p_pad + j] = XT(0);
     d.xtx[j] = 0.0;
@@ -2699,7 +2703,7 @@ __global__ void prep_columns_batched_kernel(const PrepDesc* __restrict__ descs, 
     for (int t = 0; t < B2_QMAX; ++t) m[t] = 0.0;
     bool bad = false;
     for (int i = 0; i < n; ++i) {
-      const IT g = in[static_cast<size_t>(i) * in_ld + j];
+      const IT g = src(i);
       out[static_cast<size_t>(i) * p_pad + j] = static_cast<XT>(g);
       if (g < IT(0)) bad = true;
       const double gd = static_cast<double>(g);
@@ -2708,7 +2712,7 @@ __global__ void prep_columns_batched_kernel(const PrepDesc* __restrict__ descs, 
     for (int t = 0; t < qc; ++t) d.M[static_cast<size_t>(t) * p_pad + j] = m[t];
     double s1 = 0.0;
     for (int i = 0; i < n; ++i) {
-      double x = static_cast<double>(in[static_cast<size_t>(i) * in_ld + j]);
+      double x = static_cast<double>(src(i));
       for (int t = 0; t < qc; ++t) x -= d.Q[static_cast<size_t>(i) * qc + t] * m[t];
       s1 += x;
     }
@@ -2717,7 +2721,7 @@ __global__ void prep_columns_batched_kernel(const PrepDesc* __restrict__ descs, 
     if (d.flags & 2) {
       double s2 = 0.0;
       for (int i = 0; i < n; ++i) {
-        double x = static_cast<double>(in[static_cast<size_t>(i) * in_ld + j]);
+        double x = static_cast<double>(src(i));
         for (int t = 0; t < qc; ++t) x -= d.Q[static_cast<size_t>(i) * qc + t] * m[t];
         const double c = x - mu;
         s2 += c * c;
@@ -2726,7 +2730,7 @@ __global__ void prep_columns_batched_kernel(const PrepDesc* __restrict__ descs, 
     }
     double ss = 0.0;
     for (int i = 0; i < n; ++i) {
-      double x = static_cast<double>(in[static_cast<size_t>(i) * in_ld + j]);
+      double x = static_cast<double>(src(i));
       for (int t = 0; t < qc; ++t) x -= d.Q[static_cast<size_t>(i) * qc + t] * m[t];
       const double v = (x - mu) / sd;
       ss += v * v;
@@ -2740,17 +2744,17 @@ __global__ void prep_columns_batched_kernel(const PrepDesc* __restrict__ descs, 
   double mean = 0.0, sd = 1.0;
   if (d.flags & 1) {
     double s = 0.0;
-    for (int i = 0; i < n; ++i) s += static_cast<double>(in[static_cast<size_t>(i) * in_ld + j]);
+    for (int i = 0; i < n; ++i) s += static_cast<double>(src(i));
     mean = s / n;
   }
   if (d.flags & 2) {
     // numpy.std of the centred column: sqrt(mean(|x - mean(x)|^2))
     double s1 = 0.0;
-    for (int i = 0; i < n; ++i) s1 += static_cast<double>(in[static_cast<size_t>(i) * in_ld + j]) - mean;
+    for (int i = 0; i < n; ++i) s1 += static_cast<double>(src(i)) - mean;
     const double m2 = s1 / n;
     double s2 = 0.0;
     for (int i = 0; i < n; ++i) {
-      const double c = (static_cast<double>(in[static_cast<size_t>(i) * in_ld + j]) - mean) - m2;
+      const double c = (static_cast<double>(src(i)) - mean) - m2;
       s2 += c * c;
     }
     sd = sqrt(s2 / n);
@@ -2758,7 +2762,7 @@ __global__ void prep_columns_batched_kernel(const PrepDesc* __restrict__ descs, 
   double ss = 0.0;
   bool bad = false;
   for (int i = 0; i < n; ++i) {
-    const IT g = in[static_cast<size_t>(i) * in_ld + j];
+    const IT g = src(i);
     double v = static_cast<double>(g) - mean;
     if (d.flags & 2) v /= sd;
     if (HARD) {
@@ -3008,6 +3012,237 @@ __global__ void __launch_bounds__(256) purity_kernel(const ProbDev* __restrict__
     for (int w = 1; w < static_cast<int>(blockDim.x >> 5); ++w) b = nan_min(b, red[w]);
     out[set * KMAX + k] = b;
   }
+}
+
+
+// ---------------------------------------------------------------------------------------------------------
+// Purity for hard-call storage by EXACT integer Gram matrices (infer.py:946-965).  The m selected one-byte
+// columns of block (set, ancestry) are gathered ONCE into shared memory as words of four consecutive rows,
+// laid out [row quad][column] so that the four columns of a 4 x 4 tile are one 128-bit load; every pair of
+// columns then costs n / 4 `dp4a` instructions instead of n fp64 multiply-adds on widened genotypes (and the
+// columns are no longer re-gathered from global memory once per pass over the tiles).  With S_ab = sum_i g_ia g_ib
+// and s_a = sum_i g_ia exact,
+//     sum_i x_ia x_ib = (S_ab - mu_a s_b - mu_b s_a + n mu_a mu_b) / (sd_a sd_b)          x = (g - mu) / sd
+//     sum_i x_ia x_ib = (S_ab - sum_t M_ta M_tb) / (sd_a sd_b)       x = (g - Q Q^T g) / sd, M = G^T Q (covariates)
+// which is the reference's X_sel^T X_sel on the standardised columns up to fp64 rounding of the last step.
+__host__ __device__ inline size_t purity_i8_smem_bytes(int m_pad, int nq) {
+  return static_cast<size_t>(m_pad) * nq * 4 + static_cast<size_t>(m_pad) * (sizeof(double) * (3 + B2_QMAX) + sizeof(int));
+}
+
+static __global__ void __launch_bounds__(256) purity_i8_kernel(const ProbDev* __restrict__ probs,
+                                                        const int* __restrict__ set_prob,
+                                                        const int* __restrict__ idx, const int* __restrict__ offsets,
+                                                        int m_pad_max, int nq_max, double* __restrict__ out) {
+  extern __shared__ __align__(16) unsigned char pur_smem[];
+  const int set = blockIdx.x, k = blockIdx.y;
+  const ProbDev& P = probs[set_prob[set]];
+  if (k >= P.K) return;
+  const int o0 = offsets[set], m = offsets[set + 1] - o0;
+  const int* sel = idx + o0;
+  const signed char* X = reinterpret_cast<const signed char*>(P.X[k]);
+  const int n = P.n[k], p_pad = P.p_pad;
+  const int m4 = (m + 3) / 4, m_pad = m4 * 4, nq = (n + 3) / 4;
+  unsigned* W = reinterpret_cast<unsigned*>(pur_smem);  // [nq][m_pad]
+  double* c_mean = reinterpret_cast<double*>(pur_smem + static_cast<size_t>(m_pad_max) * nq_max * 4);  // [m_pad]
+  double* c_isd = c_mean + m_pad_max;
+  double* c_sum = c_isd + m_pad_max;
+  double* c_mq = c_sum + m_pad_max;  // [B2_QMAX][m_pad_max]
+  int* c_sel = reinterpret_cast<int*>(c_mq + static_cast<size_t>(B2_QMAX) * m_pad_max);
+  const int qc = P.qc[k];
+  for (int c = threadIdx.x; c < m_pad; c += blockDim.x) {
+    const int j = c < m ? sel[c] : 0;
+    c_sel[c] = j;
+    for (int t = 0; t < qc; ++t) c_mq[static_cast<size_t>(t) * m_pad_max + c] = (c < m) ? P.Mq[k][static_cast<size_t>(t) * p_pad + j] : 0.0;
+    c_mean[c] = (c < m) ? P.cmean[static_cast<size_t>(k) * p_pad + j] : 0.0;
+    c_isd[c] = (c < m) ? P.cisd[static_cast<size_t>(k) * p_pad + j] : 0.0;
+  }
+  __syncthreads();
+  // gather: word (q, c) = rows 4q .. 4q+3 of column sel[c]; adjacent threads read neighbouring columns of one row
+  for (int e = threadIdx.x; e < nq * m_pad; e += blockDim.x) {
+    const int q = e / m_pad, c = e - q * m_pad;
+    unsigned w = 0;
+    if (c < m) {
+      const signed char* col = X + c_sel[c];
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const int r = 4 * q + t;
+        if (r < n) w |= static_cast<unsigned>(static_cast<unsigned char>(col[static_cast<size_t>(r) * p_pad])) << (8 * t);
+      }
+    }
+    W[e] = w;
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < m_pad; c += blockDim.x) {  // exact column sums
+    int sum = 0;
+    for (int q = 0; q < nq; ++q) sum = __dp4a(static_cast<int>(W[q * m_pad + c]), 0x01010101, sum);
+    c_sum[c] = static_cast<double>(sum);
+  }
+  __syncthreads();
+  double best = CUDART_INF;
+  const int ntiles = m4 * (m4 + 1) / 2;
+  const double nd = static_cast<double>(n);
+  for (int t = threadIdx.x; t < ntiles; t += blockDim.x) {
+    // row ta of the upper triangle of the m4 x m4 tile grid: first index with ta*(2*m4-ta+1)/2 <= t
+    int ta = static_cast<int>((2.0 * m4 + 1.0 - sqrt((2.0 * m4 + 1.0) * (2.0 * m4 + 1.0) - 8.0 * t)) * 0.5);
+    while (ta * (2 * m4 - ta + 1) / 2 > t) --ta;
+    while ((ta + 1) * (2 * m4 - ta) / 2 <= t) ++ta;
+    const int tb = ta + (t - ta * (2 * m4 - ta + 1) / 2);
+    int acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j] = 0;
+    const uint4* wa = reinterpret_cast<const uint4*>(W) + ta;
+    const uint4* wb = reinterpret_cast<const uint4*>(W) + tb;
+#pragma unroll 4
+    for (int q = 0; q < nq; ++q) {
+      const uint4 a = wa[q * m4], b = wb[q * m4];
+      const int av[4] = {static_cast<int>(a.x), static_cast<int>(a.y), static_cast<int>(a.z), static_cast<int>(a.w)};
+      const int bv[4] = {static_cast<int>(b.x), static_cast<int>(b.y), static_cast<int>(b.z), static_cast<int>(b.w)};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = __dp4a(av[i], bv[j], acc[i][j]);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int ca = 4 * ta + i, cb = 4 * tb + j;
+        if (ca < m && cb < m) {
+          double g = static_cast<double>(acc[i][j]);
+          if (qc > 0) {
+            for (int tq = 0; tq < qc; ++tq)
+              g -= c_mq[static_cast<size_t>(tq) * m_pad_max + ca] * c_mq[static_cast<size_t>(tq) * m_pad_max + cb];
+          } else {
+            g = g - c_mean[ca] * c_sum[cb] - c_mean[cb] * c_sum[ca] + nd * c_mean[ca] * c_mean[cb];
+          }
+          // a monomorphic column has sd = 0: the reference's standardised column is 0 / 0 = NaN and so is every
+          // correlation with it (here 1 / sd = inf must not meet a rounding-level g != 0 and turn into +-inf)
+          const double sa = c_isd[ca], sc = c_isd[cb];
+          const bool degenerate = isinf(sa) || isinf(sc) || sa != sa || sc != sc;
+          best = nan_min(best, degenerate ? CUDART_NAN : fabs(g * sa * sc / nd));
+        }
+      }
+  }
+  __shared__ double red_i8[32];
+  for (int o = 16; o > 0; o >>= 1) best = nan_min(best, __shfl_xor_sync(0xffffffffu, best, o));
+  if ((threadIdx.x & 31) == 0) red_i8[threadIdx.x >> 5] = best;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double b = red_i8[0];
+    for (int w = 1; w < static_cast<int>(blockDim.x >> 5); ++w) b = nan_min(b, red_i8[w]);
+    out[set * KMAX + k] = b;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Credible-set selection on the device (reference make_cs, infer.py:899-915): block (effect l, problem) sorts the
+// p posterior inclusion probabilities alpha_l in descending order (ties: ascending SNP index) with a bitonic
+// network in shared memory (keys = the bit patterns of the non-negative doubles), then ONE thread accumulates the
+// running sum left to right -- the order of additions of pandas' cumsum, so the cut `csum < threshold` falls where
+// the reference's does -- and the block writes order / csum / set size.  `scratch` != nullptr: loci too wide for
+// shared memory sort in global memory (one slot of n_pow2 keys + indices per block).
+constexpr int SEL_THREADS = 512;
+
+struct SelectDesc {
+  int* order;    // [L][p]
+  double* csum;  // [L][p]
+  int* sizes;    // [L]
+};
+
+__device__ __forceinline__ bool sel_before(unsigned long long ka, int ia, unsigned long long kb, int ib) {
+  return ka > kb || (ka == kb && ia < ib);
+}
+
+static __global__ void __launch_bounds__(SEL_THREADS) select_sets_kernel(const ProbDev* __restrict__ probs,
+                                                                  const SelectDesc* __restrict__ descs,
+                                                                  const int* __restrict__ prob_ids,
+                                                                  const double* __restrict__ thresholds,
+                                                                  unsigned char* __restrict__ scratch,
+                                                                  long long scratch_stride) {
+  extern __shared__ __align__(16) unsigned char sel_smem[];
+  __shared__ int s_special, s_count;
+  const int l = blockIdx.x, pi = prob_ids[blockIdx.y];
+  const ProbDev& P = probs[pi];
+  if (l >= P.L) return;
+  const SelectDesc D = descs[pi];
+  const double threshold = thresholds[pi];
+  const int p = P.p;
+  int N = 1;
+  while (N < p) N <<= 1;
+  unsigned char* base = scratch ? scratch + (static_cast<long long>(blockIdx.y) * gridDim.x + blockIdx.x) * scratch_stride
+                                : sel_smem;
+  unsigned long long* keys = reinterpret_cast<unsigned long long*>(base);
+  int* ids = reinterpret_cast<int*>(base + sizeof(unsigned long long) * N);
+  const int fb = P.meta[2];  // final output buffer; -1: the initial state is returned (alpha = 0)
+  const double* alpha = fb >= 0 ? P.out[fb].alpha + static_cast<size_t>(l) * p : nullptr;
+  if (threadIdx.x == 0) {
+    s_special = 0;
+    s_count = 0;
+  }
+  __syncthreads();
+  bool special = false;
+  for (int i = threadIdx.x; i < N; i += blockDim.x) {
+    unsigned long long key = 0ull;
+    int id = 0x7fffffff;  // padding sorts behind every real entry
+    if (i < p) {
+      const double a = alpha ? alpha[i] : 0.0;
+      id = i;
+      if (a > 0.0) key = static_cast<unsigned long long>(__double_as_longlong(a));
+      else if (a != 0.0) special = true;  // NaN or negative: sorted as the smallest, summed with its true value
+    }
+    keys[i] = key;
+    ids[i] = id;
+  }
+  if (special) s_special = 1;
+  __syncthreads();
+  for (int kk = 2; kk <= N; kk <<= 1) {
+    for (int j = kk >> 1; j > 0; j >>= 1) {
+      for (int t = threadIdx.x; t < (N >> 1); t += blockDim.x) {
+        const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+        const int q = i | j;
+        const unsigned long long ka = keys[i], kb = keys[q];
+        const int ia = ids[i], ib = ids[q];
+        const bool up = (i & kk) == 0;
+        const bool swap = up ? sel_before(kb, ib, ka, ia) : sel_before(ka, ia, kb, ib);
+        if (swap) {
+          keys[i] = kb;
+          keys[q] = ka;
+          ids[i] = ib;
+          ids[q] = ia;
+        }
+      }
+      __syncthreads();
+    }
+  }
+  if (threadIdx.x == 0) {
+    double c = 0.0;
+    if (s_special) {
+      for (int i = 0; i < p; ++i) {
+        c += alpha[ids[i]];
+        keys[i] = static_cast<unsigned long long>(__double_as_longlong(c));
+      }
+    } else {
+#pragma unroll 8
+      for (int i = 0; i < p; ++i) {
+        c += __longlong_as_double(static_cast<long long>(keys[i]));
+        keys[i] = static_cast<unsigned long long>(__double_as_longlong(c));
+      }
+    }
+  }
+  __syncthreads();
+  int below = 0;
+  for (int i = threadIdx.x; i < p; i += blockDim.x) {
+    const double c = __longlong_as_double(static_cast<long long>(keys[i]));
+    if (D.csum) D.csum[static_cast<size_t>(l) * p + i] = c;
+    if (D.order) D.order[static_cast<size_t>(l) * p + i] = ids[i];
+    below += (c < threshold) ? 1 : 0;
+  }
+  for (int o = 16; o > 0; o >>= 1) below += __shfl_xor_sync(0xffffffffu, below, o);
+  if ((threadIdx.x & 31) == 0 && below) atomicAdd(&s_count, below);
+  __syncthreads();
+  if (threadIdx.x == 0 && D.sizes) D.sizes[l] = (s_count == p) ? s_count : s_count + 1;
 }
 
 }  // namespace sb

@@ -31,6 +31,7 @@ from ._common import (
     build_priors,
     check_scalar_options,
     check_snp_counts,
+    effect_orders,
     log_convergence,
     resolve_pi,
     resolve_resid_var,
@@ -65,9 +66,38 @@ class _Prepared:
         self.no_reorder = no_reorder
 
 
+class _HardCallCache:
+    """``utils.as_hard_calls`` once per genotype matrix of an ``infer_sushie_batch`` call: a gene's full fit and the
+    row views of its cross-validation folds look at the same memory, so the check (a full pass) and the int8 copy
+    are shared -- and the engine sees one pointer, which it uploads once (``sb_ind_problem.x_rows``)."""
+
+    def __init__(self):
+        self._seen = {}
+
+    def packed(self, base: np.ndarray):
+        """(int8 matrix or None, largest entry) of a plain 2-D array."""
+        key = utils.array_key(base)
+        hit = self._seen.get(key)
+        if hit is None:
+            packed = utils.as_hard_calls(base)
+            hit = (packed, int(packed.max()) if packed is not None and packed.size else 0, base)  # (keeps `base` alive)
+            self._seen[key] = hit
+        return hit[0], hit[1]
+
+    def __call__(self, m):
+        """``m`` (array or ``utils.RowView``) as hard calls -> (int8 array / view or None, largest entry)."""
+        if isinstance(m, utils.RowView):
+            packed, top = self.packed(m.base)
+            return (None if packed is None else utils.RowView(packed, m.rows)), top
+        m = np.asarray(m)
+        if m.ndim != 2:
+            return None, 0
+        return self.packed(m)
+
+
 def _prepare(
     Xs, ys, covar, L, no_scale, no_regress, no_update, pi, resid_var, effect_var, rho,
-    max_iter, min_tol, threshold, purity, purity_method, max_select, min_snps, no_reorder, seed,
+    max_iter, min_tol, threshold, purity, purity_method, max_select, min_snps, no_reorder, seed, hard_cache=None,
 ) -> _Prepared:
     if len(Xs) == len(ys):
         n_pop = len(Xs)
@@ -103,32 +133,38 @@ def _prepare(
     hard_calls = False
     covar_q = None
 
-    def bit_plane_ok(packed):
+    hard_cache = hard_cache or _HardCallCache()
+
+    def bit_plane_ok(packed, tops):
         return (config.bit_planes and n_snps <= _capi.B2_MAX_SNPS and max(m.shape[0] for m in packed) <= _capi.B2_MAX_ROWS
-                and all(int(m.max()) <= 2 for m in packed))
+                and all(top <= 2 for top in tops))
+
+    def dense(m):
+        return np.asarray(m)  # (materialises a row view)
 
     auto = config.genotype_storage == "auto"
     if covar is not None and not no_regress and auto:
-        packed = [utils.as_hard_calls(m) for m in mats]
+        packed, tops = zip(*[hard_cache(m) for m in mats])
         cov = [np.asarray(c, dtype=float) for c in covar]
         n_basis = max(1 + (c.reshape(c.shape[0], -1).shape[1]) for c in cov)
-        if all(m is not None for m in packed) and bit_plane_ok(packed) and n_basis <= _capi.B2_MAX_COVAR_BASIS:
+        if all(m is not None for m in packed) and bit_plane_ok(packed, tops) and n_basis <= _capi.B2_MAX_COVAR_BASIS:
             covar_q = [utils.covar_basis(c) for c in cov]
             for idx in range(n_pop):
                 _, phen[idx] = utils.regress_covar(None, phen[idx], cov[idx], True)  # phenotype only
-            mats = packed
+            mats = list(packed)
             hard_calls = "b2"
     if covar is not None and covar_q is None:
         for idx in range(n_pop):
             mats[idx], phen[idx] = utils.regress_covar(
-                np.asarray(mats[idx], dtype=float), phen[idx], np.asarray(covar[idx], dtype=float), no_regress
+                np.asarray(dense(mats[idx]), dtype=float), phen[idx], np.asarray(covar[idx], dtype=float), no_regress
             )
     # hard calls that were not residualised stay one byte per entry (or bit planes) on the device
     if auto and covar_q is None and (covar is None or no_regress):
-        packed = [utils.as_hard_calls(m) for m in mats]
+        packed, tops = zip(*[hard_cache(m) for m in mats])
         if all(m is not None for m in packed):
-            mats = packed
-            hard_calls = "b2" if bit_plane_ok(packed) else "i8"
+            mats = list(packed)
+            hard_calls = "b2" if bit_plane_ok(packed, tops) else "i8"
+    # (row views that reach this point un-materialised -- hard calls or not -- are gathered on the device)
     for idx in range(n_pop):
         y = phen[idx] - np.mean(phen[idx])
         if not no_scale:
@@ -151,16 +187,16 @@ def _prepare(
     return _Prepared(problem, pi, sample_size, max_iter, min_tol, cs_args, no_reorder, hard_calls)
 
 
-def _stage(prep: _Prepared, fit) -> StagedResult:
-    """Host half of the epilogue of one fit before the purity launch: convergence log, re-order, set selection."""
+def _stage(prep: _Prepared, fit, selection=None) -> StagedResult:
+    """Host half of the epilogue of one fit before the purity launch: convergence log, set selection."""
     log_convergence(fit.n_iter, prep.max_iter, prep.min_tol, fit.elbo, fit.elbo_increase)
-    return StagedResult(fit, prep.pi, prep.sample_size, prep.no_reorder, **prep.cs_args)
+    return StagedResult(fit, prep.pi, prep.sample_size, prep.no_reorder, **prep.cs_args, selection=selection)
 
 
 def _run_prepared(preps: Sequence[_Prepared], device: int = 0, defer: bool = False) -> list:
     """Fit a list of prepared problems that share max_iter / min_tol on one GPU.
 
-    ``defer=True`` returns one zero-argument callable per problem (the host-only table assembly) instead of
+    ``defer=True`` returns one zero-argument callable per problem (the host-only result assembly) instead of
     the finished ``SushieResult`` -- the work queue runs them while the GPU is busy with the next chunk."""
     eng = _capi.get_engine(device)
     storage = config.storage_code()
@@ -173,8 +209,11 @@ def _run_prepared(preps: Sequence[_Prepared], device: int = 0, defer: bool = Fal
 
 
 def run_chunk(eng, preps, opts, stage, defer: bool) -> list:
-    """Upload -> IBSS -> download -> credible-set selection (`stage`, per fit) -> purity of every set of the
-    chunk in one launch, then the output tables of every fit, now or deferred.  ``config.trace_host`` prints the wall time of each phase."""
+    """One chunk of loci on one GPU:  upload -> IBSS -> effect order of every fit (from the small
+    ``weighted_sum_covar`` download) -> credible-set selection on the device (sort + running sum + cut, one
+    launch per width class) -> download of the posteriors straight into the effect order -> purity of every
+    set of the chunk in one launch -> results (``stage`` / finishers; the pandas tables are built on first
+    access).  ``config.trace_host`` prints the wall time of each phase."""
     t = [time.perf_counter()]
 
     def lap():
@@ -184,9 +223,12 @@ def run_chunk(eng, preps, opts, stage, defer: bool) -> list:
         lap()
         batch.run()
         lap()
-        fits = batch.fetch()
+        orders = effect_orders(batch.fetch(small_only=True), [p.no_reorder for p in preps])
+        selections = batch.select([p.cs_args["threshold"] for p in preps])
         lap()
-        staged = [stage(p, f) for p, f in zip(preps, fits)]
+        fits = batch.fetch(orders)
+        lap()
+        staged = [stage(p, f, sel) for p, f, sel in zip(preps, fits, selections)]
         lap()
         min_abs = batch.purity_many([s.purity_sets for s in staged])  # one launch for the whole chunk
         lap()
@@ -195,7 +237,8 @@ def run_chunk(eng, preps, opts, stage, defer: bool) -> list:
         d = np.diff(t) * 1e3
         print(
             f"[sushie_b200] chunk of {len(preps)} fits: upload+column statistics {d[0]:.0f} ms, IBSS {d[1]:.0f} ms, "
-            f"download {d[2]:.0f} ms, reorder+set selection {d[3]:.0f} ms, purity {d[4]:.0f} ms",
+            f"effect order + device set selection {d[2]:.0f} ms, download {d[3]:.0f} ms, staging {d[4]:.0f} ms, "
+            f"purity {d[5]:.0f} ms",
             file=sys.stderr, flush=True,
         )
     if defer:
@@ -203,7 +246,7 @@ def run_chunk(eng, preps, opts, stage, defer: bool) -> list:
     t0 = time.perf_counter()
     out = [finish() for finish in finishers]
     if config.trace_host:
-        print(f"[sushie_b200] chunk of {len(preps)} fits: output tables {1e3 * (time.perf_counter() - t0):.0f} ms",
+        print(f"[sushie_b200] chunk of {len(preps)} fits: results {1e3 * (time.perf_counter() - t0):.0f} ms",
               file=sys.stderr, flush=True)
     return out
 
@@ -250,10 +293,11 @@ def infer_sushie_batch(problems: Sequence[dict], devices: Optional[Sequence[int]
 
     t0 = time.perf_counter()
     preps = []
+    hard_cache = _HardCallCache()  # a gene's full fit and its fold views share one hard-call check and one upload
     for pr in problems:
         kw = dict(common)
         kw.update(pr)
-        preps.append(_prepare_kw(**kw))
+        preps.append(_prepare_kw(hard_cache=hard_cache, **kw))
     if config.trace_host:
         print(f"[sushie_b200] host prologue of {len(preps)} fits: {1e3 * (time.perf_counter() - t0):.0f} ms",
               file=sys.stderr, flush=True)
@@ -263,11 +307,11 @@ def infer_sushie_batch(problems: Sequence[dict], devices: Optional[Sequence[int]
 def _prepare_kw(
     Xs, ys, covar=None, L=10, no_scale=False, no_regress=False, no_update=False, pi=None, resid_var=None,
     effect_var=None, rho=None, max_iter=500, min_tol=1e-4, threshold=0.95, purity=0.5, purity_method="weighted",
-    max_select=250, min_snps=100, no_reorder=False, seed=12345,
+    max_select=250, min_snps=100, no_reorder=False, seed=12345, hard_cache=None,
 ) -> _Prepared:
     return _prepare(
         Xs, ys, covar, L, no_scale, no_regress, no_update, pi, resid_var, effect_var, rho,
-        max_iter, min_tol, threshold, purity, purity_method, max_select, min_snps, no_reorder, seed,
+        max_iter, min_tol, threshold, purity, purity_method, max_select, min_snps, no_reorder, seed, hard_cache,
     )
 
 

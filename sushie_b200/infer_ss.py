@@ -69,9 +69,9 @@ def _prepare_ss(
     return infer._Prepared(problem, pi, ns, max_iter, min_tol, cs_args, no_reorder)
 
 
-def _stage_ss(prep, fit) -> StagedResult:
+def _stage_ss(prep, fit, selection=None) -> StagedResult:
     log_convergence(fit.n_iter, prep.max_iter, prep.min_tol, fit.elbo, fit.elbo_increase)
-    return StagedResult(fit, prep.pi, prep.sample_size, prep.no_reorder, **prep.cs_args)
+    return StagedResult(fit, prep.pi, prep.sample_size, prep.no_reorder, **prep.cs_args, selection=selection)
 
 
 def _run_prepared_ss(preps: Sequence["infer._Prepared"], device: int = 0, defer: bool = False) -> list:

@@ -352,14 +352,109 @@ def test_purity_of_a_whole_chunk_in_one_launch(engine_lib, storage):
     sets[2] = []  # a locus without sets
     opts = eng.make_opts(2, 1e-4, _capi.SB_I8 if storage == "i8" else _capi.SB_F64, 1)
     with eng.create_batch(probs, opts) as b:
-        got = b.purity_many(sets)
+        got = b.purity_many(sets)  # (hard calls: the 1000-SNP set does not fit the integer kernel -> fp64 kernel)
         one = b.purity(1, sets[1])
+        small = b.purity_many([ss[:7] for ss in sets])  # hard calls: exact integer Gram matrices (dp4a)
     assert [g.shape for g in got] == [(len(s), len(x)) for s, x in zip(sets, Xstd)]
-    for g, ss, xs in zip(got, sets, Xstd):
-        for row, idx in zip(g, ss):
-            want = [np.min(np.abs(x[:, idx].T @ x[:, idx] / x.shape[0])) for x in xs]
-            np.testing.assert_allclose(row, want, rtol=1e-10, atol=1e-12)
-    np.testing.assert_array_equal(one, got[1])
+    for res in (got, small):
+        for g, ss, xs in zip(res, sets, Xstd):
+            for row, idx in zip(g, ss):
+                want = [np.min(np.abs(x[:, idx].T @ x[:, idx] / x.shape[0])) for x in xs]
+                np.testing.assert_allclose(row, want, rtol=1e-10, atol=1e-12)
+    np.testing.assert_allclose(one, got[1], rtol=1e-10, atol=1e-12)
+
+
+def test_integer_purity_kernel_with_covariates_and_monomorphic_columns(engine_lib):
+    """Bit-plane storage with covariate-residualised hard calls: min |corr| of the residualised, scaled columns from
+    the exact integer Gram matrix minus M M^T (M = G^T Q); a monomorphic column makes the purity NaN as jnp.min does."""
+    from sushie_b200 import _capi, utils
+    from sushie_b200._common import build_priors
+
+    rng = np.random.default_rng(7)
+    eng = _capi.get_engine(0)
+    k, n, p = 2, [130, 101], 400
+    G = [rng.binomial(2, rng.uniform(0.1, 0.5, size=p), size=(ni, p)).astype(np.int8) for ni in n]
+    for g in G:
+        g[0, g.std(axis=0) == 0] += 1
+    G[1][:, 17] = 1  # monomorphic in ancestry 2
+    cov = [rng.standard_normal((ni, 3)) for ni in n]
+    Q = [utils.covar_basis(c) for c in cov]
+    Xres = [g - q @ (q.T @ g) for g, q in zip(G, Q)]
+    with np.errstate(all="ignore"):
+        Xstd = [(x - x.mean(0)) / x.std(0) for x in Xres]
+    ec, adj = build_priors(k, 2, None, None, False, summary=False)
+    prob = _capi.IndProblem(G, [rng.standard_normal(ni) for ni in n], 2, None, np.ones(k), ec, adj.times, adj.plus, True,
+                            standardize=_capi.SB_CENTER | _capi.SB_SCALE, covar_q=Q)
+    clean = np.setdiff1d(np.arange(p), [17])
+    sets = [rng.choice(clean, size=m, replace=False) for m in (2, 9, 64, 250)] + [np.array([3, 17, 40])]
+    with eng.create_batch([prob], eng.make_opts(2, 1e-4, _capi.SB_B2, 1)) as b:
+        got = b.purity(0, sets)
+        # the same genotypes without covariates: the monomorphic column is 0 / 0 after standardising -> NaN purity
+        plain = _capi.IndProblem(G, [rng.standard_normal(ni) for ni in n], 2, None, np.ones(k), ec, adj.times, adj.plus,
+                                 True, standardize=_capi.SB_CENTER | _capi.SB_SCALE)
+    with eng.create_batch([plain], eng.make_opts(2, 1e-4, _capi.SB_B2, 1)) as b:
+        nan_case = b.purity(0, sets)
+    for row, idx in zip(got[:-1], sets[:-1]):
+        want = [np.min(np.abs(x[:, idx].T @ x[:, idx] / x.shape[0])) for x in Xstd]
+        np.testing.assert_allclose(row, want, rtol=1e-9, atol=1e-11)
+    # (with covariates the residual of a constant column is rounding noise, in the reference too: no claim)
+    assert np.isfinite(nan_case[-1][0]) and np.isnan(nan_case[-1][1])
+    assert np.all(np.isfinite(nan_case[:-1]))
+
+
+def test_device_set_selection_equals_numpy(engine_lib):
+    """`sb_batch_select` on fitted loci of different widths (one just past a power of two, one exactly on it): SNP
+    order = descending alpha with ties by index, csum = numpy's left-to-right cumsum bit for bit, sizes = the
+    reference's cut; per-problem thresholds."""
+    import bench
+    from sushie_b200 import _capi
+    from sushie_b200._common import build_priors
+
+    eng = _capi.get_engine(0)
+    probs = []
+    for g, p, L in ((0, 300, 3), (1, 1025, 10), (2, 2048, 5), (3, 4500, 10)):
+        Xs, ys = bench.make_gene(g, 120, p)
+        ec, adj = build_priors(3, L, None, None, False, summary=False)
+        yy, rv = bench.prep_y(ys)
+        probs.append(_capi.IndProblem(Xs, yy, L, None, rv, ec, adj.times, adj.plus, True,
+                                      standardize=_capi.SB_CENTER | _capi.SB_SCALE))
+    thr = [0.95, 0.9, 0.5, 0.99]
+    with eng.create_batch(probs, eng.make_opts(6, 1e-4, _capi.SB_B2, 1)) as b:
+        b.run()
+        fits = b.fetch()
+        sel = b.select(thr)
+    for fit, (order, csum, sizes), t in zip(fits, sel, thr):
+        L, p = fit.alpha.shape
+        for l in range(L):
+            a = fit.alpha[l]
+            want = np.lexsort((np.arange(p), -a))
+            np.testing.assert_array_equal(order[l], want)
+            c = np.cumsum(a[want])
+            np.testing.assert_array_equal(csum[l], c)
+            n_row = int(np.count_nonzero(c < t))
+            assert sizes[l] == (n_row if n_row == p else n_row + 1)
+
+
+def test_row_view_folds_equal_materialised_folds(engine_lib, geno_storage):
+    """Cross-validation folds passed as row views of the gene's matrix (one upload, rows gathered on the device) give
+    exactly the fits of the same folds passed as materialised matrices -- hard calls and dosages."""
+    import bench
+    import sushie_b200
+    from sushie_b200 import cli
+
+    Xs, ys = bench.make_gene(5, 150, 700)
+    for mats in (list(Xs), [x.astype(np.float64) + 0.125 for x in Xs]):
+        folds = cli._prepare_cv(list(mats), list(ys), 3, 12345)
+        views = [dict(Xs=mats, ys=ys)] + [dict(Xs=f.train_geno, ys=f.train_pheno) for f in folds]
+        dense = [dict(Xs=mats, ys=ys)] + [dict(Xs=[np.asarray(x) for x in f.train_geno], ys=f.train_pheno) for f in folds]
+        a = sushie_b200.infer_sushie_batch(views, L=5, max_iter=30)
+        b = sushie_b200.infer_sushie_batch(dense, L=5, max_iter=30)
+        for ra, rb in zip(a, b):
+            np.testing.assert_array_equal(ra.elbo, rb.elbo)
+            np.testing.assert_array_equal(ra.posteriors.alpha, rb.posteriors.alpha)
+            np.testing.assert_array_equal(ra.posteriors.post_mean, rb.posteriors.post_mean)
+            np.testing.assert_array_equal(ra.l_order, rb.l_order)
+            assert ra.cs.equals(rb.cs) and ra.alphas.equals(rb.alphas)
 
 
 # ---- BASELINE.json configurations at their real shapes ------------------------------------------------

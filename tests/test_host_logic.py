@@ -5,6 +5,7 @@ import os
 import re
 
 import numpy as np
+import pandas as pd
 import pytest
 
 import sushie_b200
@@ -256,13 +257,30 @@ def test_c_abi_exports_every_declared_symbol(engine_lib):
     assert declared == set(_capi.EXPORTED_SYMBOLS)
     for name in declared:
         assert hasattr(engine_lib, name), name
-    assert engine_lib.sb_version() == 100
+    assert engine_lib.sb_version() == 110
     # struct layouts on the Python side must match the C side (sizes are a cheap proxy)
-    assert ctypes.sizeof(_capi.SbOpts) == 40
-    assert ctypes.sizeof(_capi.SbResult) == 9 * 8 + 16
-    assert ctypes.sizeof(_capi.SbRunStats) == 72  # 5 x 8 + 7 x int32, padded to 8
-    assert ctypes.sizeof(_capi.SbIndProblem) == 112  # + covar_q, covar_q_cols
-    assert ctypes.sizeof(_capi.SbSsProblem) == 96
+    structs = [("sb_opts", _capi.SbOpts, 40), ("sb_result", _capi.SbResult, 96), ("sb_run_stats", _capi.SbRunStats, 72),
+               ("sb_ind_problem", _capi.SbIndProblem, 128), ("sb_ss_problem", _capi.SbSsProblem, 96),
+               ("sb_selection", _capi.SbSelection, 24)]
+    for _, py_struct, size in structs:
+        assert ctypes.sizeof(py_struct) == size
+    # ... and the sizes a C compiler gives the header itself (the header is plain C: it must compile as such)
+    import shutil
+    import subprocess
+    import tempfile
+
+    gcc = shutil.which("gcc")
+    if gcc:
+        with tempfile.TemporaryDirectory() as tmp:
+            src = os.path.join(tmp, "sizes.c")
+            with open(src, "w") as fh:
+                fh.write('#include <stdio.h>\n#include "sushie_b200.h"\nint main(void){printf("'
+                         + " ".join(["%zu"] * len(structs)) + '\\n",'
+                         + ",".join(f"sizeof({name})" for name, _, _ in structs) + ");return 0;}\n")
+            exe = os.path.join(tmp, "sizes")
+            subprocess.run([gcc, "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), src, "-o", exe], check=True)
+            got = subprocess.run([exe], check=True, capture_output=True, text=True).stdout.split()
+        assert [int(v) for v in got] == [size for _, _, size in structs]
 
 
 def test_product_never_imports_the_oracle():
@@ -348,3 +366,151 @@ def test_plan_chunks_properties_under_random_inputs():
                 assert n_chunks >= (min(n, n_workers) if n_workers > 1 else 1)
 
     check()
+
+
+# ---- device-side set selection, effect order at download time, row views, lazy tables ---------------------------
+
+
+def _device_selection_emulated(alpha, threshold):
+    """What `sb_batch_select` computes, in numpy: descending alpha with ties by ascending SNP index, the running
+    sum accumulated left to right, the set size."""
+    L, p = alpha.shape
+    order = np.stack([np.lexsort((np.arange(p), -alpha[l])) for l in range(L)]).astype(np.int32)
+    csum = np.cumsum(np.take_along_axis(alpha, order.astype(np.int64), axis=1), axis=1)
+    n_rows = np.count_nonzero(csum < threshold, axis=1)
+    sizes = np.where(n_rows == p, n_rows, n_rows + 1).astype(np.int32)
+    return order, csum, sizes
+
+
+@pytest.mark.parametrize("permuted", [False, True])
+def test_selection_from_device_equals_host_selection(permuted):
+    rng = np.random.default_rng(11)
+    L, p = 5, 700
+    alpha = rng.dirichlet(np.ones(p) * 0.03, size=L)
+    alpha[2] = rng.dirichlet(np.ones(p) * 8.0)  # diffuse: sub-sampled
+    alpha[4] = 0.0                              # the "initial state returned" case: every SNP in the set
+    l_order = np.array([3, 0, 4, 2, 1]) if permuted else np.arange(L)
+    host = cs_mod.select_sets(alpha[l_order], 0.9, 60, 5)
+    dev = cs_mod.selection_from_device(*_device_selection_emulated(alpha, 0.9), l_order, 60, 5)
+    assert dev[2] == host[2]
+    for l in range(L):
+        if l_order[l] == 4:
+            continue  # all-equal alphas: the tie order is the sort's business
+        np.testing.assert_array_equal(dev[0][l], host[0][l])
+        np.testing.assert_array_equal(dev[1][l], host[1][l])
+        np.testing.assert_array_equal(dev[3][l], host[3][l])
+    assert dev[2][list(l_order).index(4)] == p and len(dev[3][list(l_order).index(4)]) == 60
+
+
+def test_effect_orders_equal_reorder_l():
+    import types
+
+    rng = np.random.default_rng(5)
+    fits, want = [], []
+    for L, k in ((10, 3), (10, 3), (4, 2), (10, 3), (6, 1)):
+        a = rng.standard_normal((L, k, k))
+        wsc = a @ np.transpose(a, (0, 2, 1))
+        wsc[1] = wsc[0]  # an exact tie: the stable sort keeps index order
+        fits.append(types.SimpleNamespace(weighted_sum_covar=wsc))
+        post = _common.Posterior(np.zeros((L, 3)), np.zeros((L, 3, k)), np.zeros((L, 3, k, k)), wsc, np.zeros(L),
+                                 np.zeros((L, 3)))
+        want.append(_common._reorder_l(_common.Prior(None, None, np.zeros((L, k, k))), post)[2])
+    fits[3].weighted_sum_covar = np.full((10, 3, 3), np.nan)  # non-finite fit: every norm NaN -> index order
+    got = _common.effect_orders(fits, [False, True, False, False, False])
+    assert got[1] is None
+    for i in (0, 2, 4):
+        np.testing.assert_array_equal(got[i], want[i])
+        assert got[i].dtype == np.int32
+    np.testing.assert_array_equal(got[3], np.arange(10))
+
+
+def test_sushie_result_behaves_like_the_reference_named_tuple():
+    import pickle
+
+    calls = []
+
+    def tables():
+        calls.append(1)
+        return pd.DataFrame({"CSIndex": [1]}), pd.DataFrame({"SNPIndex": [0, 1]})
+
+    pri = _common.Prior(np.ones(2) / 2, np.ones((1, 1)), np.ones((1, 1, 1)))
+    post = _common.Posterior(*[np.zeros(1)] * 6)
+    res = _common.SushieResult(pri, post, np.zeros(2), np.zeros(2), None, None, np.array([[5]]), np.array([-np.inf, -1.0]),
+                               True, np.arange(1), tables=tables)
+    assert res._fields == ("priors", "posteriors", "pip_all", "pip_cs", "cs", "alphas", "sample_size", "elbo",
+                           "elbo_increase", "l_order")
+    assert not calls and res.priors is pri and len(res) == 10
+    assert list(res.cs.columns) == ["CSIndex"] and list(res.alphas.columns) == ["SNPIndex"] and calls == [1]
+    priors, posteriors, pip_all, pip_cs, cs, alphas, ns, elbo, inc, l_order = res  # unpacks like the named tuple
+    assert cs is res.cs and res[4] is cs and res[-1] is l_order and calls == [1]
+    assert set(res._asdict()) == set(res._fields)
+    twin = res._replace(elbo_increase=False)
+    assert twin.elbo_increase is False and twin.cs is cs and res.elbo_increase is True
+    back = pickle.loads(pickle.dumps(res))
+    pd.testing.assert_frame_equal(back.alphas, res.alphas)
+    with pytest.raises(ValueError):
+        res._replace(nope=1)
+    with pytest.raises(TypeError):
+        _common.SushieResult(pri, post, np.zeros(2), np.zeros(2))
+    eager = _common.SushieResult(pri, post, np.zeros(2), np.zeros(2), cs, alphas, ns, elbo, True, l_order)
+    assert eager.cs is cs
+
+
+def test_block_built_frames_equal_the_dict_constructor():
+    rng = np.random.default_rng(2)
+    n = 37
+    cols = ["SNPIndex", "alpha_l1", "in_cs_l1", "purity_l1", "kept_l1", "pip_all"]
+    f = {"alpha_l1": rng.random(n), "purity_l1": 0.25, "pip_all": rng.random(n)}
+    i = {"SNPIndex": np.arange(n), "in_cs_l1": rng.integers(0, 2, n), "kept_l1": 1}
+    got = cs_mod._frame_from_blocks(cols, f, i, n)
+    want = pd.DataFrame({"SNPIndex": np.arange(n), "alpha_l1": f["alpha_l1"], "in_cs_l1": i["in_cs_l1"],
+                         "purity_l1": np.full(n, 0.25), "kept_l1": np.full(n, 1, dtype=np.int64), "pip_all": f["pip_all"]})
+    pd.testing.assert_frame_equal(got, want)
+    got["extra"] = 1.0  # the frame must behave like any other afterwards
+    assert got.shape == (n, 7) and got.iloc[3, 1] == f["alpha_l1"][3]
+    empty = cs_mod._frame_from_blocks(["CSIndex", "alpha"], {"alpha": np.zeros(0)}, {"CSIndex": np.zeros(0, dtype=np.int64)}, 0)
+    pd.testing.assert_frame_equal(empty, pd.DataFrame({"CSIndex": np.zeros(0, dtype=np.int64), "alpha": np.zeros(0)}))
+
+
+def test_row_views_reach_the_engine_as_one_shared_matrix():
+    """A gene's full fit and its cross-validation folds (row views) must hand the engine ONE genotype pointer per
+    ancestry plus row lists -- that is what makes it upload the matrix once."""
+    import ctypes as C
+
+    from sushie_b200 import cli, infer, utils
+
+    rng = np.random.default_rng(8)
+    n, p = 60, 130
+    G = [rng.integers(0, 3, size=(n, p)).astype(np.int8) for _ in range(2)]
+    ys = [rng.standard_normal(n) for _ in range(2)]
+    folds = cli._prepare_cv(list(G), list(ys), 5, 12345)
+    assert all(isinstance(x, utils.RowView) for f in folds for x in f.train_geno)
+    np.testing.assert_array_equal(np.asarray(folds[1].train_geno[0]), G[0][folds[1].train_geno[0].rows])
+    cache = infer._HardCallCache()
+    preps = [infer._prepare_kw(Xs=G, ys=ys, hard_cache=cache)]
+    preps += [infer._prepare_kw(Xs=f.train_geno, ys=f.train_pheno, hard_cache=cache) for f in folds]
+    assert all(pr.hard_calls == "b2" for pr in preps)
+    full = preps[0].problem
+    assert full.rows is None and [x.ctypes.data for x in full.Xs] == [g.ctypes.data for g in G]
+    for pr, fold in zip(preps[1:], folds):
+        prob = pr.problem
+        assert [x.ctypes.data for x in prob.Xs] == [g.ctypes.data for g in G]  # same memory as the full fit
+        assert prob.n.tolist() == [48, 48] and prob._src_rows.tolist() == [n, n]
+        s = _capi.SbIndProblem()
+        prob.fill(s)
+        for a in range(2):
+            assert [s.x_rows[a][r] for r in range(48)] == fold.train_geno[a].rows.tolist()
+            assert s.x_src_rows[a] == n
+    s = _capi.SbIndProblem()
+    full.fill(s)
+    assert not s.x_rows and not s.x_src_rows
+    # float genotypes that are hard calls in disguise: one int8 copy shared by every view
+    Gf = [g.astype(np.float64) for g in G]
+    cache = infer._HardCallCache()
+    a = infer._prepare_kw(Xs=Gf, ys=ys, hard_cache=cache).problem
+    b = infer._prepare_kw(Xs=[utils.RowView(g, np.arange(10, 50)) for g in Gf], ys=[y[10:50] for y in ys], hard_cache=cache).problem
+    assert a.x_dtype == _capi.SB_I8 and [x.ctypes.data for x in a.Xs] == [x.ctypes.data for x in b.Xs]
+    # dosages: dense storage, the view is still gathered on the device from the caller's matrix
+    Gd = [g + 0.25 for g in Gf]
+    c = infer._prepare_kw(Xs=[utils.RowView(g, np.arange(10, 50)) for g in Gd], ys=[y[10:50] for y in ys]).problem
+    assert c.x_dtype == _capi.SB_F64 and c.rows is not None and [x.ctypes.data for x in c.Xs] == [g.ctypes.data for g in Gd]
