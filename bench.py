@@ -266,8 +266,9 @@ def config5_run(args, path, rank, local_rank, world, dist):
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     records, trace = batch.run_distributed(
-        [float(w) for w in widths], process, store=store, rank=rank, world=world, workers_per_rank=2,
-        key=f"sushie_b200/config5/{os.environ.get('MASTER_PORT', '0')}", min_items=16, max_items=64)
+        [float(w) for w in widths], process, store=store, rank=rank, world=world, workers_per_rank=args.c5_workers,
+        key=f"sushie_b200/config5/{os.environ.get('MASTER_PORT', '0')}", min_items=args.c5_min_items,
+        max_items=args.c5_max_items)
     torch.cuda.synchronize()
     wall = time.perf_counter() - t0
     sb_config.workers_per_device = inner_workers
@@ -487,6 +488,9 @@ def main():
     ap.add_argument("--ss-iters", type=int, default=20)
     ap.add_argument("--config5-genes", type=int, default=1184,
                     help="genes of the config-5 arm (fixed total for every N: strong scaling; 0 = skip)")
+    ap.add_argument("--c5-workers", type=int, default=2, help="config-5 arm: worker threads per rank pulling chunks")
+    ap.add_argument("--c5-min-items", type=int, default=16, help="config-5 arm: smallest chunk (genes)")
+    ap.add_argument("--c5-max-items", type=int, default=64, help="config-5 arm: largest chunk (genes)")
     ap.add_argument("--no-api-arm", action="store_true", help="skip the public-API end-to-end run")
     ap.add_argument("--api-genes", type=int, default=0, help="loci of the public-API end-to-end run (0 = --genes)")
     args = ap.parse_args()

@@ -128,7 +128,11 @@ typedef struct {
   int32_t storage;           /* device storage of X / LD: SB_F64 (parity mode), SB_F32, SB_I8 or SB_B2 (see above) */
   int32_t team_size;         /* thread blocks cooperating on one locus in the first phase; 0 = choose */
   int32_t flags;             /* SB_FLAG_* */
-  int32_t reserved[3];
+  int32_t reserve_sms;       /* SMs the IBSS launches leave free (0 = use the whole device).  The persistent kernel
+                                otherwise holds every SM for seconds; with several host threads feeding one GPU, the
+                                small kernels of the other threads (column statistics of the next chunk, set
+                                selection and purity of the previous one) would queue behind it */
+  int32_t reserved[2];
 } sb_opts;
 
 /* Caller-allocated result of one problem.  Any pointer may be NULL to skip that field. */

@@ -27,13 +27,25 @@ chunk_loci: int = int(os.environ.get("SUSHIE_B200_CHUNK", "0"))
 # `chunks_per_worker` per worker while a chunk keeps `min_chunk_loci` loci (two per SM)
 chunks_per_worker: int = int(os.environ.get("SUSHIE_B200_CHUNKS_PER_WORKER", "3"))
 min_chunk_loci: int = int(os.environ.get("SUSHIE_B200_MIN_CHUNK", "296"))
-# worker threads (each with its own sb_ctx and resident batch) per GPU in the batch entry points: while one sits in
-# the engine call of its chunk, the other does the host half (set selection, tables) of the previous one
-workers_per_device: int = int(os.environ.get("SUSHIE_B200_WORKERS_PER_DEVICE", "2"))
+# worker threads (each with its own sb_ctx and resident batch) per GPU in the batch entry points.  They take turns in
+# the IBSS kernel (`_capi.device_run_lock`); while one is in it, the others do the host half of their previous chunk
+# (download, sub-sampling, results) and upload their next one, so a chunk is always ready when the kernel ends --
+# three, because a worker's own epilogue -> prologue chain is serial and two workers end up in it together
+workers_per_device: int = int(os.environ.get("SUSHIE_B200_WORKERS_PER_DEVICE", "3"))
+# SMs the IBSS kernel leaves free (sb_opts.reserve_sms; default 0 = the whole device).  Measured on config-5 chunks:
+# the other workers' small kernels (column statistics, set selection, purity) are ~8 % of a chunk's device time on
+# the WHOLE GPU, so they crawl on a handful of reserved SMs; letting them queue behind the running IBSS kernel and
+# fill its tail is faster.  Kept as a switch for latency-sensitive mixes.
+reserve_sms: int = int(os.environ.get("SUSHIE_B200_RESERVE_SMS", "0"))
 # print the wall time of the host-side phases of every chunk (upload, run, download, purity, tables) to stderr
 trace_host: bool = bool(int(os.environ.get("SUSHIE_B200_TRACE_HOST", "0")))
 # device memory budget per chunk, bytes
 chunk_bytes: int = int(float(os.environ.get("SUSHIE_B200_CHUNK_GB", "24")) * (1 << 30))
+
+
+def reserve_for(device: int) -> int:
+    """``sb_opts.reserve_sms`` for a chunk about to run on ``device``."""
+    return max(0, reserve_sms)
 
 
 def storage_code() -> int:

@@ -19,6 +19,11 @@ import pandas as pd
 from . import log
 from .utils import make_pip
 
+try:  # pandas >= 2.2: a frame from ready-made (dtype-homogeneous, transposed) blocks without sanitising every column
+    from pandas.api.internals import create_dataframe_from_blocks as _FRAME_FROM_BLOCKS
+except ImportError:  # pragma: no cover - older pandas: the dict constructor
+    _FRAME_FROM_BLOCKS = None
+
 # ---- threefry2x32 counter PRNG (jax.random's default implementation) -------------------
 
 _U32 = np.uint32
@@ -203,7 +208,7 @@ def _frame_from_blocks(columns: List[str], float_cols: dict, int_cols: dict, n_r
     """A frame of float64 and int64 columns in the given column order, assembled as two ready-made blocks
     (``pandas.api.internals.create_dataframe_from_blocks``) -- the dict constructor spends ~1 ms per fit
     sanitising and consolidating 53 columns.  Older pandas: the dict constructor."""
-    make = getattr(getattr(pd.api, "internals", None), "create_dataframe_from_blocks", None)
+    make = _FRAME_FROM_BLOCKS
     if make is None:
         merged = {**float_cols, **int_cols}
         return pd.DataFrame({name: merged[name] for name in columns})

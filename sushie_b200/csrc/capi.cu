@@ -16,6 +16,7 @@
 #include <map>
 #include <memory>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/sushie_b200.h"
@@ -44,7 +45,28 @@ struct sb_ctx {
   // (pageable) buffers; pageable destinations alone ran at ~1 GB/s for the ~8 small fields of each fit
   unsigned char* pinned = nullptr;
   size_t pinned_bytes = 0;
+  // pinned buffer for the small control transfers (iteration counts, index lists, purity results).  A copy to or
+  // from PAGEABLE memory blocks inside the call until the stream reaches it, and the driver runs such copies one at
+  // a time per process: one worker thread waiting for its device -> pageable copy behind a seconds-long IBSS kernel
+  // stalled every pageable copy of the other workers (their uploads and downloads) for as long.
+  unsigned char* ctl = nullptr;
+  size_t ctl_bytes = 0;
 };
+
+// `bytes` of the context's pinned control buffer (grown on demand; contents are not preserved)
+static unsigned char* ctl_buffer(sb_ctx* ctx, size_t bytes) {
+  if (ctx->ctl_bytes >= bytes) return ctx->ctl;
+  if (ctx->ctl) cudaFreeHost(ctx->ctl);
+  ctx->ctl = nullptr;
+  ctx->ctl_bytes = 0;
+  const size_t want = std::max<size_t>(bytes + bytes / 2, size_t(4) << 20);
+  if (cudaHostAlloc(reinterpret_cast<void**>(&ctx->ctl), want, cudaHostAllocDefault) != cudaSuccess) {
+    cudaGetLastError();
+    return nullptr;
+  }
+  ctx->ctl_bytes = want;
+  return ctx->ctl;
+}
 
 struct HostProb {
   int K = 0, p = 0, L = 0, p_pad = 0, nrows = 0;
@@ -64,6 +86,7 @@ struct sb_batch {
   int n_probs = 0;
   sb_opts opts{};
   int team_size = 1;
+  int sms = 0;  // SMs available to the IBSS kernel (device SMs minus sb_opts.reserve_sms)
   int hw_cluster = 0;
   int n_teams_cap = 0;
   int smem_bytes = 0;
@@ -216,6 +239,7 @@ extern "C" int sb_destroy(sb_ctx* ctx) {
   for (auto& ev : ctx->ev)
     if (ev) cudaEventDestroy(ev);
   if (ctx->pinned) cudaFreeHost(ctx->pinned);
+  if (ctx->ctl) cudaFreeHost(ctx->ctl);
   if (ctx->ev_block) cudaEventDestroy(ctx->ev_block);
   if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
@@ -238,6 +262,21 @@ static cudaError_t sync_stream(sb_ctx* ctx) {
   cudaError_t e = cudaEventRecord(ctx->ev_block, ctx->stream);
   if (e != cudaSuccess) return e;
   return cudaEventSynchronize(ctx->ev_block);
+}
+
+// Small device -> host read through the pinned control buffer at `ctl_off`: enqueue, wait for the stream's event,
+// copy out.  (Never a device -> pageable copy: see sb_ctx::ctl.)
+static cudaError_t read_small(sb_ctx* ctx, void* dst, const void* d_src, size_t bytes, size_t ctl_off = 0) {
+  unsigned char* buf = ctl_buffer(ctx, ctl_off + bytes);
+  if (!buf) {
+    cudaError_t e = cudaMemcpyAsync(dst, d_src, bytes, cudaMemcpyDeviceToHost, ctx->stream);
+    return e != cudaSuccess ? e : sync_stream(ctx);
+  }
+  cudaError_t e = cudaMemcpyAsync(buf + ctl_off, d_src, bytes, cudaMemcpyDeviceToHost, ctx->stream);
+  if (e != cudaSuccess) return e;
+  if ((e = sync_stream(ctx)) != cudaSuccess) return e;
+  std::memcpy(dst, buf + ctl_off, bytes);
+  return cudaSuccess;
 }
 
 // Device memory comes from the device's stream-ordered pool: cudaFree (and often cudaMalloc) synchronise the WHOLE
@@ -366,8 +405,7 @@ static bool plan_geometry(int p, int n_max, int es, bool ss, int smem_budget, Ge
   return true;
 }
 
-static int choose_team(const sb_ctx* ctx, int n_probs, double bytes_per_locus, int requested, int& hw_cluster) {
-  const int S = ctx->num_sms;
+static int choose_team(const sb_ctx* ctx, int S, int n_probs, double bytes_per_locus, int requested, int& hw_cluster) {
   int c;
   if (requested > 0) {
     c = std::min(requested, S);
@@ -597,7 +635,9 @@ static int batch_create(sb_ctx* ctx, const std::vector<GenericProblem>& gp, bool
     b->NS_max = std::max(b->NS_max, geo[i].NS);
   }
   b->smem_bytes = static_cast<int>(smem_max);
-  b->team_size = choose_team(ctx, n_probs, bytes_mean, opts.team_size, b->hw_cluster);
+  // SMs the IBSS launches of this batch may occupy (sb_opts.reserve_sms are left to other streams' small kernels)
+  b->sms = std::max(1, ctx->num_sms - std::max(0, std::min(opts.reserve_sms, ctx->num_sms / 2)));
+  b->team_size = choose_team(ctx, b->sms, n_probs, bytes_mean, opts.team_size, b->hw_cluster);
   const int C = b->team_size;
 
   // arena layout
@@ -1044,7 +1084,7 @@ static int batch_create(sb_ctx* ctx, const std::vector<GenericProblem>& gp, bool
   }
   if (hard_storage(opts.storage)) {
     int bad = 0;
-    SB_CUDA_B(cudaMemcpy(&bad, b->d_ctl + 32, sizeof(int), cudaMemcpyDeviceToHost));
+    SB_CUDA_B(read_small(ctx, &bad, b->d_ctl + 32, sizeof(int)));
     if (bad) {
       ctx->err = (bad & 2) ? "SB_B2 storage needs hard-call genotypes 0 / 1 / 2"
                            : "SB_I8 storage needs hard-call genotypes in 0..127 (negative entry found)";
@@ -1176,8 +1216,7 @@ extern "C" int sb_batch_create_ss(sb_ctx* ctx, const sb_ss_problem* probs, int n
 
 // Team-size ladder for the phased schedule: hardware clusters up to 16 blocks, then
 // co-operative (global-barrier) teams up to the whole device.
-static int next_team_size(const sb_ctx* ctx, int remaining, int current) {
-  const int S = ctx->num_sms;
+static int next_team_size(const sb_ctx* ctx, int S, int remaining, int current) {
   const int ladder[] = {1, 2, 4, 8, 16, 32, 64, S};
   int best = current;
   for (int c : ladder) {
@@ -1215,7 +1254,17 @@ extern "C" int sb_batch_run(sb_ctx* ctx, sb_batch* b, sb_run_stats* stats) {
     int hw = b->hw_cluster;
       while (!ids.empty()) {
       // (re)upload the id list of this phase: a previous run leaves the last phase's list behind
-      SB_CUDA(cudaMemcpyAsync(b->d_ids + g0, ids.data(), sizeof(int) * ids.size(), cudaMemcpyHostToDevice, st));
+      {
+        // (through the pinned control buffer; its first n_probs ints are the id list, the meta table follows)
+        unsigned char* ctl = ctl_buffer(ctx, sizeof(int) * 9 * static_cast<size_t>(b->n_probs));
+        const void* src = ids.data();
+        if (ctl) {
+          // (this group's own slice: the asynchronous copy of another group's list may still be reading its slice)
+          std::memcpy(ctl + sizeof(int) * g0, ids.data(), sizeof(int) * ids.size());
+          src = ctl + sizeof(int) * g0;
+        }
+        SB_CUDA(cudaMemcpyAsync(b->d_ids + g0, src, sizeof(int) * ids.size(), cudaMemcpyHostToDevice, st));
+      }
       cudaLaunchConfig_t cfg{};
       const int block_threads = (b->storage == SB_B2) ? sb::NT_B2 : sb::NT;
       cfg.blockDim = dim3(block_threads);
@@ -1227,7 +1276,7 @@ extern "C" int sb_batch_run(sb_ctx* ctx, sb_batch* b, sb_run_stats* stats) {
       if (C == 1) {
         int per_sm = 0;
         SB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, block_threads, b->smem_bytes));
-        max_teams = per_sm * ctx->num_sms;
+        max_teams = per_sm * b->sms;
       } else if (hw) {
         attrs[na].id = cudaLaunchAttributeClusterDimension;
         attrs[na].val.clusterDim.x = C;
@@ -1243,7 +1292,7 @@ extern "C" int sb_batch_run(sb_ctx* ctx, sb_batch* b, sb_run_stats* stats) {
       } else {
         int per_sm = 0;
         SB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, block_threads, b->smem_bytes));
-        max_teams = (per_sm * ctx->num_sms) / C;
+        max_teams = (per_sm * b->sms) / C;
         attrs[na].id = cudaLaunchAttributeCooperative;
         attrs[na].val.cooperative = 1;
         ++na;
@@ -1252,7 +1301,7 @@ extern "C" int sb_batch_run(sb_ctx* ctx, sb_batch* b, sb_run_stats* stats) {
       // co-reside (two loci per SM overlap each other's barriers and posterior phases)
       const int per_sm_cap = (b->storage == SB_I8 && C == 1) ? SB_I8_BLOCKS_PER_SM : 1;
       (void)0;
-      max_teams = std::min(max_teams, per_sm_cap * ctx->num_sms / C);
+      max_teams = std::min(max_teams, per_sm_cap * b->sms / C);
       if (max_teams < 1) {
         ctx->err = "kernel does not fit on the device (team_size=" + std::to_string(C) + ", smem=" +
                    std::to_string(b->smem_bytes) + ")";
@@ -1265,7 +1314,7 @@ extern "C" int sb_batch_run(sb_ctx* ctx, sb_batch* b, sb_run_stats* stats) {
       cfg.attrs = attrs;
       cfg.numAttrs = na;
 
-      const int bigger = (b->opts.flags & SB_FLAG_SINGLE_PHASE) ? C : next_team_size(ctx, 1, C);
+      const int bigger = (b->opts.flags & SB_FLAG_SINGLE_PHASE) ? C : next_team_size(ctx, b->sms, 1, C);
       SB_CUDA(cudaMemsetAsync(b->d_queue, 0, sizeof(int) * 64, st));
       SB_CUDA(cudaMemsetAsync(b->d_ctl, 0, sizeof(int) * 64, st));
       SB_CUDA(cudaMemsetAsync(b->d_bar, 0, sizeof(unsigned) * 64 * (2 * ctx->num_sms + 8), st));
@@ -1307,15 +1356,14 @@ extern "C" int sb_batch_run(sb_ctx* ctx, sb_batch* b, sb_run_stats* stats) {
       ++phases;
       if (!lp.allow_drain) break;  // final phase: everything runs to completion
       // which loci were suspended?
-      SB_CUDA(cudaMemcpyAsync(meta.data(), b->arena + b->metas_off, sizeof(int) * 8 * b->n_probs,
-                              cudaMemcpyDeviceToHost, st));
-      SB_CUDA(sync_stream(ctx));
+      SB_CUDA(read_small(ctx, meta.data(), b->arena + b->metas_off, sizeof(int) * 8 * b->n_probs,
+                         sizeof(int) * static_cast<size_t>(b->n_probs)));
       std::vector<int> rest;
       for (int id : ids)
         if (meta[static_cast<size_t>(id) * 8 + 4] != 2) rest.push_back(id);
       ids.swap(rest);
       if (ids.empty()) break;
-      const int c_next = next_team_size(ctx, static_cast<int>(ids.size()), C);
+      const int c_next = next_team_size(ctx, b->sms, static_cast<int>(ids.size()), C);
       if (c_next != C) {
         C = c_next;
         hw = (C > 1 && C <= 16 && ctx->cluster_ok) ? 1 : 0;
@@ -1340,9 +1388,8 @@ extern "C" int sb_batch_run(sb_ctx* ctx, sb_batch* b, sb_run_stats* stats) {
     stats->n_stages = b->NS_max;
     stats->smem_bytes = b->smem_bytes;
     stats->n_run_launches = launches;
-    SB_CUDA(cudaMemcpyAsync(meta.data(), b->arena + b->metas_off, sizeof(int) * 8 * b->n_probs,
-                            cudaMemcpyDeviceToHost, st));
-    SB_CUDA(sync_stream(ctx));
+    SB_CUDA(read_small(ctx, meta.data(), b->arena + b->metas_off, sizeof(int) * 8 * b->n_probs,
+                       sizeof(int) * static_cast<size_t>(b->n_probs)));
     for (int i = 0; i < b->n_probs; ++i) {
       stats->n_iter += meta[i * 8 + 0];
       stats->n_ser += meta[i * 8 + 3];
@@ -1350,6 +1397,47 @@ extern "C" int sb_batch_run(sb_ctx* ctx, sb_batch* b, sb_run_stats* stats) {
     }
   }
   return SB_OK;
+}
+
+// One staged piece of a download: `bytes` at `stage_off` of the pinned buffer belong at `dst` (caller memory).
+struct Piece {
+  void* dst;
+  size_t stage_off, bytes;
+};
+
+// pinned -> caller copies of a staging fill.  The destinations are freshly allocated result arrays, so the copy is
+// bound by page faults of one thread (~4 GB/s, 4x slower than the PCIe transfer that fed the pinned buffer): large
+// fills are split over a few short-lived threads (SUSHIE_B200_COPY_THREADS, default 4; 1 = the calling thread only).
+static void copy_pieces(const unsigned char* pinned, const std::vector<Piece>& pieces) {
+  static const int max_threads = [] {
+    const char* env = std::getenv("SUSHIE_B200_COPY_THREADS");
+    const int hw = static_cast<int>(std::thread::hardware_concurrency());
+    int n = env ? std::atoi(env) : std::min(4, std::max(1, hw / 8));
+    return std::max(1, std::min(n, 16));
+  }();
+  size_t total = 0;
+  for (const Piece& pc : pieces) total += pc.bytes;
+  const int nt = static_cast<int>(std::min<size_t>(max_threads, total / (size_t(8) << 20) + 1));
+  if (nt <= 1) {
+    for (const Piece& pc : pieces) std::memcpy(pc.dst, pinned + pc.stage_off, pc.bytes);
+    return;
+  }
+  // contiguous runs of pieces of about equal bytes per thread
+  std::vector<size_t> cut(nt + 1, pieces.size());
+  cut[0] = 0;
+  size_t acc = 0;
+  int t = 1;
+  for (size_t i = 0; i < pieces.size() && t < nt; ++i) {
+    acc += pieces[i].bytes;
+    if (acc >= total * t / nt) cut[t++] = i + 1;
+  }
+  auto work = [&](int w) {
+    for (size_t i = cut[w]; i < cut[w + 1]; ++i) std::memcpy(pieces[i].dst, pinned + pieces[i].stage_off, pieces[i].bytes);
+  };
+  std::vector<std::thread> pool;
+  for (int w = 1; w < nt; ++w) pool.emplace_back(work, w);
+  work(0);
+  for (std::thread& th : pool) th.join();
 }
 
 // pinned staging for downloads (allocated on first use, kept by the context)
@@ -1374,20 +1462,14 @@ extern "C" int sb_batch_fetch(sb_ctx* ctx, sb_batch* b, sb_result* results) {
   cudaSetDevice(ctx->device);
   cudaStream_t st = ctx->stream;
   std::vector<int> meta(static_cast<size_t>(b->n_probs) * 8);
-  SB_CUDA(cudaMemcpyAsync(meta.data(), b->arena + b->metas_off, sizeof(int) * 8 * b->n_probs, cudaMemcpyDeviceToHost,
-                          st));
-  SB_CUDA(sync_stream(ctx));
+  SB_CUDA(read_small(ctx, meta.data(), b->arena + b->metas_off, sizeof(int) * 8 * b->n_probs));
   ensure_pinned(ctx);
-  struct Piece {
-    unsigned char* dst;
-    size_t stage_off, bytes;
-  };
   std::vector<Piece> pieces;
   size_t staged = 0;
   auto flush = [&]() -> cudaError_t {
     cudaError_t e = sync_stream(ctx);
     if (e != cudaSuccess) return e;
-    for (const Piece& pc : pieces) std::memcpy(pc.dst, ctx->pinned + pc.stage_off, pc.bytes);
+    copy_pieces(ctx->pinned, pieces);
     pieces.clear();
     staged = 0;
     return cudaSuccess;
@@ -1557,12 +1639,21 @@ extern "C" int sb_batch_select(sb_ctx* ctx, sb_batch* b, const double* threshold
     descs[i].sizes = out[i].sizes ? reinterpret_cast<int*>(d_buf + off_sizes[i]) : nullptr;
   }
   cudaError_t e;
-  if ((e = cudaMemcpyAsync(d_buf + descs_off, descs.data(), sizeof(sb::SelectDesc) * n, cudaMemcpyHostToDevice, st)) != cudaSuccess)
-    return bail(e, "select H2D descriptors");
-  if ((e = cudaMemcpyAsync(d_buf + ids_off, ids.data(), sizeof(int) * n, cudaMemcpyHostToDevice, st)) != cudaSuccess)
-    return bail(e, "select H2D ids");
-  if ((e = cudaMemcpyAsync(d_buf + thr_off, thresholds, sizeof(double) * n, cudaMemcpyHostToDevice, st)) != cudaSuccess)
-    return bail(e, "select H2D thresholds");
+  {
+    // the three small tables are contiguous at the head of d_buf: one copy from the pinned control buffer
+    const size_t head = thr_off + sizeof(double) * n;
+    unsigned char* ctl = ctl_buffer(ctx, head);
+    std::vector<unsigned char> fallback;
+    if (!ctl) {
+      fallback.resize(head);
+      ctl = fallback.data();
+    }
+    std::memcpy(ctl + descs_off, descs.data(), sizeof(sb::SelectDesc) * n);
+    std::memcpy(ctl + ids_off, ids.data(), sizeof(int) * n);
+    std::memcpy(ctl + thr_off, thresholds, sizeof(double) * n);
+    if ((e = cudaMemcpyAsync(d_buf, ctl, head, cudaMemcpyHostToDevice, st)) != cudaSuccess) return bail(e, "select H2D tables");
+    if (!fallback.empty() && (e = sync_stream(ctx)) != cudaSuccess) return bail(e, "select H2D sync");
+  }
   const double* d_thr = reinterpret_cast<const double*>(d_buf + thr_off);
   const sb::SelectDesc* d_descs = reinterpret_cast<const sb::SelectDesc*>(d_buf + descs_off);
   const int* d_ids = reinterpret_cast<const int*>(d_buf + ids_off);
@@ -1587,16 +1678,12 @@ extern "C" int sb_batch_select(sb_ctx* ctx, sb_batch* b, const double* threshold
   }
   // download through the pinned staging buffer
   ensure_pinned(ctx);
-  struct Piece {
-    void* dst;
-    size_t stage_off, bytes;
-  };
   std::vector<Piece> pieces;
   size_t staged = 0;
   auto flush = [&]() -> cudaError_t {
     cudaError_t fe = sync_stream(ctx);
     if (fe != cudaSuccess) return fe;
-    for (const Piece& pc : pieces) std::memcpy(pc.dst, ctx->pinned + pc.stage_off, pc.bytes);
+    copy_pieces(ctx->pinned, pieces);
     pieces.clear();
     staged = 0;
     return cudaSuccess;
@@ -1680,11 +1767,23 @@ extern "C" int sb_batch_purity_many(sb_ctx* ctx, sb_batch* b, int n_sets, const 
     return SB_ECUDA;
   };
   cudaError_t e;
-  if ((e = cudaMemcpyAsync(d_idx, idx, sizeof(int) * total, cudaMemcpyHostToDevice, st)) != cudaSuccess)
+  // index lists up and results down through the pinned control buffer (see sb_ctx::ctl): [idx | offsets | ids | out]
+  const size_t out_ctl = idx_b + off_b + prob_b;
+  unsigned char* ctl = ctl_buffer(ctx, out_ctl + sizeof(double) * out_n);
+  const void *h_idx = idx, *h_off = offsets, *h_prob = set_prob;
+  if (ctl) {
+    std::memcpy(ctl, idx, sizeof(int) * total);
+    std::memcpy(ctl + idx_b, offsets, sizeof(int) * (n_sets + 1));
+    std::memcpy(ctl + idx_b + off_b, set_prob, sizeof(int) * n_sets);
+    h_idx = ctl;
+    h_off = ctl + idx_b;
+    h_prob = ctl + idx_b + off_b;
+  }
+  if ((e = cudaMemcpyAsync(d_idx, h_idx, sizeof(int) * total, cudaMemcpyHostToDevice, st)) != cudaSuccess)
     return bail(e, "purity H2D idx");
-  if ((e = cudaMemcpyAsync(d_off, offsets, sizeof(int) * (n_sets + 1), cudaMemcpyHostToDevice, st)) != cudaSuccess)
+  if ((e = cudaMemcpyAsync(d_off, h_off, sizeof(int) * (n_sets + 1), cudaMemcpyHostToDevice, st)) != cudaSuccess)
     return bail(e, "purity H2D offsets");
-  if ((e = cudaMemcpyAsync(d_prob, set_prob, sizeof(int) * n_sets, cudaMemcpyHostToDevice, st)) != cudaSuccess)
+  if ((e = cudaMemcpyAsync(d_prob, h_prob, sizeof(int) * n_sets, cudaMemcpyHostToDevice, st)) != cudaSuccess)
     return bail(e, "purity H2D problem ids");
   if ((e = cudaMemsetAsync(d_out, 0, sizeof(double) * out_n, st)) != cudaSuccess) return bail(e, "purity memset");
   // grid.x is limited only by 2^31 - 1; blocks of ancestries a problem does not have exit at once
@@ -1723,9 +1822,11 @@ extern "C" int sb_batch_purity_many(sb_ctx* ctx, sb_batch* b, int n_sets, const 
   }
 #undef SB_PUR
   if ((e = cudaGetLastError()) != cudaSuccess) return bail(e, "purity launch");
-  if ((e = cudaMemcpyAsync(out_min_abs, d_out, sizeof(double) * out_n, cudaMemcpyDeviceToHost, st)) != cudaSuccess)
+  if ((e = cudaMemcpyAsync(ctl ? static_cast<void*>(ctl + out_ctl) : static_cast<void*>(out_min_abs), d_out,
+                           sizeof(double) * out_n, cudaMemcpyDeviceToHost, st)) != cudaSuccess)
     return bail(e, "purity D2H");
   if ((e = sync_stream(ctx)) != cudaSuccess) return bail(e, "purity sync");
+  if (ctl) std::memcpy(out_min_abs, ctl + out_ctl, sizeof(double) * out_n);
   dev_free(ctx, d_buf);
   return SB_OK;
 }

@@ -204,7 +204,8 @@ def _run_prepared(preps: Sequence[_Prepared], device: int = 0, defer: bool = Fal
         p.hard_calls and p.problem.x_dtype == _capi.SB_I8 and p.problem.p <= _capi.I8_MAX_SNPS for p in preps
     ):
         storage = _capi.SB_B2 if all(p.hard_calls == "b2" for p in preps) else _capi.SB_I8
-    opts = eng.make_opts(preps[0].max_iter, preps[0].min_tol, storage, config.team_size, config.single_phase)
+    opts = eng.make_opts(preps[0].max_iter, preps[0].min_tol, storage, config.team_size, config.single_phase,
+                         config.reserve_for(device))
     return run_chunk(eng, preps, opts, _stage, defer)
 
 
@@ -221,10 +222,14 @@ def run_chunk(eng, preps, opts, stage, defer: bool) -> list:
 
     with eng.create_batch([p.problem for p in preps], opts) as batch:
         lap()
-        batch.run()
+        with _capi.device_run_lock(eng.device):  # one chunk at a time in the long kernel (see there)
+            t_wait = time.perf_counter()
+            batch.run()
+            t_run = time.perf_counter()
+            # (inside the lock: launched later, the sort kernels would queue behind the next chunk's IBSS kernel)
+            selections = batch.select([p.cs_args["threshold"] for p in preps])
         lap()
         orders = effect_orders(batch.fetch(small_only=True), [p.no_reorder for p in preps])
-        selections = batch.select([p.cs_args["threshold"] for p in preps])
         lap()
         fits = batch.fetch(orders)
         lap()
@@ -236,9 +241,10 @@ def run_chunk(eng, preps, opts, stage, defer: bool) -> list:
     if config.trace_host:
         d = np.diff(t) * 1e3
         print(
-            f"[sushie_b200] chunk of {len(preps)} fits: upload+column statistics {d[0]:.0f} ms, IBSS {d[1]:.0f} ms, "
-            f"effect order + device set selection {d[2]:.0f} ms, download {d[3]:.0f} ms, staging {d[4]:.0f} ms, "
-            f"purity {d[5]:.0f} ms",
+            f"[sushie_b200] chunk of {len(preps)} fits: upload+column statistics {d[0]:.0f} ms, "
+            f"wait for the GPU {1e3 * (t_wait - t[1]):.0f} ms, IBSS {1e3 * (t_run - t_wait):.0f} ms, "
+            f"device set selection {1e3 * (t[2] - t_run):.0f} ms, effect order {d[2]:.0f} ms, download {d[3]:.0f} ms, "
+            f"staging {d[4]:.0f} ms, purity {d[5]:.0f} ms",
             file=sys.stderr, flush=True,
         )
     if defer:

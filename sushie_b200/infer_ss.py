@@ -77,7 +77,8 @@ def _stage_ss(prep, fit, selection=None) -> StagedResult:
 def _run_prepared_ss(preps: Sequence["infer._Prepared"], device: int = 0, defer: bool = False) -> list:
     """Summary-level twin of ``infer._run_prepared`` (``defer``: see there)."""
     eng = _capi.get_engine(device)
-    opts = eng.make_opts(preps[0].max_iter, preps[0].min_tol, config.storage_code(), config.team_size, config.single_phase)
+    opts = eng.make_opts(preps[0].max_iter, preps[0].min_tol, config.storage_code(), config.team_size, config.single_phase,
+                         config.reserve_for(device))
     return infer.run_chunk(eng, preps, opts, _stage_ss, defer)
 
 

@@ -457,6 +457,11 @@ def test_sushie_result_behaves_like_the_reference_named_tuple():
 
 
 def test_block_built_frames_equal_the_dict_constructor():
+    try:
+        import pandas.api.internals as internals
+        assert cs_mod._FRAME_FROM_BLOCKS is getattr(internals, "create_dataframe_from_blocks", None)
+    except ImportError:
+        assert cs_mod._FRAME_FROM_BLOCKS is None
     rng = np.random.default_rng(2)
     n = 37
     cols = ["SNPIndex", "alpha_l1", "in_cs_l1", "purity_l1", "kept_l1", "pip_all"]
