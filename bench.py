@@ -259,8 +259,11 @@ def config5_run(args, path, rank, local_rank, world, dist):
     store = dist.distributed_c10d._get_default_store() if world > 1 else None
     if world > 1:
         dist.barrier()  # every rank's genes are on disk
-    # warm-up: a few genes per rank outside the queue (imports, kernels, shuffle cache)
-    process([g for g in range(n_genes) if g % world == rank][:4])
+    # warm-up: a few genes per rank through a private queue with the same worker count (imports, kernels, and the
+    # workers' engines -- stream, events, page-locked staging -- which a long-lived process keeps between batches)
+    warm = [g for g in range(n_genes) if g % world == rank][: 2 * args.c5_workers]
+    batch.run_distributed([float(widths[g]) for g in warm], lambda ids: process([warm[i] for i in ids]),
+                          workers_per_rank=args.c5_workers, min_items=2, max_items=2)
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
@@ -290,9 +293,12 @@ def config5_run(args, path, rank, local_rank, world, dist):
                         f"n = {N_IND} (folds {N_IND - N_IND // CV_NUM}) per ancestry, k = {K_ANC}, L = {L_EFF}, to convergence",
             "genes": n_genes, "fits": n_genes * (1 + CV_NUM), "scaling": "strong (fixed total)", "n_gpus": world,
             "wall_s": wall, "genes_per_sec": n_genes / wall, "fits_per_sec": n_genes * (1 + CV_NUM) / wall,
-            "path": "per gene: load from the shared host directory, threefry fold split, infer_sushie_batch (host prologue, "
-                    "upload, IBSS, download, credible sets + purity, tables), out-of-fold r2 -- one process per GPU, two "
-                    "worker threads each, chunks pulled from one global cost-sorted list (sushie_b200.batch.StoreQueue)",
+            "path": "per gene: load from the shared host directory, threefry fold split (folds = row views of the gene's "
+                    "matrix, uploaded once), infer_sushie_batch (host prologue, upload, IBSS, device-side set selection, "
+                    "download in effect order, purity, PIPs; the full fit's tables are built, the folds' are not asked "
+                    f"for), out-of-fold r2 -- one process per GPU, {args.c5_workers} worker threads each taking turns in "
+                    "the IBSS kernel, chunks pulled from one global cost-sorted list (sushie_b200.batch.StoreQueue)",
+            "workers_per_rank": args.c5_workers, "chunk_genes": [args.c5_min_items, args.c5_max_items],
             "collective": "none on the data path; NCCL all_gather of the per-gene result records at the end",
             "chunks": sum(len(tr) for _, tr in gathered), "genes_per_rank": per_rank,
             "mean_iters_full_fit": float(np.mean([r[0] for r in recs.values()])),
@@ -486,10 +492,10 @@ def main():
     ap.add_argument("--no-ss-arm", action="store_true", help="skip the summary-level (config 4) roofline run (N=1 only)")
     ap.add_argument("--ss-p", type=int, default=10000)
     ap.add_argument("--ss-iters", type=int, default=20)
-    ap.add_argument("--config5-genes", type=int, default=1184,
+    ap.add_argument("--config5-genes", type=int, default=2368,
                     help="genes of the config-5 arm (fixed total for every N: strong scaling; 0 = skip)")
-    ap.add_argument("--c5-workers", type=int, default=2, help="config-5 arm: worker threads per rank pulling chunks")
-    ap.add_argument("--c5-min-items", type=int, default=16, help="config-5 arm: smallest chunk (genes)")
+    ap.add_argument("--c5-workers", type=int, default=3, help="config-5 arm: worker threads per rank pulling chunks")
+    ap.add_argument("--c5-min-items", type=int, default=24, help="config-5 arm: smallest chunk (genes)")
     ap.add_argument("--c5-max-items", type=int, default=64, help="config-5 arm: largest chunk (genes)")
     ap.add_argument("--no-api-arm", action="store_true", help="skip the public-API end-to-end run")
     ap.add_argument("--api-genes", type=int, default=0, help="loci of the public-API end-to-end run (0 = --genes)")
@@ -537,6 +543,8 @@ def main():
         except Exception:
             pass
         torch.set_num_threads(max(1, cores // world))
+        # ... and the engine's download-copy helper threads (read at their first use)
+        os.environ.setdefault("SUSHIE_B200_COPY_THREADS", str(max(1, min(4, cores // world // 2))))
 
     torch.cuda.set_device(local_rank)
     if world > 1:

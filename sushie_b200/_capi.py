@@ -569,21 +569,34 @@ class Batch:
 
 
 _engines = {}
+_idle_engines = {}  # device -> engines released by finished worker threads, ready to be handed to the next one
+_MAX_IDLE_ENGINES = 4
 _engines_lock = threading.Lock()
 
 
 def get_engine(device: int = 0) -> Engine:
-    """Per-(thread, device) engine cache (one ``sb_ctx`` per host thread and GPU)."""
+    """Per-(thread, device) engine (one ``sb_ctx`` per host thread and GPU).  A thread that has none takes an idle
+    one before creating it: an engine owns a stream, events and ~260 MB of page-locked staging, and pinning that much
+    memory costs tenths of a second -- seconds when the ranks of a box all start their workers at once."""
     key = (threading.get_ident(), int(device))
     with _engines_lock:
         eng = _engines.get(key)
         if eng is None:
-            eng = Engine(device)
+            idle = _idle_engines.get(int(device))
+            eng = idle.pop() if idle else None
+            if eng is not None:
+                _engines[key] = eng
+    if eng is None:
+        eng = Engine(device)  # (outside the lock: sb_init takes a while)
+        with _engines_lock:
             _engines[key] = eng
-        return eng
+    return eng
 
 
 _run_locks = {}
+# per-thread hook called when the calling thread's chunk enters the IBSS kernel (the distributed work queue uses it
+# to let the next worker of the rank pull a chunk: see batch.run_distributed)
+run_hooks = threading.local()
 
 
 def device_run_lock(device: int) -> threading.Lock:
@@ -607,12 +620,25 @@ def engines_on_device(device: int) -> int:
 
 
 def release_thread_engines() -> None:
-    """Close and forget the engines of the calling thread.  Short-lived worker threads (``batch.run_sharded``
-    starts one per GPU and call) must not leave their ``sb_ctx`` -- a stream and events -- behind."""
+    """Give the engines of the calling thread back.  Short-lived worker threads (``batch.run_sharded`` starts some per
+    call) must not leave their ``sb_ctx`` registered under a dead thread; up to ``_MAX_IDLE_ENGINES`` per GPU are kept
+    for the next worker threads, the rest are closed."""
     me = threading.get_ident()
+    surplus = []
     with _engines_lock:
-        mine = [key for key in _engines if key[0] == me]
-        engines = [_engines.pop(key) for key in mine]
+        for key in [key for key in _engines if key[0] == me]:
+            eng = _engines.pop(key)
+            idle = _idle_engines.setdefault(key[1], [])
+            (idle if len(idle) < _MAX_IDLE_ENGINES else surplus).append(eng)
+    for eng in surplus:
+        eng.close()
+
+
+def close_idle_engines() -> None:
+    """Close every pooled engine (tests; interpreter exit)."""
+    with _engines_lock:
+        engines = [eng for idle in _idle_engines.values() for eng in idle]
+        _idle_engines.clear()
     for eng in engines:
         eng.close()
 

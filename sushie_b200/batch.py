@@ -237,14 +237,32 @@ def run_distributed(costs: Sequence[float], process_chunk: Callable[[List[int]],
     trace: list = []
     errors: list = []
     lock = threading.Lock()
+    # Look-ahead of ONE chunk per rank: a worker may pull from the global queue only when no chunk of this rank is
+    # still waiting for the GPU (the gate is handed on when a chunk enters the IBSS kernel).  Every worker pulling
+    # as soon as it is free left up to `workers_per_rank` - 1 chunks parked behind one GPU at the end of a run while
+    # other ranks had run dry (8 GPUs: the slowest rank did 1.22x the mean number of genes).
+    gate = threading.Semaphore(1)
 
     def work():
         try:
             while True:
-                c = q.next()
-                if c is None:
-                    break
-                out = process_chunk(chunks[c])
+                gate.acquire()
+                handed_on = [False]
+
+                def hand_on():
+                    if not handed_on[0]:
+                        handed_on[0] = True
+                        gate.release()
+
+                _capi.run_hooks.on_start = hand_on
+                try:
+                    c = q.next()
+                    if c is None:
+                        break
+                    out = process_chunk(chunks[c])
+                finally:
+                    hand_on()  # (also when the chunk never reached the GPU)
+                    _capi.run_hooks.on_start = None
                 with lock:
                     records.extend(zip(chunks[c], out))
                     trace.append((rank, c, len(chunks[c])))

@@ -224,6 +224,9 @@ def run_chunk(eng, preps, opts, stage, defer: bool) -> list:
         lap()
         with _capi.device_run_lock(eng.device):  # one chunk at a time in the long kernel (see there)
             t_wait = time.perf_counter()
+            hook = getattr(_capi.run_hooks, "on_start", None)
+            if hook is not None:
+                hook()
             batch.run()
             t_run = time.perf_counter()
             # (inside the lock: launched later, the sort kernels would queue behind the next chunk's IBSS kernel)

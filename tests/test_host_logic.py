@@ -519,3 +519,43 @@ def test_row_views_reach_the_engine_as_one_shared_matrix():
     Gd = [g + 0.25 for g in Gf]
     c = infer._prepare_kw(Xs=[utils.RowView(g, np.arange(10, 50)) for g in Gd], ys=[y[10:50] for y in ys]).problem
     assert c.x_dtype == _capi.SB_F64 and c.rows is not None and [x.ctypes.data for x in c.Xs] == [g.ctypes.data for g in Gd]
+
+
+def test_distributed_queue_looks_one_chunk_ahead():
+    """`run_distributed`: every item exactly once; a worker pulls from the queue only when no chunk of its rank is
+    still waiting for the GPU (the gate is handed on by the hook `run_chunk` calls on entering the IBSS kernel)."""
+    import threading
+    import time
+
+    gpu = threading.Lock()
+    state = {"waiting": 0, "max_waiting": 0, "pulled": 0}
+    guard = threading.Lock()
+
+    def process(ids):
+        with guard:
+            state["waiting"] += 1
+            state["pulled"] += 1
+            state["max_waiting"] = max(state["max_waiting"], state["waiting"])
+        time.sleep(0.002)  # prologue + upload
+        with gpu:
+            with guard:
+                state["waiting"] -= 1
+            _capi.run_hooks.on_start()
+            time.sleep(0.01)  # the kernel
+        time.sleep(0.004)  # epilogue
+        return [i * i for i in ids]
+
+    costs = [float(c) for c in np.random.default_rng(0).integers(1, 50, size=90)]
+    records, trace = batch.run_distributed(costs, process, workers_per_rank=3, min_items=4, max_items=8)
+    assert sorted(records) == [(i, i * i) for i in range(90)]
+    assert sum(n for _, _, n in trace) == 90 and state["pulled"] == len(trace)
+    assert state["max_waiting"] == 1
+    assert getattr(_capi.run_hooks, "on_start", None) is None  # (the calling thread never had one)
+
+    def failing(ids):  # a chunk that dies before the GPU must not wedge the other workers
+        if 0 in ids:
+            raise RuntimeError("bad gene")
+        return process(ids)
+
+    with pytest.raises(RuntimeError, match="bad gene"):
+        batch.run_distributed(costs, failing, workers_per_rank=3, min_items=4, max_items=8)
