@@ -3,7 +3,9 @@
 Follows ``/root/reference/sushie/infer.py:835-1008`` step by step (same pandas calls:
 ``sort_values`` with its default sort kind, ``cumsum``, ``merge``), with the JAX PRNG
 sub-sampling replaced by the threefry restatement in ``oracle/threefry.py``.
-PARITY UNPINNED (see ``oracle/ibss.py``): the reference cannot be executed here.
+PARITY: pinned against the reference's own ``make_cs`` source executed through ``tests/refshim``
+(``tests/test_reference_shim.py``: three purity methods, sub-sampling; identical tables) -- see the header of
+``oracle/ibss.py`` for what that pin covers and what it does not (the third-party primitives).
 """
 from __future__ import annotations
 
