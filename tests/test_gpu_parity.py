@@ -526,3 +526,37 @@ def test_config4_full_size_fp32_storage(engine_lib, golden_config4):
     finally:
         config.precision = old
     assert_fit_matches(res, g, "c4")
+
+
+def test_device_set_selection_of_a_locus_too_wide_for_shared_memory(engine_lib):
+    """p = 17 000 pads to 32 768 sort keys (384 KB): `sb_batch_select` sorts in a global-memory scratch slot per effect.
+    Same contract as the shared-memory path; a narrow locus in the same batch takes the shared-memory launch."""
+    from sushie_b200 import _capi
+    from sushie_b200._common import build_priors
+
+    rng = np.random.default_rng(21)
+    eng = _capi.get_engine(0)
+    probs = []
+    for p, n in ((17000, [40, 30]), (700, [40, 30])):
+        Xs = [rng.standard_normal((ni, p)).astype(np.float32) for ni in n]
+        beta = np.zeros(p)
+        beta[[5, p - 3]] = [1.0, -1.0]
+        ys = [x.astype(np.float64) @ beta + rng.standard_normal(x.shape[0]) for x in Xs]
+        ys = [(y - y.mean()) / y.std() for y in ys]
+        ec, adj = build_priors(2, 3, None, None, False, summary=False)
+        probs.append(_capi.IndProblem(Xs, ys, 3, None, [np.var(y, ddof=1) for y in ys], ec, adj.times, adj.plus, True,
+                                      standardize=_capi.SB_CENTER | _capi.SB_SCALE))
+    with eng.create_batch(probs, eng.make_opts(3, 1e-4, _capi.SB_F32, 1)) as b:
+        b.run()
+        fits = b.fetch()
+        sel = b.select([0.95, 0.8])
+    for fit, (order, csum, sizes), t in zip(fits, sel, (0.95, 0.8)):
+        L, p = fit.alpha.shape
+        for l in range(L):
+            a = fit.alpha[l]
+            want = np.lexsort((np.arange(p), -a))
+            np.testing.assert_array_equal(order[l], want)
+            c = np.cumsum(a[want])
+            np.testing.assert_array_equal(csum[l], c)
+            n_row = int(np.count_nonzero(c < t))
+            assert sizes[l] == (n_row if n_row == p else n_row + 1)
