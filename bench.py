@@ -242,7 +242,7 @@ def config5_run(args, path, rank, local_rank, world, dist):
             folds = cli._prepare_cv(list(Xs), list(ys), CV_NUM, 12345)
             folds_of.append(folds)
             specs.append(dict(Xs=Xs, ys=ys))
-            specs.extend(dict(Xs=f.train_geno, ys=f.train_pheno) for f in folds)
+            specs.extend(dict(Xs=f.train_geno, ys=f.train_pheno, lazy_tables=True) for f in folds)
         fits = sushie_b200.infer_sushie_batch(specs, **kw)
         out = []
         for i, g in enumerate(ids):
@@ -725,9 +725,11 @@ def main():
         barrier()
         t0 = time.perf_counter()
         results = sushie_b200.infer_sushie_batch(api_probs, **kw)
+        # (both tables of every result exist when the call returns; reading them is inside the timed region anyway)
+        n_cs = int(sum(len(set(r.cs.CSIndex.values.tolist())) for r in results))
+        n_alpha_cols = int(sum(r.alphas.shape[1] for r in results))
         barrier()
-        api = {"ms": 1e3 * (time.perf_counter() - t0), "loci": n_api,
-               "n_cs": int(sum(len(set(r.cs.CSIndex.values.tolist())) for r in results))}
+        api = {"ms": 1e3 * (time.perf_counter() - t0), "loci": n_api, "n_cs": n_cs, "alphas_columns": n_alpha_cols}
         del results
 
     # ---- config 5 arm: the multi-GPU design itself (work queue, ragged genes, CV folds, public API)

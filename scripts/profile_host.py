@@ -42,7 +42,7 @@ def main():
             folds = cli._prepare_cv(list(Xs), list(ys), bench.CV_NUM, 12345)
             folds_of.append(folds)
             specs.append(dict(Xs=Xs, ys=ys))
-            specs.extend(dict(Xs=f.train_geno, ys=f.train_pheno) for f in folds)
+            specs.extend(dict(Xs=f.train_geno, ys=f.train_pheno, lazy_tables=True) for f in folds)
         fits = sushie_b200.infer_sushie_batch(specs, L=bench.L_EFF, max_iter=500, min_tol=1e-4, devices=[0])
         out = []
         for i, g in enumerate(ids):

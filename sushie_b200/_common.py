@@ -46,9 +46,10 @@ class SushieResult:
     ``_asdict`` and ``_replace`` behave as there.
 
     One difference: the two pandas tables (``cs``, ``alphas``) may be handed over as a zero-argument ``tables``
-    callable and are then built on first access.  Everything they are made of (set selection, purity, PIPs) is
-    computed up front; only the ``DataFrame`` assembly -- about as expensive as the fit itself at batch
-    throughput, and never looked at for e.g. cross-validation folds -- is deferred."""
+    callable and are then built on first access.  ``infer_sushie`` / ``infer_sushie_ss`` and the batch entry points
+    build them before returning, as the reference does; a batch problem marked ``lazy_tables=True`` (the CLI marks
+    cross-validation folds, whose tables nobody reads) skips the ``DataFrame`` assembly until someone asks.
+    Everything the tables are made of (set selection, purity, PIPs) is always computed up front."""
 
     _fields = ("priors", "posteriors", "pip_all", "pip_cs", "cs", "alphas", "sample_size", "elbo", "elbo_increase",
                "l_order")
@@ -359,13 +360,14 @@ class StagedResult:
     start the next chunk before results are assembled."""
 
     def __init__(self, fit, pi, sample_size, no_reorder, threshold, purity, purity_method, max_select, seed,
-                 selection=None):
+                 selection=None, lazy_tables=False):
         from . import cs as _cs
 
         if purity_method not in ("weighted", "max", "min"):
             raise ValueError(f"Invalid purity method {purity_method}. Choose from 'weighted', 'max', or 'min'.")
         self._fit, self._sample_size = fit, sample_size
         self._purity, self._purity_method = purity, purity_method
+        self._lazy_tables = lazy_tables
         self._priors, self._posteriors, self._l_order = _reordered(fit, pi, no_reorder)
         log.logger.debug("Computing credible sets.")
         if selection is not None:
@@ -381,7 +383,8 @@ class StagedResult:
 
         def finish() -> SushieResult:
             # purity, kept sets and PIPs now (cheap, and the reference's log line needs them); the two pandas
-            # tables on first access
+            # tables here too (the batch entry points run this on a finisher thread, under the GPU's next chunk)
+            # unless the caller said it will not look at them (`lazy_tables`: cross-validation folds)
             alpha, log_bf = self._posteriors.alpha, self._posteriors.log_bf
             selection = self._selection
             purities, kept, pip_all, pip_cs = _cs.summarise_sets(
@@ -391,9 +394,12 @@ class StagedResult:
                 return _cs.frames(alpha, log_bf, selection, purities, kept, pip_all, pip_cs)
 
             log.logger.debug("Inference and credible set computation complete. Beginning to write results.")
-            return SushieResult(
+            result = SushieResult(
                 self._priors, self._posteriors, pip_all, pip_cs, None, None, self._sample_size, self._fit.elbo,
                 self._fit.elbo_increase, self._l_order, tables=tables,
             )
+            if not self._lazy_tables:
+                result._build()
+            return result
 
         return finish

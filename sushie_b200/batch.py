@@ -32,17 +32,18 @@ def estimate_bytes(prep) -> int:
 
 
 def plan_chunks(preps: Sequence, chunk_bytes: Optional[int] = None, chunk_loci: Optional[int] = None,
-                n_workers: int = 1) -> List[List[int]]:
+                n_workers: int = 1, n_devices: Optional[int] = None) -> List[List[int]]:
     """Group problem indices into chunks.
 
     Problems that cannot share a launch configuration (different ``max_iter`` /
     ``min_tol``, or hard-call vs dense genotype storage) never share a chunk.  Within a group, indices are sorted by descending
     cost (longest-processing-time first) and cut where the memory budget or the locus
     cap is reached.  With several workers and no explicit cap (``chunk_loci`` = 0) a group is cut into at least one
-    chunk per worker, and into up to ``config.chunks_per_worker`` per worker while the chunks keep at least
-    ``config.min_chunk_loci`` loci, so the workers finish together.  One worker keeps a group in one chunk:
-    measured on a B200, three chunks of 300 ragged loci cost more device time (a tail per chunk and per kernel
-    variant) than overlapping their table assembly gains."""
+    chunk per DEVICE (``n_devices``; default: one device per worker), and into up to ``config.chunks_per_worker`` per
+    worker while the chunks keep at least ``config.min_chunk_loci`` loci (two per SM).  The workers of one GPU take
+    turns in the IBSS kernel, so cutting a small group into one chunk per worker would only run its loci one after
+    the other instead of side by side on the SMs: chunks are for pipelining the host half of big batches, and a
+    group below ``2 * min_chunk_loci`` loci per device stays whole."""
     chunk_bytes = config.chunk_bytes if chunk_bytes is None else chunk_bytes
     chunk_loci = config.chunk_loci if chunk_loci is None else chunk_loci
     groups: Dict[Tuple, List[int]] = {}
@@ -58,7 +59,8 @@ def plan_chunks(preps: Sequence, chunk_bytes: Optional[int] = None, chunk_loci: 
         if chunk_loci:
             caps = [chunk_loci]
         elif n_workers > 1:
-            n_cut = max(n_workers, min(config.chunks_per_worker * n_workers, len(ids) // max(1, config.min_chunk_loci)))
+            n_dev = n_workers if n_devices is None else max(1, n_devices)
+            n_cut = max(n_dev, min(config.chunks_per_worker * n_workers, len(ids) // max(1, config.min_chunk_loci)))
             n_cut = min(n_cut, len(ids))
             caps = [len(ids) // n_cut + (1 if c < len(ids) % n_cut else 0) for c in range(n_cut)]
         cur: List[int] = []
@@ -177,7 +179,7 @@ def run_sharded(preps: Sequence, runner: Callable, devices: Optional[Sequence[in
     devices = list(devices)
     # several worker threads per GPU: the host half of one chunk overlaps the device half of the next
     workers = [d for d in devices for _ in range(max(1, config.workers_per_device))]
-    chunks = plan_chunks(preps, n_workers=len(workers))
+    chunks = plan_chunks(preps, n_workers=len(workers), n_devices=len(devices))
     q = ChunkQueue(len(chunks))
     results: list = [None] * len(preps)
     trace: list = []

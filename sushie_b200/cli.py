@@ -233,7 +233,8 @@ def _cv_specs(args, cv_data: List[io.CVData], pi) -> List[dict]:
               resid_var=args.resid_var, effect_var=args.effect_var, rho=args.rho, max_iter=args.max_iter,
               min_tol=args.min_tol, threshold=args.threshold, purity=args.purity, max_select=args.max_select,
               seed=args.seed)
-    return [dict(kw, Xs=fold.train_geno, ys=fold.train_pheno) for fold in cv_data[: args.cv_num]]
+    # (only the folds' posterior means are read, cli.py:404-410: their output tables are not assembled)
+    return [dict(kw, Xs=fold.train_geno, ys=fold.train_pheno, lazy_tables=True) for fold in cv_data[: args.cv_num]]
 
 
 def _cv_scores(cv_data: List[io.CVData], fits) -> List[List[float]]:

@@ -204,67 +204,91 @@ def summarise_sets(alpha, ns, min_abs, purity: float, purity_method: str, select
     return purities, kept, pip_all, pip_cs
 
 
-def _frame_from_blocks(columns: List[str], float_cols: dict, int_cols: dict, n_rows: int) -> pd.DataFrame:
-    """A frame of float64 and int64 columns in the given column order, assembled as two ready-made blocks
-    (``pandas.api.internals.create_dataframe_from_blocks``) -- the dict constructor spends ~1 ms per fit
-    sanitising and consolidating 53 columns.  Older pandas: the dict constructor."""
-    make = _FRAME_FROM_BLOCKS
-    if make is None:
-        merged = {**float_cols, **int_cols}
-        return pd.DataFrame({name: merged[name] for name in columns})
+@functools.lru_cache(maxsize=64)
+def _alphas_layout(n_l: int):
+    """Column index of the ``alphas`` table for ``n_l`` effects and where its float64 / int64 columns sit (building
+    the string index costs more than filling the frame, and it is the same for every locus)."""
+    columns, floats, ints = ["SNPIndex"], [], ["SNPIndex"]
+    for ldx in range(n_l):
+        tag = f"l{ldx + 1}"
+        columns += [f"alpha_{tag}", f"in_cs_{tag}", f"purity_{tag}", f"kept_{tag}", f"log_bf_{tag}"]
+        floats += [f"alpha_{tag}", f"purity_{tag}", f"log_bf_{tag}"]
+        ints += [f"in_cs_{tag}", f"kept_{tag}"]
+    columns += ["pip_all", "pip_cs"]
+    floats += ["pip_all", "pip_cs"]
+    return _layout(columns, floats, ints)
+
+
+def _layout(columns: List[str], floats: List[str], ints: List[str]):
     position = {name: i for i, name in enumerate(columns)}
-    blocks = []
-    for cols, dtype in ((float_cols, np.float64), (int_cols, np.int64)):
-        if not cols:
-            continue
-        block = np.empty((len(cols), n_rows), dtype=dtype)
-        for r, values in enumerate(cols.values()):
-            block[r] = values
-        blocks.append((block, np.asarray([position[name] for name in cols], dtype=np.intp)))
-    return make(blocks, index=pd.RangeIndex(n_rows), columns=pd.Index(columns))
+    index = pd.Index(columns)
+    return (index, tuple(columns), tuple(floats), np.asarray([position[c] for c in floats], dtype=np.intp),
+            tuple(ints), np.asarray([position[c] for c in ints], dtype=np.intp))
+
+
+_CS_LAYOUT = None
+
+
+def _cs_layout():
+    global _CS_LAYOUT
+    if _CS_LAYOUT is None:
+        _CS_LAYOUT = _layout(["CSIndex", "SNPIndex", "alpha", "c_alpha", "pip_all", "pip_cs"],
+                             ["alpha", "c_alpha", "pip_all", "pip_cs"], ["CSIndex", "SNPIndex"])
+    return _CS_LAYOUT
+
+
+def _frame_from_blocks(layout, float_block: np.ndarray, int_block: np.ndarray) -> pd.DataFrame:
+    """A frame of float64 and int64 columns in the layout's column order from its two ready-made blocks
+    (``[columns of the dtype, rows]``; ``pandas.api.internals.create_dataframe_from_blocks``) -- the dict constructor
+    spends ~1 ms per fit sanitising and consolidating 53 columns.  Older pandas: the dict constructor."""
+    index, columns, floats, float_pos, ints, int_pos = layout
+    n_rows = float_block.shape[1]
+    if _FRAME_FROM_BLOCKS is None:
+        merged = {name: float_block[r] for r, name in enumerate(floats)}
+        merged.update({name: int_block[r] for r, name in enumerate(ints)})
+        return pd.DataFrame({name: merged[name] for name in columns})
+    return _FRAME_FROM_BLOCKS([(float_block, float_pos), (int_block, int_pos)], index=pd.RangeIndex(n_rows), columns=index)
 
 
 def frames(alpha, log_bf, selection, purities, kept, pip_all, pip_cs):
     """The ``cs`` and ``alphas`` tables in the reference's schema (``infer.py:897-1008``) from the selected sets."""
     n_l, p = alpha.shape
     orders, csums, sizes, _ = selection
-    columns = ["SNPIndex"]
-    float_cols, int_cols = {}, {"SNPIndex": np.arange(p)}
+    layout = _alphas_layout(n_l)
+    fb = np.empty((3 * n_l + 2, p))                    # alpha, purity, log_bf per effect; pip_all, pip_cs
+    ib = np.zeros((2 * n_l + 1, p), dtype=np.int64)    # SNPIndex; in_cs, kept per effect
+    ib[0] = np.arange(p)
     cs_parts = []
     for ldx in range(n_l):
         order, csum, size = orders[ldx], csums[ldx], sizes[ldx]
-        in_cs = np.zeros(p, dtype=np.int64)
-        in_cs[order[:size]] = 1
-        tag = f"l{ldx + 1}"
-        columns += [f"alpha_{tag}", f"in_cs_{tag}", f"purity_{tag}", f"kept_{tag}", f"log_bf_{tag}"]
-        float_cols[f"alpha_{tag}"] = alpha[ldx]
-        int_cols[f"in_cs_{tag}"] = in_cs
-        float_cols[f"purity_{tag}"] = purities[ldx]
-        int_cols[f"kept_{tag}"] = int(kept[ldx])
-        float_cols[f"log_bf_{tag}"] = log_bf[ldx]
+        fb[3 * ldx] = alpha[ldx]
+        fb[3 * ldx + 1] = purities[ldx]
+        fb[3 * ldx + 2] = log_bf[ldx]
+        ib[2 * ldx + 1, order[:size]] = 1
+        ib[2 * ldx + 2] = int(kept[ldx])
         if kept[ldx]:
             sel = np.asarray(order[:size])
-            cs_parts.append((np.full(size, ldx + 1, dtype=np.int64), sel.astype(np.int64), alpha[ldx][sel], csum[:size]))
-    columns += ["pip_all", "pip_cs"]
-    float_cols["pip_all"] = pip_all
-    float_cols["pip_cs"] = pip_cs
-    full_alphas = _frame_from_blocks(columns, float_cols, int_cols, p)
+            cs_parts.append((ldx + 1, sel, alpha[ldx][sel], csum[:size]))
+    fb[3 * n_l] = pip_all
+    fb[3 * n_l + 1] = pip_cs
+    full_alphas = _frame_from_blocks(layout, fb, ib)
 
     # one frame for all kept sets, built in one go (a frame per effect, or adding columns afterwards, costs
     # more than the fit at batch throughput)
-    if cs_parts:
-        cs_index = np.concatenate([c[0] for c in cs_parts])
-        snp_in_cs = np.concatenate([c[1] for c in cs_parts])
-        cs_alpha = np.concatenate([c[2] for c in cs_parts])
-        cs_c_alpha = np.concatenate([c[3] for c in cs_parts])
-    else:
-        cs_index = snp_in_cs = np.zeros(0, dtype=np.int64)
-        cs_alpha = cs_c_alpha = np.zeros(0)
-    cs = _frame_from_blocks(
-        ["CSIndex", "SNPIndex", "alpha", "c_alpha", "pip_all", "pip_cs"],
-        {"alpha": cs_alpha, "c_alpha": cs_c_alpha, "pip_all": pip_all[snp_in_cs], "pip_cs": pip_cs[snp_in_cs]},
-        {"CSIndex": cs_index, "SNPIndex": snp_in_cs}, len(snp_in_cs),
-    )
+    n_rows = sum(len(part[1]) for part in cs_parts)
+    cfb = np.empty((4, n_rows))                         # alpha, c_alpha, pip_all, pip_cs
+    cib = np.empty((2, n_rows), dtype=np.int64)         # CSIndex, SNPIndex
+    pos = 0
+    for cs_index, sel, a_sel, c_sel in cs_parts:
+        end = pos + len(sel)
+        cib[0, pos:end] = cs_index
+        cib[1, pos:end] = sel
+        cfb[0, pos:end] = a_sel
+        cfb[1, pos:end] = c_sel
+        pos = end
+    cfb[2] = pip_all[cib[1]]
+    cfb[3] = pip_cs[cib[1]]
+    cs = _frame_from_blocks(_cs_layout(), cfb, cib)
     return cs, full_alphas
 
 

@@ -52,8 +52,10 @@ __all__ = [
 class _Prepared:
     """One validated problem: engine arguments + what the epilogue needs."""
 
-    def __init__(self, problem, pi, sample_size, max_iter, min_tol, cs_args, no_reorder, hard_calls=False):
+    def __init__(self, problem, pi, sample_size, max_iter, min_tol, cs_args, no_reorder, hard_calls=False,
+                 lazy_tables=False):
         self.problem = problem
+        self.lazy_tables = lazy_tables  # the caller will not read `cs` / `alphas` (built on first access if it does)
         # device storage class of the genotypes: False = dense matrix at `config.precision`; "i8" = integers in
         # 0..127, not residualised (one byte per entry); "b2" = additionally only 0 / 1 / 2 and inside the limits of
         # the bit-plane traversal (look-up tables instead of fp64 multiply-adds on widened genotypes)
@@ -190,7 +192,8 @@ def _prepare(
 def _stage(prep: _Prepared, fit, selection=None) -> StagedResult:
     """Host half of the epilogue of one fit before the purity launch: convergence log, set selection."""
     log_convergence(fit.n_iter, prep.max_iter, prep.min_tol, fit.elbo, fit.elbo_increase)
-    return StagedResult(fit, prep.pi, prep.sample_size, prep.no_reorder, **prep.cs_args, selection=selection)
+    return StagedResult(fit, prep.pi, prep.sample_size, prep.no_reorder, **prep.cs_args, selection=selection,
+                        lazy_tables=prep.lazy_tables)
 
 
 def _run_prepared(preps: Sequence[_Prepared], device: int = 0, defer: bool = False) -> list:
@@ -296,6 +299,8 @@ def infer_sushie_batch(problems: Sequence[dict], devices: Optional[Sequence[int]
 
     ``problems`` is a sequence of dicts with at least ``Xs`` and ``ys`` (plus any
     per-locus ``infer_sushie`` keyword); ``common`` holds keywords shared by all loci.
+    One extra keyword, per locus or common: ``lazy_tables=True`` leaves the ``cs`` / ``alphas`` frames of that
+    result to be built on first access (for fits whose tables are never read: cross-validation folds).
     Loci are sharded over ``devices`` by a host work queue (``sushie_b200.batch``);
     results come back in input order."""
     from . import batch as _batch
@@ -316,12 +321,14 @@ def infer_sushie_batch(problems: Sequence[dict], devices: Optional[Sequence[int]
 def _prepare_kw(
     Xs, ys, covar=None, L=10, no_scale=False, no_regress=False, no_update=False, pi=None, resid_var=None,
     effect_var=None, rho=None, max_iter=500, min_tol=1e-4, threshold=0.95, purity=0.5, purity_method="weighted",
-    max_select=250, min_snps=100, no_reorder=False, seed=12345, hard_cache=None,
+    max_select=250, min_snps=100, no_reorder=False, seed=12345, hard_cache=None, lazy_tables=False,
 ) -> _Prepared:
-    return _prepare(
+    prep = _prepare(
         Xs, ys, covar, L, no_scale, no_regress, no_update, pi, resid_var, effect_var, rho,
         max_iter, min_tol, threshold, purity, purity_method, max_select, min_snps, no_reorder, seed, hard_cache,
     )
+    prep.lazy_tables = bool(lazy_tables)
+    return prep
 
 
 def make_cs(

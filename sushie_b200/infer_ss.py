@@ -29,7 +29,7 @@ __all__ = ["infer_sushie_ss", "infer_sushie_ss_batch"]
 def _prepare_ss(
     lds, ns, zs, L=10, no_update=False, pi=None, resid_var=None, effect_var=None, rho=None, max_iter=500,
     min_tol=1e-4, threshold=0.95, purity=0.5, purity_method="weighted", max_select=250, min_snps=100,
-    no_reorder=False, seed=12345,
+    no_reorder=False, seed=12345, lazy_tables=False,
 ) -> "infer._Prepared":
     ns = np.asarray(ns)
     n_pop = ns.shape[0]
@@ -66,12 +66,13 @@ def _prepare_ss(
         adj.times, adj.plus, em_update=not no_update,
     )
     cs_args = dict(threshold=threshold, purity=purity, purity_method=purity_method, max_select=max_select, seed=seed)
-    return infer._Prepared(problem, pi, ns, max_iter, min_tol, cs_args, no_reorder)
+    return infer._Prepared(problem, pi, ns, max_iter, min_tol, cs_args, no_reorder, lazy_tables=bool(lazy_tables))
 
 
 def _stage_ss(prep, fit, selection=None) -> StagedResult:
     log_convergence(fit.n_iter, prep.max_iter, prep.min_tol, fit.elbo, fit.elbo_increase)
-    return StagedResult(fit, prep.pi, prep.sample_size, prep.no_reorder, **prep.cs_args, selection=selection)
+    return StagedResult(fit, prep.pi, prep.sample_size, prep.no_reorder, **prep.cs_args, selection=selection,
+                        lazy_tables=prep.lazy_tables)
 
 
 def _run_prepared_ss(preps: Sequence["infer._Prepared"], device: int = 0, defer: bool = False) -> list:

@@ -225,6 +225,12 @@ def test_auto_chunking_gives_every_worker_a_chunk(monkeypatch):
     eight = batch.plan_chunks(preps, n_workers=8)                # small chunks rather than idle GPUs
     assert len(eight) == 8 and sorted(i for c in eight for i in c) == list(range(1300))
     assert len(batch.plan_chunks(preps[:5], n_workers=8)) == 5
+    # several workers per GPU (they take turns in the IBSS kernel): chunks are for pipelining big batches, a small
+    # group stays whole on its device instead of running its loci one chunk after the other
+    assert len(batch.plan_chunks(preps[:6], n_workers=3, n_devices=1)) == 1
+    assert len(batch.plan_chunks(preps[:500], n_workers=3, n_devices=1)) == 1
+    assert sorted(len(c) for c in batch.plan_chunks(preps[:1000], n_workers=3, n_devices=1)) == [333, 333, 334]
+    assert sorted(len(c) for c in batch.plan_chunks(preps[:6], n_workers=6, n_devices=2)) == [3, 3]
 
 
 @pytest.mark.parametrize("devices", [[0], [0, 1, 2]])
@@ -332,6 +338,14 @@ def test_staged_epilogue_equals_one_shot_assembly(no_reorder):
     np.testing.assert_array_equal(one.posteriors.alpha, two.posteriors.alpha)
     with pytest.raises(ValueError, match="Invalid purity method"):
         _common.StagedResult(fit, None, ns, True, 0.9, 0.5, "median", 50, 7)
+    # the tables exist when the finisher returns, unless the problem was marked `lazy_tables`
+    assert two._tables is None
+    lazy = _common.StagedResult(fit, None, ns, no_reorder, **cs_args, lazy_tables=True)
+    three = lazy.finisher(min_abs(lazy.purity_sets))()
+    assert three._tables is not None
+    np.testing.assert_array_equal(three.pip_cs, two.pip_cs)  # (PIPs never wait for the tables)
+    pd_testing.assert_frame_equal(three.alphas, two.alphas)
+    assert three._tables is None
 
 
 def test_plan_chunks_properties_under_random_inputs():
@@ -456,25 +470,57 @@ def test_sushie_result_behaves_like_the_reference_named_tuple():
     assert eager.cs is cs
 
 
-def test_block_built_frames_equal_the_dict_constructor():
+def test_block_built_frames_equal_the_dict_constructor(monkeypatch):
     try:
         import pandas.api.internals as internals
         assert cs_mod._FRAME_FROM_BLOCKS is getattr(internals, "create_dataframe_from_blocks", None)
     except ImportError:
         assert cs_mod._FRAME_FROM_BLOCKS is None
     rng = np.random.default_rng(2)
-    n = 37
-    cols = ["SNPIndex", "alpha_l1", "in_cs_l1", "purity_l1", "kept_l1", "pip_all"]
-    f = {"alpha_l1": rng.random(n), "purity_l1": 0.25, "pip_all": rng.random(n)}
-    i = {"SNPIndex": np.arange(n), "in_cs_l1": rng.integers(0, 2, n), "kept_l1": 1}
-    got = cs_mod._frame_from_blocks(cols, f, i, n)
-    want = pd.DataFrame({"SNPIndex": np.arange(n), "alpha_l1": f["alpha_l1"], "in_cs_l1": i["in_cs_l1"],
-                         "purity_l1": np.full(n, 0.25), "kept_l1": np.full(n, 1, dtype=np.int64), "pip_all": f["pip_all"]})
-    pd.testing.assert_frame_equal(got, want)
-    got["extra"] = 1.0  # the frame must behave like any other afterwards
-    assert got.shape == (n, 7) and got.iloc[3, 1] == f["alpha_l1"][3]
-    empty = cs_mod._frame_from_blocks(["CSIndex", "alpha"], {"alpha": np.zeros(0)}, {"CSIndex": np.zeros(0, dtype=np.int64)}, 0)
-    pd.testing.assert_frame_equal(empty, pd.DataFrame({"CSIndex": np.zeros(0, dtype=np.int64), "alpha": np.zeros(0)}))
+    L, p = 3, 41
+    alpha = rng.dirichlet(np.ones(p) * 0.05, size=L)
+    log_bf = rng.standard_normal((L, p))
+    selection = cs_mod.select_sets(alpha, 0.9, 10, 3)
+    purities, kept = np.array([0.9, 0.2, 0.7]), np.array([True, False, True])
+    pip_all, pip_cs = utils.make_pip(alpha), utils.make_pip(alpha[[0, 2]])
+
+    # the reference's schema written out column by column with the dict constructor
+    cols = {"SNPIndex": np.arange(p)}
+    rows = []
+    for l in range(L):
+        order, csum, size = selection[0][l], selection[1][l], selection[2][l]
+        in_cs = np.zeros(p, dtype=np.int64)
+        in_cs[order[:size]] = 1
+        cols[f"alpha_l{l + 1}"] = alpha[l]
+        cols[f"in_cs_l{l + 1}"] = in_cs
+        cols[f"purity_l{l + 1}"] = np.full(p, purities[l])
+        cols[f"kept_l{l + 1}"] = np.full(p, int(kept[l]), dtype=np.int64)
+        cols[f"log_bf_l{l + 1}"] = log_bf[l]
+        if kept[l]:
+            rows.append(pd.DataFrame({"CSIndex": np.full(size, l + 1, dtype=np.int64), "SNPIndex": order[:size].astype(np.int64),
+                                      "alpha": alpha[l][order[:size]], "c_alpha": csum[:size]}))
+    cols["pip_all"], cols["pip_cs"] = pip_all, pip_cs
+    want_alphas = pd.DataFrame(cols)
+    want_cs = pd.concat(rows, ignore_index=True)
+    want_cs["pip_all"] = pip_all[want_cs.SNPIndex.values]
+    want_cs["pip_cs"] = pip_cs[want_cs.SNPIndex.values]
+
+    for use_blocks in (True, False):  # the block path and the older-pandas path give the same frames
+        if not use_blocks:
+            monkeypatch.setattr(cs_mod, "_FRAME_FROM_BLOCKS", None)
+        elif cs_mod._FRAME_FROM_BLOCKS is None:
+            continue
+        cs, alphas = cs_mod.frames(alpha, log_bf, selection, purities, kept, pip_all, pip_cs)
+        pd.testing.assert_frame_equal(alphas, want_alphas)  # values, dtypes, column order, index
+        pd.testing.assert_frame_equal(cs, want_cs)
+        alphas["extra"] = 1.0  # the frame must behave like any other afterwards
+        assert alphas.shape == (p, 5 * L + 4) and alphas.iloc[3, 1] == alpha[0, 3]
+    # no kept set: an empty cs frame with the right columns and dtypes
+    cs, _ = cs_mod.frames(alpha, log_bf, selection, purities, np.zeros(L, dtype=bool), pip_all, np.zeros(p))
+    pd.testing.assert_frame_equal(cs, pd.DataFrame({"CSIndex": np.zeros(0, dtype=np.int64), "SNPIndex": np.zeros(0, dtype=np.int64),
+                                                   "alpha": np.zeros(0), "c_alpha": np.zeros(0), "pip_all": np.zeros(0),
+                                                   "pip_cs": np.zeros(0)}))
+    assert cs_mod._alphas_layout(L)[0] is cs_mod._alphas_layout(L)[0]  # one shared column index per effect count
 
 
 def test_row_views_reach_the_engine_as_one_shared_matrix():
