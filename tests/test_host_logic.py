@@ -541,6 +541,14 @@ def test_row_views_reach_the_engine_as_one_shared_matrix():
     preps = [infer._prepare_kw(Xs=G, ys=ys, hard_cache=cache)]
     preps += [infer._prepare_kw(Xs=f.train_geno, ys=f.train_pheno, hard_cache=cache) for f in folds]
     assert all(pr.hard_calls == "b2" for pr in preps)
+    # what the CLI passes for the folds (`_cv_specs`): their tables are not assembled unless somebody reads them
+    import argparse
+    ns_args = argparse.Namespace(L=3, no_scale=False, no_regress=False, no_update=False, resid_var=None, effect_var=None,
+                                 rho=None, max_iter=50, min_tol=1e-3, threshold=0.95, purity=0.5, max_select=250,
+                                 seed=12345, cv_num=5)
+    specs = cli._cv_specs(ns_args, folds, None)
+    assert len(specs) == 5 and all(sp["lazy_tables"] for sp in specs)
+    assert infer._prepare_kw(**specs[0]).lazy_tables and not preps[0].lazy_tables
     full = preps[0].problem
     assert full.rows is None and [x.ctypes.data for x in full.Xs] == [g.ctypes.data for g in G]
     for pr, fold in zip(preps[1:], folds):
