@@ -613,3 +613,77 @@ def test_distributed_queue_looks_one_chunk_ahead():
 
     with pytest.raises(RuntimeError, match="bad gene"):
         batch.run_distributed(costs, failing, workers_per_rank=3, min_items=4, max_items=8)
+
+
+def test_run_chunk_epilogue_with_a_stand_in_engine():
+    """`infer.run_chunk` end to end on the CPU with a stand-in for the device batch: effect order from the small
+    download, posteriors delivered in that order, set selection handed over in engine order, one purity call per
+    chunk, tables built eagerly or on demand -- and the result equal to the host-only `build_tables` path."""
+    import types
+
+    from sushie_b200 import infer
+
+    L, p, k = 4, 300, 2
+    alpha = np.random.default_rng(1).dirichlet(np.ones(p) * 0.05, size=L)
+    wsc = np.stack([np.eye(k) * w for w in (0.3, 2.0, 1.0, 0.1)])
+    calls = []
+
+    class Batch:
+        def __init__(self, n):
+            self.n = n
+
+        def __enter__(self):
+            return self
+
+        def __exit__(self, *exc):
+            return False
+
+        def run(self):
+            calls.append("run")
+
+        def fetch(self, effect_orders=None, small_only=False):
+            calls.append("fetch_small" if small_only else "fetch")
+            fits = []
+            for i in range(self.n):
+                order = np.arange(L) if effect_orders is None or effect_orders[i] is None else effect_orders[i]
+                f = _capi.RawFit(k, p, L, 20, small_only)
+                f.weighted_sum_covar[:] = wsc[order]
+                if not small_only:
+                    f.alpha[:] = alpha[order]
+                    f.log_bf[:] = np.log(alpha[order] + 1e-300)
+                    f.effect_covar[:] = wsc[order]
+                    f.post_mean[:], f.post_mean_sq[:], f.kl[:], f.resid_var[:] = 0.0, 0.0, 0.0, 1.0
+                    if effect_orders is not None and effect_orders[i] is not None:
+                        f.l_order = np.asarray(order, dtype=np.int32)
+                f.n_iter, f.elbo, f.elbo_increase = 2, np.array([-np.inf, -2.0, -1.0]), True
+                fits.append(f)
+            return fits
+
+        def select(self, thresholds):
+            calls.append("select")
+            return [_device_selection_emulated(alpha, t) for t in thresholds]
+
+        def purity_many(self, sets_per_problem):
+            calls.append("purity")
+            return [np.full((len(sets), k), 0.9) for sets in sets_per_problem]
+
+    engine = types.SimpleNamespace(device=0, create_batch=lambda problems, opts: Batch(len(problems)))
+    ns = np.array([[100], [100]])
+    cs_args = dict(threshold=0.9, purity=0.5, purity_method="weighted", max_select=50, seed=1)
+    preps = [infer._Prepared(types.SimpleNamespace(), None, ns, 20, 1e-4, cs_args, no_reorder, lazy_tables=lazy)
+             for no_reorder, lazy in ((False, False), (False, True), (True, False))]
+    out = infer.run_chunk(engine, preps, None, infer._stage, False)
+    assert calls == ["run", "select", "fetch_small", "fetch", "purity"]
+    assert out[0]._tables is None and out[1]._tables is not None and out[2]._tables is None
+    np.testing.assert_array_equal(out[0].l_order, [1, 2, 0, 3])
+    np.testing.assert_array_equal(out[2].l_order, np.arange(L))
+    for res in out:
+        lo = np.asarray(res.l_order)
+        want = cs_mod.build_tables(alpha[lo], np.log(alpha[lo] + 1e-300), ns, lambda sets: np.full((len(sets), k), 0.9),
+                                   0.9, 0.5, "weighted", 50, 1)
+        pd.testing.assert_frame_equal(res.cs, want[0])
+        pd.testing.assert_frame_equal(res.alphas, want[1])
+        np.testing.assert_array_equal(res.pip_all, want[2])
+        np.testing.assert_array_equal(res.posteriors.weighted_sum_covar, wsc[lo])
+    deferred = infer.run_chunk(engine, preps[:1], None, infer._stage, True)
+    assert callable(deferred[0]) and deferred[0]().cs.equals(out[0].cs)
