@@ -612,13 +612,6 @@ def device_run_lock(device: int) -> threading.Lock:
         return lock
 
 
-def engines_on_device(device: int) -> int:
-    """Host threads that currently hold an engine (a ``sb_ctx``) on ``device`` -- more than one means their kernels
-    share the GPU (work-queue workers)."""
-    with _engines_lock:
-        return sum(1 for _, dev in _engines if dev == int(device))
-
-
 def release_thread_engines() -> None:
     """Give the engines of the calling thread back.  Short-lived worker threads (``batch.run_sharded`` starts some per
     call) must not leave their ``sb_ctx`` registered under a dead thread; up to ``_MAX_IDLE_ENGINES`` per GPU are kept
